@@ -1,0 +1,181 @@
+/*
+ * pdelab_b200.h — C ABI of the B200-native operator-evaluation path.
+ *
+ * This is the drop-in boundary.  The reference (dune-pdelab) has no FFI of its
+ * own: the path lives behind the C++ class template Dune::PDELab::GridOperator
+ * (dune/pdelab/gridoperator/gridoperator.hh:30-35).  Each entry point below names the reference
+ * member it replaces; the C++ mirror in dune-pdelab_b200/host/gridoperator.hh forwards to these
+ * symbols, and INTEGRATION.md shows the binding a PDELab maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only, no C++/torch types;
+ *  - every function returns 0 on success, non-zero on error; pdb200_last_error() gives the text
+ *    (the reference throws Dune::Exception, e.g. gridoperator.hh:195; the C++ mirror rethrows);
+ *  - vector/matrix pointers may be HOST or DEVICE memory (detected with
+ *    cudaPointerGetAttributes).  Host pointers are staged through pinned buffers and the call is
+ *    synchronous on return; device pointers run on the handle's stream and are asynchronous;
+ *  - results are ACCUMULATED into r / y / values exactly like the reference engines
+ *    (gridoperator/default/residualengine.hh:184-188, jacobianapplyengine.hh:197-202);
+ *  - there is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ *
+ * Data model of the coefficient fields.  The reference takes a C++ parameter class with call-backs
+ * (localoperator/convectiondiffusionparameter.hh:135-209).  Across a C ABI these become arrays,
+ * sampled exactly where the reference evaluates the call-backs:
+ *   A       per cell (cell centre; permeabilityIsConstantPerCell()==true, :139-142)
+ *   b, c    per cell (cell-wise constant fields)
+ *   f       per cell and volume quadrature point  f[cell*nq + q],  q = q0 + m*(q1 + m*q2)
+ *   bctype  per boundary face (int8: Dirichlet=1, Neumann=-1, Outflow=-2, None=-3, :111-115)
+ *   g,j,o   per boundary face and face quadrature point  g[bface*nfq + q], q = t0 + m*t1 over the
+ *           tangential directions in increasing order
+ * with m = (2*degree+intorderadd)/2 + 1 Gauss-Legendre points per direction in ascending order
+ * (convectiondiffusiondg.hh:139-140).  Boundary faces are numbered direction-major:
+ * for d in 0..dim-1, for side in {0 (lower), 1 (upper)}: faces lexicographic in the tangential
+ * cell coordinates; pdb200_boundary_face_offset() returns the first index of each (d,side) group.
+ */
+#ifndef PDELAB_B200_H
+#define PDELAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* finite element space: finiteelementmap/qkdg.hh:36-76 (QkDG, Lagrange basis) and
+ * finiteelementmap/qkfem.hh:17-78 (conforming Qk, k in {1,2}) */
+enum { PDB200_SPACE_QKDG = 0, PDB200_SPACE_QK = 1 };
+/* ConvectionDiffusionDGMethod::Type, convectiondiffusiondg.hh:31 */
+enum { PDB200_DG_NIPG = 0, PDB200_DG_SIPG = 1, PDB200_DG_IIPG = 2 };
+/* ConvectionDiffusionDGWeights::Type, convectiondiffusiondg.hh:36 */
+enum { PDB200_DG_WEIGHTS_ON = 0, PDB200_DG_WEIGHTS_OFF = 1 };
+/* ConvectionDiffusionBoundaryConditions::Type, convectiondiffusionparameter.hh:113 */
+enum { PDB200_BC_DIRICHLET = 1, PDB200_BC_NEUMANN = -1, PDB200_BC_OUTFLOW = -2, PDB200_BC_NONE = -3 };
+/* layout of the diffusion tensor array */
+enum { PDB200_A_IDENTITY = 0, PDB200_A_SCALAR = 1, PDB200_A_DIAGONAL = 2, PDB200_A_FULL = 3 };
+/* kind of the six outer sides of the (local) grid box */
+enum { PDB200_SIDE_DOMAIN = 0,     /* physical boundary: alpha_boundary is integrated            */
+       PDB200_SIDE_PROCESSOR = 1   /* processor boundary of an overlapping partition: nothing is
+                                      integrated (default/assembler.hh:239-250) and the cells that
+                                      touch it are constrained (constraints/p0.hh:31-41)          */ };
+/* kernel selection */
+enum { PDB200_KERNEL_AUTO = 0, PDB200_KERNEL_GENERIC = 1, PDB200_KERNEL_FAST = 2 };
+
+typedef struct pdb200_problem {
+  int32_t dim;            /* 2 or 3                                                              */
+  int32_t cells[3];       /* YaspGrid cells per direction (of the LOCAL box incl. overlap)       */
+  double  lower[3];       /* lower-left corner of the local box                                  */
+  double  upper[3];       /* upper-right corner of the local box                                 */
+  int32_t space;          /* PDB200_SPACE_*                                                      */
+  int32_t degree;         /* k                                                                   */
+  int32_t dg_method;      /* PDB200_DG_*      (ConvectionDiffusionDG ctor, :85-102)              */
+  int32_t dg_weights;     /* PDB200_DG_WEIGHTS_*                                                 */
+  double  dg_alpha;       /* penalty constant alpha                                              */
+  int32_t intorderadd;    /* extra quadrature order                                              */
+  int32_t a_mode;         /* PDB200_A_*                                                          */
+  const double* A;        /* [cells * {1, dim, dim*dim}] (row-major tensor) or NULL              */
+  const double* b;        /* [cells * dim] or NULL (= 0)                                         */
+  const double* c;        /* [cells] or NULL (= 0)                                               */
+  const double* f;        /* [cells * m^dim] or NULL (= 0)                                       */
+  const int8_t* bctype;   /* [boundary faces] or NULL (= all Dirichlet)                          */
+  const double* g;        /* [boundary faces * m^(dim-1)] or NULL (= 0)                          */
+  const double* j;        /* same layout, Neumann flux, or NULL                                  */
+  const double* o;        /* same layout, outflow flux, or NULL                                  */
+  int32_t side_kind[3][2];/* PDB200_SIDE_* for (direction, lower/upper)                          */
+  int32_t device;         /* CUDA device ordinal                                                 */
+  int32_t kernel;         /* PDB200_KERNEL_*                                                     */
+} pdb200_problem;
+
+typedef struct pdb200_operator* pdb200_handle;
+
+/* text of the last error on the calling thread (replaces Dune::Exception::what()) */
+const char* pdb200_last_error(void);
+
+/* GridOperator::GridOperator(gfsu,cu,gfsv,cv,lop,mb), gridoperator.hh:76-89 — builds the DOF
+ * numbering (ordering/leafgridviewordering.hh:120-197), the constraint set
+ * (constraints/conforming.hh:53-93, constraints/p0.hh:31-41) and uploads the coefficient fields.
+ * All arrays in *p may be host or device memory; they are copied. */
+int pdb200_create(const pdb200_problem* p, pdb200_handle* out);
+int pdb200_destroy(pdb200_handle h);
+
+/* re-upload coefficient arrays (same shapes); NULL members of *p are left unchanged */
+int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p);
+
+/* GridOperator::globalSizeU()/globalSizeV(), gridoperator.hh:104-113 */
+int pdb200_num_dofs(pdb200_handle h, uint64_t* n);
+int pdb200_local_size(pdb200_handle h, uint32_t* n);          /* DOFs per cell, (k+1)^dim      */
+int pdb200_num_boundary_faces(pdb200_handle h, uint64_t* n);
+int pdb200_boundary_face_offset(pdb200_handle h, int dir, int side, uint64_t* first);
+int pdb200_quadrature_size(pdb200_handle h, uint32_t* m);     /* Gauss points per direction    */
+/* ascending Gauss-Legendre abscissae on [0,1] and weights, m entries each (host arrays) */
+int pdb200_quadrature(pdb200_handle h, double* points, double* weights);
+
+/* container index of local DOF i of cell `cell`: LFSIndexCache::containerIndex,
+ * gridfunctionspace/lfsindexcache.hh:603-633 + ordering/leaforderingbase.hh:97-203.
+ * Writes (k+1)^dim entries (host array). */
+int pdb200_cell_dof_indices(pdb200_handle h, uint64_t cell, uint64_t* idx);
+
+/* constrained DOFs (constraints(bctype,gfs,cc), constraints/common/constraints.hh:588-687).
+ * Two-call protocol: idx == NULL returns the count. Sorted ascending. */
+int pdb200_constrained_dofs(pdb200_handle h, uint64_t* count, uint64_t* idx);
+
+/* GridOperator::residual(x, r), gridoperator.hh:176-181:   r += R(x), constrained rows := 0 */
+int pdb200_residual(pdb200_handle h, const double* x, double* r);
+
+/* GridOperator::jacobian_apply(z, y) (linear variant), gridoperator.hh:192-197:  y += J z,
+ * constrained rows := 0 (jacobianapplyengine.hh:249-254) */
+int pdb200_jacobian_apply(pdb200_handle h, const double* z, double* y);
+
+/* GridOperator::jacobian_apply(u, z, y) (non-linear variant), gridoperator.hh:200-205.  Both
+ * supported local operators are linear, so like the reference this always fails (:202-203). */
+int pdb200_jacobian_apply_nonlinear(pdb200_handle h, const double* u, const double* z, double* y);
+
+/* BCRSMatrixBackend::buildPattern -> GridOperator::fill_pattern(p), gridoperator.hh:168-173,
+ * backend/istl/bcrsmatrixbackend.hh:90-121,225-241.  Scalar CSR over DOFs, column indices
+ * ascending inside a row (dune-istl setIndices).  size_t-compatible output (host or device). */
+int pdb200_pattern_size(pdb200_handle h, uint64_t* nrows, uint64_t* nnz);
+int pdb200_pattern(pdb200_handle h, uint64_t* rowptr, uint64_t* colidx);
+/* same pattern with 32-bit column indices (device-native layout) */
+int pdb200_pattern_i32(pdb200_handle h, uint64_t* rowptr, uint32_t* colidx);
+
+/* DG with ISTL::VectorBackend<Blocking::fixed,n>: block CSR over cells, blocks are row-major
+ * FieldMatrix<double,n,n> stored contiguously (backend/common/aliasedmatrixview.hh:93-97). */
+int pdb200_block_pattern_size(pdb200_handle h, uint64_t* nblockrows, uint64_t* nblocks);
+int pdb200_block_pattern(pdb200_handle h, uint64_t* rowptr, uint64_t* colidx);
+
+/* GridOperator::jacobian(x, A), gridoperator.hh:184-189: values += dR/dx in the order of
+ * pdb200_pattern (layout 0) or pdb200_block_pattern (layout 1); afterwards constrained rows are
+ * cleared and get a unit diagonal (assemblerutilities.hh:666-684, bcrsmatrix.hh:254-258). */
+enum { PDB200_LAYOUT_CSR = 0, PDB200_LAYOUT_BCSR = 1 };
+int pdb200_jacobian(pdb200_handle h, const double* x, double* values, int layout);
+
+/* y = A x with the assembled matrix (dune-istl BCRSMatrix::mv as used by
+ * backend/istl/seqistlsolverbackend.hh MatrixAdapter) — used to check jacobian against
+ * jacobian_apply on the device. */
+int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const double* x, double* y);
+
+/* Halo exchange support for the overlapping partition (replaces the AddDataHandle/CopyDataHandle
+ * communication of boilerplate/pdelab.hh:872-880 + gridfunctionspace/genericdatahandle.hh).
+ * pack copies the DOFs of the owned cell layer next to side (dir,side) — the layer at distance
+ * `overlap` from the box face — into a contiguous DEVICE buffer; unpack writes a received buffer
+ * into the ghost layer of that side.  The transport (NCCL send/recv) is done by the caller. */
+int pdb200_halo_layer_size(pdb200_handle h, int dir, uint64_t* ndoubles);
+int pdb200_halo_pack(pdb200_handle h, const double* x, int dir, int side, double* buf);
+int pdb200_halo_unpack(pdb200_handle h, double* x, int dir, int side, const double* buf);
+
+/* stream control for device-pointer calls: `stream` is a cudaStream_t */
+int pdb200_set_stream(pdb200_handle h, void* stream);
+int pdb200_synchronize(pdb200_handle h);
+
+/* number of kernel launches issued by this handle so far (bench.py "gpu_launches") */
+int pdb200_launch_count(pdb200_handle h, uint64_t* n);
+/* name of the kernel variant the last jacobian_apply / residual used ("dg_fast_q2_3d", ...) */
+const char* pdb200_last_kernel(pdb200_handle h);
+
+/* library / build identification */
+const char* pdb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDELAB_B200_H */
