@@ -1,0 +1,130 @@
+// common.cuh — shared definitions of the sm_100a operator-evaluation kernels.
+//
+// Reference paths in comments are relative to /root/reference/dune/pdelab/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/pdelab_b200.h"
+
+namespace pdb {
+
+constexpr int MAX_K = 4;            // highest polynomial degree with a compiled kernel
+constexpr int MAX_N1 = MAX_K + 1;   // 1-D basis functions
+constexpr int MAX_M = MAX_K + 1;    // Gauss points per direction (intorderadd in {0,1})
+constexpr int MAX_PTS = MAX_M + 2;  // Gauss points, then xi = 0, then xi = 1
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct DevParams {
+  int dim, k, n1, n, m, nq, nfq;
+  int N[3];
+  long long ncells, ndofs;
+  double h[3], ih[3], area[3], vol;
+  double theta, alpha;
+  int weights_on, a_mode, dg;
+  int side_kind[3][2];
+  long long bf_off[3][2];
+  const double *A, *b, *c, *f, *g, *j, *o;
+  const int8_t* bctype;
+  // 1-D tables: P[pt][i] = p_i(x_pt), DP[pt][i] = p_i'(x_pt)  (finiteelement/qkdglagrange.hh:55-79)
+  double P[MAX_PTS * MAX_N1], DP[MAX_PTS * MAX_N1], wq[MAX_M];
+};
+
+// exactly integrated 1-D matrices of the Lagrange basis on [0,1] used by the Kronecker kernels
+struct Kron1D {
+  double M[MAX_N1 * MAX_N1];      // mass
+  double Minv[MAX_N1 * MAX_N1];
+  double d0[MAX_N1], d1[MAX_N1];  // p_i'(0), p_i'(1)
+  // t_i += E0[i]*(a u'(0)) + E1[i]*(a u'(1)) + m0[i]*FL + mk[i]*FR + q0[i]*GL + q1[i]*GR   (k = 2)
+  double E0[MAX_N1], E1[MAX_N1], m0[MAX_N1], mk[MAX_N1], q0[MAX_N1], q1[MAX_N1];
+  double MinvK[MAX_N1 * MAX_N1];  // Minv * stiffness
+};
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define PDB_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      throw pdb::Error(std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+__host__ __device__ inline long long cell_index(const int N[3], int x, int y, int z) {
+  return x + (long long)N[0] * (y + (long long)N[1] * z);
+}
+
+// boundary-face number of face (dir, side) of the cell (x,y,z); numbering of pdelab_b200.h
+__host__ __device__ inline long long bface_index(const DevParams& P, const int c[3], int dir, int side) {
+  long long idx = 0, stride = 1;
+  for (int d = 0; d < P.dim; d++)
+    if (d != dir) {
+      idx += stride * c[d];
+      stride *= P.N[d];
+    }
+  return P.bf_off[dir][side] + idx;
+}
+
+__device__ inline void load_A(const DevParams& P, long long cell, double A[3][3]) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A[i][j] = 0.0;
+  switch (P.a_mode) {
+    case PDB200_A_IDENTITY:
+      for (int i = 0; i < P.dim; i++) A[i][i] = 1.0;
+      break;
+    case PDB200_A_SCALAR: {
+      double v = __ldg(P.A + cell);
+      for (int i = 0; i < P.dim; i++) A[i][i] = v;
+    } break;
+    case PDB200_A_DIAGONAL:
+      for (int i = 0; i < P.dim; i++) A[i][i] = __ldg(P.A + cell * P.dim + i);
+      break;
+    default:
+      for (int i = 0; i < P.dim; i++)
+        for (int j = 0; j < P.dim; j++) A[i][j] = __ldg(P.A + cell * P.dim * P.dim + i * P.dim + j);
+  }
+}
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+
+struct Operator;  // operator.cu
+
+// dg_generic.cu: reference-order gather kernels, any supported (dim,k), any coefficient mode
+void launch_dg_generic(const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+                       int* errflag, cudaStream_t s);
+// dg_fast.cu: Kronecker-factorised kernel (k = 2, dim = 3, diagonal A, b = 0)
+bool dg_fast_supported(const DevParams& P);
+struct FastPlan;
+FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K);
+void dg_fast_plan_destroy(FastPlan*);
+void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual,
+                    bool overwrite, cudaStream_t s);
+
+
+// halo.cu: pack / unpack one cell layer of a DG vector
+void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);
+
+// fem.cu: conforming Qk residual / jacobian_apply (coloured scatter)
+struct FemPlan;
+FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev);
+void fem_plan_destroy(FemPlan*);
+void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+                       cudaStream_t s);
+
+// matrix.cu: sparsity pattern (CSR / block CSR), assembled Jacobian, SpMV
+struct MatrixPlan;
+MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s);
+void matrix_plan_destroy(MatrixPlan*);
+void matrix_pattern_size(MatrixPlan*, int layout, uint64_t* nrows, uint64_t* nnz);
+int matrix_pattern_write(MatrixPlan*, int layout, void* rowptr, bool rowptr_dev, void* colidx, bool colidx_dev,
+                         bool col32, cudaStream_t s);
+int matrix_assemble(MatrixPlan*, int layout, double* values, bool values_dev, bool fresh, int* errflag,
+                    cudaStream_t s);
+int matrix_mv(MatrixPlan*, int layout, const double* values, const double* x, double* y, cudaStream_t s);
+
+}  // namespace pdb

@@ -1,0 +1,421 @@
+// dg_fast.cu — bandwidth-oriented jacobian_apply for the headline configuration:
+//   QkDG k = 2, dim = 3, cell-wise constant DIAGONAL diffusion tensor, b = 0, optional c,
+//   SIPG/NIPG/IIPG with or without harmonic weights, Dirichlet / Neumann / None boundary faces.
+//
+// What it computes is exactly GridOperator::jacobian_apply for ConvectionDiffusionDG
+// (gridoperator/gridoperator.hh:192-197 -> localoperator/convectiondiffusiondg.hh:106-188,
+// 271-471, 684-879), but not with the reference's quadrature loops.  On an axis-aligned grid
+// with cell-wise constant diagonal A every integrand is a product of 1-D polynomials of degree
+// <= 2k, which the reference's (k+1)-point Gauss rule integrates exactly, so the operator equals
+//     y_e = |K| (M (x) M (x) M) [ sum_d (1/h_d) M^-1 L_d(z_{e-d}, z_e, z_{e+d}) + c_e z_e ]
+// with M the exact 1-D mass matrix and L_d the 1-D SIPG operator along direction d (volume
+// stiffness + both face terms, coefficients from A_dd of the cell and its two d-neighbours).
+// Derivation and the numpy statement of the same formula: DESIGN.md §5, tests/kron_reference.py.
+// Results agree with the quadrature form to rounding (tests: <= 1e-12 relative to the oracle).
+//
+// Mapping to the machine (B200, sm_100a):
+//   * CTA = 8x4x4 cells, one thread per cell (128 threads, 3 CTAs/SM).
+//   * The cell tile plus its face halo (320 cells * 216 B = 69 KB) is brought into shared memory
+//     by 5 TMA tensor copies (cp.async.bulk.tensor.4d) completing on one mbarrier; out-of-domain
+//     cells are zero-filled by the TMA unit.  The global tensor is viewed as
+//     [54 doubles = 2 cells][Nx/2][Ny][Nz] so that all strides are multiples of 16 B.
+//   * A thread keeps its 27 DOFs and 27 accumulators in registers; neighbour traces and normal
+//     derivatives are read from the shared tile (lane mapping chosen so that the 216-B cell
+//     stride is bank-conflict free).
+//   * The result tile is staged in shared memory and written with ONE TMA tensor store, so global
+//     traffic is fully coalesced: 8 B/DOF read (+ halo re-reads served by L2) + 8 B/DOF written.
+
+#include <cuda.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace pdb {
+
+namespace {
+
+constexpr int TX = 8, TY = 4, TZ = 4;
+constexpr int NLOC = 27;
+constexpr int ROWX = TX + 4;                      // cells per x-row in smem: x0-2 .. x0+TX+1
+constexpr int R0 = 0;                             // x-rows   [TZ][TY][ROWX] cells
+constexpr int R1 = R0 + TZ * TY * ROWX * NLOC;    // y-halo lower  [TZ][TX]
+constexpr int R2 = R1 + TZ * TX * NLOC;           // y-halo upper
+constexpr int R3 = R2 + TZ * TX * NLOC;           // z-halo lower  [TY][TX]
+constexpr int R4 = R3 + TY * TX * NLOC;           // z-halo upper
+constexpr int SMEM_DOUBLES = R4 + TY * TX * NLOC;
+constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;      // 69,120 B
+static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 && (R4 * 8) % 128 == 0,
+              "TMA destinations must be 128-byte aligned");
+
+struct FastConst {
+  double E0[3], E1[3], m0[3], mk[3], q0[3], q1[3];  // see Kron1D
+  double Mm[9];                                     // 1-D mass matrix
+  double ih2[3];                                    // 1/h_d^2
+  double alpha_pen;                                 // alpha * k (k + dim - 1)
+  double theta, vol;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ double load_adiag(const DevParams& P, long long cell, int d) {
+  switch (P.a_mode) {
+    case PDB200_A_IDENTITY: return 1.0;
+    case PDB200_A_SCALAR: return __ldg(P.A + cell);
+    case PDB200_A_DIAGONAL: return __ldg(P.A + cell * 3 + d);
+    default: return __ldg(P.A + cell * 9 + d * 4);
+  }
+}
+
+// One face of the 1-D operator along a direction: returns the four scalars
+//   cs = w_self a / h^2, co = w_other a_other / h^2, cg = alpha pen harm / h^2 (penalty),
+// following convectiondiffusiondg.hh:326-346 (interior) and :717-734 (Dirichlet boundary).
+// kind: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None/Neumann/Outflow with b=0,
+// processor boundary).
+__device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double alpha_pen, int weights_on,
+                                          double& cs, double& co, double& cg) {
+  if (kind == 0) {
+    double ws, wo, harm;
+    if (weights_on) {
+      const double inv = 1.0 / (a + ao + 1e-20);
+      ws = ao * inv;
+      wo = a * inv;
+      harm = 2.0 * a * ao * inv;
+    } else {
+      ws = wo = 0.5;
+      harm = 1.0;
+    }
+    cs = ws * a * ih2;
+    co = wo * ao * ih2;
+    cg = alpha_pen * harm * ih2;
+  } else if (kind == 1) {
+    cs = a * ih2;
+    co = 0.0;
+    cg = alpha_pen * (weights_on ? a : 1.0) * ih2;
+  } else {
+    cs = co = cg = 0.0;
+  }
+}
+
+// Adds (1/h_d) M^-1 L_d(l, o, r) for the nine lines of a cell along direction S-stride.
+//   S = 1 (x), 3 (y), 9 (z): stride of the local node index along the direction.
+template <int S>
+__device__ __forceinline__ void sweep(const double (&o)[NLOC], double (&t)[NLOC], const double* __restrict__ nl,
+                                      const double* __restrict__ nr, const FastConst& F, double A0, double csL,
+                                      double coL, double cgL, double csR, double coR, double cgR) {
+  // t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
+  double P1[3], P2[3], P3[3], P4[3], P5[3], P6[3];
+  const double ctL = -F.theta * csL, ctR = F.theta * csR;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    P1[i] = F.E0[i] * A0 + F.m0[i] * csL;
+    P2[i] = F.E1[i] * A0 - F.mk[i] * csR;
+    P3[i] = F.m0[i] * coL;
+    P4[i] = -F.mk[i] * coR;
+    P5[i] = F.m0[i] * cgL + F.q0[i] * ctL;
+    P6[i] = F.mk[i] * cgR + F.q1[i] * ctR;
+  }
+  constexpr int SA = S == 1 ? 3 : 1;  // strides of the two tangential node indices
+  constexpr int SB = S == 9 ? 3 : 9;
+#pragma unroll
+  for (int b = 0; b < 3; b++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int base = a * SA + b * SB;
+      const double o0 = o[base], o1 = o[base + S], o2 = o[base + 2 * S];
+      const double l0 = nl[base], l1 = nl[base + S], l2 = nl[base + 2 * S];
+      const double r0 = nr[base], r1 = nr[base + S], r2 = nr[base + 2 * S];
+      // p'(0) = (-3, 4, -1), p'(1) = (1, -4, 3) for the quadratic Lagrange basis on {0, 1/2, 1}
+      const double dls = 4.0 * o1 - (3.0 * o0 + o2);
+      const double drs = (o0 + 3.0 * o2) - 4.0 * o1;
+      const double dlo = (l0 + 3.0 * l2) - 4.0 * l1;
+      const double dro = 4.0 * r1 - (3.0 * r0 + r2);
+      const double jl = o0 - l2, jr = o2 - r0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        t[base + i * S] += P1[i] * dls + P2[i] * drs + P3[i] * dlo + P4[i] * dro + P5[i] * jl + P6[i] * jr;
+    }
+}
+
+// v <- (M along stride S) v, optionally scaled
+template <int S>
+__device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)[9], double scale) {
+  constexpr int SA = S == 1 ? 3 : 1;
+  constexpr int SB = S == 9 ? 3 : 9;
+#pragma unroll
+  for (int b = 0; b < 3; b++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int base = a * SA + b * SB;
+      const double v0 = t[base], v1 = t[base + S], v2 = t[base + 2 * S];
+      t[base] = scale * (Mm[0] * v0 + Mm[1] * v1 + Mm[2] * v2);
+      t[base + S] = scale * (Mm[3] * v0 + Mm[4] * v1 + Mm[5] * v2);
+      t[base + 2 * S] = scale * (Mm[6] * v0 + Mm[7] * v1 + Mm[8] * v2);
+    }
+}
+
+__global__ void __launch_bounds__(TX* TY* TZ, 3)
+    dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
+                         const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
+                         const DevParams P, const FastConst F) {
+  extern __shared__ __align__(128) double tile[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, SMEM_BYTES);
+    tma_load_4d(tile + R0, &tm_rows, 0, x0 / 2 - 1, y0, z0, &bar);
+    tma_load_4d(tile + R1, &tm_yh, 0, x0 / 2, y0 - 1, z0, &bar);
+    tma_load_4d(tile + R2, &tm_yh, 0, x0 / 2, y0 + TY, z0, &bar);
+    tma_load_4d(tile + R3, &tm_zh, 0, x0 / 2, y0, z0 - 1, &bar);
+    tma_load_4d(tile + R4, &tm_zh, 0, x0 / 2, y0, z0 + TZ, &bar);
+  }
+
+  // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
+  // stride maps the 16 lanes of a 64-bit shared access onto 16 distinct bank pairs
+  const int lane = tid & 31;
+  const int cx = lane & 7;
+  const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
+  const int cz = tid >> 5;
+  const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
+  const bool active = gx < P.N[0] && gy < P.N[1] && gz < P.N[2];
+
+  // ---- per-cell coefficients (overlaps the TMA latency) ---------------------------------------
+  double A0[3], csL[3], coL[3], cgL[3], csR[3], coR[3], cgR[3];
+  double creact = 0.0;
+  bool constrained = false;
+  if (active) {
+    const long long cell = cell_index(P.N, gx, gy, gz);
+    const int g[3] = {gx, gy, gz};
+    const long long stride[3] = {1, (long long)P.N[0], (long long)P.N[0] * P.N[1]};
+    if (P.c) creact = __ldg(P.c + cell);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const double a = load_adiag(P, cell, d);
+      A0[d] = a * F.ih2[d];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const bool onb = side ? g[d] == P.N[d] - 1 : g[d] == 0;
+        int kind = 0;
+        double ao = 0.0;
+        if (!onb) {
+          ao = load_adiag(P, cell + (side ? stride[d] : -stride[d]), d);
+        } else if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
+          kind = 2;
+          constrained = true;
+        } else {
+          const int bct = P.bctype ? (int)P.bctype[bface_index(P, g, d, side)] : (int)PDB200_BC_DIRICHLET;
+          kind = bct == PDB200_BC_DIRICHLET ? 1 : 2;
+        }
+        double cs, co, cg;
+        face_coef(kind, a, ao, F.ih2[d], F.alpha_pen, P.weights_on, cs, co, cg);
+        if (side == 0) {
+          csL[d] = cs;
+          coL[d] = co;
+          cgL[d] = cg;
+        } else {
+          csR[d] = cs;
+          coR[d] = co;
+          cgR[d] = cg;
+        }
+      }
+    }
+  }
+
+  // ---- shared-memory addresses of the cell and its six face neighbours -------------------------
+  const int so = R0 + ((cz * TY + cy) * ROWX + cx + 2) * NLOC;
+  const int xl = so - NLOC, xr = so + NLOC;
+  const int yl = cy > 0 ? so - ROWX * NLOC : R1 + (cz * TX + cx) * NLOC;
+  const int yr = cy < TY - 1 ? so + ROWX * NLOC : R2 + (cz * TX + cx) * NLOC;
+  const int zl = cz > 0 ? so - TY * ROWX * NLOC : R3 + (cy * TX + cx) * NLOC;
+  const int zr = cz < TZ - 1 ? so + TY * ROWX * NLOC : R4 + (cy * TX + cx) * NLOC;
+
+  mbar_wait(&bar, 0);
+
+  double o[NLOC], t[NLOC];
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NLOC; i++) {
+      o[i] = tile[so + i];
+      t[i] = creact * o[i];
+    }
+    sweep<1>(o, t, tile + xl, tile + xr, F, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
+    sweep<3>(o, t, tile + yl, tile + yr, F, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
+    sweep<9>(o, t, tile + zl, tile + zr, F, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
+    mass_sweep<1>(t, F.Mm, 1.0);
+    mass_sweep<3>(t, F.Mm, 1.0);
+    mass_sweep<9>(t, F.Mm, F.vol);
+    if (constrained) {  // constraints/p0.hh:31-41 + constrain_residual (jacobianapplyengine.hh:249-254)
+#pragma unroll
+      for (int i = 0; i < NLOC; i++) t[i] = 0.0;
+    }
+  }
+  __syncthreads();  // every thread is done reading the input tile: reuse R0 as the output stage
+  if (active) {
+    const int dst = ((cz * TY + cy) * TX + cx) * NLOC;
+#pragma unroll
+    for (int i = 0; i < NLOC; i++) tile[dst + i] = t[i];
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+    tma_store_commit_and_wait();
+  }
+}
+
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ t, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] += t[i];
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct FastPlan {
+  FastConst F;
+  EncodeFn encode = nullptr;
+  struct Maps {
+    const void* ptr = nullptr;
+    CUtensorMap rows, yh, zh, core;
+  };
+  std::vector<Maps> cache;  // tensor maps embed the global address: keep the most recent few
+  double* scratch = nullptr;
+  long long scratch_n = 0;
+};
+
+bool dg_fast_supported(const DevParams& P) {
+  return P.dg && P.dim == 3 && P.k == 2 && P.m >= 3 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
+         P.N[0] % 2 == 0;
+}
+
+FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
+  FastPlan* plan = new FastPlan;
+  FastConst& F = plan->F;
+  for (int i = 0; i < 3; i++) {
+    F.E0[i] = K.E0[i];
+    F.E1[i] = K.E1[i];
+    F.m0[i] = K.m0[i];
+    F.mk[i] = K.mk[i];
+    F.q0[i] = K.q0[i];
+    F.q1[i] = K.q1[i];
+    F.ih2[i] = 1.0 / (P.h[i] * P.h[i]);
+    for (int j = 0; j < 3; j++) F.Mm[i * 3 + j] = K.M[i * MAX_N1 + j];
+  }
+  F.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
+  F.theta = P.theta;
+  F.vol = P.vol;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled is not available in this driver");
+  plan->encode = (EncodeFn)fn;
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return plan;
+}
+
+void dg_fast_plan_destroy(FastPlan* plan) {
+  if (!plan) return;
+  if (plan->scratch) cudaFree(plan->scratch);
+  delete plan;
+}
+
+static void encode_map(FastPlan* plan, CUtensorMap* m, const void* ptr, const DevParams& P, int bx, int by, int bz) {
+  cuuint64_t gdim[4] = {54, (cuuint64_t)P.N[0] / 2, (cuuint64_t)P.N[1], (cuuint64_t)P.N[2]};
+  cuuint64_t gstr[3] = {432, 216ull * P.N[0], 216ull * P.N[0] * P.N[1]};
+  cuuint32_t box[4] = {54, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = plan->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
+static FastPlan::Maps& get_maps(FastPlan* plan, const void* ptr, const DevParams& P) {
+  for (auto& m : plan->cache)
+    if (m.ptr == ptr) return m;
+  if ((uintptr_t)ptr % 16 != 0) throw Error("fast DG kernel: vectors must be 16-byte aligned");
+  if (plan->cache.size() >= 16) plan->cache.erase(plan->cache.begin());
+  FastPlan::Maps m;
+  m.ptr = ptr;
+  encode_map(plan, &m.rows, ptr, P, ROWX / 2, TY, TZ);
+  encode_map(plan, &m.yh, ptr, P, TX / 2, 1, TZ);
+  encode_map(plan, &m.zh, ptr, P, TX / 2, TY, 1);
+  encode_map(plan, &m.core, ptr, P, TX / 2, TY, TZ);
+  plan->cache.push_back(m);
+  return plan->cache.back();
+}
+
+void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+                    cudaStream_t s) {
+  if (residual) throw Error("fast DG kernel implements jacobian_apply only");
+  double* out = y;
+  if (!overwrite) {  // accumulate semantics (y += J z) through a scratch vector
+    if (plan->scratch_n < P.ndofs) {
+      if (plan->scratch) cudaFree(plan->scratch);
+      PDB_CUDA(cudaMalloc(&plan->scratch, P.ndofs * sizeof(double)));
+      plan->scratch_n = P.ndofs;
+    }
+    out = plan->scratch;
+  }
+  const FastPlan::Maps mx = get_maps(plan, x, P);
+  const FastPlan::Maps my = get_maps(plan, out, P);
+  dim3 grid((P.N[0] + TX - 1) / TX, (P.N[1] + TY - 1) / TY, (P.N[2] + TZ - 1) / TZ);
+  dg_fast_q2_3d_kernel<<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F);
+  PDB_CUDA(cudaGetLastError());
+  if (!overwrite) {
+    axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, P.ndofs);
+    PDB_CUDA(cudaGetLastError());
+  }
+}
+
+}  // namespace pdb

@@ -1,0 +1,510 @@
+// operator.cu — the C ABI of include/pdelab_b200.h: operator handle, coefficient upload, DOF
+// numbering queries, host/device pointer staging and kernel dispatch.
+//
+// Mirrors Dune::PDELab::GridOperator (gridoperator/gridoperator.hh:30-244): the handle owns what
+// the reference's GridOperator references (function-space sizes, constraints, local-operator
+// parameters) and exposes residual / jacobian_apply / jacobian / fill_pattern.
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_tables.h"
+
+using namespace pdb;
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+struct pdb200_operator {
+  DevParams P;
+  Kron1D K;
+  int device = 0;
+  int kernel_choice = PDB200_KERNEL_AUTO;
+  cudaStream_t stream = nullptr;
+  // device copies of the coefficient arrays
+  std::vector<void*> owned;
+  // staging for host-pointer calls
+  double *dx = nullptr, *dy = nullptr;
+  int* errflag = nullptr;
+  FastPlan* fast = nullptr;
+  FemPlan* fem = nullptr;
+  MatrixPlan* matrix = nullptr;
+  uint64_t launches = 0;
+  const char* last_kernel = "";
+  std::vector<double> xq, wq;
+
+  ~pdb200_operator() {
+    cudaSetDevice(device);
+    for (void* p : owned) cudaFree(p);
+    if (dx) cudaFree(dx);
+    if (dy) cudaFree(dy);
+    if (errflag) cudaFree(errflag);
+    dg_fast_plan_destroy(fast);
+    fem_plan_destroy(fem);
+    matrix_plan_destroy(matrix);
+  }
+};
+
+namespace {
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+const T* upload(pdb200_operator* op, const T* src, size_t count) {
+  if (!src || count == 0) return nullptr;
+  T* d = nullptr;
+  PDB_CUDA(cudaMalloc(&d, count * sizeof(T)));
+  op->owned.push_back(d);
+  PDB_CUDA(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyDefault));
+  return d;
+}
+
+size_t a_count(const DevParams& P) {
+  switch (P.a_mode) {
+    case PDB200_A_IDENTITY: return 0;
+    case PDB200_A_SCALAR: return (size_t)P.ncells;
+    case PDB200_A_DIAGONAL: return (size_t)P.ncells * P.dim;
+    default: return (size_t)P.ncells * P.dim * P.dim;
+  }
+}
+
+long long num_bfaces(const DevParams& P) {
+  long long n = 0;
+  for (int d = 0; d < P.dim; d++) n += 2 * (P.ncells / P.N[d]);
+  return n;
+}
+
+void ensure_device(pdb200_operator* op) { PDB_CUDA(cudaSetDevice(op->device)); }
+
+void check_errflag(pdb200_operator* op) {
+  int flag = 0;
+  PDB_CUDA(cudaMemcpyAsync(&flag, op->errflag, sizeof(int), cudaMemcpyDeviceToHost, op->stream));
+  PDB_CUDA(cudaStreamSynchronize(op->stream));
+  if (flag) {
+    PDB_CUDA(cudaMemsetAsync(op->errflag, 0, sizeof(int), op->stream));
+    throw Error("Outflow boundary condition on inflow!");  // convectiondiffusiondg.hh:802-806
+  }
+}
+
+enum class Mode { Residual, JacobianApply, OnTheFly };
+
+// run one vector kernel on device pointers
+void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mode) {
+  const DevParams& P = op->P;
+  const bool residual = mode == Mode::Residual;
+  const bool overwrite = mode == Mode::OnTheFly;
+  if (!P.dg) {
+    launch_fem_vector(op->fem, P, x, y, residual, overwrite, op->stream);
+    op->last_kernel = residual ? "fem_residual" : "fem_jacobian_apply";
+    op->launches += 2;
+    return;
+  }
+  bool use_fast = !residual && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
+  if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast)
+    throw Error("PDB200_KERNEL_FAST requested but the configuration has no fast kernel "
+                "(needs QkDG k=2, dim=3, diagonal A, b=0, even cells[0], jacobian_apply)");
+  if (use_fast) {
+    if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
+    launch_dg_fast(op->fast, P, x, y, residual, overwrite, op->stream);
+    op->last_kernel = "dg_fast_q2_3d";
+    op->launches += overwrite ? 1 : 2;
+  } else {
+    launch_dg_generic(P, x, y, residual, overwrite, op->errflag, op->stream);
+    op->last_kernel = residual ? "dg_generic_residual" : "dg_generic_jacobian_apply";
+    op->launches += 1;
+  }
+}
+
+void run_vector(pdb200_operator* op, const double* x, double* y, Mode mode) {
+  ensure_device(op);
+  const DevParams& P = op->P;
+  const bool xd = is_device_pointer(x), yd = is_device_pointer(y);
+  const size_t bytes = (size_t)P.ndofs * sizeof(double);
+  const double* xdev = x;
+  double* ydev = y;
+  if (!xd) {
+    if (!op->dx) PDB_CUDA(cudaMalloc(&op->dx, bytes));
+    PDB_CUDA(cudaMemcpyAsync(op->dx, x, bytes, cudaMemcpyHostToDevice, op->stream));
+    xdev = op->dx;
+  }
+  if (!yd) {
+    if (!op->dy) PDB_CUDA(cudaMalloc(&op->dy, bytes));
+    if (mode != Mode::OnTheFly) PDB_CUDA(cudaMemcpyAsync(op->dy, y, bytes, cudaMemcpyHostToDevice, op->stream));
+    ydev = op->dy;
+  }
+  run_vector_device(op, xdev, ydev, mode);
+  if (!yd) {
+    PDB_CUDA(cudaMemcpyAsync(y, op->dy, bytes, cudaMemcpyDeviceToHost, op->stream));
+  }
+  if (!xd || !yd) {
+    // host-visible results: synchronous on return like the reference (SURVEY.md §8b "Threading")
+    if (P.dg && (P.bctype != nullptr) && (P.b != nullptr))
+      check_errflag(op);
+    else
+      PDB_CUDA(cudaStreamSynchronize(op->stream));
+  }
+}
+
+}  // namespace
+
+#define PDB_TRY try {
+#define PDB_CATCH                    \
+  }                                  \
+  catch (const std::exception& e) {  \
+    g_last_error = e.what();         \
+    return 1;                        \
+  }                                  \
+  return 0;
+#define PDB_CHECK_HANDLE(h) \
+  if (!(h)) throw Error("null operator handle")
+
+extern "C" {
+
+const char* pdb200_last_error(void) { return g_last_error.c_str(); }
+const char* pdb200_version(void) { return "pdelab_b200 0.1 (sm_100a)"; }
+
+int pdb200_create(const pdb200_problem* p, pdb200_handle* out) {
+  PDB_TRY
+  if (!p || !out) throw Error("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error("no CUDA device available: pdelab_b200 has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) throw Error("invalid CUDA device ordinal");
+  if (p->dim != 2 && p->dim != 3) throw Error("dim must be 2 or 3");
+  if (p->space != PDB200_SPACE_QKDG && p->space != PDB200_SPACE_QK) throw Error("unknown finite element space");
+  if (p->degree < 1 || p->degree > MAX_K) throw Error("degree must be in 1..4");
+  if (p->space == PDB200_SPACE_QK && p->degree > 2)
+    throw Error("conforming Qk is available for k in {1,2} (finiteelementmap/qkfem.hh:17-78)");
+  if (p->intorderadd < 0 || p->intorderadd > 1)
+    throw Error("intorderadd must be 0 or 1 (k+1 Gauss points per direction)");
+  std::unique_ptr<pdb200_operator> op(new pdb200_operator);
+  op->device = p->device;
+  op->kernel_choice = p->kernel;
+  PDB_CUDA(cudaSetDevice(op->device));
+  DevParams& P = op->P;
+  std::memset(&P, 0, sizeof(P));
+  P.dim = p->dim;
+  P.k = p->degree;
+  P.n1 = P.k + 1;
+  P.dg = p->space == PDB200_SPACE_QKDG;
+  P.m = (2 * P.k + p->intorderadd) / 2 + 1;  // convectiondiffusiondg.hh:139, convectiondiffusionfem.hh:93
+  P.n = P.nq = P.nfq = 1;
+  P.ncells = 1;
+  P.vol = 1.0;
+  for (int d = 0; d < 3; d++) {
+    P.N[d] = d < P.dim ? p->cells[d] : 1;
+    if (P.N[d] < 1) throw Error("cells must be positive");
+    P.h[d] = d < P.dim ? (p->upper[d] - p->lower[d]) / P.N[d] : 1.0;
+    if (!(P.h[d] > 0.0)) throw Error("upper must be greater than lower");
+    P.ih[d] = 1.0 / P.h[d];
+    if (d < P.dim) {
+      P.n *= P.n1;
+      P.nq *= P.m;
+      if (d > 0) P.nfq *= P.m;
+      P.ncells *= P.N[d];
+      P.vol *= P.h[d];
+    }
+    for (int s = 0; s < 2; s++) P.side_kind[d][s] = p->side_kind[d][s];
+  }
+  for (int d = 0; d < 3; d++) {
+    P.area[d] = 1.0;
+    for (int e = 0; e < P.dim; e++)
+      if (e != d) P.area[d] *= P.h[e];
+  }
+  long long nbf = 0;
+  for (int d = 0; d < P.dim; d++)
+    for (int s = 0; s < 2; s++) {
+      P.bf_off[d][s] = nbf;
+      nbf += P.ncells / P.N[d];
+    }
+  P.ndofs = host_num_dofs(P);
+  P.theta = 1.0;  // convectiondiffusiondg.hh:99-101
+  if (p->dg_method == PDB200_DG_SIPG) P.theta = -1.0;
+  if (p->dg_method == PDB200_DG_IIPG) P.theta = 0.0;
+  P.alpha = p->dg_alpha;
+  P.weights_on = p->dg_weights == PDB200_DG_WEIGHTS_ON;
+  P.a_mode = p->a_mode;
+  if (P.a_mode < 0 || P.a_mode > 3) throw Error("invalid a_mode");
+  if (P.a_mode != PDB200_A_IDENTITY && !p->A) throw Error("a_mode needs the array A");
+  host_fill_tables(P, op->K, op->xq, op->wq);
+  P.A = upload(op.get(), p->A, a_count(P));
+  P.b = upload(op.get(), p->b, (size_t)P.ncells * P.dim);
+  P.c = upload(op.get(), p->c, (size_t)P.ncells);
+  P.f = upload(op.get(), p->f, (size_t)P.ncells * P.nq);
+  P.bctype = upload(op.get(), p->bctype, (size_t)nbf);
+  P.g = upload(op.get(), p->g, (size_t)nbf * P.nfq);
+  P.j = upload(op.get(), p->j, (size_t)nbf * P.nfq);
+  P.o = upload(op.get(), p->o, (size_t)nbf * P.nfq);
+  PDB_CUDA(cudaMalloc(&op->errflag, sizeof(int)));
+  PDB_CUDA(cudaMemset(op->errflag, 0, sizeof(int)));
+  if (!P.dg) op->fem = fem_plan_create(P, p->bctype ? op->P.bctype : nullptr);
+  *out = op.release();
+  PDB_CATCH
+}
+
+int pdb200_destroy(pdb200_handle h) {
+  PDB_TRY
+  delete h;
+  PDB_CATCH
+}
+
+int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  DevParams& P = h->P;
+  const long long nbf = num_bfaces(P);
+  auto upd = [&](const void* dst, const void* src, size_t bytes, const char* name) {
+    if (!src) return;
+    if (!dst) throw Error(std::string("update_coefficients: array was not given at create time: ") + name);
+    PDB_CUDA(cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyDefault, h->stream));
+  };
+  upd(P.A, p->A, a_count(P) * 8, "A");
+  upd(P.b, p->b, (size_t)P.ncells * P.dim * 8, "b");
+  upd(P.c, p->c, (size_t)P.ncells * 8, "c");
+  upd(P.f, p->f, (size_t)P.ncells * P.nq * 8, "f");
+  upd(P.g, p->g, (size_t)nbf * P.nfq * 8, "g");
+  upd(P.j, p->j, (size_t)nbf * P.nfq * 8, "j");
+  upd(P.o, p->o, (size_t)nbf * P.nfq * 8, "o");
+  if (p->bctype) throw Error("update_coefficients: bctype changes the constraint set; create a new operator");
+  PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+
+int pdb200_num_dofs(pdb200_handle h, uint64_t* n) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  *n = (uint64_t)h->P.ndofs;
+  PDB_CATCH
+}
+int pdb200_local_size(pdb200_handle h, uint32_t* n) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  *n = (uint32_t)h->P.n;
+  PDB_CATCH
+}
+int pdb200_num_boundary_faces(pdb200_handle h, uint64_t* n) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  *n = (uint64_t)num_bfaces(h->P);
+  PDB_CATCH
+}
+int pdb200_boundary_face_offset(pdb200_handle h, int dir, int side, uint64_t* first) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  if (dir < 0 || dir >= h->P.dim || side < 0 || side > 1) throw Error("invalid (dir, side)");
+  *first = (uint64_t)h->P.bf_off[dir][side];
+  PDB_CATCH
+}
+int pdb200_quadrature_size(pdb200_handle h, uint32_t* m) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  *m = (uint32_t)h->P.m;
+  PDB_CATCH
+}
+int pdb200_quadrature(pdb200_handle h, double* points, double* weights) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  for (int i = 0; i < h->P.m; i++) {
+    points[i] = h->xq[i];
+    weights[i] = h->wq[i];
+  }
+  PDB_CATCH
+}
+
+int pdb200_cell_dof_indices(pdb200_handle h, uint64_t cell, uint64_t* idx) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  if (cell >= (uint64_t)h->P.ncells) throw Error("cell index out of range");
+  host_cell_dof_indices(h->P, (long long)cell, idx);
+  PDB_CATCH
+}
+
+int pdb200_constrained_dofs(pdb200_handle h, uint64_t* count, uint64_t* idx) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  std::vector<int8_t> bct;
+  if (h->P.bctype) {
+    bct.resize(num_bfaces(h->P));
+    PDB_CUDA(cudaMemcpy(bct.data(), h->P.bctype, bct.size(), cudaMemcpyDeviceToHost));
+  }
+  std::vector<uint64_t> list = host_constrained_dofs(h->P, bct.empty() ? nullptr : bct.data());
+  *count = list.size();
+  if (idx) std::memcpy(idx, list.data(), list.size() * sizeof(uint64_t));
+  PDB_CATCH
+}
+
+int pdb200_residual(pdb200_handle h, const double* x, double* r) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  run_vector(h, x, r, Mode::Residual);
+  PDB_CATCH
+}
+
+int pdb200_jacobian_apply(pdb200_handle h, const double* z, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  run_vector(h, z, y, Mode::JacobianApply);
+  PDB_CATCH
+}
+
+int pdb200_onthefly_apply(pdb200_handle h, const double* x, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  run_vector(h, x, y, Mode::OnTheFly);
+  PDB_CATCH
+}
+
+int pdb200_jacobian_apply_nonlinear(pdb200_handle h, const double*, const double*, double*) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  // gridoperator/gridoperator.hh:202-203
+  throw Error("jacobian_apply(u,z,y) with linearisation point called for a linear local operator");
+  PDB_CATCH
+}
+
+int pdb200_pattern_size(pdb200_handle h, uint64_t* nrows, uint64_t* nnz) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->matrix) h->matrix = matrix_plan_create(h->P, h->fem, h->stream);
+  matrix_pattern_size(h->matrix, 0, nrows, nnz);
+  PDB_CATCH
+}
+int pdb200_block_pattern_size(pdb200_handle h, uint64_t* nrows, uint64_t* nnz) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->P.dg) throw Error("block pattern is defined for QkDG spaces (Blocking::fixed)");
+  if (!h->matrix) h->matrix = matrix_plan_create(h->P, h->fem, h->stream);
+  matrix_pattern_size(h->matrix, 1, nrows, nnz);
+  PDB_CATCH
+}
+
+static void pattern_out(pdb200_handle h, int layout, void* rowptr, void* colidx, bool col32) {
+  ensure_device(h);
+  if (!h->matrix) h->matrix = matrix_plan_create(h->P, h->fem, h->stream);
+  h->launches += matrix_pattern_write(h->matrix, layout, rowptr, is_device_pointer(rowptr), colidx,
+                                      is_device_pointer(colidx), col32, h->stream);
+}
+
+int pdb200_pattern(pdb200_handle h, uint64_t* rowptr, uint64_t* colidx) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  pattern_out(h, 0, rowptr, colidx, false);
+  PDB_CATCH
+}
+int pdb200_pattern_i32(pdb200_handle h, uint64_t* rowptr, uint32_t* colidx) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  pattern_out(h, 0, rowptr, colidx, true);
+  PDB_CATCH
+}
+int pdb200_block_pattern(pdb200_handle h, uint64_t* rowptr, uint64_t* colidx) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  if (!h->P.dg) throw Error("block pattern is defined for QkDG spaces (Blocking::fixed)");
+  pattern_out(h, 1, rowptr, colidx, false);
+  PDB_CATCH
+}
+
+static void jacobian_impl(pdb200_handle h, double* values, int layout, bool fresh) {
+  ensure_device(h);
+  if (layout != PDB200_LAYOUT_CSR && layout != PDB200_LAYOUT_BCSR) throw Error("unknown matrix layout");
+  if (layout == PDB200_LAYOUT_BCSR && !h->P.dg) throw Error("BCSR layout is defined for QkDG spaces");
+  if (!h->matrix) h->matrix = matrix_plan_create(h->P, h->fem, h->stream);
+  h->launches += matrix_assemble(h->matrix, layout, values, is_device_pointer(values), fresh, h->errflag, h->stream);
+  if (h->P.dg && h->P.bctype && h->P.b) check_errflag(h);
+}
+
+int pdb200_jacobian(pdb200_handle h, const double* x, double* values, int layout) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  (void)x;  // both local operators are linear: the Jacobian does not depend on x
+  jacobian_impl(h, values, layout, false);
+  PDB_CATCH
+}
+
+int pdb200_jacobian_fresh(pdb200_handle h, const double* x, double* values, int layout) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  (void)x;
+  jacobian_impl(h, values, layout, true);
+  PDB_CATCH
+}
+
+int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const double* x, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->matrix) h->matrix = matrix_plan_create(h->P, h->fem, h->stream);
+  if (!is_device_pointer(values) || !is_device_pointer(x) || !is_device_pointer(y))
+    throw Error("csr_mv expects device pointers");
+  h->launches += matrix_mv(h->matrix, layout, values, x, y, h->stream);
+  PDB_CATCH
+}
+
+int pdb200_halo_layer_size(pdb200_handle h, int dir, uint64_t* ndoubles) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  if (!h->P.dg) throw Error("halo exchange helpers are implemented for QkDG spaces");
+  if (dir < 0 || dir >= h->P.dim) throw Error("invalid direction");
+  *ndoubles = (uint64_t)(h->P.ncells / h->P.N[dir]) * h->P.n;
+  PDB_CATCH
+}
+int pdb200_halo_pack(pdb200_handle h, const double* x, int dir, int side, double* buf) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->P.dg) throw Error("halo exchange helpers are implemented for QkDG spaces");
+  launch_halo_copy(h->P, const_cast<double*>(x), buf, dir, side, /*pack=*/true, h->stream);
+  h->launches += 1;
+  PDB_CATCH
+}
+int pdb200_halo_unpack(pdb200_handle h, double* x, int dir, int side, const double* buf) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->P.dg) throw Error("halo exchange helpers are implemented for QkDG spaces");
+  launch_halo_copy(h->P, x, const_cast<double*>(buf), dir, side, /*pack=*/false, h->stream);
+  h->launches += 1;
+  PDB_CATCH
+}
+
+int pdb200_set_stream(pdb200_handle h, void* stream) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  h->stream = (cudaStream_t)stream;
+  PDB_CATCH
+}
+int pdb200_synchronize(pdb200_handle h) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+int pdb200_launch_count(pdb200_handle h, uint64_t* n) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  *n = h->launches;
+  PDB_CATCH
+}
+const char* pdb200_last_kernel(pdb200_handle h) { return h ? h->last_kernel : ""; }
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+"""ctypes binding of libpdelab_b200.so and the host-side mirror of PDELab's GridOperator.
+
+`GridOperator` keeps the reference's method names and argument meaning
+(dune/pdelab/gridoperator/gridoperator.hh:167-205): residual(x, r), jacobian_apply(z, y),
+jacobian(x, A), fill_pattern(); results are accumulated, errors are raised as exceptions
+(`PDELabError` replaces Dune::Exception).  There is no CPU implementation behind it: if the
+CUDA library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import Problem, ProblemSpec
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libpdelab_b200.so"))
+
+
+class PDELabError(RuntimeError):
+    """Raised where the reference throws Dune::Exception."""
+
+
+_lib = None
+
+# every symbol declared in include/pdelab_b200.h (checked by tests/test_abi.py)
+SYMBOLS = [
+    "pdb200_last_error", "pdb200_create", "pdb200_destroy", "pdb200_update_coefficients",
+    "pdb200_num_dofs", "pdb200_local_size", "pdb200_num_boundary_faces", "pdb200_boundary_face_offset",
+    "pdb200_quadrature_size", "pdb200_quadrature", "pdb200_cell_dof_indices", "pdb200_constrained_dofs",
+    "pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply", "pdb200_jacobian_apply_nonlinear",
+    "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
+    "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
+    "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
+    "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
+]
+
+
+def load_library():
+    """Load the CUDA library (built in-tree by __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PDELabError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(pdelab_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.pdb200_last_error.restype = C.c_char_p
+    lib.pdb200_last_kernel.restype = C.c_char_p
+    lib.pdb200_last_kernel.argtypes = [C.c_void_p]
+    lib.pdb200_version.restype = C.c_char_p
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    lib.pdb200_create.argtypes = [C.POINTER(Problem), C.POINTER(C.c_void_p)]
+    for name in ("pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply"):
+        getattr(lib, name).argtypes = [vp, vp, vp]
+    lib.pdb200_jacobian_apply_nonlinear.argtypes = [vp, vp, vp, vp]
+    lib.pdb200_jacobian.argtypes = [vp, vp, vp, C.c_int]
+    lib.pdb200_jacobian_fresh.argtypes = [vp, vp, vp, C.c_int]
+    lib.pdb200_csr_mv.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.pdb200_pattern_size.argtypes = [vp, u64p, u64p]
+    lib.pdb200_block_pattern_size.argtypes = [vp, u64p, u64p]
+    for name in ("pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern"):
+        getattr(lib, name).argtypes = [vp, vp, vp]
+    lib.pdb200_halo_layer_size.argtypes = [vp, C.c_int, u64p]
+    lib.pdb200_halo_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    lib.pdb200_halo_unpack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    lib.pdb200_set_stream.argtypes = [vp, vp]
+    lib.pdb200_cell_dof_indices.argtypes = [vp, C.c_uint64, vp]
+    lib.pdb200_constrained_dofs.argtypes = [vp, u64p, vp]
+    lib.pdb200_quadrature.argtypes = [vp, vp, vp]
+    lib.pdb200_boundary_face_offset.argtypes = [vp, C.c_int, C.c_int, u64p]
+    for name in ("pdb200_destroy", "pdb200_synchronize"):
+        getattr(lib, name).argtypes = [vp]
+    lib.pdb200_update_coefficients.argtypes = [vp, C.POINTER(Problem)]
+    lib.pdb200_num_dofs.argtypes = [vp, u64p]
+    lib.pdb200_num_boundary_faces.argtypes = [vp, u64p]
+    lib.pdb200_launch_count.argtypes = [vp, u64p]
+    lib.pdb200_local_size.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.pdb200_quadrature_size.argtypes = [vp, C.POINTER(C.c_uint32)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host) or torch tensor (host or device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype in (np.float64, np.uint64, np.uint32, np.int64) and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(f"expected numpy array or torch tensor, got {type(a)}")
+
+
+class GridOperator:
+    """Host mirror of Dune::PDELab::GridOperator for the CUDA path.
+
+    Vectors are flat float64 arrays in the reference's container order
+    (ISTL::BlockVector, backend/istl/vector.hh): numpy arrays (host memory, staged through the
+    device inside the call) or torch CUDA tensors (used in place).
+    """
+
+    def __init__(self, spec: ProblemSpec):
+        self.lib = load_library()
+        self.spec = spec
+        self._p = spec.c_struct()
+        h = C.c_void_p()
+        self._h = None
+        self._chk(self.lib.pdb200_create(C.byref(self._p), C.byref(h)))
+        self._h = h
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PDELabError(self.lib.pdb200_last_error().decode())
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.pdb200_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    close = __del__
+
+    # sizes ---------------------------------------------------------------------------------
+    def globalSizeU(self):
+        n = C.c_uint64()
+        self._chk(self.lib.pdb200_num_dofs(self._h, C.byref(n)))
+        return n.value
+
+    globalSizeV = globalSizeU
+
+    def quadrature(self):
+        m = C.c_uint32()
+        self._chk(self.lib.pdb200_quadrature_size(self._h, C.byref(m)))
+        x, w = np.zeros(m.value), np.zeros(m.value)
+        self._chk(self.lib.pdb200_quadrature(self._h, x.ctypes.data, w.ctypes.data))
+        return x, w
+
+    def boundary_face_offset(self, d, side):
+        n = C.c_uint64()
+        self._chk(self.lib.pdb200_boundary_face_offset(self._h, d, side, C.byref(n)))
+        return n.value
+
+    def cell_dof_indices(self, cell):
+        idx = np.zeros(self.spec.local_size, dtype=np.uint64)
+        self._chk(self.lib.pdb200_cell_dof_indices(self._h, cell, idx.ctypes.data))
+        return idx
+
+    def constrained_dofs(self):
+        n = C.c_uint64()
+        self._chk(self.lib.pdb200_constrained_dofs(self._h, C.byref(n), None))
+        idx = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._chk(self.lib.pdb200_constrained_dofs(self._h, C.byref(n), idx.ctypes.data))
+        return idx
+
+    # the hot path --------------------------------------------------------------------------
+    def residual(self, x, r):
+        """r += R(x); constrained rows := 0   (gridoperator.hh:176-181)."""
+        self._chk(self.lib.pdb200_residual(self._h, _ptr(x), _ptr(r)))
+        return r
+
+    def jacobian_apply(self, *args):
+        """jacobian_apply(z, y): y += J z.  jacobian_apply(u, z, y) raises for these linear
+        local operators exactly like the reference (gridoperator.hh:192-205)."""
+        if len(args) == 3:
+            u, z, y = args
+            self._chk(self.lib.pdb200_jacobian_apply_nonlinear(self._h, _ptr(u), _ptr(z), _ptr(y)))
+            return y
+        z, y = args
+        self._chk(self.lib.pdb200_jacobian_apply(self._h, _ptr(z), _ptr(y)))
+        return y
+
+    def apply(self, x, y):
+        """OnTheFlyOperator::apply: y = J x  (backend/istl/seqistlsolverbackend.hh:66-76)."""
+        self._chk(self.lib.pdb200_onthefly_apply(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def update_coefficients(self, **arrays):
+        spec = self.spec.replace(**{k: None for k in self.spec.arrays})
+        for k, v in arrays.items():
+            spec.arrays[k] = v
+        p = spec.c_struct()
+        self._chk(self.lib.pdb200_update_coefficients(self._h, C.byref(p)))
+
+    # matrix --------------------------------------------------------------------------------
+    def pattern_size(self, block=False):
+        nr, nnz = C.c_uint64(), C.c_uint64()
+        fn = self.lib.pdb200_block_pattern_size if block else self.lib.pdb200_pattern_size
+        self._chk(fn(self._h, C.byref(nr), C.byref(nnz)))
+        return nr.value, nnz.value
+
+    def fill_pattern(self, block=False, rowptr=None, colidx=None, index32=False):
+        """Sparsity pattern (CSR over DOFs, or block CSR over cells) as (rowptr, colidx)."""
+        nr, nnz = self.pattern_size(block)
+        if rowptr is None:
+            rowptr = np.zeros(nr + 1, dtype=np.uint64)
+        if colidx is None:
+            colidx = np.zeros(nnz, dtype=np.uint32 if index32 else np.uint64)
+        if block:
+            fn = self.lib.pdb200_block_pattern
+        else:
+            fn = self.lib.pdb200_pattern_i32 if index32 else self.lib.pdb200_pattern
+        self._chk(fn(self._h, _ptr(rowptr), _ptr(colidx)))
+        return rowptr, colidx
+
+    def jacobian(self, x, values, layout=abi.LAYOUT_CSR, fresh=False):
+        """values += dR/dx (fresh=False, gridoperator.hh:184-189) or values = dR/dx (fresh=True:
+        `A = 0; go.jacobian(x, A)`, stationary/linearproblem.hh:221-226)."""
+        fn = self.lib.pdb200_jacobian_fresh if fresh else self.lib.pdb200_jacobian
+        self._chk(fn(self._h, _ptr(x), _ptr(values), layout))
+        return values
+
+    def csr_mv(self, values, x, y, layout=abi.LAYOUT_CSR):
+        self._chk(self.lib.pdb200_csr_mv(self._h, _ptr(values), layout, _ptr(x), _ptr(y)))
+        return y
+
+    # halo ----------------------------------------------------------------------------------
+    def halo_layer_size(self, d):
+        n = C.c_uint64()
+        self._chk(self.lib.pdb200_halo_layer_size(self._h, d, C.byref(n)))
+        return n.value
+
+    def halo_pack(self, x, d, side, buf):
+        self._chk(self.lib.pdb200_halo_pack(self._h, _ptr(x), d, side, _ptr(buf)))
+
+    def halo_unpack(self, x, d, side, buf):
+        self._chk(self.lib.pdb200_halo_unpack(self._h, _ptr(x), d, side, _ptr(buf)))
+
+    # misc ----------------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._chk(self.lib.pdb200_set_stream(self._h, stream_ptr))
+
+    def synchronize(self):
+        self._chk(self.lib.pdb200_synchronize(self._h))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._chk(self.lib.pdb200_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def last_kernel(self):
+        return self.lib.pdb200_last_kernel(self._h).decode()

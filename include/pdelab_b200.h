@@ -126,6 +126,11 @@ int pdb200_residual(pdb200_handle h, const double* x, double* r);
  * constrained rows := 0 (jacobianapplyengine.hh:249-254) */
 int pdb200_jacobian_apply(pdb200_handle h, const double* z, double* y);
 
+/* OnTheFlyOperator::apply(x, y), backend/istl/seqistlsolverbackend.hh:66-76:  y = 0; y += J x.
+ * The zeroing is fused into the kernel (y is written, never read): this is the call a Krylov
+ * solver makes once per iteration and the one bench.py times. */
+int pdb200_onthefly_apply(pdb200_handle h, const double* x, double* y);
+
 /* GridOperator::jacobian_apply(u, z, y) (non-linear variant), gridoperator.hh:200-205.  Both
  * supported local operators are linear, so like the reference this always fails (:202-203). */
 int pdb200_jacobian_apply_nonlinear(pdb200_handle h, const double* u, const double* z, double* y);
@@ -148,6 +153,9 @@ int pdb200_block_pattern(pdb200_handle h, uint64_t* rowptr, uint64_t* colidx);
  * cleared and get a unit diagonal (assemblerutilities.hh:666-684, bcrsmatrix.hh:254-258). */
 enum { PDB200_LAYOUT_CSR = 0, PDB200_LAYOUT_BCSR = 1 };
 int pdb200_jacobian(pdb200_handle h, const double* x, double* values, int layout);
+/* `*A = 0.0; go.jacobian(x, *A);` as issued by StationaryLinearProblemSolver::apply
+ * (stationary/linearproblem.hh:221-226) with the zeroing fused: values are written, never read. */
+int pdb200_jacobian_fresh(pdb200_handle h, const double* x, double* values, int layout);
 
 /* y = A x with the assembled matrix (dune-istl BCRSMatrix::mv as used by
  * backend/istl/seqistlsolverbackend.hh MatrixAdapter) — used to check jacobian against

@@ -1,0 +1,131 @@
+"""Parity of the CUDA QkDG path with the CPU oracle (-m gpu, through the C ABI)."""
+import numpy as np
+import pytest
+
+from pdelab_b200 import abi
+from problems import dg_problem, mt_vector, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12  # north_star: relative tolerance 1e-12 in fp64 (norm-relative)
+
+
+def _ops(spec):
+    from oracle import Oracle
+    from pdelab_b200.capi import GridOperator
+    return GridOperator(spec), Oracle(spec)
+
+
+GENERIC_CASES = [
+    dict(cells=(5, 4), degree=1), dict(cells=(5, 4), degree=2, a="full", with_b=True, with_c=True),
+    dict(cells=(4, 3), degree=3, a="diagonal", with_c=True), dict(cells=(3, 3), degree=4, a="full", with_b=True),
+    dict(cells=(3, 2, 1), degree=1, a="full", with_b=True, with_c=True),
+    dict(cells=(4, 3, 2), degree=2, a="full", with_b=True, with_c=True, extent=(1.0, 0.7, 1.3)),
+    dict(cells=(4, 3, 2), degree=2, a="scalar"), dict(cells=(1, 1, 1), degree=2, a="diagonal"),
+    dict(cells=(2, 2, 2), degree=3, a="full", with_b=True), dict(cells=(2, 2, 2), degree=4, a="diagonal", with_c=True),
+    dict(cells=(4, 3, 2), degree=2, a="full", with_b=True, bc="mixed"),
+    dict(cells=(4, 3, 2), degree=2, a="scalar", method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF),
+    dict(cells=(4, 3, 2), degree=2, a="scalar", method=abi.DG_IIPG, intorderadd=1),
+]
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_generic_jacobian_apply_matches_oracle(cuda_lib, case):
+    spec = dg_problem(kernel=abi.KERNEL_GENERIC, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    y0 = mt_vector(spec.num_dofs, seed=7)          # results are accumulated into y
+    y = go.jacobian_apply(z, y0.copy())
+    assert go.last_kernel() == "dg_generic_jacobian_apply"
+    assert rel_err(y, orc.jacobian_apply(z, y0.copy())) < TOL
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_generic_residual_matches_oracle(cuda_lib, case):
+    case = dict(case, with_f=True)
+    if case.get("bc", "dirichlet") == "dirichlet":
+        case["bc"] = "dirichlet_g"
+    spec = dg_problem(kernel=abi.KERNEL_GENERIC, **case)
+    go, orc = _ops(spec)
+    x = mt_vector(spec.num_dofs)
+    r0 = mt_vector(spec.num_dofs, seed=9)
+    r = go.residual(x, r0.copy())
+    assert rel_err(r, orc.residual(x, r0.copy())) < TOL
+
+
+FAST_CASES = [
+    dict(cells=(8, 4, 4)), dict(cells=(16, 8, 8), a="diagonal", with_c=True),
+    dict(cells=(6, 5, 3), a="scalar", extent=(1.0, 0.7, 1.3)),            # partial tiles, anisotropic h
+    dict(cells=(2, 1, 1), a="identity"), dict(cells=(10, 9, 7), a="diagonal", bc="mixed"),
+    dict(cells=(12, 4, 5), a="scalar", method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF, alpha=1.0),
+    dict(cells=(12, 4, 5), a="diagonal", method=abi.DG_IIPG),
+    dict(cells=(24, 20, 12), a="scalar"),
+]
+
+
+@pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_fast_jacobian_apply_matches_oracle(cuda_lib, case):
+    spec = dg_problem(degree=2, kernel=abi.KERNEL_FAST, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    want = orc.jacobian_apply(z)
+    y = go.apply(z, np.full(spec.num_dofs, np.nan))          # OnTheFlyOperator: y = J z
+    assert go.last_kernel() == "dg_fast_q2_3d"
+    assert rel_err(y, want) < TOL
+    y0 = mt_vector(spec.num_dofs, seed=7)
+    y = go.jacobian_apply(z, y0.copy())                      # accumulate form
+    assert rel_err(y, want + y0) < TOL
+
+
+def test_fast_and_generic_agree_on_device_tensors(cuda_lib):
+    import torch
+    spec = dg_problem((32, 16, 12), degree=2, a="scalar")
+    from pdelab_b200.capi import GridOperator
+    fast = GridOperator(spec.replace(kernel=abi.KERNEL_FAST))
+    gen = GridOperator(spec.replace(kernel=abi.KERNEL_GENERIC))
+    z = torch.from_numpy(mt_vector(spec.num_dofs)).cuda()
+    yf, yg = torch.zeros_like(z), torch.zeros_like(z)
+    fast.apply(z, yf)
+    gen.apply(z, yg)
+    fast.synchronize(), gen.synchronize()
+    assert rel_err(yf.cpu().numpy(), yg.cpu().numpy()) < TOL
+
+
+def test_linearity_and_affinity_full_size_property(cuda_lib):
+    """Size-independent properties at a size the oracle cannot do in seconds:
+    J(a u + v) = a J u + J v."""
+    import torch
+    spec = dg_problem((64, 64, 32), degree=2, a="scalar")
+    from pdelab_b200.capi import GridOperator
+    go = GridOperator(spec)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.rand(spec.num_dofs, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.rand(spec.num_dofs, dtype=torch.float64, device="cuda", generator=g)
+    Ju, Jv, Jw = (torch.empty_like(u) for _ in range(3))
+    go.apply(u, Ju), go.apply(v, Jv), go.apply(2.5 * u + v, Jw)
+    go.synchronize()
+    err = (Jw - (2.5 * Ju + Jv)).abs().max() / Jw.abs().max()
+    assert err.item() < TOL
+    # SIPG with b = 0 is symmetric: v.Ju = u.Jv
+    s1, s2 = torch.dot(v, Ju).item(), torch.dot(u, Jv).item()
+    assert abs(s1 - s2) / abs(s1) < 1e-11
+
+
+def test_nonlinear_variant_throws_like_reference(cuda_lib):
+    from pdelab_b200.capi import GridOperator, PDELabError
+    spec = dg_problem((2, 2), degree=1)
+    go = GridOperator(spec)
+    z = np.zeros(spec.num_dofs)
+    with pytest.raises(PDELabError):
+        go.jacobian_apply(z, z, z.copy())
+
+
+def test_outflow_on_inflow_throws(cuda_lib):
+    from pdelab_b200.capi import GridOperator, PDELabError
+    spec = dg_problem((3, 3), degree=1, a="identity")
+    nc = spec.ncells
+    b = np.tile(np.array([1.0, 0.0]), (nc, 1))
+    bct = np.full(spec.num_boundary_faces, abi.BC_OUTFLOW, dtype=np.int8)   # x=0 side is inflow
+    go = GridOperator(spec.replace(b=b, bctype=bct))
+    z = np.ones(spec.num_dofs)
+    with pytest.raises(PDELabError, match="Outflow"):
+        go.jacobian_apply(z, np.zeros_like(z))
