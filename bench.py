@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — DG Q2 3D jacobian_apply throughput (BASELINE.json metric) on 1..8 B200.
+
+A "step" is one OnTheFlyOperator::apply (y = J z, backend/istl/seqistlsolverbackend.hh:66-76) of
+the ConvectionDiffusionDG SIPG operator on a QkDG k=2 YaspGrid with 128^3 cells per GPU
+(BASELINE.json configs[1]); N > 1 ranks form an overlapping Cartesian partition (weak scaling)
+and exchange the ghost cell layer of z over NCCL before every apply.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port (the reference
+cannot be built in this image) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dune-pdelab_b200", "python"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "dg_q2_3d_jacobian_apply_dof_per_s"
+UNIT = "DOF/s"
+ALPHA = 3.0  # SIPG, weightsOn, alpha=3 (test/matrixfree/matrix_free_linear.cc:105-108)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz, self.thread = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(cells, threads=None):
+    """The oracle port timed on the host cores on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import Oracle
+    from problems import dg_problem
+    spec = dg_problem((cells,) * 3, degree=2, a="scalar", alpha=ALPHA)
+    try:
+        orc = Oracle(spec, native=True)   # -O3 -march=native build made on this box
+        build = "g++ -O3 -march=native -fopenmp"
+    except Exception:
+        orc = Oracle(spec, native=False)
+        build = "g++ -O2 -fopenmp"
+    threads = threads or max(1, min(orc.max_threads(), os.cpu_count() or 1))
+    z = np.random.default_rng(0).random(spec.num_dofs)
+    y = np.zeros_like(z)
+    orc.jacobian_apply(z[:], y, threads=threads)  # warm-up (page faults)
+    best = 1e30
+    for _ in range(2):
+        y[:] = 0.0
+        t0 = time.perf_counter()
+        orc.jacobian_apply(z, y, threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": spec.num_dofs / best, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one jacobian_apply on {cells}^3 cells ({spec.num_dofs} DOFs), same operator and "
+                      f"coefficients family, {build}, best of 2, {best:.3f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = []
+    base = None
+    for _ in range(max(1, args.warmup > 0)):
+        base = cpu_baseline(args.ref_cells)
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline(args.ref_cells)
+        t_all.append(base["value"])
+    v = float(np.median(t_all))
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ConvectionDiffusionDG SIPG QkDG k=2 3D jacobian_apply (CPU oracle port of the "
+                               "reference algorithm; bounded sample)", "cells": [args.ref_cells] * 3},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pdelab_b200 import abi
+    from pdelab_b200.capi import GridOperator
+    from pdelab_b200.partition import OverlappingPartition, HaloExchanger, exchange_cell_field
+    from problems import kappa_field
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    C = args.cells
+    part = OverlappingPartition.weak((C, C, C), world, rank, overlap=1)
+    ncl = int(np.prod(part.local_cells))
+    # synthetic coefficient field kappa_e = 10^(2u-1), generated on the device per rank
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    kappa = 10.0 ** (2.0 * torch.rand(ncl, dtype=torch.float64, device=dev, generator=g) - 1.0)
+    if world == 1 and ncl <= 200_000:
+        kappa = torch.from_numpy(kappa_field(ncl)).to(dev)
+    if world > 1:  # ghost cells carry the owner's coefficient (set-up, not timed)
+        exchange_cell_field(kappa.view(part.local_cells[::-1]), part, dist)
+    spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QKDG, degree=2, lower=part.local_lower,
+                           upper=part.local_upper, method=abi.DG_SIPG, weights=abi.DG_WEIGHTS_ON, alpha=ALPHA,
+                           a_mode=abi.A_SCALAR, A=kappa, side_kind=part.side_kind, device=local_rank)
+    go = GridOperator(spec)
+    go.set_stream(torch.cuda.current_stream().cuda_stream)
+    halo = HaloExchanger(go, part, dev) if world > 1 else None
+    ndofs = spec.num_dofs
+    owned_dofs = int(np.prod(part.owned_cells)) * 27
+    z = torch.rand(ndofs, dtype=torch.float64, device=dev, generator=g)
+    y = torch.empty_like(z)
+
+    def step():
+        if halo is not None:
+            halo.exchange(z)
+        go.apply(z, y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = go.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = go.launch_count() - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    ms_step = ms_total / args.steps
+    value = owned_dofs * world / (ms_step * 1e-3)
+
+    # kernel-only duration of the dominant kernel (no halo exchange) for the roofline
+    ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ek0.record()
+    for _ in range(args.steps):
+        go.apply(z, y)
+    ek1.record()
+    torch.cuda.synchronize()
+    ms_kernel = ek0.elapsed_time(ek1) / args.steps
+    kernel_name = go.last_kernel()
+    peak, peak_src = measured_peak()
+    alg_bytes = 16.0 * ndofs + 8.0 * ncl  # 8 B read z + 8 B write y per DOF + 8 B kappa per cell
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                rec = json.load(f)
+            if rec.get("cells") == [C, C, C] and rec.get("kernel") == kernel_name:
+                traffic = rec.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # end to end through the C ABI with HOST buffers (pinned): H2D z, apply, D2H y inside the timed region
+    e2e_steps = max(1, min(args.steps, 10))
+    zh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+    yh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+    zh.copy_(z)
+
+    def e2e_step():
+        if halo is None:
+            go.apply(zh, yh)     # host pointers through the C ABI: H2D, kernel, D2H, synchronous on return
+        else:
+            z.copy_(zh, non_blocking=True)
+            halo.exchange(z)
+            go.apply(z, y)
+            yh.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = owned_dofs * world / te.item()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"ConvectionDiffusionDG SIPG QkDG k=2 on 3D YaspGrid {C}^3 cells per GPU: matrix-free "
+                            "jacobian_apply (OnTheFlyOperator::apply), fp64",
+                "cells_per_gpu": [C, C, C], "global_cells": list(part.global_cells), "dofs_per_gpu": owned_dofs,
+                "partition": "x".join(str(v) for v in part.procs), "overlap": 1 if world > 1 else 0,
+                "coefficients": "cell-wise scalar kappa=10^(2u-1), b=0, c=0, all-Dirichlet, alpha=3",
+                "cache": f"input+output {2 * ndofs * 8 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                "kernel": kernel_name,
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ndofs * 8, "d2h_bytes_per_step": ndofs * 8,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": ms_kernel,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.ref_cells)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=128, help="cells per direction per GPU")
+    ap.add_argument("--ref-cells", type=int, default=64, help="cells per direction of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

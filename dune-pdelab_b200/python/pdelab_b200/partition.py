@@ -1,0 +1,201 @@
+"""Overlapping Cartesian partition of a YaspGrid and the ghost-layer exchange for QkDG vectors.
+
+Host-side logic only (index arithmetic + torch.distributed plumbing); the data movement on the
+device is done by the pack/unpack kernels of the C ABI (csrc/halo.cu).
+
+What it mirrors in the reference: an overlapping YaspGrid (overlap >= 1) splits the cell index
+box into a Cartesian processor grid; every rank stores its interior block plus `overlap` ghost
+cell layers towards each neighbour and the GridOperator assembles on interior + overlap cells
+without any communication (gridoperator/default/assembler.hh:116).  Consistency of
+the input vector is restored before the operator by an owner -> ghost copy
+(Dune::PDELab::CopyDataHandle over InteriorBorder_All_Interface, boilerplate/pdelab.hh:872-880,
+gridfunctionspace/genericdatahandle.hh); rows of cells touching the processor boundary are
+zeroed through P0ParallelConstraints (constraints/p0.hh:31-41).  ConvectionDiffusionDG couples
+cells through faces only, so the six face neighbours suffice.
+"""
+import numpy as np
+
+from . import abi
+
+
+def processor_grid(world, dim=3, split_x=False):
+    """Cartesian processor grid, as cubic as possible, larger factors last.
+
+    By default direction 0 is not split (2 -> 1x1x2, 4 -> 1x2x2, 8 -> 1x2x4): the x-rows of a
+    QkDG vector stay contiguous and the local cell count in x stays even, which the TMA tiling of
+    the fast kernel needs (csrc/dg_fast.cu); for cubic per-rank boxes every face costs the same
+    message size, and a rank still has at most 3 neighbours at 8 ranks, exactly like 2x2x2.
+    split_x=True gives YaspGrid's default most-cubic grid (2x2x2 at 8 ranks)."""
+    ndim = dim if split_x else dim - 1
+    best = None
+
+    def rec(rem, k, cur):
+        nonlocal best
+        if k == 1:
+            cand = sorted(cur + [rem])
+            score = (max(cand) - min(cand), cand)
+            if best is None or score < best[0]:
+                best = (score, cand)
+            return
+        for f in range(1, rem + 1):
+            if rem % f == 0:
+                rec(rem // f, k - 1, cur + [f])
+
+    rec(world, ndim, [])
+    grid = best[1]
+    return tuple(grid) if split_x else (1,) + tuple(grid)
+
+
+class OverlappingPartition:
+    """One rank's view of the overlapping partition."""
+
+    def __init__(self, global_cells, procs, rank, overlap=1, lower=None, upper=None):
+        self.dim = len(global_cells)
+        self.global_cells = tuple(int(v) for v in global_cells)
+        self.procs = tuple(int(v) for v in procs)
+        self.world = int(np.prod(self.procs))
+        self.rank = int(rank)
+        self.overlap = int(overlap)
+        lower = tuple(lower) if lower is not None else (0.0,) * self.dim
+        upper = tuple(upper) if upper is not None else (1.0,) * self.dim
+        assert 0 <= rank < self.world
+        # rank = px + Px*(py + Py*pz)  (lexicographic torus coordinates, x fastest)
+        c, r = [], self.rank
+        for d in range(self.dim):
+            c.append(r % self.procs[d])
+            r //= self.procs[d]
+        self.coords = tuple(c)
+        self.owned_lo, self.owned_hi, self.local_lo, self.local_hi = [], [], [], []
+        self.side_kind = [[abi.SIDE_DOMAIN, abi.SIDE_DOMAIN] for _ in range(3)]
+        self.neighbour = [[None, None] for _ in range(3)]
+        for d in range(self.dim):
+            n, p, i = self.global_cells[d], self.procs[d], self.coords[d]
+            lo, hi = (n * i) // p, (n * (i + 1)) // p
+            self.owned_lo.append(lo)
+            self.owned_hi.append(hi)
+            llo, lhi = lo, hi
+            if i > 0:
+                llo -= self.overlap
+                self.side_kind[d][0] = abi.SIDE_PROCESSOR
+                self.neighbour[d][0] = self.rank_of(tuple(cc - (1 if dd == d else 0) for dd, cc in enumerate(self.coords)))
+            if i < p - 1:
+                lhi += self.overlap
+                self.side_kind[d][1] = abi.SIDE_PROCESSOR
+                self.neighbour[d][1] = self.rank_of(tuple(cc + (1 if dd == d else 0) for dd, cc in enumerate(self.coords)))
+            self.local_lo.append(llo)
+            self.local_hi.append(lhi)
+        self.owned_cells = tuple(h - l for l, h in zip(self.owned_lo, self.owned_hi))
+        self.local_cells = tuple(h - l for l, h in zip(self.local_lo, self.local_hi))
+        hs = [(upper[d] - lower[d]) / self.global_cells[d] for d in range(self.dim)]
+        self.local_lower = tuple(lower[d] + hs[d] * self.local_lo[d] for d in range(self.dim))
+        self.local_upper = tuple(lower[d] + hs[d] * self.local_hi[d] for d in range(self.dim))
+
+    @classmethod
+    def weak(cls, cells_per_rank, world, rank, overlap=1):
+        procs = processor_grid(world, len(cells_per_rank))
+        glob = tuple(c * p for c, p in zip(cells_per_rank, procs))
+        return cls(glob, procs, rank, overlap)
+
+    @classmethod
+    def strong(cls, global_cells, world, rank, overlap=1):
+        return cls(global_cells, processor_grid(world, len(global_cells)), rank, overlap)
+
+    def rank_of(self, coords):
+        r, stride = 0, 1
+        for d in range(self.dim):
+            r += stride * coords[d]
+            stride *= self.procs[d]
+        return r
+
+    # index helpers -------------------------------------------------------------------------
+    def local_cell_grid(self):
+        """Global lexicographic cell index of every local cell, shape local_cells[::-1]."""
+        axes = [np.arange(self.local_lo[d], self.local_hi[d]) for d in range(self.dim)]
+        idx = np.zeros(self.local_cells[::-1], dtype=np.int64)
+        stride = 1
+        for d in range(self.dim):
+            shape = [1] * self.dim
+            shape[self.dim - 1 - d] = -1
+            idx = idx + stride * axes[d].reshape(shape)
+            stride *= self.global_cells[d]
+        return idx
+
+    def owned_mask(self):
+        """Boolean array over local cells (shape local_cells[::-1]): owned (interior) cells."""
+        m = np.ones(self.local_cells[::-1], dtype=bool)
+        for d in range(self.dim):
+            ax = self.dim - 1 - d
+            sel = np.zeros(self.local_cells[d], dtype=bool)
+            sel[self.owned_lo[d] - self.local_lo[d]: self.owned_hi[d] - self.local_lo[d]] = True
+            shape = [1] * self.dim
+            shape[ax] = -1
+            m &= sel.reshape(shape)
+        return m
+
+    def exchanges(self):
+        """(direction, side, neighbour rank) for every processor side of this rank."""
+        return [(d, s, self.neighbour[d][s]) for d in range(self.dim) for s in range(2)
+                if self.neighbour[d][s] is not None]
+
+
+class HaloExchanger:
+    """Owner -> ghost copy of a QkDG vector across the six face neighbours (overlap = 1).
+
+    pack/unpack default to the CUDA kernels behind the C ABI (pdb200_halo_pack / _unpack); the
+    transport is torch.distributed point-to-point (NCCL over NVLink on the GPU box, gloo in the
+    CPU tests, which inject their own pack/unpack).
+    """
+
+    def __init__(self, go, part, device, pack=None, unpack=None, layer_size=None, dist=None):
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        assert part.overlap == 1, "the pack/unpack kernels move one cell layer"
+        self.dist, self.part, self.torch = dist, part, torch
+        self.pack = pack or go.halo_pack
+        self.unpack = unpack or go.halo_unpack
+        size = layer_size or go.halo_layer_size
+        self.send, self.recv = {}, {}
+        for d, s, _ in part.exchanges():
+            n = size(d)
+            self.send[(d, s)] = torch.empty(n, dtype=torch.float64, device=device)
+            self.recv[(d, s)] = torch.empty(n, dtype=torch.float64, device=device)
+        self.bytes_per_exchange = sum(t.numel() * 8 for t in self.send.values())
+
+    def exchange(self, x):
+        """Fill the ghost layers of x with the neighbours' owned values."""
+        dist = self.dist
+        ops = []
+        for d, s, nbr in self.part.exchanges():
+            self.pack(x, d, s, self.send[(d, s)])
+            ops.append(dist.P2POp(dist.isend, self.send[(d, s)], nbr))
+            ops.append(dist.P2POp(dist.irecv, self.recv[(d, s)], nbr))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for d, s, _ in self.part.exchanges():
+            self.unpack(x, d, s, self.recv[(d, s)])
+
+
+def exchange_cell_field(field, part, dist):
+    """Owner -> ghost copy of a per-cell field (torch tensor of shape local_cells[::-1] + trailing
+    dims), used once at set-up for the coefficient arrays.  Plain tensor slicing: not a hot path."""
+    import torch
+    ops, recvs = [], []
+    for d, s, nbr in part.exchanges():
+        ax = part.dim - 1 - d
+        n = part.local_cells[d]
+        src = 1 if s == 0 else n - 2
+        dst = 0 if s == 0 else n - 1
+        sendbuf = field.select(ax, src).contiguous()
+        recvbuf = torch.empty_like(sendbuf)
+        ops.append(dist.P2POp(dist.isend, sendbuf, nbr))
+        ops.append(dist.P2POp(dist.irecv, recvbuf, nbr))
+        recvs.append((ax, dst, recvbuf))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for ax, dst, buf in recvs:
+        field.select(ax, dst).copy_(buf)
+    return field
