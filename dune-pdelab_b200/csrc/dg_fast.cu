@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -50,7 +51,7 @@ static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 
 
 struct FastConst {
   double E0[3], E1[3], m0[3], mk[3], q0[3], q1[3];  // see Kron1D
-  double Mm[9];                                     // 1-D mass matrix
+  double Mm[9], Mv[9];                              // 1-D mass matrix, and |K| * mass matrix
   double ih2[3];                                    // 1/h_d^2
   double alpha_pen;                                 // alpha * k (k + dim - 1)
   double theta, vol;
@@ -97,62 +98,61 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+template <int AMODE>
 __device__ __forceinline__ double load_adiag(const DevParams& P, long long cell, int d) {
-  switch (P.a_mode) {
-    case PDB200_A_IDENTITY: return 1.0;
-    case PDB200_A_SCALAR: return __ldg(P.A + cell);
-    case PDB200_A_DIAGONAL: return __ldg(P.A + cell * 3 + d);
-    default: return __ldg(P.A + cell * 9 + d * 4);
-  }
+  if (AMODE == PDB200_A_IDENTITY) return 1.0;
+  if (AMODE == PDB200_A_SCALAR) return __ldg(P.A + cell);
+  if (AMODE == PDB200_A_DIAGONAL) return __ldg(P.A + cell * 3 + d);
+  return __ldg(P.A + cell * 9 + d * 4);
 }
 
-// One face of the 1-D operator along a direction: returns the four scalars
+// One face of the 1-D operator along a direction: the three scalars
 //   cs = w_self a / h^2, co = w_other a_other / h^2, cg = alpha pen harm / h^2 (penalty),
 // following convectiondiffusiondg.hh:326-346 (interior) and :717-734 (Dirichlet boundary).
 // kind: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None/Neumann/Outflow with b=0,
 // processor boundary).
 __device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double alpha_pen, int weights_on,
                                           double& cs, double& co, double& cg) {
-  if (kind == 0) {
-    double ws, wo, harm;
-    if (weights_on) {
-      const double inv = 1.0 / (a + ao + 1e-20);
-      ws = ao * inv;
-      wo = a * inv;
-      harm = 2.0 * a * ao * inv;
-    } else {
-      ws = wo = 0.5;
-      harm = 1.0;
-    }
-    cs = ws * a * ih2;
-    co = wo * ao * ih2;
-    cg = alpha_pen * harm * ih2;
-  } else if (kind == 1) {
-    cs = a * ih2;
-    co = 0.0;
-    cg = alpha_pen * (weights_on ? a : 1.0) * ih2;
+  double ws, wo, harm;
+  if (weights_on) {
+    const double inv = 1.0 / (a + ao + 1e-20);
+    ws = ao * inv;
+    wo = a * inv;
+    harm = 2.0 * a * ao * inv;
   } else {
-    cs = co = cg = 0.0;
+    ws = wo = 0.5;
+    harm = 1.0;
   }
+  if (kind == 1) {
+    ws = 1.0;
+    wo = 0.0;
+    harm = weights_on ? a : 1.0;
+  }
+  if (kind == 2) ws = wo = harm = 0.0;
+  cs = ws * a * ih2;
+  co = wo * ao * ih2;
+  cg = alpha_pen * harm * ih2;
 }
 
 // Adds (1/h_d) M^-1 L_d(l, o, r) for the nine lines of a cell along direction S-stride.
 //   S = 1 (x), 3 (y), 9 (z): stride of the local node index along the direction.
-template <int S>
-__device__ __forceinline__ void sweep(const double (&o)[NLOC], double (&t)[NLOC], const double* __restrict__ nl,
-                                      const double* __restrict__ nr, const FastConst& F, double A0, double csL,
-                                      double coL, double cgL, double csR, double coR, double cgR) {
-  // t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
+//   t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
+// The own values are re-read from shared memory in every sweep instead of being kept in 54
+// registers: the kernel is fp64-issue bound, not LDS bound, and the registers buy occupancy.
+template <int S, bool FIRST>
+__device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)[NLOC], const double* __restrict__ nl,
+                                      const double* __restrict__ nr, const FastConst& F, double creact, double A0,
+                                      double csL, double coL, double cgL, double csR, double coR, double cgR) {
   double P1[3], P2[3], P3[3], P4[3], P5[3], P6[3];
   const double ctL = -F.theta * csL, ctR = F.theta * csR;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    P1[i] = F.E0[i] * A0 + F.m0[i] * csL;
-    P2[i] = F.E1[i] * A0 - F.mk[i] * csR;
+    P1[i] = fma(F.E0[i], A0, F.m0[i] * csL);
+    P2[i] = fma(F.E1[i], A0, -F.mk[i] * csR);
     P3[i] = F.m0[i] * coL;
     P4[i] = -F.mk[i] * coR;
-    P5[i] = F.m0[i] * cgL + F.q0[i] * ctL;
-    P6[i] = F.mk[i] * cgR + F.q1[i] * ctR;
+    P5[i] = fma(F.m0[i], cgL, F.q0[i] * ctL);
+    P6[i] = fma(F.mk[i], cgR, F.q1[i] * ctR);
   }
   constexpr int SA = S == 1 ? 3 : 1;  // strides of the two tangential node indices
   constexpr int SB = S == 9 ? 3 : 9;
@@ -161,24 +161,33 @@ __device__ __forceinline__ void sweep(const double (&o)[NLOC], double (&t)[NLOC]
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       const int base = a * SA + b * SB;
-      const double o0 = o[base], o1 = o[base + S], o2 = o[base + 2 * S];
+      const double o0 = no[base], o1 = no[base + S], o2 = no[base + 2 * S];
       const double l0 = nl[base], l1 = nl[base + S], l2 = nl[base + 2 * S];
       const double r0 = nr[base], r1 = nr[base + S], r2 = nr[base + 2 * S];
       // p'(0) = (-3, 4, -1), p'(1) = (1, -4, 3) for the quadratic Lagrange basis on {0, 1/2, 1}
-      const double dls = 4.0 * o1 - (3.0 * o0 + o2);
-      const double drs = (o0 + 3.0 * o2) - 4.0 * o1;
-      const double dlo = (l0 + 3.0 * l2) - 4.0 * l1;
-      const double dro = 4.0 * r1 - (3.0 * r0 + r2);
+      const double dls = fma(4.0, o1, -fma(3.0, o0, o2));
+      const double drs = fma(-4.0, o1, fma(3.0, o2, o0));
+      const double dlo = fma(-4.0, l1, fma(3.0, l2, l0));
+      const double dro = fma(4.0, r1, -fma(3.0, r0, r2));
       const double jl = o0 - l2, jr = o2 - r0;
+      const double ov[3] = {o0, o1, o2};
 #pragma unroll
-      for (int i = 0; i < 3; i++)
-        t[base + i * S] += P1[i] * dls + P2[i] * drs + P3[i] * dlo + P4[i] * dro + P5[i] * jl + P6[i] * jr;
+      for (int i = 0; i < 3; i++) {
+        double acc = FIRST ? creact * ov[i] : t[base + i * S];
+        acc = fma(P1[i], dls, acc);
+        acc = fma(P2[i], drs, acc);
+        acc = fma(P3[i], dlo, acc);
+        acc = fma(P4[i], dro, acc);
+        acc = fma(P5[i], jl, acc);
+        acc = fma(P6[i], jr, acc);
+        t[base + i * S] = acc;
+      }
     }
 }
 
-// v <- (M along stride S) v, optionally scaled
+// v <- (M along stride S) v
 template <int S>
-__device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)[9], double scale) {
+__device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)[9]) {
   constexpr int SA = S == 1 ? 3 : 1;
   constexpr int SB = S == 9 ? 3 : 9;
 #pragma unroll
@@ -187,13 +196,14 @@ __device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)
     for (int a = 0; a < 3; a++) {
       const int base = a * SA + b * SB;
       const double v0 = t[base], v1 = t[base + S], v2 = t[base + 2 * S];
-      t[base] = scale * (Mm[0] * v0 + Mm[1] * v1 + Mm[2] * v2);
-      t[base + S] = scale * (Mm[3] * v0 + Mm[4] * v1 + Mm[5] * v2);
-      t[base + 2 * S] = scale * (Mm[6] * v0 + Mm[7] * v1 + Mm[8] * v2);
+      t[base] = fma(Mm[2], v2, fma(Mm[1], v1, Mm[0] * v0));
+      t[base + S] = fma(Mm[5], v2, fma(Mm[4], v1, Mm[3] * v0));
+      t[base + 2 * S] = fma(Mm[8], v2, fma(Mm[7], v1, Mm[6] * v0));
     }
 }
 
-__global__ void __launch_bounds__(TX* TY* TZ, 3)
+template <int AMODE, int MINB>
+__global__ void __launch_bounds__(TX* TY* TZ, MINB)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
                          const DevParams P, const FastConst F) {
@@ -225,7 +235,8 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
   const bool active = gx < P.N[0] && gy < P.N[1] && gz < P.N[2];
 
-  // ---- per-cell coefficients (overlaps the TMA latency) ---------------------------------------
+  // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
+  // before the first use so that the L2 round trips overlap instead of adding up. -----------------
   double A0[3], csL[3], coL[3], cgL[3], csR[3], coR[3], cgR[3];
   double creact = 0.0;
   bool constrained = false;
@@ -233,37 +244,36 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     const long long cell = cell_index(P.N, gx, gy, gz);
     const int g[3] = {gx, gy, gz};
     const long long stride[3] = {1, (long long)P.N[0], (long long)P.N[0] * P.N[1]};
-    if (P.c) creact = __ldg(P.c + cell);
+    double a[3], ao[3][2];
+    int kind[3][2];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      const double a = load_adiag(P, cell, d);
-      A0[d] = a * F.ih2[d];
+      a[d] = load_adiag<AMODE>(P, cell, d);
 #pragma unroll
       for (int side = 0; side < 2; side++) {
         const bool onb = side ? g[d] == P.N[d] - 1 : g[d] == 0;
-        int kind = 0;
-        double ao = 0.0;
-        if (!onb) {
-          ao = load_adiag(P, cell + (side ? stride[d] : -stride[d]), d);
-        } else if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
-          kind = 2;
-          constrained = true;
-        } else {
-          const int bct = P.bctype ? (int)P.bctype[bface_index(P, g, d, side)] : (int)PDB200_BC_DIRICHLET;
-          kind = bct == PDB200_BC_DIRICHLET ? 1 : 2;
-        }
-        double cs, co, cg;
-        face_coef(kind, a, ao, F.ih2[d], F.alpha_pen, P.weights_on, cs, co, cg);
-        if (side == 0) {
-          csL[d] = cs;
-          coL[d] = co;
-          cgL[d] = cg;
-        } else {
-          csR[d] = cs;
-          coR[d] = co;
-          cgR[d] = cg;
-        }
+        kind[d][side] = onb ? 1 : 0;
+        ao[d][side] = load_adiag<AMODE>(P, onb ? cell : cell + (side ? stride[d] : -stride[d]), d);
       }
+    }
+    if (P.c) creact = __ldg(P.c + cell);
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+      for (int side = 0; side < 2; side++)
+        if (kind[d][side]) {  // rare: cells on the box surface
+          if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
+            kind[d][side] = 2;
+            constrained = true;
+          } else if (P.bctype) {
+            kind[d][side] = P.bctype[bface_index(P, g, d, side)] == PDB200_BC_DIRICHLET ? 1 : 2;
+          }
+        }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      A0[d] = a[d] * F.ih2[d];
+      face_coef(kind[d][0], a[d], ao[d][0], F.ih2[d], F.alpha_pen, P.weights_on, csL[d], coL[d], cgL[d]);
+      face_coef(kind[d][1], a[d], ao[d][1], F.ih2[d], F.alpha_pen, P.weights_on, csR[d], coR[d], cgR[d]);
     }
   }
 
@@ -277,19 +287,14 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
 
   mbar_wait(&bar, 0);
 
-  double o[NLOC], t[NLOC];
+  double t[NLOC];
   if (active) {
-#pragma unroll
-    for (int i = 0; i < NLOC; i++) {
-      o[i] = tile[so + i];
-      t[i] = creact * o[i];
-    }
-    sweep<1>(o, t, tile + xl, tile + xr, F, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
-    sweep<3>(o, t, tile + yl, tile + yr, F, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
-    sweep<9>(o, t, tile + zl, tile + zr, F, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
-    mass_sweep<1>(t, F.Mm, 1.0);
-    mass_sweep<3>(t, F.Mm, 1.0);
-    mass_sweep<9>(t, F.Mm, F.vol);
+    sweep<1, true>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
+    sweep<3, false>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
+    sweep<9, false>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
+    mass_sweep<1>(t, F.Mm);
+    mass_sweep<3>(t, F.Mm);
+    mass_sweep<9>(t, F.Mv);
     if (constrained) {  // constraints/p0.hh:31-41 + constrain_residual (jacobianapplyengine.hh:249-254)
 #pragma unroll
       for (int i = 0; i < NLOC; i++) t[i] = 0.0;
@@ -331,6 +336,7 @@ struct FastPlan {
   std::vector<Maps> cache;  // tensor maps embed the global address: keep the most recent few
   double* scratch = nullptr;
   long long scratch_n = 0;
+  int minb = 3;
 };
 
 bool dg_fast_supported(const DevParams& P) {
@@ -349,7 +355,10 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
     F.q0[i] = K.q0[i];
     F.q1[i] = K.q1[i];
     F.ih2[i] = 1.0 / (P.h[i] * P.h[i]);
-    for (int j = 0; j < 3; j++) F.Mm[i * 3 + j] = K.M[i * MAX_N1 + j];
+    for (int j = 0; j < 3; j++) {
+      F.Mm[i * 3 + j] = K.M[i * MAX_N1 + j];
+      F.Mv[i * 3 + j] = K.M[i * MAX_N1 + j] * P.vol;
+    }
   }
   F.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
   F.theta = P.theta;
@@ -359,7 +368,14 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   PDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled is not available in this driver");
   plan->encode = (EncodeFn)fn;
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const char* env = getenv("PDB200_FAST_MINB");  // tuning knob: resident CTAs per SM the kernel is compiled for
+  plan->minb = env ? atoi(env) : 3;
+  if (plan->minb != 2 && plan->minb != 3) throw Error("PDB200_FAST_MINB must be 2 or 3");
+#define PDB_SET_SMEM(AM, MB) \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  PDB_SET_SMEM(PDB200_A_IDENTITY, 2) PDB_SET_SMEM(PDB200_A_SCALAR, 2) PDB_SET_SMEM(PDB200_A_DIAGONAL, 2)
+  PDB_SET_SMEM(PDB200_A_IDENTITY, 3) PDB_SET_SMEM(PDB200_A_SCALAR, 3) PDB_SET_SMEM(PDB200_A_DIAGONAL, 3)
+#undef PDB_SET_SMEM
   return plan;
 }
 
@@ -410,7 +426,19 @@ void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double*
   const FastPlan::Maps mx = get_maps(plan, x, P);
   const FastPlan::Maps my = get_maps(plan, out, P);
   dim3 grid((P.N[0] + TX - 1) / TX, (P.N[1] + TY - 1) / TY, (P.N[2] + TZ - 1) / TZ);
-  dg_fast_q2_3d_kernel<<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F);
+#define PDB_LAUNCH(AM, MB) \
+  dg_fast_q2_3d_kernel<AM, MB><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F)
+  const int am = P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR ? P.a_mode : PDB200_A_DIAGONAL;
+  if (plan->minb == 2) {
+    if (am == PDB200_A_IDENTITY) PDB_LAUNCH(PDB200_A_IDENTITY, 2);
+    else if (am == PDB200_A_SCALAR) PDB_LAUNCH(PDB200_A_SCALAR, 2);
+    else PDB_LAUNCH(PDB200_A_DIAGONAL, 2);
+  } else {
+    if (am == PDB200_A_IDENTITY) PDB_LAUNCH(PDB200_A_IDENTITY, 3);
+    else if (am == PDB200_A_SCALAR) PDB_LAUNCH(PDB200_A_SCALAR, 3);
+    else PDB_LAUNCH(PDB200_A_DIAGONAL, 3);
+  }
+#undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
   if (!overwrite) {
     axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, P.ndofs);
