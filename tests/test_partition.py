@@ -1,0 +1,138 @@
+"""Overlapping partition + ghost-layer exchange: host logic on CPU with gloo, world_size 2 and 4.
+
+The distributed result on owned cells must equal the single-domain oracle on the global grid
+(SURVEY.md §8e "Parity definition").  On CPU the pack/unpack kernels are replaced by torch
+indexing injected into HaloExchanger; the operator is the CPU oracle (this is a test of the
+partition/exchange logic, not of the CUDA path — tests/test_gpu_multi.py covers that)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pdelab_b200 import abi
+from pdelab_b200.partition import HaloExchanger, OverlappingPartition, exchange_cell_field, processor_grid
+
+
+def test_processor_grid():
+    assert processor_grid(1) == (1, 1, 1)
+    assert processor_grid(2) == (1, 1, 2)
+    assert processor_grid(4) == (1, 2, 2)
+    assert processor_grid(8) == (1, 2, 4)
+    assert processor_grid(8, split_x=True) == (2, 2, 2)
+    assert processor_grid(4, dim=2, split_x=True) == (2, 2)
+
+
+@pytest.mark.parametrize("cells,procs", [((8, 6, 4), (1, 2, 2)), ((6, 6, 6), (2, 2, 2)), ((7, 5), (2, 2)), ((4, 4, 9), (1, 1, 3))])
+def test_owned_cells_tile_the_grid(cells, procs):
+    world = int(np.prod(procs))
+    seen = np.zeros(cells[::-1], dtype=int)
+    for r in range(world):
+        p = OverlappingPartition(cells, procs, r)
+        gidx = p.local_cell_grid()
+        own = p.owned_mask()
+        np.add.at(seen.reshape(-1), gidx[own], 1)
+        # ghost layers only towards neighbours; the processor sides are flagged
+        for d in range(len(cells)):
+            for s in range(2):
+                has_nbr = p.neighbour[d][s] is not None
+                assert (p.side_kind[d][s] == abi.SIDE_PROCESSOR) == has_nbr
+                if has_nbr:
+                    q = OverlappingPartition(cells, procs, p.neighbour[d][s])
+                    assert q.neighbour[d][1 - s] == r
+        assert tuple(h - l for l, h in zip(p.local_lo, p.local_hi)) == p.local_cells
+    assert np.all(seen == 1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _layer_index(part, n, d, layer):
+    """flat DOF indices of cell layer `layer` normal to d, lexicographic tangential order"""
+    lc = part.local_cells
+    axes = [np.arange(lc[dd]) if dd != d else np.array([layer]) for dd in range(part.dim)]
+    grids = np.meshgrid(*axes[::-1], indexing="ij")[::-1]
+    cell = np.zeros_like(grids[0])
+    stride = 1
+    for dd in range(part.dim):
+        cell = cell + stride * grids[dd]
+        stride *= lc[dd]
+    return (cell.reshape(-1, 1) * n + np.arange(n)).reshape(-1)
+
+
+def _worker(rank, world, port, cells, degree, out):
+    sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "oracle"), os.path.dirname(__file__)]
+    from oracle import Oracle
+    from problems import kappa_field, mt_vector
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dim = len(cells)
+        part = OverlappingPartition.strong(cells, world, rank) if dim == 3 else \
+            OverlappingPartition(cells, processor_grid(world, 2, split_x=True), rank)
+        n = (degree + 1) ** dim
+        ncg = int(np.prod(cells))
+        zg = mt_vector(ncg * n).reshape(ncg, n)
+        kg = kappa_field(ncg)
+        gidx = part.local_cell_grid().reshape(-1)
+        own = part.owned_mask().reshape(-1)
+        # owned values from the global vector, ghosts poisoned: the exchange must fill them
+        z = torch.full((gidx.size, n), float("nan"), dtype=torch.float64)
+        z[own] = torch.from_numpy(zg[gidx[own]])
+        z = z.reshape(-1)
+        kap = torch.full((gidx.size,), float("nan"), dtype=torch.float64)
+        kap[own] = torch.from_numpy(kg[gidx[own]])
+        exchange_cell_field(kap.view(part.local_cells[::-1]), part, dist)
+
+        def pack(x, d, s, buf):
+            layer = 1 if s == 0 else part.local_cells[d] - 2
+            buf.copy_(x[torch.from_numpy(_layer_index(part, n, d, layer))])
+
+        def unpack(x, d, s, buf):
+            layer = 0 if s == 0 else part.local_cells[d] - 1
+            x[torch.from_numpy(_layer_index(part, n, d, layer))] = buf
+
+        halo = HaloExchanger(None, part, "cpu", pack=pack, unpack=unpack,
+                             layer_size=lambda d: int(np.prod(part.local_cells)) // part.local_cells[d] * n, dist=dist)
+        halo.exchange(z)
+        # face neighbours only: corner/edge ghosts may stay NaN in the vector but are never read by owned rows
+        zl = torch.nan_to_num(z, nan=1e300).numpy()
+        kl = torch.nan_to_num(kap, nan=1.0).numpy()
+        spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QKDG, degree=degree, lower=part.local_lower,
+                               upper=part.local_upper, alpha=3.0, a_mode=abi.A_SCALAR, A=kl, side_kind=part.side_kind)
+        y = Oracle(spec).jacobian_apply(zl).reshape(-1, n)
+        # rows of cells touching a processor side are zero (P0ParallelConstraints): those are ghosts
+        gspec = abi.ProblemSpec(cells, space=abi.SPACE_QKDG, degree=degree, alpha=3.0, a_mode=abi.A_SCALAR, A=kg)
+        want = Oracle(gspec).jacobian_apply(zg.reshape(-1)).reshape(-1, n)
+        err = np.abs(y[own] - want[gidx[own]]).max() / np.abs(want).max()
+        ghosts_zero = bool(np.all(y[~own] == 0.0)) if (~own).any() else True
+        out.put((rank, float(err), ghosts_zero, int(own.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cells,degree", [(2, (4, 3, 6), 2), (4, (4, 6, 6), 1), (4, (6, 6), 2)])
+def test_distributed_apply_matches_global_oracle(world, cells, degree):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cells, degree, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(r[3] for r in res) == int(np.prod(cells))
+    for rank, err, ghosts_zero, _ in res:
+        assert err < 1e-12, (rank, err)
+        assert ghosts_zero
