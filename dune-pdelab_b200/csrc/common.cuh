@@ -115,6 +115,9 @@ FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev);
 void fem_plan_destroy(FemPlan*);
 void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                        cudaStream_t s);
+struct QkLayout;  // host_tables.h
+const QkLayout& fem_plan_layout(const FemPlan*);
+const uint64_t* fem_plan_constrained(const FemPlan*, long long* n);  // device list of constrained DOFs
 
 // matrix.cu: sparsity pattern (CSR / block CSR), assembled Jacobian, SpMV
 struct MatrixPlan;

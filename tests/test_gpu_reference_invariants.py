@@ -1,0 +1,38 @@
+"""The reference's integration tests (see tests/test_reference_invariants.py) through the CUDA path."""
+import numpy as np
+import pytest
+
+from manufactured import GpuOps, bicgstab, l2_error_squared, solve_stationary
+from test_reference_invariants import make_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["testconvectiondiffusiondg", "testfastdgassembler", "matrix_free_linear"])
+def test_dg_manufactured_solution_matrix_based(cuda_lib, name):
+    spec, x0, u, thr = make_case(name)
+    x, _ = solve_stationary(GpuOps(spec), x0)
+    err = l2_error_squared(spec, x, u)
+    assert np.isfinite(err) and err <= thr, err
+
+
+def test_testmatrixfree_q2_matrix_based_and_matrix_free(cuda_lib):
+    spec, x0, u, thr = make_case("testmatrixfree")
+    ops = GpuOps(spec)
+    x, _ = solve_stationary(ops, x0)
+    assert l2_error_squared(spec, x, u) <= thr
+    xmf, its = solve_stationary(ops, x0, matrix_free=True, reduction=1e-10)
+    assert l2_error_squared(spec, xmf, u) <= thr
+
+
+def test_matrix_free_linear_same_iteration_count(cuda_lib):
+    spec, x0, u, thr = make_case("matrix_free_linear")
+    ops = GpuOps(spec)
+    r = ops.residual(x0)
+    J = ops.matrix()
+    _, it_mb = bicgstab(lambda v: J @ v, r, 1e-10)
+    z_mf, it_mf = bicgstab(ops.jacobian_apply, r, 1e-10)
+    # the assembled product runs in scipy on the host, the matrix-free one on the GPU: different
+    # summation orders may move the stopping test by one iteration (the CPU suite asserts equality)
+    assert abs(it_mb - it_mf) <= 1
+    assert l2_error_squared(spec, x0 - z_mf, u) <= thr
