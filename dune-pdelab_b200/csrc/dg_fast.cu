@@ -50,11 +50,12 @@ static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 
               "TMA destinations must be 128-byte aligned");
 
 struct FastConst {
-  double E0[3], E1[3], m0[3], mk[3], q0[3], q1[3];  // see Kron1D
-  double Mm[9], Mv[9];                              // 1-D mass matrix, and |K| * mass matrix
-  double ih2[3];                                    // 1/h_d^2
-  double alpha_pen;                                 // alpha * k (k + dim - 1)
-  double theta, vol;
+  // see Kron1D; all six vectors are pre-multiplied by |K| / 30^3 so that the three mass sweeps can
+  // use the integer matrix 30 M = [[4,2,-1],[2,16,2],[-1,2,4]] of the quadratic Lagrange basis
+  double E0[3], E1[3], m0[3], mk[3], q0[3], q1[3];
+  double ih2[3];     // 1/h_d^2
+  double alpha_pen;  // alpha * k (k + dim - 1)
+  double theta, scale;  // scale = |K| / 27000
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,27 +112,41 @@ __device__ __forceinline__ double load_adiag(const DevParams& P, long long cell,
 // following convectiondiffusiondg.hh:326-346 (interior) and :717-734 (Dirichlet boundary).
 // kind: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None/Neumann/Outflow with b=0,
 // processor boundary).
+// 1/x for positive normal x: MUFU.RCP64H seed (~20 bits) + Newton steps (rel. error ~1e-16).
+// Branch-free on purpose: the IEEE division's slow-path call serialises the six face set-ups.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 __device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double alpha_pen, int weights_on,
                                           double& cs, double& co, double& cg) {
-  double ws, wo, harm;
+  if (kind == 2) {
+    cs = co = cg = 0.0;
+    return;
+  }
+  if (kind == 1) {  // Dirichlet boundary: w_self = 1, harmonic average = a (weights on) or 1
+    cs = a * ih2;
+    co = 0.0;
+    cg = alpha_pen * (weights_on ? a : 1.0) * ih2;
+    return;
+  }
   if (weights_on) {
-    const double inv = 1.0 / (a + ao + 1e-20);
-    ws = ao * inv;
-    wo = a * inv;
-    harm = 2.0 * a * ao * inv;
+    // w_self a = w_other a_other = a a_other / (a + a_other + 1e-20) = harmonic average / 2
+    const double hh = a * ao * ih2 * fast_rcp(a + ao + 1e-20);
+    cs = co = hh;
+    cg = (alpha_pen + alpha_pen) * hh;
   } else {
-    ws = wo = 0.5;
-    harm = 1.0;
+    cs = 0.5 * a * ih2;
+    co = 0.5 * ao * ih2;
+    cg = alpha_pen * ih2;
   }
-  if (kind == 1) {
-    ws = 1.0;
-    wo = 0.0;
-    harm = weights_on ? a : 1.0;
-  }
-  if (kind == 2) ws = wo = harm = 0.0;
-  cs = ws * a * ih2;
-  co = wo * ao * ih2;
-  cg = alpha_pen * harm * ih2;
 }
 
 // Adds (1/h_d) M^-1 L_d(l, o, r) for the nine lines of a cell along direction S-stride.
@@ -139,7 +154,7 @@ __device__ __forceinline__ void face_coef(int kind, double a, double ao, double 
 //   t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
 // The own values are re-read from shared memory in every sweep instead of being kept in 54
 // registers: the kernel is fp64-issue bound, not LDS bound, and the registers buy occupancy.
-template <int S, bool FIRST>
+template <int S, bool FIRST, bool HAS_C>
 __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)[NLOC], const double* __restrict__ nl,
                                       const double* __restrict__ nr, const FastConst& F, double creact, double A0,
                                       double csL, double coL, double cgL, double csR, double coR, double cgR) {
@@ -173,8 +188,11 @@ __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)
       const double ov[3] = {o0, o1, o2};
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        double acc = FIRST ? creact * ov[i] : t[base + i * S];
-        acc = fma(P1[i], dls, acc);
+        double acc;
+        if (FIRST)
+          acc = HAS_C ? fma(P1[i], dls, creact * ov[i]) : P1[i] * dls;
+        else
+          acc = fma(P1[i], dls, t[base + i * S]);
         acc = fma(P2[i], drs, acc);
         acc = fma(P3[i], dlo, acc);
         acc = fma(P4[i], dro, acc);
@@ -185,9 +203,10 @@ __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)
     }
 }
 
-// v <- (M along stride S) v
+// v <- (30 M along stride S) v with 30 M = [[4,2,-1],[2,16,2],[-1,2,4]]; the factor |K|/30^3 is
+// already inside t (FastConst)
 template <int S>
-__device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)[9]) {
+__device__ __forceinline__ void mass_sweep(double (&t)[NLOC]) {
   constexpr int SA = S == 1 ? 3 : 1;
   constexpr int SB = S == 9 ? 3 : 9;
 #pragma unroll
@@ -196,13 +215,14 @@ __device__ __forceinline__ void mass_sweep(double (&t)[NLOC], const double (&Mm)
     for (int a = 0; a < 3; a++) {
       const int base = a * SA + b * SB;
       const double v0 = t[base], v1 = t[base + S], v2 = t[base + 2 * S];
-      t[base] = fma(Mm[2], v2, fma(Mm[1], v1, Mm[0] * v0));
-      t[base + S] = fma(Mm[5], v2, fma(Mm[4], v1, Mm[3] * v0));
-      t[base + 2 * S] = fma(Mm[8], v2, fma(Mm[7], v1, Mm[6] * v0));
+      const double e = v0 + v2;
+      t[base] = fma(4.0, v0, fma(2.0, v1, -v2));
+      t[base + S] = fma(16.0, v1, e + e);
+      t[base + 2 * S] = fma(4.0, v2, fma(2.0, v1, -v0));
     }
 }
 
-template <int AMODE, int MINB>
+template <int AMODE, int MINB, bool HAS_C>
 __global__ void __launch_bounds__(TX* TY* TZ, MINB)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
@@ -256,7 +276,7 @@ __global__ void __launch_bounds__(TX* TY* TZ, MINB)
         ao[d][side] = load_adiag<AMODE>(P, onb ? cell : cell + (side ? stride[d] : -stride[d]), d);
       }
     }
-    if (P.c) creact = __ldg(P.c + cell);
+    if (HAS_C) creact = __ldg(P.c + cell) * F.scale;
 #pragma unroll
     for (int d = 0; d < 3; d++)
 #pragma unroll
@@ -289,12 +309,12 @@ __global__ void __launch_bounds__(TX* TY* TZ, MINB)
 
   double t[NLOC];
   if (active) {
-    sweep<1, true>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
-    sweep<3, false>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
-    sweep<9, false>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
-    mass_sweep<1>(t, F.Mm);
-    mass_sweep<3>(t, F.Mm);
-    mass_sweep<9>(t, F.Mv);
+    sweep<1, true, HAS_C>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
+    sweep<3, false, HAS_C>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
+    sweep<9, false, HAS_C>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
+    mass_sweep<1>(t);
+    mass_sweep<3>(t);
+    mass_sweep<9>(t);
     if (constrained) {  // constraints/p0.hh:31-41 + constrain_residual (jacobianapplyengine.hh:249-254)
 #pragma unroll
       for (int i = 0; i < NLOC; i++) t[i] = 0.0;
@@ -347,22 +367,18 @@ bool dg_fast_supported(const DevParams& P) {
 FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   FastPlan* plan = new FastPlan;
   FastConst& F = plan->F;
+  F.scale = P.vol / 27000.0;
   for (int i = 0; i < 3; i++) {
-    F.E0[i] = K.E0[i];
-    F.E1[i] = K.E1[i];
-    F.m0[i] = K.m0[i];
-    F.mk[i] = K.mk[i];
-    F.q0[i] = K.q0[i];
-    F.q1[i] = K.q1[i];
+    F.E0[i] = K.E0[i] * F.scale;
+    F.E1[i] = K.E1[i] * F.scale;
+    F.m0[i] = K.m0[i] * F.scale;
+    F.mk[i] = K.mk[i] * F.scale;
+    F.q0[i] = K.q0[i] * F.scale;
+    F.q1[i] = K.q1[i] * F.scale;
     F.ih2[i] = 1.0 / (P.h[i] * P.h[i]);
-    for (int j = 0; j < 3; j++) {
-      F.Mm[i * 3 + j] = K.M[i * MAX_N1 + j];
-      F.Mv[i * 3 + j] = K.M[i * MAX_N1 + j] * P.vol;
-    }
   }
   F.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
   F.theta = P.theta;
-  F.vol = P.vol;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   PDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -371,8 +387,9 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   const char* env = getenv("PDB200_FAST_MINB");  // tuning knob: resident CTAs per SM the kernel is compiled for
   plan->minb = env ? atoi(env) : 3;
   if (plan->minb != 2 && plan->minb != 3) throw Error("PDB200_FAST_MINB must be 2 or 3");
-#define PDB_SET_SMEM(AM, MB) \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define PDB_SET_SMEM(AM, MB)                                                                                          \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   PDB_SET_SMEM(PDB200_A_IDENTITY, 2) PDB_SET_SMEM(PDB200_A_SCALAR, 2) PDB_SET_SMEM(PDB200_A_DIAGONAL, 2)
   PDB_SET_SMEM(PDB200_A_IDENTITY, 3) PDB_SET_SMEM(PDB200_A_SCALAR, 3) PDB_SET_SMEM(PDB200_A_DIAGONAL, 3)
 #undef PDB_SET_SMEM
@@ -426,8 +443,13 @@ void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double*
   const FastPlan::Maps mx = get_maps(plan, x, P);
   const FastPlan::Maps my = get_maps(plan, out, P);
   dim3 grid((P.N[0] + TX - 1) / TX, (P.N[1] + TY - 1) / TY, (P.N[2] + TZ - 1) / TZ);
-#define PDB_LAUNCH(AM, MB) \
-  dg_fast_q2_3d_kernel<AM, MB><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F)
+#define PDB_LAUNCH(AM, MB)                                                                                          \
+  do {                                                                                                              \
+    if (P.c)                                                                                                        \
+      dg_fast_q2_3d_kernel<AM, MB, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F); \
+    else                                                                                                            \
+      dg_fast_q2_3d_kernel<AM, MB, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F); \
+  } while (0)
   const int am = P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR ? P.a_mode : PDB200_A_DIAGONAL;
   if (plan->minb == 2) {
     if (am == PDB200_A_IDENTITY) PDB_LAUNCH(PDB200_A_IDENTITY, 2);
