@@ -26,6 +26,8 @@
 // reference's (k+1)-point Gauss rule integrates the same polynomials exactly, so values agree to
 // rounding); QkDG blocks are integrated with the reference's quadrature loops.
 
+#include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -139,157 +141,121 @@ int device_row_scan(F f, u64 n, u64* out /* n+1, device */, cudaStream_t s) {
 
 // ---- conforming Qk: rows are lattice points -------------------------------------------------
 
-// container index -> lattice point (inverse of qk_lattice_index)
-__device__ __forceinline__ void qk_index_to_lattice(const QkLayout& L, long long idx, int p[3]) {
-  p[0] = p[1] = p[2] = 0;
-  if (L.k == 1) {
-    for (int d = 0; d < L.dim; d++) {
-      p[d] = (int)(idx % (L.N[d] + 1));
-      idx /= L.N[d] + 1;
-    }
-    return;
-  }
-  int edim = 0;
-  for (int e = 1; e <= L.dim; e++)
-    if (idx >= L.block_off[e]) edim = e;
-  idx -= L.block_off[edim];
-  int s = 0;
-  for (int g = 0; g < (1 << L.dim); g++)
-    if (__popc(g) == edim && idx >= L.group_off[g]) s = g;  // group offsets ascend with g inside a block
-  idx -= L.group_off[s];
-  for (int d = 0; d < L.dim; d++) {
-    const int ext = (s >> d) & 1;
-    const int sz = ext ? L.N[d] : L.N[d] + 1;
-    p[d] = 2 * (int)(idx % sz) + ext;
-    idx /= sz;
-  }
+// n / d for 32-bit n with a precomputed multiplier (libdivide's branch-free u32 scheme)
+struct FastDiv {
+  uint32_t d, magic;
+  int more;  // d == 1: more = -1
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  if (f.more < 0) return n;
+  const uint32_t q = __umulhi(f.magic, n);
+  return (((n - q) >> 1) + q) >> f.more;
 }
+
+// Row decode of a conforming space: rows (container indices) are grouped by entity type; inside a
+// group they are lexicographic in the anchor coordinates (ordering/leafgridviewordering.hh:166-184
+// + YaspGrid index sets).  Built on the host from QkLayout; all indices fit 32 bits here.
+struct QkDecode {
+  int dim, k, ng;
+  int N[3];
+  uint32_t start[9];       // first row of group g (container order), start[ng] = number of rows
+  uint8_t sbits[8];        // extension bitset of group g
+  uint8_t group_of_s[8];   // inverse map
+  uint32_t sz0[8], sz1[8];
+  FastDiv d0[8], d1[8];
+};
 
 struct QkRow {
   int p[3], lo[3], hi[3];
-  int len;
+  int len, shape;
 };
 
-// the columns of row p: all lattice points of the cells that contain p (FullVolumePattern)
-__device__ __forceinline__ QkRow qk_row(const QkLayout& L, long long row) {
+// the columns of a row: all lattice points of the cells that contain the row's lattice point
+// (FullVolumePattern, localoperator/pattern.hh:13-25)
+__device__ __forceinline__ QkRow qk_row(const QkDecode& D, uint32_t row) {
   QkRow R;
-  qk_index_to_lattice(L, row, R.p);
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++)
+    if (i < D.ng && row >= D.start[i]) g = i;
+  uint32_t r = row - D.start[g];
+  const uint32_t q0 = fast_div(r, D.d0[g]);
+  const uint32_t a0 = r - q0 * D.sz0[g];
+  const uint32_t q1 = fast_div(q0, D.d1[g]);
+  const uint32_t a1 = q0 - q1 * D.sz1[g];
+  const int a[3] = {(int)a0, (int)a1, (int)q1};
+  const int s = D.sbits[g], k = D.k;
   R.len = 1;
+  R.shape = 0;
+#pragma unroll
   for (int d = 0; d < 3; d++) {
-    R.lo[d] = R.hi[d] = 0;
-    if (d >= L.dim) continue;
-    const int k = L.k, pd = R.p[d];
-    if (pd % k != 0) {
-      R.lo[d] = (pd / k) * k;
-      R.hi[d] = R.lo[d] + k;
+    R.p[d] = R.lo[d] = R.hi[d] = 0;
+    if (d >= D.dim) continue;
+    const int pd = k * a[d] + ((s >> d) & 1);
+    R.p[d] = pd;
+    if ((s >> d) & 1) {  // interior node of a cell (k = 2 only)
+      R.lo[d] = pd - 1;
+      R.hi[d] = pd + 1;
     } else {
       R.lo[d] = max(pd - k, 0);
-      R.hi[d] = min(pd + k, k * L.N[d]);
+      R.hi[d] = min(pd + k, k * D.N[d]);
     }
-    R.len *= R.hi[d] - R.lo[d] + 1;
+    const int len = R.hi[d] - R.lo[d] + 1;
+    R.len *= len;
+    R.shape |= (len == 2 * k + 1 ? 1 : 0) << d;
   }
   return R;
 }
 
-// slot (position inside the row, ascending container index) -> column lattice point
-__device__ __forceinline__ void qk_slot_to_lattice(const QkLayout& L, const QkRow& R, int slot, int q[3]) {
-  q[0] = q[1] = q[2] = 0;
-  if (L.k == 1) {
-    for (int d = 0; d < L.dim; d++) {
-      const int cnt = R.hi[d] - R.lo[d] + 1;
-      q[d] = R.lo[d] + slot % cnt;
-      slot /= cnt;
-    }
-    return;
-  }
-  // groups in container order: by entity dimension, then by bitset value
-  for (int edim = 0; edim <= L.dim; edim++)
-    for (int s = 0; s < (1 << L.dim); s++) {
-      if (__popc(s) != edim) continue;
-      int cnt[3] = {1, 1, 1}, first[3] = {0, 0, 0}, total = 1;
-      for (int d = 0; d < L.dim; d++) {
-        const int par = (s >> d) & 1;
-        first[d] = R.lo[d] + (((R.lo[d] & 1) != par) ? 1 : 0);
-        cnt[d] = first[d] <= R.hi[d] ? (R.hi[d] - first[d]) / 2 + 1 : 0;
-        total *= cnt[d];
-      }
-      if (slot < total) {
-        for (int d = 0; d < L.dim; d++) {
-          q[d] = first[d] + 2 * (slot % cnt[d]);
-          slot /= cnt[d];
-        }
-        return;
-      }
-      slot -= total;
-    }
+// lattice point -> container index (LFSIndexCache::containerIndex, lfsindexcache.hh:603-633)
+__device__ __forceinline__ uint32_t qk_col_index(const QkDecode& D, const int q[3]) {
+  if (D.k == 1) return (uint32_t)q[0] + D.sz0[0] * ((uint32_t)q[1] + D.sz1[0] * (uint32_t)q[2]);
+  const int s = (q[0] & 1) | ((q[1] & 1) << 1) | ((q[2] & 1) << 2);
+  const int g = D.group_of_s[s];
+  return D.start[g] + (uint32_t)(q[0] >> 1) + D.sz0[g] * ((uint32_t)(q[1] >> 1) + D.sz1[g] * (uint32_t)(q[2] >> 1));
 }
 
 struct QkRowLen {
-  QkLayout L;
-  __device__ u64 operator()(u64 row) const { return (u64)qk_row(L, (long long)row).len; }
+  QkDecode D;
+  __device__ u64 operator()(u64 row) const { return (u64)qk_row(D, (uint32_t)row).len; }
 };
 
-template <typename IDX>
-__global__ void __launch_bounds__(256)
-    qk_colidx_kernel(const QkLayout L, const u64* __restrict__ rowptr, u64 nrows, IDX* __restrict__ colidx) {
-  const u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= nrows) return;
-  const QkRow R = qk_row(L, (long long)row);
-  const u64 start = rowptr[row];
-  for (int slot = lane; slot < R.len; slot += 32) {
-    int q[3];
-    qk_slot_to_lattice(L, R, slot, q);
-    colidx[start + slot] = (IDX)qk_lattice_index(L, q);
-  }
-}
+// ---- slot decode tables --------------------------------------------------------------------
+// The box of a row starts at an even lattice index in every direction (k = 2), so the order of
+// its columns depends only on the box SHAPE (len_d in {k+1, 2k+1}): 8 shapes.  Two small tables
+// per shape, built on the host by sorting the box offsets with the container-index key:
+//   slot2off[shape][slot] = d0 | d1 << 3 | d2 << 6     (offset of the column inside the box)
+//   off2slot[shape][d0 + 5 (d1 + 5 d2)] = slot
+struct QkLut {
+  uint16_t slot2off[8][125];
+  uint8_t off2slot[8][125];
+};
 
-// local matrix entry (i = test, j = trial) of cell `cell`:  jacobian_volume,
-// convectiondiffusionfem.hh:140-203, with exactly integrated 1-D factors
-__device__ __forceinline__ double qk_volume_entry(const DevParams& P, const Mat1D& T, long long cell, const int li[3],
-                                                  const int lj[3]) {
-  const int n1 = P.n1;
-  double m[3] = {1, 1, 1}, kk[3] = {0, 0, 0}, cij[3] = {0, 0, 0}, cji[3] = {0, 0, 0};
-  for (int d = 0; d < P.dim; d++) {
-    m[d] = T.M[li[d] * n1 + lj[d]];
-    kk[d] = T.K[li[d] * n1 + lj[d]];
-    cij[d] = T.C[li[d] * n1 + lj[d]];
-    cji[d] = T.C[lj[d] * n1 + li[d]];
+// unit local matrices: the local Jacobian of a cell with cell-wise constant coefficients is
+//   sum_t w_t(cell) T_t,   T_t[i * n + j] (i = test, j = trial), built on the host from the exactly
+// integrated 1-D matrices (jacobian_volume, convectiondiffusionfem.hh:140-203)
+constexpr int QK_MAX_TABLES = 13;
+struct QkTables {
+  int nt;                    // number of tables
+  int kind[QK_MAX_TABLES];   // 0: kappa (scalar A), 1: A[a][b], 2: -b[a], 3: c
+  int ia[QK_MAX_TABLES], ib[QK_MAX_TABLES];
+};
+
+// weight w_t of the cell (uniform over the lanes that work on one row)
+__device__ __forceinline__ double qk_cell_weight(const DevParams& P, const QkTables& Q, long long cell, int t) {
+  switch (Q.kind[t]) {
+    case 0: return P.a_mode == PDB200_A_IDENTITY ? 1.0 : __ldg(P.A + cell);
+    case 1:
+      return P.a_mode == PDB200_A_DIAGONAL ? __ldg(P.A + cell * P.dim + Q.ia[t])
+                                           : __ldg(P.A + cell * P.dim * P.dim + Q.ia[t] * P.dim + Q.ib[t]);
+    case 2: return -__ldg(P.b + cell * P.dim + Q.ia[t]);
+    default: return __ldg(P.c + cell);
   }
-  double A[3][3];
-  load_A(P, cell, A);
-  double v = 0.0;
-  for (int a = 0; a < P.dim; a++) {
-    double t = kk[a];
-    for (int d = 0; d < P.dim; d++)
-      if (d != a) t *= m[d];
-    v += A[a][a] * P.ih[a] * P.ih[a] * t;
-  }
-  if (P.a_mode == PDB200_A_FULL)
-    for (int a = 0; a < P.dim; a++)
-      for (int b = 0; b < P.dim; b++) {
-        if (a == b) continue;
-        // int (d_b phi_j)(d_a phi_i): direction a carries p_i' p_j, direction b carries p_i p_j'
-        double t = cij[a] * cji[b];
-        for (int d = 0; d < P.dim; d++)
-          if (d != a && d != b) t *= m[d];
-        v += A[a][b] * P.ih[a] * P.ih[b] * t;
-      }
-  if (P.b)
-    for (int a = 0; a < P.dim; a++) {
-      double t = cij[a];
-      for (int d = 0; d < P.dim; d++)
-        if (d != a) t *= m[d];
-      v -= __ldg(P.b + cell * P.dim + a) * P.ih[a] * t;
-    }
-  if (P.c) v += __ldg(P.c + cell) * m[0] * m[1] * m[2];
-  return v * P.vol;
 }
 
 // jacobian_boundary (outflow faces only), convectiondiffusionfem.hh:279-325
 __device__ __forceinline__ double qk_boundary_entry(const DevParams& P, const Mat1D& T, long long cell, const int c[3],
                                                     const int li[3], const int lj[3]) {
-  if (!P.bctype || !P.b) return 0.0;
   double v = 0.0;
   for (int dir = 0; dir < P.dim; dir++)
     for (int side = 0; side < 2; side++) {
@@ -306,63 +272,168 @@ __device__ __forceinline__ double qk_boundary_entry(const DevParams& P, const Ma
   return v;
 }
 
-__global__ void __launch_bounds__(256)
-    qk_assemble_kernel(const DevParams P, const QkLayout L, const Mat1D T, const u64* __restrict__ rowptr, u64 nrows,
-                       const unsigned char* __restrict__ constrained, double* __restrict__ values, int fresh) {
-  const u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+constexpr int QK_THREADS = 256;
+
+// G lanes work on one row (G = 32 for n = 27, 16 for n = 9, 8 for n <= 8)
+template <int G, typename IDX>
+__global__ void __launch_bounds__(QK_THREADS)
+    qk_colidx_kernel(const QkDecode D, const QkLut* __restrict__ lut_g, const u64* __restrict__ rowptr, u64 nrows,
+                     IDX* __restrict__ colidx) {
+  __shared__ QkLut lut;
+  for (int i = threadIdx.x; i < (int)(sizeof(QkLut) / 4); i += QK_THREADS) ((uint32_t*)&lut)[i] = ((const uint32_t*)lut_g)[i];
+  __syncthreads();
+  const int lane = threadIdx.x % G;
+  const u64 row = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
   if (row >= nrows) return;
-  const QkRow R = qk_row(L, (long long)row);
+  const QkRow R = qk_row(D, (uint32_t)row);
   const u64 start = rowptr[row];
-  const bool con = constrained && constrained[row];
-  const int k = P.k;
-  for (int slot = lane; slot < R.len; slot += 32) {
-    int q[3];
-    qk_slot_to_lattice(L, R, slot, q);
-    if (con) {  // set_trivial_rows: clear the row, unit diagonal
-      values[start + slot] = (q[0] == R.p[0] && q[1] == R.p[1] && q[2] == R.p[2]) ? 1.0 : 0.0;
-      continue;
-    }
-    // cells containing both lattice points, per direction
-    int c0[3] = {0, 0, 0}, nc[3] = {1, 1, 1};
-    for (int d = 0; d < P.dim; d++) {
-      const int lo = max(R.p[d], q[d]), hi = min(R.p[d], q[d]);  // cell c contains both iff k c <= hi, lo <= k c + k
-      int first = (lo - k + k - 1) / k;                          // ceil((lo - k) / k), lo - k >= -k
-      if (lo - k < 0) first = 0;
-      int last = hi / k;
-      if (last > P.N[d] - 1) last = P.N[d] - 1;
-      c0[d] = first;
-      nc[d] = last - first + 1;
-    }
-    double v = 0.0;
-    for (int a2 = 0; a2 < nc[2]; a2++)
-      for (int a1 = 0; a1 < nc[1]; a1++)
-        for (int a0 = 0; a0 < nc[0]; a0++) {
-          const int c[3] = {c0[0] + a0, c0[1] + a1, c0[2] + a2};
-          const int li[3] = {R.p[0] - k * c[0], R.p[1] - k * c[1], R.p[2] - k * c[2]};
-          const int lj[3] = {q[0] - k * c[0], q[1] - k * c[1], q[2] - k * c[2]};
-          const long long cell = cell_index(P.N, c[0], c[1], c[2]);
-          v += qk_volume_entry(P, T, cell, li, lj) + qk_boundary_entry(P, T, cell, c, li, lj);
-        }
-    values[start + slot] = fresh ? v : values[start + slot] + v;
+  for (int slot = lane; slot < R.len; slot += G) {
+    const int off = lut.slot2off[R.shape][slot];
+    const int q[3] = {R.lo[0] + (off & 7), R.lo[1] + ((off >> 3) & 7), R.lo[2] + (off >> 6)};
+    colidx[start + slot] = (IDX)qk_col_index(D, q);
   }
 }
 
-__global__ void qk_mv_kernel(const QkLayout L, const u64* __restrict__ rowptr, u64 nrows,
-                             const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y) {
-  const u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= nrows) return;
-  const QkRow R = qk_row(L, (long long)row);
-  const u64 start = rowptr[row];
-  double acc = 0.0;
-  for (int slot = lane; slot < R.len; slot += 32) {
-    int q[3];
-    qk_slot_to_lattice(L, R, slot, q);
-    acc = fma(values[start + slot], __ldg(x + qk_lattice_index(L, q)), acc);
+// Row-gather assembly.  For every row: loop over the <= 2^dim cells that contain the row's lattice
+// point in ascending cell order (uniform trip count, invalid candidates are predicated off); lane j
+// adds the cell's local entry (i, j) into the row buffer in shared memory at the slot of column
+// j; then the buffer is written out contiguously.  scatter_jacobian + UncachedMatrixView::add
+// (assemblerutilities.hh:449-460, uncachedmatrixview.hh:259-262) without search or atomics.
+// outflow boundary terms of one (row, cell) pass — rare, kept out of line
+template <int DIM, int K>
+__device__ __forceinline__ double qk_outflow_entry(const DevParams& P, const Mat1D& T1, int c0, int c1, int c2, int i, int j) {
+  constexpr int N1 = K + 1;
+  const int c[3] = {c0, c1, c2};
+  const int li[3] = {i % N1, (i / N1) % N1, i / (N1 * N1)};
+  const int lj[3] = {j % N1, (j / N1) % N1, j / (N1 * N1)};
+  return qk_boundary_entry(P, T1, cell_index(P.N, c0, c1, c2), c, li, lj);
+}
+
+// NT1: a single unit table (scalar or identity diffusion, no b, no c) — the cell weights then
+// travel by warp shuffle; otherwise they are staged in shared memory.
+template <int G, int DIM, int K, bool NT1, bool OUTFLOW>
+__global__ void __launch_bounds__(QK_THREADS)
+    qk_assemble_kernel(const DevParams P, const QkDecode D, const Mat1D T1, const QkTables Q,
+                       const double* __restrict__ tables_g, const QkLut* __restrict__ lut_g,
+                       const u64* __restrict__ rowptr, u64 nrows, const unsigned char* __restrict__ constrained,
+                       double* __restrict__ values, int fresh) {
+  constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  constexpr int MAXLEN = DIM == 3 ? (2 * K + 1) * (2 * K + 1) * (2 * K + 1) : (2 * K + 1) * (2 * K + 1);
+  constexpr int ROWS_PER_CTA = QK_THREADS / G;
+  constexpr int NCAND = DIM == 3 ? 8 : 4;
+  extern __shared__ double sm[];
+  const int nt = NT1 ? 1 : Q.nt;
+  double* tab = sm;                                    // [nt][N*N]
+  double* buf = tab + nt * N * N;                      // [ROWS_PER_CTA][MAXLEN]
+  double* wbuf = buf + ROWS_PER_CTA * MAXLEN;          // [ROWS_PER_CTA][NCAND][nt]   (unused if NT1)
+  const uint8_t* off2slot = (const uint8_t*)(wbuf + (NT1 ? 0 : ROWS_PER_CTA * NCAND * nt));  // [8][125]
+  for (int i = threadIdx.x; i < nt * N * N; i += QK_THREADS) tab[i] = tables_g[i];
+  for (int i = threadIdx.x; i < 250; i += QK_THREADS) ((uint32_t*)off2slot)[i] = ((const uint32_t*)lut_g->off2slot)[i];
+  __syncthreads();
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  // lanes that work on the same row: trip counts and branches below are uniform inside a group
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+  double* rb = buf + grp * MAXLEN;
+  double* wb = wbuf + grp * NCAND * nt;
+  const u64 row0 = (u64)blockIdx.x * ROWS_PER_CTA + grp;
+  const u64 rstride = (u64)gridDim.x * ROWS_PER_CTA;
+  const int joff = (lane % N1) + 5 * (((lane / N1) % N1) + 5 * (lane / (N1 * N1)));
+  const int N0c = P.N[0], N1c = P.N[1], N2c = P.N[2];
+  for (u64 row = row0; row < nrows; row += rstride) {
+    const QkRow R = qk_row(D, (uint32_t)row);
+    const u64 start = rowptr[row];
+    const uint8_t* o2s = off2slot + R.shape * 125;
+    if (constrained && constrained[row]) {  // set_trivial_rows: clear the row, unit diagonal
+      const int diag = o2s[(R.p[0] - R.lo[0]) + 5 * ((R.p[1] - R.lo[1]) + 5 * (R.p[2] - R.lo[2]))];
+      for (int s = lane; s < R.len; s += G) values[start + s] = s == diag ? 1.0 : 0.0;
+      continue;
+    }
+    // the two candidate cells per direction, floor((p-1)/K) and floor(p/K), and whether they exist
+    int cl[3] = {0, 0, 0};
+    bool v0[3] = {true, true, true}, v1[3] = {false, false, false};
+    const int Nc[3] = {N0c, N1c, N2c};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const int pd = R.p[d], c = pd / K;
+      if (pd % K != 0) {
+        cl[d] = c;
+      } else {
+        cl[d] = c - 1;
+        v0[d] = c - 1 >= 0;
+        v1[d] = c < Nc[d];
+      }
+    }
+    // weights of the candidate cells: one round of loads
+    double wreg = 0.0;
+    if (NT1) {
+      if (lane < NCAND) {
+        const int a0 = lane & 1, a1 = (lane >> 1) & 1, a2 = lane >> 2;
+        const bool ok = (a0 ? v1[0] : v0[0]) && (a1 ? v1[1] : v0[1]) && (DIM == 3 ? (a2 ? v1[2] : v0[2]) : a2 == 0);
+        if (ok) wreg = P.a_mode == PDB200_A_IDENTITY ? 1.0 : __ldg(P.A + cell_index(P.N, cl[0] + a0, cl[1] + a1, cl[2] + a2));
+      }
+    } else {
+#pragma unroll
+      for (int ci = 0; ci < NCAND; ci++) {
+        const int a0 = ci & 1, a1 = (ci >> 1) & 1, a2 = ci >> 2;
+        const bool ok = (a0 ? v1[0] : v0[0]) && (a1 ? v1[1] : v0[1]) && (DIM == 3 ? (a2 ? v1[2] : v0[2]) : a2 == 0);
+        if (ok) {
+          const long long cell = cell_index(P.N, cl[0] + a0, cl[1] + a1, cl[2] + a2);
+          for (int t = lane; t < nt; t += G) wb[ci * nt + t] = qk_cell_weight(P, Q, cell, t);
+        }
+      }
+    }
+    for (int s = lane; s < R.len; s += G) rb[s] = 0.0;
+    __syncwarp(gmask);
+    // passes over the candidate cells in ascending cell order (the reference's scatter order)
+#pragma unroll
+    for (int ci = 0; ci < NCAND; ci++) {
+      const int a0 = ci & 1, a1 = (ci >> 1) & 1, a2 = ci >> 2;
+      const bool ok = (a0 ? v1[0] : v0[0]) && (a1 ? v1[1] : v0[1]) && (DIM == 3 ? (a2 ? v1[2] : v0[2]) : a2 == 0);
+      const double w1 = NT1 ? __shfl_sync(gmask, wreg, ci, G) : 0.0;
+      if (!ok) continue;
+      const int c0 = cl[0] + a0, c1 = cl[1] + a1, c2 = DIM == 3 ? cl[2] + a2 : 0;
+      const int i = (R.p[0] - K * c0) + N1 * ((R.p[1] - K * c1) + N1 * (DIM == 3 ? R.p[2] - K * c2 : 0));
+      const int pbase = (K * c0 - R.lo[0]) + 5 * ((K * c1 - R.lo[1]) + 5 * (DIM == 3 ? K * c2 - R.lo[2] : 0));
+      if (lane < N) {
+        double v;
+        if (NT1) {
+          v = w1 * tab[i * N + lane];
+        } else {
+          v = 0.0;
+          for (int t = 0; t < nt; t++) v = fma(wb[ci * nt + t], tab[(t * N + i) * N + lane], v);
+        }
+        if (OUTFLOW) v += qk_outflow_entry<DIM, K>(P, T1, c0, c1, c2, i, lane);
+        rb[o2s[pbase + joff]] += v;
+      }
+      __syncwarp(gmask);
+    }
+    for (int s = lane; s < R.len; s += G) values[start + s] = fresh ? rb[s] : values[start + s] + rb[s];
+    __syncwarp(gmask);
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if (lane == 0) y[row] = acc;
+}
+
+template <int G>
+__global__ void __launch_bounds__(QK_THREADS)
+    qk_mv_kernel(const QkDecode D, const QkLut* __restrict__ lut_g, const u64* __restrict__ rowptr, u64 nrows,
+                 const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ QkLut lut;
+  for (int i = threadIdx.x; i < (int)(sizeof(QkLut) / 4); i += QK_THREADS) ((uint32_t*)&lut)[i] = ((const uint32_t*)lut_g)[i];
+  __syncthreads();
+  const int lane = threadIdx.x % G;
+  const u64 row = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
+  const bool live = row < nrows;
+  double acc = 0.0;
+  if (live) {
+    const QkRow R = qk_row(D, (uint32_t)row);
+    const u64 start = rowptr[row];
+    for (int slot = lane; slot < R.len; slot += G) {
+      const int off = lut.slot2off[R.shape][slot];
+      const int q[3] = {R.lo[0] + (off & 7), R.lo[1] + ((off >> 3) & 7), R.lo[2] + (off >> 6)};
+      acc = fma(values[start + slot], __ldg(x + qk_col_index(D, q)), acc);
+    }
+  }
+  for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+  if (live && lane == 0) y[row] = acc;
 }
 
 __global__ void set_flags_kernel(unsigned char* __restrict__ flags, const uint64_t* __restrict__ idx, long long n) {
@@ -639,10 +710,175 @@ struct MatrixPlan {
   DevParams P;
   QkLayout L;
   Mat1D T;
+  QkDecode D;
+  QkTables Q;
+  double* tables = nullptr;  // Qk: unit local matrices (device)
+  QkLut* lut = nullptr;      // Qk: slot decode tables (device)
   u64 nrows = 0, nnz = 0, nbrows = 0, nblocks = 0;
   u64* rowptr = nullptr;           // Qk: scalar CSR row pointers; DG: block row pointers (cells)
   unsigned char* flags = nullptr;  // Qk: constrained rows
 };
+
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.magic = 0;
+  f.more = -1;
+  if (d <= 1) return f;
+  int L = 31;
+  while (!((d >> L) & 1)) L--;  // floor(log2 d)
+  if ((d & (d - 1)) == 0) {
+    f.more = L - 1;
+    return f;
+  }
+  const unsigned __int128 num = (unsigned __int128)1 << (32 + L);
+  uint64_t m = (uint64_t)(num / d);
+  const uint64_t rem = (uint64_t)(num - (unsigned __int128)m * d);
+  m += m;
+  const uint64_t twice_rem = rem + rem;
+  if (twice_rem >= d) m += 1;
+  f.magic = (uint32_t)(m + 1);
+  f.more = L;
+  return f;
+}
+
+static QkDecode make_qk_decode(const DevParams& P, const QkLayout& L) {
+  if ((unsigned long long)L.ndofs >= 0xffffffffull) throw Error("conforming matrix path: needs fewer than 2^32 DOFs");
+  QkDecode D;
+  std::memset(&D, 0, sizeof(D));
+  D.dim = P.dim;
+  D.k = P.k;
+  for (int d = 0; d < 3; d++) D.N[d] = P.N[d];
+  auto set_group = [&](int g, int s, uint32_t start) {
+    D.start[g] = start;
+    D.sbits[g] = (uint8_t)s;
+    D.group_of_s[s] = (uint8_t)g;
+    const uint32_t z0 = ((s >> 0) & 1) ? P.N[0] : P.N[0] + 1;
+    const uint32_t z1 = P.dim > 1 ? (((s >> 1) & 1) ? P.N[1] : P.N[1] + 1) : 1;
+    D.sz0[g] = z0;
+    D.sz1[g] = z1;
+    D.d0[g] = make_fastdiv(z0);
+    D.d1[g] = make_fastdiv(z1);
+  };
+  if (P.k == 1) {
+    D.ng = 1;
+    set_group(0, 0, 0);
+  } else {
+    int g = 0;
+    for (int edim = 0; edim <= P.dim; edim++)
+      for (int s = 0; s < (1 << P.dim); s++) {
+        int pc = 0;
+        for (int d = 0; d < P.dim; d++) pc += (s >> d) & 1;
+        if (pc == edim) set_group(g++, s, (uint32_t)(L.block_off[edim] + L.group_off[s]));
+      }
+    D.ng = g;
+  }
+  D.start[D.ng] = (uint32_t)L.ndofs;
+  // self-check of the multipliers on the values that occur
+  for (int g = 0; g < D.ng; g++)
+    for (uint32_t n : {0u, 1u, D.sz0[g] - 1, D.sz0[g], D.sz0[g] + 1, 0x7fffffffu, 0xfffffffeu, (uint32_t)L.ndofs}) {
+      auto hostdiv = [](uint32_t n, const FastDiv& f) -> uint32_t {
+        if (f.more < 0) return n;
+        const uint32_t q = (uint32_t)(((uint64_t)f.magic * n) >> 32);
+        return (((n - q) >> 1) + q) >> f.more;
+      };
+      if (hostdiv(n, D.d0[g]) != n / D.sz0[g] || hostdiv(n, D.d1[g]) != n / D.sz1[g]) throw Error("fast division self-check failed");
+    }
+  return D;
+}
+
+// slot decode tables and unit local matrices of the conforming space (host side, one-off)
+static void build_qk_tables(MatrixPlan* plan) {
+  const DevParams& P = plan->P;
+  const int dim = P.dim, k = P.k, n1 = P.n1, n = P.n;
+  // --- LUT: columns of a box sorted by container index.  k = 1: lexicographic.  k = 2: by entity
+  // dimension (number of odd offsets), then extension bitset, then lexicographic anchors.
+  std::vector<QkLut> lut(1);
+  std::memset(&lut[0], 0, sizeof(QkLut));
+  for (int sh = 0; sh < 8; sh++) {
+    int len[3] = {1, 1, 1};
+    for (int d = 0; d < dim; d++) len[d] = ((sh >> d) & 1) ? 2 * k + 1 : k + 1;
+    if (dim == 2 && (sh & 4)) continue;
+    struct Item { int key; int d[3]; };
+    std::vector<Item> items;
+    for (int d2 = 0; d2 < len[2]; d2++)
+      for (int d1 = 0; d1 < len[1]; d1++)
+        for (int d0 = 0; d0 < len[0]; d0++) {
+          Item it;
+          it.d[0] = d0; it.d[1] = d1; it.d[2] = d2;
+          int sbits = 0, edim = 0;
+          if (k == 2) {
+            sbits = (d0 & 1) | ((d1 & 1) << 1) | ((d2 & 1) << 2);
+            edim = (d0 & 1) + (d1 & 1) + (d2 & 1);
+          }
+          // anchors are offsets / 2 inside the group: lexicographic order of the offsets is the same
+          it.key = ((edim * 8 + sbits) * 8 + d2) * 64 + d1 * 8 + d0;
+          items.push_back(it);
+        }
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+    for (size_t slot = 0; slot < items.size(); slot++) {
+      const int* d = items[slot].d;
+      lut[0].slot2off[sh][slot] = (uint16_t)(d[0] | (d[1] << 3) | (d[2] << 6));
+      lut[0].off2slot[sh][d[0] + 5 * (d[1] + 5 * d[2])] = (uint8_t)slot;
+    }
+  }
+  PDB_CUDA(cudaMalloc(&plan->lut, sizeof(QkLut)));
+  PDB_CUDA(cudaMemcpy(plan->lut, lut.data(), sizeof(QkLut), cudaMemcpyHostToDevice));
+  // --- unit local matrices
+  QkTables& Q = plan->Q;
+  Q.nt = 0;
+  auto add = [&](int kind, int a, int b) {
+    Q.kind[Q.nt] = kind;
+    Q.ia[Q.nt] = a;
+    Q.ib[Q.nt] = b;
+    Q.nt++;
+  };
+  if (P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR) add(0, 0, 0);
+  else if (P.a_mode == PDB200_A_DIAGONAL)
+    for (int a = 0; a < dim; a++) add(1, a, a);
+  else
+    for (int a = 0; a < dim; a++)
+      for (int b = 0; b < dim; b++) add(1, a, b);
+  if (P.b)
+    for (int a = 0; a < dim; a++) add(2, a, 0);
+  if (P.c) add(3, 0, 0);
+  const Mat1D& T = plan->T;
+  std::vector<double> tab((size_t)Q.nt * n * n, 0.0);
+  for (int t = 0; t < Q.nt; t++)
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        int li[3] = {0, 0, 0}, lj[3] = {0, 0, 0}, ii = i, jj = j;
+        for (int d = 0; d < dim; d++) {
+          li[d] = ii % n1; ii /= n1;
+          lj[d] = jj % n1; jj /= n1;
+        }
+        auto stiff = [&](int a, int b) {  // int (d_b phi_j)(d_a phi_i) * |K|
+          long double v = P.vol * P.ih[a] * P.ih[b];
+          for (int d = 0; d < dim; d++) {
+            if (a == b) v *= d == a ? T.K[li[d] * n1 + lj[d]] : T.M[li[d] * n1 + lj[d]];
+            else if (d == a) v *= T.C[li[d] * n1 + lj[d]];
+            else if (d == b) v *= T.C[lj[d] * n1 + li[d]];
+            else v *= T.M[li[d] * n1 + lj[d]];
+          }
+          return v;
+        };
+        long double v = 0;
+        if (Q.kind[t] == 0) {
+          for (int a = 0; a < dim; a++) v += stiff(a, a);
+        } else if (Q.kind[t] == 1) {
+          v = stiff(Q.ia[t], Q.ib[t]);
+        } else if (Q.kind[t] == 2) {  // int phi_j d_a phi_i * |K|   (enters with weight -b_a)
+          v = P.vol * P.ih[Q.ia[t]];
+          for (int d = 0; d < dim; d++) v *= d == Q.ia[t] ? T.C[li[d] * n1 + lj[d]] : T.M[li[d] * n1 + lj[d]];
+        } else {
+          v = P.vol;
+          for (int d = 0; d < dim; d++) v *= T.M[li[d] * n1 + lj[d]];
+        }
+        tab[((size_t)t * n + i) * n + j] = (double)v;
+      }
+  PDB_CUDA(cudaMalloc(&plan->tables, tab.size() * sizeof(double)));
+  PDB_CUDA(cudaMemcpy(plan->tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
 
 MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s) {
   MatrixPlan* plan = new MatrixPlan;
@@ -660,7 +896,8 @@ MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s)
       plan->L = fem_plan_layout(fem);
       plan->nrows = (u64)P.ndofs;
       PDB_CUDA(cudaMalloc(&plan->rowptr, (plan->nrows + 1) * sizeof(u64)));
-      QkRowLen f{plan->L};
+      plan->D = make_qk_decode(P, plan->L);
+      QkRowLen f{plan->D};
       device_row_scan(f, plan->nrows, plan->rowptr, s);
       PDB_CUDA(cudaMemcpy(&plan->nnz, plan->rowptr + plan->nrows, sizeof(u64), cudaMemcpyDeviceToHost));
       long long ncon = 0;
@@ -689,6 +926,7 @@ MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s)
           plan->T.K[i * n1 + j] = (double)K;
           plan->T.C[i * n1 + j] = (double)C;
         }
+      build_qk_tables(plan);
     }
     PDB_CUDA(cudaStreamSynchronize(s));
   } catch (...) {
@@ -702,6 +940,8 @@ void matrix_plan_destroy(MatrixPlan* p) {
   if (!p) return;
   if (p->rowptr) cudaFree(p->rowptr);
   if (p->flags) cudaFree(p->flags);
+  if (p->tables) cudaFree(p->tables);
+  if (p->lut) cudaFree(p->lut);
   delete p;
 }
 
@@ -734,11 +974,13 @@ int matrix_pattern_write(MatrixPlan* p, int layout, void* rowptr, bool rowptr_de
       dg_colidx_kernel<u64><<<(unsigned)P.ncells, 128, 0, s>>>(P, p->rowptr, layout == PDB200_LAYOUT_BCSR, rp, (u64*)ci);
   } else {
     PDB_CUDA(cudaMemcpyAsync(rp, p->rowptr, (nr + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-    const u64 blocks = (nr * 32 + 255) / 256;
-    if (col32)
-      qk_colidx_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>(p->L, p->rowptr, nr, (uint32_t*)ci);
-    else
-      qk_colidx_kernel<u64><<<(unsigned)blocks, 256, 0, s>>>(p->L, p->rowptr, nr, (u64*)ci);
+    const int G = P.n > 16 ? 32 : (P.n > 8 ? 16 : 8);
+    const u64 blocks = (nr * G + QK_THREADS - 1) / QK_THREADS;
+#define PDB_COLIDX(GG)                                                                                        \
+  if (col32) qk_colidx_kernel<GG, uint32_t><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, nr, (uint32_t*)ci); \
+  else qk_colidx_kernel<GG, u64><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, nr, (u64*)ci)
+    if (G == 32) { PDB_COLIDX(32); } else if (G == 16) { PDB_COLIDX(16); } else { PDB_COLIDX(8); }
+#undef PDB_COLIDX
   }
   PDB_CUDA(cudaGetLastError());
   if (!rowptr_dev) {
@@ -755,6 +997,43 @@ int matrix_pattern_write(MatrixPlan* p, int layout, void* rowptr, bool rowptr_de
   return launches;
 }
 
+template <int G, int DIM, int K, bool NT1, bool OUTFLOW>
+static void launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+  constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  constexpr int MAXLEN = DIM == 3 ? (2 * K + 1) * (2 * K + 1) * (2 * K + 1) : (2 * K + 1) * (2 * K + 1);
+  constexpr int ROWS_PER_CTA = QK_THREADS / G;
+  constexpr int NCAND = DIM == 3 ? 8 : 4;
+  const int nt = NT1 ? 1 : p->Q.nt;
+  const size_t smem = ((size_t)nt * N * N + (size_t)ROWS_PER_CTA * MAXLEN + (NT1 ? 0 : (size_t)ROWS_PER_CTA * NCAND * nt)) * sizeof(double) + 1000;
+  auto kern = qk_assemble_kernel<G, DIM, K, NT1, OUTFLOW>;
+  PDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148, per_sm = 1;
+  PDB_CUDA(cudaGetDevice(&dev));
+  PDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QK_THREADS, smem));
+  const u64 want = (p->nrows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  const unsigned blocks = (unsigned)std::min<u64>(want, (u64)sms * std::max(per_sm, 1));
+  kern<<<blocks, QK_THREADS, smem, s>>>(p->P, p->D, p->T, p->Q, p->tables, p->lut, p->rowptr, p->nrows, p->flags, v,
+                                        fresh ? 1 : 0);
+}
+
+template <int G, int DIM, int K>
+static void launch_qk_assemble_nt(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+  const bool outflow = p->P.bctype != nullptr && p->P.b != nullptr;  // jacobian_boundary has outflow terms only
+  if (outflow) launch_qk_assemble_t<G, DIM, K, false, true>(p, v, fresh, s);
+  else if (p->Q.nt == 1) launch_qk_assemble_t<G, DIM, K, true, false>(p, v, fresh, s);
+  else launch_qk_assemble_t<G, DIM, K, false, false>(p, v, fresh, s);
+}
+
+static void launch_qk_assemble(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+  const DevParams& P = p->P;
+  if (P.dim == 2 && P.k == 1) launch_qk_assemble_nt<8, 2, 1>(p, v, fresh, s);
+  else if (P.dim == 2 && P.k == 2) launch_qk_assemble_nt<16, 2, 2>(p, v, fresh, s);
+  else if (P.dim == 3 && P.k == 1) launch_qk_assemble_nt<8, 3, 1>(p, v, fresh, s);
+  else if (P.dim == 3 && P.k == 2) launch_qk_assemble_nt<32, 3, 2>(p, v, fresh, s);
+  else throw Error("conforming Jacobian: unsupported (dim, degree)");
+}
+
 int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, bool fresh, int* errflag,
                     cudaStream_t s) {
   const DevParams& P = p->P;
@@ -766,8 +1045,7 @@ int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, 
   if (P.dg) {
     dg_assemble_kernel<<<(unsigned)P.ncells, 128, 0, s>>>(P, p->rowptr, layout == PDB200_LAYOUT_BCSR, v, fresh ? 1 : 0, errflag);
   } else {
-    const u64 blocks = (p->nrows * 32 + 255) / 256;
-    qk_assemble_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, p->L, p->T, p->rowptr, p->nrows, p->flags, v, fresh ? 1 : 0);
+    launch_qk_assemble(p, v, fresh, s);
   }
   PDB_CUDA(cudaGetLastError());
   if (!values_dev) {
@@ -783,8 +1061,11 @@ int matrix_mv(MatrixPlan* p, int layout, const double* values, const double* x, 
   if (P.dg) {
     dg_mv_kernel<<<(unsigned)P.ncells, 128, 0, s>>>(P, p->rowptr, layout == PDB200_LAYOUT_BCSR, values, x, y);
   } else {
-    const u64 blocks = (p->nrows * 32 + 255) / 256;
-    qk_mv_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->L, p->rowptr, p->nrows, values, x, y);
+    const int G = P.n > 16 ? 32 : (P.n > 8 ? 16 : 8);
+    const u64 blocks = (p->nrows * G + QK_THREADS - 1) / QK_THREADS;
+    if (G == 32) qk_mv_kernel<32><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
+    else if (G == 16) qk_mv_kernel<16><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
+    else qk_mv_kernel<8><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
   }
   PDB_CUDA(cudaGetLastError());
   return 1;
