@@ -99,12 +99,13 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// cell indices fit 32 bits on one GPU (512^3 = 2^27 cells); only the byte offset is 64-bit
 template <int AMODE>
-__device__ __forceinline__ double load_adiag(const DevParams& P, long long cell, int d) {
+__device__ __forceinline__ double load_adiag(const DevParams& P, int cell, int d) {
   if (AMODE == PDB200_A_IDENTITY) return 1.0;
   if (AMODE == PDB200_A_SCALAR) return __ldg(P.A + cell);
-  if (AMODE == PDB200_A_DIAGONAL) return __ldg(P.A + cell * 3 + d);
-  return __ldg(P.A + cell * 9 + d * 4);
+  if (AMODE == PDB200_A_DIAGONAL) return __ldg(P.A + (long long)cell * 3 + d);
+  return __ldg(P.A + (long long)cell * 9 + d * 4);
 }
 
 // One face of the 1-D operator along a direction: the three scalars
@@ -112,41 +113,39 @@ __device__ __forceinline__ double load_adiag(const DevParams& P, long long cell,
 // following convectiondiffusiondg.hh:326-346 (interior) and :717-734 (Dirichlet boundary).
 // kind: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None/Neumann/Outflow with b=0,
 // processor boundary).
-// 1/x for positive normal x: MUFU.RCP64H seed (~20 bits) + Newton steps (rel. error ~1e-16).
-// Branch-free on purpose: the IEEE division's slow-path call serialises the six face set-ups.
+// 1/x for positive normal x: MUFU.RCP64H seed (>= 20 bits) + two Newton steps with a quadratic
+// correction in the first (error 2^-20 -> 2^-60 -> rounding).  Branch-free on purpose: the IEEE
+// division's slow-path call serialises the six face set-ups.
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
+  y = fma(y, fma(e, e, e), y);  // y (1 + e + e^2): cubic convergence
   e = fma(-x, y, 1.0);
   return fma(y, e, y);
 }
 
-__device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double alpha_pen, int weights_on,
-                                          double& cs, double& co, double& cg) {
-  if (kind == 2) {
-    cs = co = cg = 0.0;
-    return;
-  }
-  if (kind == 1) {  // Dirichlet boundary: w_self = 1, harmonic average = a (weights on) or 1
-    cs = a * ih2;
-    co = 0.0;
-    cg = alpha_pen * (weights_on ? a : 1.0) * ih2;
-    return;
-  }
-  if (weights_on) {
+// Branch-free (selects only) so that the six reciprocal chains of a cell interleave.  The penalty
+// coefficient is not returned: cg = alpha_pen (cs + co) with weights on (interior: 2 alpha_pen hh,
+// Dirichlet: alpha_pen a / h^2), alpha_pen / h^2 wherever cs != 0 with weights off (penalty_coef).
+template <bool WEIGHTS_ON>
+__device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double& cs, double& co) {
+  const double aih = a * ih2;
+  double csi, coi;  // interior face
+  if (WEIGHTS_ON) {
     // w_self a = w_other a_other = a a_other / (a + a_other + 1e-20) = harmonic average / 2
-    const double hh = a * ao * ih2 * fast_rcp(a + ao + 1e-20);
-    cs = co = hh;
-    cg = (alpha_pen + alpha_pen) * hh;
+    csi = coi = aih * ao * fast_rcp(a + ao + 1e-20);
   } else {
-    cs = 0.5 * a * ih2;
-    co = 0.5 * ao * ih2;
-    cg = alpha_pen * ih2;
+    csi = 0.5 * aih;
+    coi = 0.5 * ao * ih2;
   }
+  cs = kind == 0 ? csi : (kind == 1 ? aih : 0.0);  // Dirichlet boundary: w_self = 1
+  co = kind == 0 ? coi : 0.0;
+}
+template <bool WEIGHTS_ON>
+__device__ __forceinline__ double penalty_coef(double cs, double co, double ih2, double alpha_pen) {
+  if (WEIGHTS_ON) return alpha_pen * (cs + co);
+  return cs != 0.0 ? alpha_pen * ih2 : 0.0;
 }
 
 // Adds (1/h_d) M^-1 L_d(l, o, r) for the nine lines of a cell along direction S-stride.
@@ -154,12 +153,14 @@ __device__ __forceinline__ void face_coef(int kind, double a, double ao, double 
 //   t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
 // The own values are re-read from shared memory in every sweep instead of being kept in 54
 // registers: the kernel is fp64-issue bound, not LDS bound, and the registers buy occupancy.
-template <int S, bool FIRST, bool HAS_C>
+template <int S, bool FIRST, bool HAS_C, bool WEIGHTS_ON>
 __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)[NLOC], const double* __restrict__ nl,
                                       const double* __restrict__ nr, const FastConst& F, double creact, double A0,
-                                      double csL, double coL, double cgL, double csR, double coR, double cgR) {
+                                      double ih2, double csL, double coL, double csR, double coR) {
   double P1[3], P2[3], P3[3], P4[3], P5[3], P6[3];
   const double ctL = -F.theta * csL, ctR = F.theta * csR;
+  const double cgL = penalty_coef<WEIGHTS_ON>(csL, coL, ih2, F.alpha_pen);
+  const double cgR = penalty_coef<WEIGHTS_ON>(csR, coR, ih2, F.alpha_pen);
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     P1[i] = fma(F.E0[i], A0, F.m0[i] * csL);
@@ -216,14 +217,15 @@ __device__ __forceinline__ void mass_sweep(double (&t)[NLOC]) {
       const int base = a * SA + b * SB;
       const double v0 = t[base], v1 = t[base + S], v2 = t[base + 2 * S];
       const double e = v0 + v2;
-      t[base] = fma(4.0, v0, fma(2.0, v1, -v2));
+      const double w = fma(2.0, v1, -e);  // 4 v0 + 2 v1 - v2 = 5 v0 + (2 v1 - v0 - v2)
+      t[base] = fma(5.0, v0, w);
       t[base + S] = fma(16.0, v1, e + e);
-      t[base + 2 * S] = fma(4.0, v2, fma(2.0, v1, -v0));
+      t[base + 2 * S] = fma(5.0, v2, w);
     }
 }
 
-template <int AMODE, int MINB, bool HAS_C>
-__global__ void __launch_bounds__(TX* TY* TZ, MINB)
+template <int AMODE, bool HAS_C, bool WEIGHTS_ON>
+__global__ void __launch_bounds__(TX* TY* TZ, 3)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
                          const DevParams P, const FastConst F) {
@@ -253,17 +255,19 @@ __global__ void __launch_bounds__(TX* TY* TZ, MINB)
   const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
   const int cz = tid >> 5;
   const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
-  const bool active = gx < P.N[0] && gy < P.N[1] && gz < P.N[2];
+  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
+  const bool active = gx < Nx && gy < Ny && gz < Nz;
 
   // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
-  // before the first use so that the L2 round trips overlap instead of adding up. -----------------
-  double A0[3], csL[3], coL[3], cgL[3], csR[3], coR[3], cgR[3];
+  // before the first use so that the L2 round trips overlap instead of adding up; everything up
+  // to the reciprocals is branch-free so that the six face set-ups interleave. -------------------
+  double A0[3], csL[3], coL[3], csR[3], coR[3];
   double creact = 0.0;
   bool constrained = false;
   if (active) {
-    const long long cell = cell_index(P.N, gx, gy, gz);
-    const int g[3] = {gx, gy, gz};
-    const long long stride[3] = {1, (long long)P.N[0], (long long)P.N[0] * P.N[1]};
+    const int cell = gx + Nx * (gy + Ny * gz);
+    const int stride[3] = {1, Nx, Nx * Ny};
+    const bool onb[3][2] = {{gx == 0, gx == Nx - 1}, {gy == 0, gy == Ny - 1}, {gz == 0, gz == Nz - 1}};
     double a[3], ao[3][2];
     int kind[3][2];
 #pragma unroll
@@ -271,29 +275,33 @@ __global__ void __launch_bounds__(TX* TY* TZ, MINB)
       a[d] = load_adiag<AMODE>(P, cell, d);
 #pragma unroll
       for (int side = 0; side < 2; side++) {
-        const bool onb = side ? g[d] == P.N[d] - 1 : g[d] == 0;
-        kind[d][side] = onb ? 1 : 0;
-        ao[d][side] = load_adiag<AMODE>(P, onb ? cell : cell + (side ? stride[d] : -stride[d]), d);
+        kind[d][side] = onb[d][side] ? 1 : 0;
+        ao[d][side] = load_adiag<AMODE>(P, onb[d][side] ? cell : cell + (side ? stride[d] : -stride[d]), d);
       }
     }
     if (HAS_C) creact = __ldg(P.c + cell) * F.scale;
+    const bool any_b = onb[0][0] | onb[0][1] | onb[1][0] | onb[1][1] | onb[2][0] | onb[2][1];
+    if (any_b) {  // rare: cells on the box surface
+      // boundary-face numbers of pdelab_b200.h: tangential coordinates lexicographic, lower direction fastest
+      const long long bf[3] = {gy + (long long)Ny * gz, gx + (long long)Nx * gz, gx + (long long)Nx * gy};
 #pragma unroll
-    for (int d = 0; d < 3; d++)
+      for (int d = 0; d < 3; d++)
 #pragma unroll
-      for (int side = 0; side < 2; side++)
-        if (kind[d][side]) {  // rare: cells on the box surface
-          if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
-            kind[d][side] = 2;
-            constrained = true;
-          } else if (P.bctype) {
-            kind[d][side] = P.bctype[bface_index(P, g, d, side)] == PDB200_BC_DIRICHLET ? 1 : 2;
+        for (int side = 0; side < 2; side++)
+          if (onb[d][side]) {
+            if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
+              kind[d][side] = 2;
+              constrained = true;
+            } else if (P.bctype) {
+              kind[d][side] = P.bctype[P.bf_off[d][side] + bf[d]] == PDB200_BC_DIRICHLET ? 1 : 2;
+            }
           }
-        }
+    }
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       A0[d] = a[d] * F.ih2[d];
-      face_coef(kind[d][0], a[d], ao[d][0], F.ih2[d], F.alpha_pen, P.weights_on, csL[d], coL[d], cgL[d]);
-      face_coef(kind[d][1], a[d], ao[d][1], F.ih2[d], F.alpha_pen, P.weights_on, csR[d], coR[d], cgR[d]);
+      face_coef<WEIGHTS_ON>(kind[d][0], a[d], ao[d][0], F.ih2[d], csL[d], coL[d]);
+      face_coef<WEIGHTS_ON>(kind[d][1], a[d], ao[d][1], F.ih2[d], csR[d], coR[d]);
     }
   }
 
@@ -309,9 +317,9 @@ __global__ void __launch_bounds__(TX* TY* TZ, MINB)
 
   double t[NLOC];
   if (active) {
-    sweep<1, true, HAS_C>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], csL[0], coL[0], cgL[0], csR[0], coR[0], cgR[0]);
-    sweep<3, false, HAS_C>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], csL[1], coL[1], cgL[1], csR[1], coR[1], cgR[1]);
-    sweep<9, false, HAS_C>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], csL[2], coL[2], cgL[2], csR[2], coR[2], cgR[2]);
+    sweep<1, true, HAS_C, WEIGHTS_ON>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], F.ih2[0], csL[0], coL[0], csR[0], coR[0]);
+    sweep<3, false, HAS_C, WEIGHTS_ON>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], F.ih2[1], csL[1], coL[1], csR[1], coR[1]);
+    sweep<9, false, HAS_C, WEIGHTS_ON>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], F.ih2[2], csL[2], coL[2], csR[2], coR[2]);
     mass_sweep<1>(t);
     mass_sweep<3>(t);
     mass_sweep<9>(t);
@@ -356,7 +364,6 @@ struct FastPlan {
   std::vector<Maps> cache;  // tensor maps embed the global address: keep the most recent few
   double* scratch = nullptr;
   long long scratch_n = 0;
-  int minb = 3;
 };
 
 bool dg_fast_supported(const DevParams& P) {
@@ -384,14 +391,12 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   PDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled is not available in this driver");
   plan->encode = (EncodeFn)fn;
-  const char* env = getenv("PDB200_FAST_MINB");  // tuning knob: resident CTAs per SM the kernel is compiled for
-  plan->minb = env ? atoi(env) : 3;
-  if (plan->minb != 2 && plan->minb != 3) throw Error("PDB200_FAST_MINB must be 2 or 3");
-#define PDB_SET_SMEM(AM, MB)                                                                                          \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  PDB_SET_SMEM(PDB200_A_IDENTITY, 2) PDB_SET_SMEM(PDB200_A_SCALAR, 2) PDB_SET_SMEM(PDB200_A_DIAGONAL, 2)
-  PDB_SET_SMEM(PDB200_A_IDENTITY, 3) PDB_SET_SMEM(PDB200_A_SCALAR, 3) PDB_SET_SMEM(PDB200_A_DIAGONAL, 3)
+#define PDB_SET_SMEM(AM, HC, WO)                                                                          \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                SMEM_BYTES));
+#define PDB_SET_SMEM4(AM) PDB_SET_SMEM(AM, false, false) PDB_SET_SMEM(AM, false, true) PDB_SET_SMEM(AM, true, false) PDB_SET_SMEM(AM, true, true)
+  PDB_SET_SMEM4(PDB200_A_IDENTITY) PDB_SET_SMEM4(PDB200_A_SCALAR) PDB_SET_SMEM4(PDB200_A_DIAGONAL)
+#undef PDB_SET_SMEM4
 #undef PDB_SET_SMEM
   return plan;
 }
@@ -443,23 +448,20 @@ void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double*
   const FastPlan::Maps mx = get_maps(plan, x, P);
   const FastPlan::Maps my = get_maps(plan, out, P);
   dim3 grid((P.N[0] + TX - 1) / TX, (P.N[1] + TY - 1) / TY, (P.N[2] + TZ - 1) / TZ);
-#define PDB_LAUNCH(AM, MB)                                                                                          \
-  do {                                                                                                              \
-    if (P.c)                                                                                                        \
-      dg_fast_q2_3d_kernel<AM, MB, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F); \
-    else                                                                                                            \
-      dg_fast_q2_3d_kernel<AM, MB, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F); \
+#define PDB_LAUNCH(AM, HC, WO) \
+  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F)
+#define PDB_LAUNCH_A(AM)                                \
+  do {                                                  \
+    if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \
+    else if (P.c) PDB_LAUNCH(AM, true, false);          \
+    else if (P.weights_on) PDB_LAUNCH(AM, false, true); \
+    else PDB_LAUNCH(AM, false, false);                  \
   } while (0)
   const int am = P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR ? P.a_mode : PDB200_A_DIAGONAL;
-  if (plan->minb == 2) {
-    if (am == PDB200_A_IDENTITY) PDB_LAUNCH(PDB200_A_IDENTITY, 2);
-    else if (am == PDB200_A_SCALAR) PDB_LAUNCH(PDB200_A_SCALAR, 2);
-    else PDB_LAUNCH(PDB200_A_DIAGONAL, 2);
-  } else {
-    if (am == PDB200_A_IDENTITY) PDB_LAUNCH(PDB200_A_IDENTITY, 3);
-    else if (am == PDB200_A_SCALAR) PDB_LAUNCH(PDB200_A_SCALAR, 3);
-    else PDB_LAUNCH(PDB200_A_DIAGONAL, 3);
-  }
+  if (am == PDB200_A_IDENTITY) PDB_LAUNCH_A(PDB200_A_IDENTITY);
+  else if (am == PDB200_A_SCALAR) PDB_LAUNCH_A(PDB200_A_SCALAR);
+  else PDB_LAUNCH_A(PDB200_A_DIAGONAL);
+#undef PDB_LAUNCH_A
 #undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
   if (!overwrite) {
