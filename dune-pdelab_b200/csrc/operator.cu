@@ -326,6 +326,18 @@ int pdb200_quadrature(pdb200_handle h, double* points, double* weights) {
   PDB_CATCH
 }
 
+int pdb200_gauss_legendre(int m, double* points, double* weights) {
+  PDB_TRY
+  if (m < 1 || m > 16 || !points || !weights) throw Error("gauss_legendre: 1 <= m <= 16 and non-null outputs");
+  std::vector<long double> x, w;
+  host_gauss(m, x, w);
+  for (int i = 0; i < m; i++) {
+    points[i] = (double)x[i];
+    weights[i] = (double)w[i];
+  }
+  PDB_CATCH
+}
+
 int pdb200_cell_dof_indices(pdb200_handle h, uint64_t cell, uint64_t* idx) {
   PDB_TRY
   PDB_CHECK_HANDLE(h);

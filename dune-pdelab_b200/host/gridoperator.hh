@@ -1,0 +1,943 @@
+// gridoperator.hh — C++ host mirror of PDELab's operator-evaluation interface over the C ABI of
+// include/pdelab_b200.h (libpdelab_b200.so, hand-written sm_100a kernels).  Header-only, C++17.
+//
+// What it mirrors (paths relative to /root/reference/dune/pdelab/):
+//   GridOperator<GFSU,GFSV,LOP,MB,DF,RF,JF,CU,CV>        gridoperator/gridoperator.hh:30-244
+//   GridOperatorTraits                                  gridoperator/common/gridoperatorutilities.hh:31-80
+//   ConvectionDiffusionDG<Param,FEM> (ctor arguments)   localoperator/convectiondiffusiondg.hh:85-102
+//   ConvectionDiffusionFEM<Param,FEM>                   localoperator/convectiondiffusionfem.hh:38-61
+//   ConvectionDiffusionBoundaryConditions / parameter-class call-backs
+//                                                       localoperator/convectiondiffusionparameter.hh:111-209
+//   Backend::Vector / Backend::native                   backend/istl/vector.hh, backend/interface.hh
+//   ISTL::BCRSMatrixBackend, BCRSMatrix(go)             backend/istl/bcrsmatrixbackend.hh, bcrsmatrix.hh:78-82
+//   OnTheFlyOperator                                    backend/istl/seqistlsolverbackend.hh:44-100
+//   constraints(), interpolate(), set_nonconstrained_dofs()
+//                                                       constraints/common/constraints.hh:588-687,796-802,
+//                                                       gridfunctionspace/interpolate.hh
+// Same member names, argument meaning and error behaviour (exceptions; B200::Exception plays the
+// role of Dune::Exception), so a PDELab program switches by changing the namespace of these types.
+// The user's parameter class keeps the reference's call-back interface; the call-backs are sampled
+// once, at exactly the points the reference evaluates them, into the arrays the C ABI takes.
+//
+// The structured grid, finite element maps and function spaces are light descriptors (the CUDA
+// path derives all index maps in closed form); with the DUNE core modules present a maintainer
+// wires the real types in as shown in INTEGRATION.md.
+//
+// There is no CPU implementation behind this header: every compute member forwards to the CUDA
+// library and throws if it reports an error (e.g. "no CUDA device available").
+#ifndef PDELAB_B200_HOST_GRIDOPERATOR_HH
+#define PDELAB_B200_HOST_GRIDOPERATOR_HH
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <exception>
+#include <memory>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/pdelab_b200.h"
+
+namespace Dune {
+namespace PDELab {
+namespace B200 {
+
+// ---- error convention -------------------------------------------------------------------------
+// The reference throws Dune::Exception (DUNE_THROW, e.g. gridoperator.hh:195,203).
+class Exception : public std::exception {
+ public:
+  explicit Exception(std::string msg) : msg_(std::move(msg)) {}
+  const char* what() const noexcept override { return msg_.c_str(); }
+
+ private:
+  std::string msg_;
+};
+
+inline void check(int rc, const char* where) {
+  if (rc != 0) throw Exception(std::string(where) + ": " + pdb200_last_error());
+}
+
+// ---- dense helpers (stand-ins for Dune::FieldVector / FieldMatrix) ------------------------------
+template <class T, int n>
+struct FieldVector : std::array<T, n> {
+  FieldVector() { this->fill(T(0)); }
+  FieldVector(T v) { this->fill(v); }  // NOLINT: Dune::FieldVector is implicitly constructible from a scalar
+  FieldVector(std::initializer_list<T> l) {
+    this->fill(T(0));
+    std::copy(l.begin(), l.end(), this->begin());
+  }
+  static constexpr int dimension = n;
+  T two_norm2() const {
+    T s = 0;
+    for (T v : *this) s += v * v;
+    return s;
+  }
+  T two_norm() const { return std::sqrt(two_norm2()); }
+  FieldVector& operator-=(const FieldVector& o) {
+    for (int i = 0; i < n; i++) (*this)[i] -= o[i];
+    return *this;
+  }
+  FieldVector& operator+=(const FieldVector& o) {
+    for (int i = 0; i < n; i++) (*this)[i] += o[i];
+    return *this;
+  }
+  T operator*(const FieldVector& o) const {
+    T s = 0;
+    for (int i = 0; i < n; i++) s += (*this)[i] * o[i];
+    return s;
+  }
+};
+template <class T, int n, int m>
+struct FieldMatrix : std::array<FieldVector<T, m>, n> {
+  FieldMatrix() = default;
+  FieldMatrix(T v) {  // NOLINT
+    for (auto& r : *this) r.fill(v);
+  }
+};
+
+// ---- structured grid --------------------------------------------------------------------------
+template <int dim>
+class YaspGridView;
+
+// Dune::YaspGrid<dim>(L, N): equidistant axis-aligned grid on [0,L] (dune-grid, used by every
+// reference test of this path, e.g. test/testconvectiondiffusiondg.cc:52-58)
+template <int dim_>
+class YaspGrid {
+ public:
+  static constexpr int dimension = dim_;
+  using ctype = double;
+  using LeafGridView = YaspGridView<dim_>;
+  YaspGrid(const FieldVector<double, dim_>& L, const std::array<int, dim_>& N) : upper_(L), cells_(N) {}
+  YaspGrid(const FieldVector<double, dim_>& lower, const FieldVector<double, dim_>& upper, const std::array<int, dim_>& N)
+      : lower_(lower), upper_(upper), cells_(N) {}
+  LeafGridView leafGridView() const;
+  const FieldVector<double, dim_>& lower() const { return lower_; }
+  const FieldVector<double, dim_>& upper() const { return upper_; }
+  const std::array<int, dim_>& cells() const { return cells_; }
+  // outer sides that are processor boundaries of an overlapping partition
+  std::array<std::array<int, 2>, 3> side_kind{{{0, 0}, {0, 0}, {0, 0}}};
+
+ private:
+  FieldVector<double, dim_> lower_{}, upper_;
+  std::array<int, dim_> cells_;
+};
+
+// geometry of an axis-aligned cell or face: the closed forms of SURVEY.md Appendix A
+template <int dim, int mydim>
+struct BoxGeometry {
+  FieldVector<double, dim> lo, ext;  // lower corner, edge lengths (ext[dir] = 0 for a face)
+  int normal_dir = -1;               // face: direction of the normal
+  FieldVector<double, dim> global(const FieldVector<double, mydim>& x) const {
+    FieldVector<double, dim> g = lo;
+    int t = 0;
+    for (int d = 0; d < dim; d++)
+      if (d != normal_dir) g[d] += ext[d] * x[t++];
+    return g;
+  }
+  FieldVector<double, dim> center() const { return global(FieldVector<double, mydim>(0.5)); }
+  double volume() const {
+    double v = 1;
+    for (int d = 0; d < dim; d++)
+      if (d != normal_dir) v *= ext[d];
+    return v;
+  }
+};
+
+template <int dim>
+struct Cell {
+  static constexpr int dimension = dim;
+  std::array<int, dim> coord;
+  long long index;
+  BoxGeometry<dim, dim> geo;
+  const BoxGeometry<dim, dim>& geometry() const { return geo; }
+};
+
+template <int dim>
+struct Intersection {
+  Cell<dim> inside_;
+  int dir, side;  // indexInInside = 2*dir + side (YaspGrid)
+  BoxGeometry<dim, dim - 1> geo;
+  const Cell<dim>& inside() const { return inside_; }
+  int indexInInside() const { return 2 * dir + side; }
+  bool boundary() const { return true; }
+  const BoxGeometry<dim, dim - 1>& geometry() const { return geo; }
+  // reference coordinates of a face point inside the cell (geometryInInside().global(x))
+  struct InInside {
+    int dir, side;
+    FieldVector<double, dim> global(const FieldVector<double, dim - 1>& x) const {
+      FieldVector<double, dim> g;
+      int t = 0;
+      for (int d = 0; d < dim; d++) g[d] = d == dir ? double(side) : x[t++];
+      return g;
+    }
+  };
+  InInside geometryInInside() const { return InInside{dir, side}; }
+  FieldVector<double, dim> centerUnitOuterNormal() const {
+    FieldVector<double, dim> n;
+    n[dir] = side ? 1.0 : -1.0;
+    return n;
+  }
+  FieldVector<double, dim> unitOuterNormal(const FieldVector<double, dim - 1>&) const { return centerUnitOuterNormal(); }
+};
+
+template <int dim_>
+class YaspGridView {
+ public:
+  static constexpr int dimension = dim_;
+  using ctype = double;
+  using Grid = YaspGrid<dim_>;
+  explicit YaspGridView(const Grid& g) : grid_(&g) {}
+  const Grid& grid() const { return *grid_; }
+  long long size(int codim) const {
+    if (codim != 0) throw Exception("YaspGridView::size: only codim 0 is counted by the descriptor");
+    long long n = 1;
+    for (int v : grid_->cells()) n *= v;
+    return n;
+  }
+  double h(int d) const { return (grid_->upper()[d] - grid_->lower()[d]) / grid_->cells()[d]; }
+  Cell<dim_> cell(long long index) const {
+    Cell<dim_> c;
+    c.index = index;
+    long long r = index;
+    for (int d = 0; d < dim_; d++) {
+      c.coord[d] = int(r % grid_->cells()[d]);
+      r /= grid_->cells()[d];
+      c.geo.ext[d] = h(d);
+      c.geo.lo[d] = grid_->lower()[d] + h(d) * c.coord[d];
+    }
+    return c;
+  }
+  // boundary face with the numbering of pdelab_b200.h (direction-major, tangential lexicographic)
+  Intersection<dim_> boundaryFace(int dir, int side, long long tang) const {
+    std::array<int, dim_> cc{};
+    long long r = tang;
+    for (int d = 0; d < dim_; d++)
+      if (d != dir) {
+        cc[d] = int(r % grid_->cells()[d]);
+        r /= grid_->cells()[d];
+      }
+    cc[dir] = side ? grid_->cells()[dir] - 1 : 0;
+    long long idx = 0, stride = 1;
+    for (int d = 0; d < dim_; d++) {
+      idx += stride * cc[d];
+      stride *= grid_->cells()[d];
+    }
+    Intersection<dim_> is;
+    is.inside_ = cell(idx);
+    is.dir = dir;
+    is.side = side;
+    is.geo.lo = is.inside_.geo.lo;
+    is.geo.ext = is.inside_.geo.ext;
+    is.geo.normal_dir = dir;
+    if (side) is.geo.lo[dir] += is.inside_.geo.ext[dir];
+    return is;
+  }
+
+ private:
+  const Grid* grid_;
+};
+template <int dim_>
+inline YaspGridView<dim_> YaspGrid<dim_>::leafGridView() const {
+  return YaspGridView<dim_>(*this);
+}
+
+// ---- finite element maps and function spaces ------------------------------------------------------
+// QkDGLocalFiniteElementMap<D,R,k,d> (finiteelementmap/qkdg.hh:36-76, Lagrange basis)
+template <class D, class R, int k, int d>
+struct QkDGLocalFiniteElementMap {
+  static constexpr int degree = k, dimension = d, space = PDB200_SPACE_QKDG;
+  static constexpr std::size_t maxLocalSize() {
+    std::size_t n = 1;
+    for (int i = 0; i < d; i++) n *= k + 1;
+    return n;
+  }
+};
+// QkLocalFiniteElementMap<GV,D,R,k> (finiteelementmap/qkfem.hh:17-78)
+template <class GV, class D, class R, int k>
+struct QkLocalFiniteElementMap {
+  static constexpr int degree = k, dimension = GV::dimension, space = PDB200_SPACE_QK;
+  explicit QkLocalFiniteElementMap(const GV&) {}
+  QkLocalFiniteElementMap() = default;
+  static constexpr std::size_t maxLocalSize() {
+    std::size_t n = 1;
+    for (int i = 0; i < GV::dimension; i++) n *= k + 1;
+    return n;
+  }
+};
+
+struct NoConstraints {};
+struct ConformingDirichletConstraints {};  // constraints/conforming.hh:36-139
+struct P0ParallelConstraints {};           // constraints/p0.hh (selected through YaspGrid::side_kind)
+
+namespace ISTL {
+enum class Blocking { none, fixed };
+// flat and fixed-block vectors are the same bytes (test/test-blocked-istl-ordering.cc:65-72)
+template <Blocking blocking = Blocking::none, std::size_t block_size = 1>
+struct VectorBackend {};
+struct BCRSMatrixBackend {
+  explicit BCRSMatrixBackend(std::size_t entries_per_row = 0) : entries_per_row_(entries_per_row) {}
+  std::size_t avg_entries_per_row() const { return entries_per_row_; }
+  std::size_t entries_per_row_;
+};
+}  // namespace ISTL
+
+template <class GV, class FEM, class CON = NoConstraints, class VBE = ISTL::VectorBackend<>>
+class GridFunctionSpace {
+ public:
+  using Traits = GridFunctionSpace;
+  using GridViewType = GV;
+  using GridView = GV;
+  using FiniteElementMapType = FEM;
+  using ConstraintsType = CON;
+  using Backend = VBE;
+  using SizeType = std::size_t;
+  // GridFunctionSpace::ConstraintsContainer<E>::Type: the constrained DOFs (all with empty
+  // linear combination = Dirichlet), constraints/common/constraintstransformation.hh
+  template <class E>
+  struct ConstraintsContainer {
+    struct Type {
+      std::vector<std::uint64_t> dofs;  // ascending
+      void clear() { dofs.clear(); }
+      std::size_t size() const { return dofs.size(); }
+      bool containsNonDirichletConstraints() const { return false; }
+    };
+  };
+  GridFunctionSpace(const GV& gv, const FEM& fem) : gv_(gv), fem_(fem) {}
+  const GV& gridView() const { return gv_; }
+  const FEM& finiteElementMap() const { return fem_; }
+  void name(const std::string& n) { name_ = n; }
+  const std::string& name() const { return name_; }
+  void update() {}
+  SizeType maxLocalSize() const { return FEM::maxLocalSize(); }
+  SizeType size() const {
+    SizeType n = 1;
+    if (FEM::space == PDB200_SPACE_QKDG) {
+      n = FEM::maxLocalSize();
+      for (int v : gv_.grid().cells()) n *= v;
+    } else {
+      for (int v : gv_.grid().cells()) n *= FEM::degree * v + 1;
+    }
+    return n;
+  }
+  SizeType globalSize() const { return size(); }
+
+ private:
+  GV gv_;
+  FEM fem_;
+  std::string name_;
+};
+
+// ---- vectors ------------------------------------------------------------------------------------
+namespace Backend {
+// Backend::Vector<GFS,E>: one contiguous E[N] in container order (backend/istl/vector.hh)
+template <class GFS, class E>
+class Vector {
+ public:
+  using ElementType = E;
+  using Container = std::vector<E>;
+  using GridFunctionSpace = GFS;
+  explicit Vector(const GFS& gfs, E v = E(0)) : gfs_(&gfs), data_(gfs.size(), v) {}
+  Vector& operator=(E v) {
+    std::fill(data_.begin(), data_.end(), v);
+    return *this;
+  }
+  std::size_t N() const { return data_.size(); }
+  std::size_t flatsize() const { return data_.size(); }
+  E* data() { return data_.data(); }
+  const E* data() const { return data_.data(); }
+  E& operator[](std::size_t i) { return data_[i]; }
+  const E& operator[](std::size_t i) const { return data_[i]; }
+  Vector& operator+=(const Vector& o) {
+    for (std::size_t i = 0; i < data_.size(); i++) data_[i] += o.data_[i];
+    return *this;
+  }
+  Vector& operator-=(const Vector& o) {
+    for (std::size_t i = 0; i < data_.size(); i++) data_[i] -= o.data_[i];
+    return *this;
+  }
+  Vector& operator*=(E a) {
+    for (E& v : data_) v *= a;
+    return *this;
+  }
+  Vector& axpy(E a, const Vector& x) {
+    for (std::size_t i = 0; i < data_.size(); i++) data_[i] += a * x.data_[i];
+    return *this;
+  }
+  E dot(const Vector& o) const {
+    E s = 0;
+    for (std::size_t i = 0; i < data_.size(); i++) s += data_[i] * o.data_[i];
+    return s;
+  }
+  E two_norm() const { return std::sqrt(dot(*this)); }
+  E infinity_norm() const {
+    E s = 0;
+    for (E v : data_) s = std::max(s, std::abs(v));
+    return s;
+  }
+  const GFS& gridFunctionSpace() const { return *gfs_; }
+  Container& native() { return data_; }
+  const Container& native() const { return data_; }
+
+ private:
+  const GFS* gfs_;
+  Container data_;
+};
+template <class V>
+auto native(V& v) -> decltype(v.native()) {
+  return v.native();
+}
+}  // namespace Backend
+
+// ---- boundary-condition and DG enums (same names as the reference) -------------------------------
+struct ConvectionDiffusionBoundaryConditions {
+  enum Type { Dirichlet = 1, Neumann = -1, Outflow = -2, None = -3 };  // convectiondiffusionparameter.hh:113
+};
+struct ConvectionDiffusionDGMethod {
+  enum Type { NIPG, SIPG, IIPG };  // convectiondiffusiondg.hh:31
+};
+struct ConvectionDiffusionDGWeights {
+  enum Type { weightsOn, weightsOff };  // convectiondiffusiondg.hh:36
+};
+
+// Traits the user's parameter class is written against (convectiondiffusionparameter.hh:39-105)
+template <class GV, class RF>
+struct ConvectionDiffusionParameterTraits {
+  using GridViewType = GV;
+  static constexpr int dimDomain = GV::dimension;
+  using DomainFieldType = double;
+  using DomainType = FieldVector<double, GV::dimension>;
+  using IntersectionDomainType = FieldVector<double, GV::dimension - 1>;
+  using RangeFieldType = RF;
+  using RangeType = FieldVector<RF, GV::dimension>;
+  using PermTensorType = FieldMatrix<RF, GV::dimension, GV::dimension>;
+  using ElementType = Cell<GV::dimension>;
+  using IntersectionType = Intersection<GV::dimension>;
+};
+
+// ConvectionDiffusionModelProblem (convectiondiffusionparameter.hh:124-209): the defaults a user's
+// parameter class inherits — A = I, b = 0, c = 0, f = 0, Dirichlet everywhere, g = j = o = 0.
+template <class GV, class RF>
+class ConvectionDiffusionModelProblem {
+ public:
+  using BCType = ConvectionDiffusionBoundaryConditions::Type;
+  using Traits = ConvectionDiffusionParameterTraits<GV, RF>;
+  static constexpr bool permeabilityIsConstantPerCell() { return true; }
+  template <class E, class X>
+  typename Traits::PermTensorType A(const E&, const X&) const {
+    typename Traits::PermTensorType I(RF(0));
+    for (int i = 0; i < Traits::dimDomain; i++) I[i][i] = 1.0;
+    return I;
+  }
+  template <class E, class X>
+  typename Traits::RangeType b(const E&, const X&) const {
+    return typename Traits::RangeType(RF(0));
+  }
+  template <class E, class X>
+  RF c(const E&, const X&) const {
+    return 0.0;
+  }
+  template <class E, class X>
+  RF f(const E&, const X&) const {
+    return 0.0;
+  }
+  template <class I, class X>
+  BCType bctype(const I&, const X&) const {
+    return ConvectionDiffusionBoundaryConditions::Dirichlet;
+  }
+  template <class E, class X>
+  RF g(const E&, const X&) const {
+    return 0.0;
+  }
+  template <class I, class X>
+  RF j(const I&, const X&) const {
+    return 0.0;
+  }
+  template <class I, class X>
+  RF o(const I&, const X&) const {
+    return 0.0;
+  }
+  void setTime(RF) {}
+};
+
+// ---- local operators: carry the constructor arguments of the reference ----------------------------
+template <class Param, class FEM>
+class ConvectionDiffusionDG {
+ public:
+  static constexpr bool isDG = true;
+  using ParameterType = Param;
+  // convectiondiffusiondg.hh:85-102 (same defaults)
+  ConvectionDiffusionDG(Param& param, ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::SIPG,
+                        ConvectionDiffusionDGWeights::Type weights = ConvectionDiffusionDGWeights::weightsOn,
+                        double alpha = 1.0, int intorderadd = 0)
+      : param_(&param), method(method), weights(weights), alpha(alpha), intorderadd(intorderadd) {}
+  static constexpr bool isLinear = true;
+  Param& parameters() const { return *param_; }
+  void setTime(double t) { param_->setTime(t); }
+  Param* param_;
+  ConvectionDiffusionDGMethod::Type method;
+  ConvectionDiffusionDGWeights::Type weights;
+  double alpha;
+  int intorderadd;
+};
+
+template <class Param, class FEM>
+class ConvectionDiffusionFEM {
+ public:
+  static constexpr bool isDG = false;
+  using ParameterType = Param;
+  explicit ConvectionDiffusionFEM(Param& param, int intorderadd = 0) : param_(&param), intorderadd(intorderadd) {}
+  static constexpr bool isLinear = true;
+  Param& parameters() const { return *param_; }
+  Param* param_;
+  int intorderadd;
+  // members the DG operator has; unused by the conforming path
+  ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::SIPG;
+  ConvectionDiffusionDGWeights::Type weights = ConvectionDiffusionDGWeights::weightsOn;
+  double alpha = 0.0;
+};
+
+// ConvectionDiffusionBoundaryConditionAdapter (convectiondiffusionparameter.hh:217-248)
+template <class Param>
+struct ConvectionDiffusionBoundaryConditionAdapter {
+  explicit ConvectionDiffusionBoundaryConditionAdapter(const Param& p) : param(&p) {}
+  template <class I, class X>
+  bool isDirichlet(const I& is, const X& x) const {
+    return param->bctype(is, x) == ConvectionDiffusionBoundaryConditions::Dirichlet;
+  }
+  const Param* param;
+};
+// ConvectionDiffusionDirichletExtensionAdapter (convectiondiffusionparameter.hh:255-300): u = g
+template <class Param>
+struct ConvectionDiffusionDirichletExtensionAdapter {
+  template <class GV>
+  ConvectionDiffusionDirichletExtensionAdapter(const GV&, Param& p) : param(&p) {}
+  template <class E, class X>
+  double evaluate(const E& e, const X& x) const {
+    return param->g(e, x);
+  }
+  Param* param;
+};
+
+// ---- sampling of the parameter call-backs into the arrays of the C ABI ---------------------------
+namespace detail {
+
+template <int dim>
+struct Sampled {
+  int a_mode = PDB200_A_IDENTITY;
+  std::vector<double> A, b, c, f, g, j, o;
+  std::vector<std::int8_t> bctype;
+  bool has_b = false, has_c = false, has_f = false, has_g = false, has_j = false, has_o = false;
+};
+
+template <class GV, class Param>
+Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree, int intorderadd) {
+  constexpr int dim = GV::dimension;
+  Sampled<dim> S;
+  if (!param.permeabilityIsConstantPerCell())
+    throw Exception("pdelab_b200: permeabilityIsConstantPerCell() must be true (A is sampled at the cell centre, "
+                    "convectiondiffusiondg.hh:127-131)");
+  const int m = (2 * degree + intorderadd) / 2 + 1;  // convectiondiffusiondg.hh:139
+  std::vector<double> xq(m), wq(m);
+  check(pdb200_gauss_legendre(m, xq.data(), wq.data()), "pdb200_gauss_legendre");
+  const long long ncells = gv.size(0);
+  int nq = 1, nfq = 1;
+  for (int d = 0; d < dim; d++) nq *= m;
+  for (int d = 1; d < dim; d++) nfq *= m;
+  S.A.resize(ncells * dim * dim);
+  S.b.resize(ncells * dim);
+  S.c.resize(ncells);
+  S.f.resize(ncells * nq);
+  bool diag = true, scalar = true, ident = true;
+  const FieldVector<double, dim> centre(0.5);
+  for (long long e = 0; e < ncells; e++) {
+    const auto cell = gv.cell(e);
+    const auto A = param.A(cell, centre);
+    for (int i = 0; i < dim; i++)
+      for (int j = 0; j < dim; j++) {
+        S.A[(e * dim + i) * dim + j] = A[i][j];
+        if (i != j && A[i][j] != 0.0) diag = false;
+        if (i == j && A[i][i] != A[0][0]) scalar = false;
+        if (i == j && A[i][i] != 1.0) ident = false;
+      }
+    const auto b = param.b(cell, centre);
+    for (int i = 0; i < dim; i++) {
+      S.b[e * dim + i] = b[i];
+      S.has_b |= b[i] != 0.0;
+    }
+    S.c[e] = param.c(cell, centre);
+    S.has_c |= S.c[e] != 0.0;
+    for (int q = 0; q < nq; q++) {
+      FieldVector<double, dim> x;
+      int r = q;
+      for (int d = 0; d < dim; d++) {
+        x[d] = xq[r % m];
+        r /= m;
+      }
+      const double f = param.f(cell, x);
+      S.f[e * nq + q] = f;
+      S.has_f |= f != 0.0;
+    }
+  }
+  // compress A to the cheapest layout that represents it exactly (selects the Kronecker kernel)
+  if (diag) {
+    std::vector<double> a;
+    if (ident) {
+      S.a_mode = PDB200_A_IDENTITY;
+    } else if (scalar) {
+      S.a_mode = PDB200_A_SCALAR;
+      a.resize(ncells);
+      for (long long e = 0; e < ncells; e++) a[e] = S.A[e * dim * dim];
+    } else {
+      S.a_mode = PDB200_A_DIAGONAL;
+      a.resize(ncells * dim);
+      for (long long e = 0; e < ncells; e++)
+        for (int i = 0; i < dim; i++) a[e * dim + i] = S.A[(e * dim + i) * dim + i];
+    }
+    S.A.swap(a);
+  } else {
+    S.a_mode = PDB200_A_FULL;
+  }
+  // boundary faces in the numbering of pdelab_b200.h
+  long long nbf = 0;
+  for (int d = 0; d < dim; d++) nbf += 2 * (ncells / gv.grid().cells()[d]);
+  S.bctype.resize(nbf);
+  S.g.assign(nbf * nfq, 0.0);
+  S.j.assign(nbf * nfq, 0.0);
+  S.o.assign(nbf * nfq, 0.0);
+  long long bf = 0;
+  const FieldVector<double, dim - 1> fcentre(0.5);
+  for (int d = 0; d < dim; d++)
+    for (int side = 0; side < 2; side++) {
+      const long long nt = ncells / gv.grid().cells()[d];
+      for (long long t = 0; t < nt; t++, bf++) {
+        const auto is = gv.boundaryFace(d, side, t);
+        const auto bc = param.bctype(is, fcentre);
+        S.bctype[bf] = (std::int8_t)bc;
+        for (int q = 0; q < nfq; q++) {
+          FieldVector<double, dim - 1> xf;
+          int r = q;
+          for (int i = 0; i < dim - 1; i++) {
+            xf[i] = xq[r % m];
+            r /= m;
+          }
+          const auto xin = is.geometryInInside().global(xf);
+          if (bc == ConvectionDiffusionBoundaryConditions::Dirichlet) {
+            S.g[bf * nfq + q] = param.g(is.inside(), xin);  // convectiondiffusiondg.hh:842
+            S.has_g |= S.g[bf * nfq + q] != 0.0;
+          } else if (bc == ConvectionDiffusionBoundaryConditions::Neumann) {
+            S.j[bf * nfq + q] = param.j(is, xf);  // :778
+            S.has_j |= S.j[bf * nfq + q] != 0.0;
+          } else if (bc == ConvectionDiffusionBoundaryConditions::Outflow) {
+            S.o[bf * nfq + q] = param.o(is, xf);  // :813
+            S.has_o |= S.o[bf * nfq + q] != 0.0;
+          }
+        }
+      }
+    }
+  return S;
+}
+
+}  // namespace detail
+
+// ---- the assembled Jacobian container -----------------------------------------------------------
+template <class GO>
+class BCRSMatrixContainer;
+
+// ---- GridOperator -------------------------------------------------------------------------------
+template <class GFSU, class GFSV, class LOP, class MB, class DF, class RF, class JF,
+          class CU = typename GFSU::template ConstraintsContainer<RF>::Type,
+          class CV = typename GFSV::template ConstraintsContainer<RF>::Type>
+class GridOperator {
+ public:
+  using GV = typename GFSU::GridView;
+  static constexpr int dim = GV::dimension;
+  using FEM = typename GFSU::FiniteElementMapType;
+  // GridOperatorTraits (gridoperator/common/gridoperatorutilities.hh:31-80)
+  struct Traits {
+    using TrialGridFunctionSpace = GFSU;
+    using TestGridFunctionSpace = GFSV;
+    using TrialGridFunctionSpaceConstraints = CU;
+    using TestGridFunctionSpaceConstraints = CV;
+    using MatrixBackend = MB;
+    using DomainField = DF;
+    using RangeField = RF;
+    using JacobianField = JF;
+    using Domain = Backend::Vector<GFSU, DF>;
+    using Range = Backend::Vector<GFSV, RF>;
+    using Jacobian = BCRSMatrixContainer<GridOperator>;
+    using LocalOperator = LOP;
+  };
+  using Domain = typename Traits::Domain;
+  using Range = typename Traits::Range;
+  using Jacobian = typename Traits::Jacobian;
+  struct Pattern {  // scalar CSR, columns ascending (bcrsmatrixbackend.hh:90-121)
+    std::vector<std::uint64_t> rowptr, colidx;
+  };
+  template <class T>
+  struct MatrixContainer {
+    using Type = Jacobian;
+  };
+
+  // local assembler facade: what OnTheFlyOperator / StationaryLinearProblemSolver touch
+  // (gridoperator/default/localassembler.hh)
+  struct LocalAssembler {
+    LOP* lop;
+    const CU* cu;
+    const CV* cv;
+    LOP& localOperator() const { return *lop; }
+    const CU& trialConstraints() const { return *cu; }
+    const CV& testConstraints() const { return *cv; }
+    static constexpr bool isLinear() { return true; }
+    void setTime(double) {}
+    void setWeight(double w) {
+      if (w != 1.0) throw Exception("pdelab_b200: engine weights other than 1 are not supported");
+    }
+  };
+
+  // gridoperator.hh:76-82
+  GridOperator(const GFSU& gfsu, const CU& cu, const GFSV& gfsv, const CV& cv, LOP& lop, const MB& mb = MB())
+      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&cu), cv_(&cv), la_{&lop, &cu, &cv} {
+    init();
+  }
+  // gridoperator.hh:85-89 (empty constraints)
+  GridOperator(const GFSU& gfsu, const GFSV& gfsv, LOP& lop, const MB& mb = MB())
+      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&empty_cu_), cv_(&empty_cv_), la_{&lop, &empty_cu_, &empty_cv_} {
+    init();
+  }
+  GridOperator(const GridOperator&) = delete;
+  GridOperator& operator=(const GridOperator&) = delete;
+  ~GridOperator() {
+    if (h_) pdb200_destroy(h_);
+  }
+
+  const GFSU& trialGridFunctionSpace() const { return gfsu_; }
+  const GFSV& testGridFunctionSpace() const { return gfsv_; }
+  typename GFSU::SizeType globalSizeU() const { return num_dofs(); }  // gridoperator.hh:104-107
+  typename GFSV::SizeType globalSizeV() const { return num_dofs(); }
+  LocalAssembler& localAssembler() const { return la_; }
+  const MB& matrixBackend() const { return mb_; }
+  pdb200_handle handle() const { return h_; }  // for stream control / device-pointer calls
+
+  // re-sample the parameter call-backs (the reference re-evaluates them on every assembly)
+  void update() {
+    if (h_) pdb200_destroy(h_);
+    h_ = nullptr;
+    init();
+  }
+
+  // gridoperator.hh:168-173
+  void fill_pattern(Pattern& p) const {
+    std::uint64_t nr = 0, nnz = 0;
+    check(pdb200_pattern_size(h_, &nr, &nnz), "fill_pattern");
+    p.rowptr.assign(nr + 1, 0);
+    p.colidx.assign(nnz, 0);
+    check(pdb200_pattern(h_, p.rowptr.data(), p.colidx.data()), "fill_pattern");
+  }
+  // gridoperator.hh:176-181:  r += R(x)
+  void residual(const Domain& x, Range& r) const { check(pdb200_residual(h_, x.data(), r.data()), "residual"); }
+  // gridoperator.hh:184-189:  A += dR/dx
+  void jacobian(const Domain& x, Jacobian& a) const {
+    check(pdb200_jacobian(h_, x.data(), a.values().data(), PDB200_LAYOUT_CSR), "jacobian");
+  }
+  // gridoperator.hh:192-197:  y += J z (linear problems)
+  void jacobian_apply(const Domain& z, Range& y) const {
+    check(pdb200_jacobian_apply(h_, z.data(), y.data()), "jacobian_apply");
+  }
+  // gridoperator.hh:200-205: throws for a linear local operator, like the reference
+  void jacobian_apply(const Domain& u, const Domain& z, Range& y) const {
+    check(pdb200_jacobian_apply_nonlinear(h_, u.data(), z.data(), y.data()), "jacobian_apply");
+  }
+  // y = J x with the zeroing fused (OnTheFlyOperator::apply); raw pointers may be device memory
+  void onthefly_apply(const double* x, double* y) const { check(pdb200_onthefly_apply(h_, x, y), "apply"); }
+  void residual(const double* x, double* r) const { check(pdb200_residual(h_, x, r), "residual"); }
+  void jacobian_apply(const double* z, double* y) const { check(pdb200_jacobian_apply(h_, z, y), "jacobian_apply"); }
+
+  void make_consistent(Jacobian&) const {}  // sequential / overlapping: nothing to add (gridoperator.hh:207-212)
+
+  // gridoperator.hh:144-165: interpolate f into x on the constrained DOFs' space (Lagrange nodes),
+  // then copy the unconstrained entries of xold
+  template <class F>
+  void interpolate(const Domain& xold, F& f, Domain& x) const {
+    B200_interpolate(f, x);
+    const auto con = constrained();
+    std::vector<char> is_con(x.N(), 0);
+    for (auto i : con) is_con[i] = 1;
+    for (std::size_t i = 0; i < x.N(); i++)
+      if (!is_con[i]) x[i] = xold[i];
+  }
+
+  // Lagrange interpolation of f (evaluate(cell, xlocal)) at the nodes j/k of every cell
+  template <class F>
+  void B200_interpolate(F& f, Domain& x) const {
+    const auto& gv = gfsu_.gridView();
+    constexpr int k = FEM::degree;
+    const int n = (int)FEM::maxLocalSize();
+    std::vector<std::uint64_t> idx(n);
+    for (long long e = 0; e < gv.size(0); e++) {
+      const auto cell = gv.cell(e);
+      check(pdb200_cell_dof_indices(h_, (std::uint64_t)e, idx.data()), "interpolate");
+      for (int i = 0; i < n; i++) {
+        FieldVector<double, dim> xl;
+        int r = i;
+        for (int d = 0; d < dim; d++) {
+          xl[d] = double(r % (k + 1)) / k;
+          r /= k + 1;
+        }
+        x[idx[i]] = f.evaluate(cell, xl);
+      }
+    }
+  }
+
+  std::vector<std::uint64_t> constrained() const {
+    std::uint64_t n = 0;
+    check(pdb200_constrained_dofs(h_, &n, nullptr), "constraints");
+    std::vector<std::uint64_t> idx(n);
+    if (n) check(pdb200_constrained_dofs(h_, &n, idx.data()), "constraints");
+    return idx;
+  }
+  std::string lastKernel() const { return pdb200_last_kernel(h_); }
+  // the problem description handed to the C ABI (tests hand the same struct to the CPU oracle)
+  const pdb200_problem& problem() const { return p_; }
+
+ private:
+  std::size_t num_dofs() const {
+    std::uint64_t n = 0;
+    check(pdb200_num_dofs(h_, &n), "globalSize");
+    return (std::size_t)n;
+  }
+  void init() {
+    static_assert(std::is_same<GFSU, GFSV>::value, "Galerkin: trial and test space coincide on this path");
+    const auto& gv = gfsu_.gridView();
+    S_ = detail::sample_parameters(gv, lop_.parameters(), FEM::degree, lop_.intorderadd);
+    auto& S = S_;
+    pdb200_problem& p = p_;
+    p = pdb200_problem{};
+    p.dim = dim;
+    for (int d = 0; d < 3; d++) {
+      p.cells[d] = d < dim ? gv.grid().cells()[d] : 1;
+      p.lower[d] = d < dim ? gv.grid().lower()[d] : 0.0;
+      p.upper[d] = d < dim ? gv.grid().upper()[d] : 1.0;
+      for (int s = 0; s < 2; s++) p.side_kind[d][s] = gv.grid().side_kind[d][s];
+    }
+    p.space = FEM::space;
+    p.degree = FEM::degree;
+    p.dg_method = lop_.method == ConvectionDiffusionDGMethod::SIPG   ? PDB200_DG_SIPG
+                  : lop_.method == ConvectionDiffusionDGMethod::NIPG ? PDB200_DG_NIPG
+                                                                     : PDB200_DG_IIPG;
+    p.dg_weights = lop_.weights == ConvectionDiffusionDGWeights::weightsOn ? PDB200_DG_WEIGHTS_ON : PDB200_DG_WEIGHTS_OFF;
+    p.dg_alpha = lop_.alpha;
+    p.intorderadd = lop_.intorderadd;
+    p.a_mode = S.a_mode;
+    p.A = S.A.empty() ? nullptr : S.A.data();
+    p.b = S.has_b ? S.b.data() : nullptr;
+    p.c = S.has_c ? S.c.data() : nullptr;
+    p.f = S.has_f ? S.f.data() : nullptr;
+    p.bctype = S.bctype.data();
+    p.g = S.has_g ? S.g.data() : nullptr;
+    p.j = S.has_j ? S.j.data() : nullptr;
+    p.o = S.has_o ? S.o.data() : nullptr;
+    p.device = 0;
+    p.kernel = PDB200_KERNEL_AUTO;
+    check(pdb200_create(&p, &h_), "GridOperator");
+  }
+
+  const GFSU& gfsu_;
+  const GFSV& gfsv_;
+  LOP& lop_;
+  MB mb_;
+  CU empty_cu_{};
+  CV empty_cv_{};
+  const CU* cu_;
+  const CV* cv_;
+  mutable LocalAssembler la_;
+  detail::Sampled<dim> S_;  // sampled call-backs (kept alive: p_ points into them)
+  pdb200_problem p_{};
+  pdb200_handle h_ = nullptr;
+};
+
+// Backend::Matrix / ISTL::BCRSMatrixContainer constructed from the grid operator
+// (backend/istl/bcrsmatrix.hh:78-82 -> MB::buildPattern -> go.fill_pattern)
+template <class GO>
+class BCRSMatrixContainer {
+ public:
+  using ElementType = double;
+  explicit BCRSMatrixContainer(const GO& go) {
+    go.fill_pattern(p_);
+    v_.assign(p_.colidx.size(), 0.0);
+  }
+  BCRSMatrixContainer& operator=(double s) {
+    std::fill(v_.begin(), v_.end(), s);
+    return *this;
+  }
+  std::size_t N() const { return p_.rowptr.size() - 1; }
+  std::size_t M() const { return N(); }
+  std::size_t nonzeroes() const { return v_.size(); }
+  const std::vector<std::uint64_t>& rowptr() const { return p_.rowptr; }
+  const std::vector<std::uint64_t>& colidx() const { return p_.colidx; }
+  std::vector<double>& values() { return v_; }
+  const std::vector<double>& values() const { return v_; }
+  // entry access like BCRSMatrix::operator()(ri, ci) (backend/istl/bcrsmatrix.hh:212-215)
+  double operator()(std::size_t i, std::size_t j) const {
+    auto b = p_.colidx.begin() + p_.rowptr[i], e = p_.colidx.begin() + p_.rowptr[i + 1];
+    auto it = std::lower_bound(b, e, (std::uint64_t)j);
+    if (it == e || *it != j) throw Exception("BCRSMatrix: entry not in pattern");
+    return v_[it - p_.colidx.begin()];
+  }
+  // y = A x (dune-istl BCRSMatrix::mv), host loop: the container lives in host memory here
+  template <class X, class Y>
+  void mv(const X& x, Y& y) const {
+    for (std::size_t i = 0; i < N(); i++) {
+      double s = 0;
+      for (std::uint64_t k = p_.rowptr[i]; k < p_.rowptr[i + 1]; k++) s += v_[k] * x[p_.colidx[k]];
+      y[i] = s;
+    }
+  }
+
+ private:
+  typename GO::Pattern p_;
+  std::vector<double> v_;
+};
+
+// OnTheFlyOperator (backend/istl/seqistlsolverbackend.hh:44-100): y = J x / y += alpha J x
+template <class X, class Y, class GO>
+class OnTheFlyOperator {
+ public:
+  using domain_type = X;
+  using range_type = Y;
+  using field_type = double;
+  explicit OnTheFlyOperator(const GO& go) : go_(go) {}
+  void apply(const X& x, Y& y) const { go_.onthefly_apply(x.data(), y.data()); }  // :66-76
+  void applyscaleadd(field_type alpha, const X& x, Y& y) const {               // :78-90
+    Y t(y.gridFunctionSpace(), 0.0);
+    go_.jacobian_apply(x, t);
+    y.axpy(alpha, t);
+  }
+
+ private:
+  const GO& go_;
+};
+
+// constraints(bctype, gfs, cc) (constraints/common/constraints.hh:588-687): the constrained set is
+// derived by the library from the per-face boundary types; it needs an operator handle, so the
+// grid operator offers it — this overload fills cc from a grid operator built on the same spaces.
+template <class GO, class CC>
+void constraints(const GO& go, CC& cc) {
+  cc.dofs = go.constrained();
+}
+// set_nonconstrained_dofs(cc, v, x) (constraints/common/constraints.hh:796-802)
+template <class CC, class V>
+void set_nonconstrained_dofs(const CC& cc, double v, V& x) {
+  std::vector<char> is_con(x.N(), 0);
+  for (auto i : cc.dofs) is_con[i] = 1;
+  for (std::size_t i = 0; i < x.N(); i++)
+    if (!is_con[i]) x[i] = v;
+}
+
+}  // namespace B200
+}  // namespace PDELab
+}  // namespace Dune
+
+#endif  // PDELAB_B200_HOST_GRIDOPERATOR_HH

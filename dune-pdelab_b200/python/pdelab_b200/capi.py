@@ -28,7 +28,7 @@ _lib = None
 SYMBOLS = [
     "pdb200_last_error", "pdb200_create", "pdb200_destroy", "pdb200_update_coefficients",
     "pdb200_num_dofs", "pdb200_local_size", "pdb200_num_boundary_faces", "pdb200_boundary_face_offset",
-    "pdb200_quadrature_size", "pdb200_quadrature", "pdb200_cell_dof_indices", "pdb200_constrained_dofs",
+    "pdb200_quadrature_size", "pdb200_quadrature", "pdb200_gauss_legendre", "pdb200_cell_dof_indices", "pdb200_constrained_dofs",
     "pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply", "pdb200_jacobian_apply_nonlinear",
     "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
@@ -70,6 +70,7 @@ def load_library():
     lib.pdb200_cell_dof_indices.argtypes = [vp, C.c_uint64, vp]
     lib.pdb200_constrained_dofs.argtypes = [vp, u64p, vp]
     lib.pdb200_quadrature.argtypes = [vp, vp, vp]
+    lib.pdb200_gauss_legendre.argtypes = [C.c_int, vp, vp]
     lib.pdb200_boundary_face_offset.argtypes = [vp, C.c_int, C.c_int, u64p]
     for name in ("pdb200_destroy", "pdb200_synchronize"):
         getattr(lib, name).argtypes = [vp]

@@ -110,6 +110,11 @@ int pdb200_quadrature_size(pdb200_handle h, uint32_t* m);     /* Gauss points pe
 /* ascending Gauss-Legendre abscissae on [0,1] and weights, m entries each (host arrays) */
 int pdb200_quadrature(pdb200_handle h, double* points, double* weights);
 
+/* The same rule without an operator handle (pure host table; no device needed): callers use it to
+ * sample f, g, j, o at the points the reference evaluates them (common/quadraturerules.hh:117-120).
+ * m = (2*degree + intorderadd)/2 + 1; ascending abscissae on [0,1]. */
+int pdb200_gauss_legendre(int m, double* points, double* weights);
+
 /* container index of local DOF i of cell `cell`: LFSIndexCache::containerIndex,
  * gridfunctionspace/lfsindexcache.hh:603-633 + ordering/leaforderingbase.hh:97-203.
  * Writes (k+1)^dim entries (host array). */

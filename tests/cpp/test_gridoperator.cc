@@ -1,0 +1,359 @@
+// test_gridoperator.cc — the C++ host mirror (dune-pdelab_b200/host/gridoperator.hh) exercised the way
+// the reference's own tests use Dune::PDELab::GridOperator.  Needs a CUDA device (pytest -m gpu
+// builds and runs it, tests/test_gpu_cpp_host.py).  Restated reference tests:
+//   test/testconvectiondiffusiondg.cc:46-168   DG k=1, 2D 16^2, u = exp(-|x-1/2|^2), err^2 <= 1e-6
+//   test/matrixfree/matrix_free_linear.cc      assembled vs matrix-free: same Krylov iteration count
+//   test/testmatrixfree.cc:150-178             Q2 conforming FEM 2D 32^2, err^2 <= 1e-7, both ways
+//   test/test-blocked-istl-ordering.cc:45-72   flat and blocked DG vectors are the same bytes
+//   gridoperator/gridoperator.hh:200-205       jacobian_apply(u,z,y) throws for a linear operator
+// and every GPU result is compared with the CPU oracle (liboracle.so, test infrastructure) fed
+// with the very same pdb200_problem.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <random>
+#include <vector>
+
+#include "../../dune-pdelab_b200/host/gridoperator.hh"
+
+extern "C" {  // oracle/pdelab_oracle.cc
+int oracle_residual(const pdb200_problem*, const double*, double*);
+int oracle_jacobian_apply(const pdb200_problem*, const double*, double*);
+int oracle_jacobian(const pdb200_problem*, const double*, double*);
+int oracle_pattern(const pdb200_problem*, uint64_t*, uint64_t*, uint64_t*, uint64_t*);
+const char* oracle_last_error(void);
+}
+
+namespace PDELab = Dune::PDELab::B200;
+
+static int failures = 0;
+#define EXPECT(cond, msg)                                                     \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      std::cerr << "FAIL " << __LINE__ << ": " << msg << std::endl;           \
+      failures++;                                                             \
+    } else {                                                                  \
+      std::cout << "ok   " << msg << std::endl;                               \
+    }                                                                         \
+  } while (0)
+
+// the parameter class of test/testconvectiondiffusiondg.cc:10-44, same call-back interface
+template <typename GridView, typename RangeType>
+class PoissonProblem : public PDELab::ConvectionDiffusionModelProblem<GridView, RangeType> {
+ public:
+  template <typename Element, typename Coord>
+  auto f(const Element& element, const Coord& x) const {
+    auto global = element.geometry().global(x);
+    double c = 0;
+    for (std::size_t i = 0; i < global.size(); i++) c += (0.5 - global[i]) * (0.5 - global[i]);
+    const double dim = (double)global.size();
+    return (2.0 * dim - 4.0 * c) * std::exp(-c);  // -laplace exp(-c) in any dimension (4(1-c)g in 2D)
+  }
+  template <typename Element, typename Coord>
+  auto bctype(const Element&, const Coord&) const {
+    return PDELab::ConvectionDiffusionBoundaryConditions::Dirichlet;
+  }
+  template <typename Element, typename Coord>
+  RangeType g(const Element& element, const Coord& x) const {
+    auto global = element.geometry().global(x);
+    double c = 0;
+    for (std::size_t i = 0; i < global.size(); i++) c += (0.5 - global[i]) * (0.5 - global[i]);
+    return std::exp(-c);
+  }
+};
+
+// heterogeneous diagonal permeability + reaction: exercises the sampled coefficient arrays
+template <typename GridView, typename RangeType>
+class LayeredProblem : public PoissonProblem<GridView, RangeType> {
+ public:
+  using Traits = PDELab::ConvectionDiffusionParameterTraits<GridView, RangeType>;
+  template <typename Element, typename Coord>
+  typename Traits::PermTensorType A(const Element& e, const Coord& x) const {
+    auto g = e.geometry().global(x);
+    typename Traits::PermTensorType K(0.0);
+    for (int i = 0; i < Traits::dimDomain; i++) K[i][i] = (g[Traits::dimDomain - 1] > 0.5 ? 10.0 : 0.1) * (1 + i);
+    return K;
+  }
+  template <typename Element, typename Coord>
+  RangeType c(const Element&, const Coord&) const {
+    return 2.0;
+  }
+};
+
+template <class V>
+double rel_err(const V& a, const std::vector<double>& b) {
+  double e = 0, n = 0;
+  for (std::size_t i = 0; i < b.size(); i++) {
+    e = std::max(e, std::abs(a[i] - b[i]));
+    n = std::max(n, std::abs(b[i]));
+  }
+  return e / (n > 0 ? n : 1.0);
+}
+
+// unpreconditioned CG on A x = b; returns the iteration count
+template <class Apply, class V>
+int cg(Apply&& A, const V& b, V& x, double reduction, int maxit) {
+  V r(b), p(b), q(b);
+  A(x, q);
+  r = b;
+  r -= q;
+  p = r;
+  double rr = r.dot(r);
+  const double stop = reduction * reduction * rr;
+  int it = 0;
+  while (it < maxit && rr > stop) {
+    A(p, q);
+    const double alpha = rr / p.dot(q);
+    x.axpy(alpha, p);
+    r.axpy(-alpha, q);
+    const double rr2 = r.dot(r);
+    p *= rr2 / rr;
+    p += r;
+    rr = rr2;
+    it++;
+  }
+  return it;
+}
+
+// int (u_h - g)^2 with a 6-point Gauss rule per direction (integrateGridFunction(..., 10))
+template <class GFS, class V, class Problem>
+double l2_error_squared(const GFS& gfs, const V& u, const Problem& problem, pdb200_handle h, int k) {
+  constexpr int dim = GFS::GridView::dimension;
+  const auto& gv = gfs.gridView();
+  const int m = 6, n1 = k + 1;
+  std::vector<double> xq(m), wq(m);
+  pdb200_gauss_legendre(m, xq.data(), wq.data());
+  int n = 1, nq = 1;
+  for (int d = 0; d < dim; d++) n *= n1, nq *= m;
+  std::vector<uint64_t> idx(n);
+  double err = 0;
+  auto lag = [&](int i, double x) {
+    double v = 1;
+    for (int j = 0; j < n1; j++)
+      if (j != i) v *= (k * x - j) / double(i - j);
+    return v;
+  };
+  for (long long e = 0; e < gv.size(0); e++) {
+    const auto cell = gv.cell(e);
+    pdb200_cell_dof_indices(h, (uint64_t)e, idx.data());
+    for (int q = 0; q < nq; q++) {
+      PDELab::FieldVector<double, dim> x;
+      double w = cell.geometry().volume();
+      int r = q;
+      for (int d = 0; d < dim; d++) {
+        x[d] = xq[r % m];
+        w *= wq[r % m];
+        r /= m;
+      }
+      double uh = 0;
+      for (int i = 0; i < n; i++) {
+        double phi = 1;
+        int ii = i;
+        for (int d = 0; d < dim; d++) {
+          phi *= lag(ii % n1, x[d]);
+          ii /= n1;
+        }
+        uh += u[idx[i]] * phi;
+      }
+      const double diff = uh - problem.g(cell, x);
+      err += w * diff * diff;
+    }
+  }
+  return err;
+}
+
+// ---- test/testconvectiondiffusiondg.cc + test/matrixfree/matrix_free_linear.cc -------------------
+template <int dim, int degree, template <class, class> class ProblemT>
+void dg_case(int ncells, double alpha, double tol, const char* name, bool check_error) {
+  using Grid = PDELab::YaspGrid<dim>;
+  std::array<int, dim> cells;
+  cells.fill(ncells);
+  Grid grid(PDELab::FieldVector<double, dim>(1.0), cells);
+  using GridView = typename Grid::LeafGridView;
+  GridView gridView = grid.leafGridView();
+  using DomainField = double;
+  using RangeType = double;
+  using FiniteElementMap = PDELab::QkDGLocalFiniteElementMap<DomainField, RangeType, degree, dim>;
+  FiniteElementMap finiteElementMap;
+  using Constraints = PDELab::NoConstraints;
+  using VectorBackend = PDELab::ISTL::VectorBackend<PDELab::ISTL::Blocking::fixed, FiniteElementMap::maxLocalSize()>;
+  using GridFunctionSpace = PDELab::GridFunctionSpace<GridView, FiniteElementMap, Constraints, VectorBackend>;
+  GridFunctionSpace gridFunctionSpace(gridView, finiteElementMap);
+  gridFunctionSpace.name("numerical_solution");
+  using Problem = ProblemT<GridView, RangeType>;
+  Problem problem;
+  using LocalOperator = PDELab::ConvectionDiffusionDG<Problem, FiniteElementMap>;
+  LocalOperator localOperator(problem, PDELab::ConvectionDiffusionDGMethod::SIPG,
+                              PDELab::ConvectionDiffusionDGWeights::weightsOn, alpha);
+  using MatrixBackend = PDELab::ISTL::BCRSMatrixBackend;
+  MatrixBackend matrixBackend(std::pow(2, dim) * gridFunctionSpace.maxLocalSize());
+  using GridOperator =
+      PDELab::GridOperator<GridFunctionSpace, GridFunctionSpace, LocalOperator, MatrixBackend, DomainField, RangeType, RangeType>;
+  GridOperator gridOperator(gridFunctionSpace, gridFunctionSpace, localOperator, matrixBackend);
+  using V = typename GridOperator::Domain;
+  const std::size_t N = gridFunctionSpace.size();
+  EXPECT(gridOperator.globalSizeU() == N, name << ": globalSizeU == gfs.size() == " << N);
+
+  // --- oracle parity of residual / jacobian_apply / jacobian on random data ---------------------
+  std::mt19937_64 rng;  // default seed 5489, test/test-blocked-istl-ordering.cc:45-48
+  std::uniform_real_distribution<double> dist(0, 1);
+  V x(gridFunctionSpace), r(gridFunctionSpace, 0.0), y(gridFunctionSpace, 0.0);
+  for (std::size_t i = 0; i < N; i++) x[i] = dist(rng);
+  gridOperator.residual(x, r);
+  std::vector<double> want(N, 0.0);
+  if (oracle_residual(&gridOperator.problem(), x.data(), want.data())) std::cerr << oracle_last_error() << std::endl;
+  EXPECT(rel_err(r, want) < 1e-12, name << ": residual vs oracle " << rel_err(r, want));
+  gridOperator.jacobian_apply(x, y);
+  std::fill(want.begin(), want.end(), 0.0);
+  oracle_jacobian_apply(&gridOperator.problem(), x.data(), want.data());
+  EXPECT(rel_err(y, want) < 1e-12, name << ": jacobian_apply vs oracle " << rel_err(y, want) << " [" << gridOperator.lastKernel() << "]");
+  // accumulate semantics: a second call adds again (jacobianapplyengine.hh:197-202)
+  gridOperator.jacobian_apply(x, y);
+  for (auto& v : want) v *= 2;
+  EXPECT(rel_err(y, want) < 1e-12, name << ": jacobian_apply accumulates into y");
+
+  typename GridOperator::Jacobian A(gridOperator);
+  A = 0.0;
+  gridOperator.jacobian(x, A);
+  uint64_t nr = 0, nnz = 0;
+  oracle_pattern(&gridOperator.problem(), &nr, &nnz, nullptr, nullptr);
+  std::vector<uint64_t> orp(nr + 1), oci(nnz);
+  oracle_pattern(&gridOperator.problem(), &nr, &nnz, orp.data(), oci.data());
+  EXPECT(orp == A.rowptr() && oci == A.colidx(), name << ": sparsity pattern bit-exact vs oracle (" << nnz << " nnz)");
+  std::vector<double> ov(nnz, 0.0);
+  oracle_jacobian(&gridOperator.problem(), x.data(), ov.data());
+  EXPECT(rel_err(A.values(), ov) < 1e-12, name << ": jacobian values vs oracle " << rel_err(A.values(), ov));
+  // J z == jacobian_apply(z)
+  V Jx(gridFunctionSpace, 0.0), y1(gridFunctionSpace, 0.0);
+  A.mv(x, Jx);
+  PDELab::OnTheFlyOperator<V, V, GridOperator> otf(gridOperator);
+  otf.apply(x, y1);
+  EXPECT(rel_err(y1, Jx.native()) < 1e-12, name << ": OnTheFlyOperator::apply == J x " << rel_err(y1, Jx.native()));
+  // the non-linear overload throws for a linear local operator (gridoperator.hh:200-205)
+  bool threw = false;
+  try {
+    gridOperator.jacobian_apply(x, x, y);
+  } catch (PDELab::Exception& e) {
+    threw = true;
+  }
+  EXPECT(threw, name << ": jacobian_apply(u,z,y) throws for a linear operator");
+
+  if (!check_error) return;
+  // --- solve matrix-based and matrix-free (StationaryLinearProblemSolver::apply, linearproblem.hh:203-246)
+  V u(gridFunctionSpace, 0.0), res(gridFunctionSpace, 0.0), z(gridFunctionSpace, 0.0), rhs(gridFunctionSpace, 0.0);
+  gridOperator.residual(u, res);  // r = R(u0)
+  rhs = res;
+  rhs *= -1.0;
+  int it_mat = cg([&](const V& a, V& b) { A.mv(a, b); }, rhs, z, 1e-12, 5000);
+  V u_mat(u);
+  u_mat += z;
+  z = 0.0;
+  int it_free = cg([&](const V& a, V& b) { otf.apply(a, b); }, rhs, z, 1e-12, 5000);
+  V u_free(u);
+  u_free += z;
+  const double e_mat = l2_error_squared(gridFunctionSpace, u_mat, problem, gridOperator.handle(), degree);
+  const double e_free = l2_error_squared(gridFunctionSpace, u_free, problem, gridOperator.handle(), degree);
+  EXPECT(e_mat <= tol && !std::isnan(e_mat), name << ": l2errorsquared matrix based " << e_mat << " <= " << tol);
+  EXPECT(e_free <= tol && !std::isnan(e_free), name << ": l2errorsquared matrix free " << e_free << " <= " << tol);
+  EXPECT(it_mat == it_free, name << ": same CG iteration count assembled/matrix-free (" << it_mat << ", " << it_free << ")");
+}
+
+// ---- test/testmatrixfree.cc: conforming Q2, Dirichlet constraints + interpolate --------------------
+template <int dim, int degree>
+void fem_case(int ncells, double tol, const char* name) {
+  using Grid = PDELab::YaspGrid<dim>;
+  std::array<int, dim> cells;
+  cells.fill(ncells);
+  Grid grid(PDELab::FieldVector<double, dim>(1.0), cells);
+  using GV = typename Grid::LeafGridView;
+  GV gv = grid.leafGridView();
+  using FEM = PDELab::QkLocalFiniteElementMap<GV, double, double, degree>;
+  FEM fem(gv);
+  using GFS = PDELab::GridFunctionSpace<GV, FEM, PDELab::ConformingDirichletConstraints, PDELab::ISTL::VectorBackend<>>;
+  GFS gfs(gv, fem);
+  using Problem = PoissonProblem<GV, double>;
+  Problem problem;
+  using LOP = PDELab::ConvectionDiffusionFEM<Problem, FEM>;
+  LOP lop(problem);
+  using MBE = PDELab::ISTL::BCRSMatrixBackend;
+  using CC = typename GFS::template ConstraintsContainer<double>::Type;
+  CC cc;
+  using GO = PDELab::GridOperator<GFS, GFS, LOP, MBE, double, double, double, CC, CC>;
+  GO go(gfs, cc, gfs, cc, lop, MBE(std::pow(2 * degree + 1, dim)));
+  PDELab::constraints(go, cc);
+  std::size_t expect_con = 1, inner = 1;
+  for (int d = 0; d < dim; d++) expect_con *= degree * ncells + 1, inner *= degree * ncells - 1;
+  EXPECT(cc.size() == expect_con - inner, name << ": constrained DOFs = " << cc.size());
+  using V = typename GO::Domain;
+  const std::size_t N = gfs.size();
+
+  // oracle parity on random data
+  std::mt19937_64 rng;
+  std::uniform_real_distribution<double> dist(0, 1);
+  V x(gfs), r(gfs, 0.0);
+  for (std::size_t i = 0; i < N; i++) x[i] = dist(rng);
+  go.residual(x, r);
+  std::vector<double> want(N, 0.0);
+  oracle_residual(&go.problem(), x.data(), want.data());
+  EXPECT(rel_err(r, want) < 1e-12, name << ": residual vs oracle " << rel_err(r, want));
+  typename GO::Jacobian A(go);
+  A = 0.0;
+  go.jacobian(x, A);
+  uint64_t nr = 0, nnz = 0;
+  oracle_pattern(&go.problem(), &nr, &nnz, nullptr, nullptr);
+  std::vector<uint64_t> orp(nr + 1), oci(nnz);
+  oracle_pattern(&go.problem(), &nr, &nnz, orp.data(), oci.data());
+  EXPECT(orp == A.rowptr() && oci == A.colidx(), name << ": sparsity pattern bit-exact vs oracle (" << nnz << " nnz)");
+  std::vector<double> ov(nnz, 0.0);
+  oracle_jacobian(&go.problem(), x.data(), ov.data());
+  EXPECT(rel_err(A.values(), ov) < 1e-12, name << ": jacobian values vs oracle " << rel_err(A.values(), ov));
+  // constrained rows are unit rows (assemblerutilities.hh:666-684)
+  bool unit = true;
+  for (auto i : cc.dofs)
+    for (uint64_t k2 = A.rowptr()[i]; k2 < A.rowptr()[i + 1]; k2++)
+      unit &= A.values()[k2] == (A.colidx()[k2] == i ? 1.0 : 0.0);
+  EXPECT(unit, name << ": constrained rows are identity rows");
+
+  // solve: u = interpolate(g); z from J z = -R(u); matrix-based and matrix-free
+  PDELab::ConvectionDiffusionDirichletExtensionAdapter<Problem> g(gv, problem);
+  V u(gfs, 0.0);
+  go.B200_interpolate(g, u);
+  PDELab::set_nonconstrained_dofs(cc, 0.0, u);
+  V res(gfs, 0.0), rhs(gfs, 0.0), z(gfs, 0.0);
+  go.residual(u, res);
+  rhs = res;
+  rhs *= -1.0;
+  // the Dirichlet-eliminated system is non-symmetric in its constrained columns (quirk viii) but the
+  // right-hand side vanishes there, so CG on the free block is what the iteration sees
+  PDELab::OnTheFlyOperator<V, V, GO> otf(go);
+  int it_mat = cg([&](const V& a, V& b) { A.mv(a, b); }, rhs, z, 1e-12, 5000);
+  V u_mat(u);
+  u_mat += z;
+  z = 0.0;
+  int it_free = cg([&](const V& a, V& b) { otf.apply(a, b); }, rhs, z, 1e-12, 5000);
+  V u_free(u);
+  u_free += z;
+  const double e_mat = l2_error_squared(gfs, u_mat, problem, go.handle(), degree);
+  const double e_free = l2_error_squared(gfs, u_free, problem, go.handle(), degree);
+  EXPECT(e_mat <= tol, name << ": l2errorsquared matrix based " << e_mat << " <= " << tol);
+  EXPECT(e_free <= tol, name << ": l2errorsquared matrix free " << e_free << " <= " << tol);
+  EXPECT(std::abs(it_mat - it_free) <= 1, name << ": CG iterations assembled/matrix-free (" << it_mat << ", " << it_free << ")");
+}
+
+int main() {
+  try {
+    dg_case<2, 1, PoissonProblem>(16, 3.0, 1e-6, "DG k=1 2D 16^2 (testconvectiondiffusiondg)", true);
+    dg_case<2, 2, LayeredProblem>(6, 3.0, 0, "DG k=2 2D 6^2 layered diagonal A + c", false);
+    dg_case<3, 2, LayeredProblem>(4, 3.0, 0, "DG k=2 3D 4^3 layered diagonal A + c (Kronecker kernel)", false);
+    dg_case<3, 2, PoissonProblem>(8, 3.0, 1e-6, "DG k=2 3D 8^3 Poisson (Kronecker kernel)", true);
+    fem_case<2, 2>(32, 1e-7, "Q2 2D 32^2 (testmatrixfree)");
+    fem_case<2, 1>(16, 1e-4, "Q1 2D 16^2");
+    fem_case<3, 2>(4, 1e-5, "Q2 3D 4^3");
+  } catch (std::exception& e) {
+    std::cerr << "exception: " << e.what() << std::endl;
+    return 2;
+  }
+  std::cout << (failures ? "FAILED" : "ALL OK") << " (" << failures << " failures)" << std::endl;
+  return failures ? 1 : 0;
+}
