@@ -146,7 +146,7 @@ def run_ours(args):
     import torch.distributed as dist
     from pdelab_b200 import abi
     from pdelab_b200.capi import GridOperator
-    from pdelab_b200.partition import OverlappingPartition, HaloExchanger, exchange_cell_field
+    from pdelab_b200.partition import OverlappingPartition, HaloExchanger, P2PHaloExchanger, exchange_cell_field
     from problems import kappa_field
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,16 +174,30 @@ def run_ours(args):
                            a_mode=abi.A_SCALAR, A=kappa, side_kind=part.side_kind, device=local_rank)
     go = GridOperator(spec)
     go.set_stream(torch.cuda.current_stream().cuda_stream)
-    halo = HaloExchanger(go, part, dev) if world > 1 else None
+    halo, halo_kind = None, "none"
+    if world > 1:
+        # default: peer-to-peer mailboxes over NVLink with the exchange hidden behind the interior
+        # tiles (csrc/halo.cu); --halo nccl: pack -> NCCL send/recv -> unpack, then the full kernel
+        if args.halo == "p2p":
+            try:
+                halo, halo_kind = P2PHaloExchanger(go, part, dist), "p2p-mailbox (CUDA IPC over NVLink), overlapped"
+            except Exception as e:  # noqa: BLE001  (no peer access on this box: say so, use NCCL)
+                print(f"rank {rank}: p2p halo unavailable ({e}); using NCCL", file=sys.stderr)
+        if halo is None:
+            halo, halo_kind = HaloExchanger(go, part, dev), "pack + NCCL send/recv + unpack, not overlapped"
     ndofs = spec.num_dofs
     owned_dofs = int(np.prod(part.owned_cells)) * 27
     z = torch.rand(ndofs, dtype=torch.float64, device=dev, generator=g)
     y = torch.empty_like(z)
 
     def step():
-        if halo is not None:
+        if halo is None:
+            go.apply(z, y)
+        elif isinstance(halo, P2PHaloExchanger):
+            halo.apply(z, y)
+        else:
             halo.exchange(z)
-        go.apply(z, y)
+            go.apply(z, y)
 
     def barrier():
         if world > 1:
@@ -204,6 +218,7 @@ def run_ours(args):
     e1.record()
     barrier()
     clocks = sampler.stop()
+    go.synchronize()  # raises if a peer-to-peer wait timed out
     ms_total = e0.elapsed_time(e1)
     launches = go.launch_count() - l0
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -253,8 +268,7 @@ def run_ours(args):
             go.apply(zh, yh)     # host pointers through the C ABI: H2D, kernel, D2H, synchronous on return
         else:
             z.copy_(zh, non_blocking=True)
-            halo.exchange(z)
-            go.apply(z, y)
+            step()
             yh.copy_(y, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -282,7 +296,7 @@ def run_ours(args):
                 "partition": "x".join(str(v) for v in part.procs), "overlap": 1 if world > 1 else 0,
                 "coefficients": "cell-wise scalar kappa=10^(2u-1), b=0, c=0, all-Dirichlet, alpha=3",
                 "cache": f"input+output {2 * ndofs * 8 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                "kernel": kernel_name,
+                "kernel": kernel_name, "halo": halo_kind,
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ndofs * 8, "d2h_bytes_per_step": ndofs * 8,
@@ -308,6 +322,7 @@ def main():
     ap.add_argument("--cells", type=int, default=128, help="cells per direction per GPU")
     ap.add_argument("--ref-cells", type=int, default=64, help="cells per direction of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost-layer exchange for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

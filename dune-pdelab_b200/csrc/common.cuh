@@ -102,12 +102,23 @@ bool dg_fast_supported(const DevParams& P);
 struct FastPlan;
 FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K);
 void dg_fast_plan_destroy(FastPlan*);
-void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual,
-                    bool overwrite, cudaStream_t s);
+// part: PDB200_PART_*; returns the number of kernel launches
+int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual,
+                   bool overwrite, int part, cudaStream_t s);
 
 
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);
+// halo.cu: peer-to-peer mailbox exchange over NVLink (CUDA IPC), see pdelab_b200.h
+struct P2PHalo;
+P2PHalo* p2p_create(const DevParams& P, pdb200_ipc_handle* mine);
+void p2p_connect(P2PHalo*, const DevParams& P, int dir, int side, const pdb200_ipc_handle* peer);
+void p2p_destroy(P2PHalo*);
+int p2p_push(P2PHalo*, const DevParams& P, const double* x, cudaStream_t s);       // returns launches
+int p2p_wait_unpack(P2PHalo*, const DevParams& P, double* x, cudaStream_t s);
+void p2p_check(P2PHalo*);  // throws if a spin-wait timed out
+cudaStream_t p2p_stream(P2PHalo*);
+cudaEvent_t p2p_event(P2PHalo*, int i);
 
 // fem.cu: conforming Qk residual / jacobian_apply (coloured scatter)
 struct FemPlan;

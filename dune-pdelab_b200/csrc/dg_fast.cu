@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -56,6 +57,19 @@ struct FastConst {
   double ih2[3];     // 1/h_d^2
   double alpha_pen;  // alpha * k (k + dim - 1)
   double theta, scale;  // scale = |K| / 27000
+};
+
+// Where the tiles sit in the local box.  Ghost layers in y and z (processor sides of an overlapping
+// partition) are kept OUT of the tiling: the tile origin is shifted by the lower ghost layer and
+// the active range ends before the upper one, so every rank tiles exactly its owned cells (same
+// work as a single-GPU run of that size); ghost rows are zeroed by the tiles next to them.
+// x is never shifted: the TMA view pairs cells along x (ghost cells in x are computed and zeroed
+// through the `constrained` path instead).
+struct TileFrame {
+  int off[3];  // first tile of this launch
+  int org[3];  // cell coordinate of tile (0,0,0)
+  int lim[3];  // exclusive upper bound of the tiled cell range
+  double* out; // the output vector (ghost rows are written with plain stores)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -228,11 +242,12 @@ template <int AMODE, bool HAS_C, bool WEIGHTS_ON>
 __global__ void __launch_bounds__(TX* TY* TZ, 3)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
-                         const DevParams P, const FastConst F) {
+                         const DevParams P, const FastConst F, const TileFrame TF) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
+  const int x0 = (blockIdx.x + TF.off[0]) * TX, y0 = TF.org[1] + (blockIdx.y + TF.off[1]) * TY,
+            z0 = TF.org[2] + (blockIdx.z + TF.off[2]) * TZ;
 
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   const int cz = tid >> 5;
   const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
   const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
-  const bool active = gx < Nx && gy < Ny && gz < Nz;
+  const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
 
   // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
   // before the first use so that the L2 round trips overlap instead of adding up; everything up
@@ -329,17 +344,35 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     }
   }
   __syncthreads();  // every thread is done reading the input tile: reuse R0 as the output stage
-  if (active) {
+  {  // the TMA store writes the whole box (clipped to the vector): cells of the box outside the
+     // tiled range are ghost rows, which are zero
     const int dst = ((cz * TY + cy) * TX + cx) * NLOC;
 #pragma unroll
-    for (int i = 0; i < NLOC; i++) tile[dst + i] = t[i];
+    for (int i = 0; i < NLOC; i++) tile[dst + i] = active ? t[i] : 0.0;
   }
   fence_proxy_async();
   __syncthreads();
-  if (tid == 0) {
-    tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
-    tma_store_commit_and_wait();
+  if (tid == 0) tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+
+  // ---- rows of the ghost layers in y / z next to this tile := 0 (constraints/p0.hh:31-41 +
+  // constrain_residual); only tiles at the ends of the tiled range take this path ----------------
+  const bool gzl = TF.org[2] && z0 == TF.org[2], gzu = TF.lim[2] < Nz && z0 + TZ >= TF.lim[2];
+  const bool gyl = TF.org[1] && y0 == TF.org[1], gyu = TF.lim[1] < Ny && y0 + TY >= TF.lim[1];
+  if (gzl | gzu | gyl | gyu) {
+    const int ya = gyl ? 0 : y0, yb = gyu ? Ny : min(y0 + TY, TF.lim[1]);
+    const int za = gzl ? 0 : z0, zb = gzu ? Nz : min(z0 + TZ, TF.lim[2]);
+    const int nx = (min(x0 + TX, Nx) - x0) * NLOC;
+    double* __restrict__ yout = TF.out;
+    for (int zz = za; zz < zb; zz++)
+      for (int yy = ya; yy < yb; yy++) {
+        const bool ghost = (TF.org[1] && yy == 0) || (TF.lim[1] < Ny && yy == Ny - 1) || (TF.org[2] && zz == 0) ||
+                           (TF.lim[2] < Nz && zz == Nz - 1);
+        if (!ghost) continue;
+        double* row = yout + (((long long)zz * Ny + yy) * Nx + x0) * NLOC;
+        for (int i = tid; i < nx; i += TX * TY * TZ) row[i] = 0.0;
+      }
   }
+  if (tid == 0) tma_store_commit_and_wait();
 }
 
 __global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ t, long long n) {
@@ -433,9 +466,41 @@ static FastPlan::Maps& get_maps(FastPlan* plan, const void* ptr, const DevParams
   return plan->cache.back();
 }
 
-void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
-                    cudaStream_t s) {
+// Tiles whose face halo reads a ghost cell layer (a side of kind PDB200_SIDE_PROCESSOR) are the
+// "boundary" part; the rest, a box of tiles, is the "interior" part, which can run while the halo
+// exchange is in flight.  Returns the interior tile box [lo, hi) per direction.
+static void tile_frame(const DevParams& P, TileFrame& F, int nt[3]) {
+  const int T[3] = {TX, TY, TZ};
+  for (int d = 0; d < 3; d++) {
+    const bool glo = d > 0 && P.side_kind[d][0] == PDB200_SIDE_PROCESSOR;
+    const bool ghi = d > 0 && P.side_kind[d][1] == PDB200_SIDE_PROCESSOR;
+    F.off[d] = 0;
+    F.org[d] = glo ? 1 : 0;
+    F.lim[d] = P.N[d] - (ghi ? 1 : 0);
+    nt[d] = std::max(0, (F.lim[d] - F.org[d] + T[d] - 1) / T[d]);
+  }
+}
+
+static void interior_tile_box(const DevParams& P, const TileFrame& F, const int nt[3], int lo[3], int hi[3]) {
+  const int T[3] = {TX, TY, TZ};
+  for (int d = 0; d < 3; d++) {
+    lo[d] = 0;
+    hi[d] = nt[d];
+    // tile t covers cells [org + t T, org + (t+1) T) and reads one more layer on either side
+    if (P.side_kind[d][0] == PDB200_SIDE_PROCESSOR) lo[d] = 1;  // tile 0 reads the ghost layer 0
+    if (P.side_kind[d][1] == PDB200_SIDE_PROCESSOR) {
+      int t = 0;
+      while (t < nt[d] && F.org[d] + (t + 1) * T[d] < P.N[d] - 1) t++;  // first tile that reaches layer N-1
+      hi[d] = t;
+    }
+    if (hi[d] < lo[d]) hi[d] = lo[d];
+  }
+}
+
+int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+                   int part, cudaStream_t s) {
   if (residual) throw Error("fast DG kernel implements jacobian_apply only");
+  if (part != PDB200_PART_ALL && !overwrite) throw Error("partial application needs the overwrite form");
   double* out = y;
   if (!overwrite) {  // accumulate semantics (y += J z) through a scratch vector
     if (plan->scratch_n < P.ndofs) {
@@ -447,9 +512,37 @@ void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double*
   }
   const FastPlan::Maps mx = get_maps(plan, x, P);
   const FastPlan::Maps my = get_maps(plan, out, P);
-  dim3 grid((P.N[0] + TX - 1) / TX, (P.N[1] + TY - 1) / TY, (P.N[2] + TZ - 1) / TZ);
+  TileFrame TF;
+  int nt[3];
+  tile_frame(P, TF, nt);
+  TF.out = out;
+  // boxes of tiles to launch: {offset, extent}
+  int boxes[7][6], nboxes = 0;
+  auto add = [&](int ox, int oy, int oz, int ex, int ey, int ez) {
+    if (ex <= 0 || ey <= 0 || ez <= 0) return;
+    const int b[6] = {ox, oy, oz, ex, ey, ez};
+    for (int i = 0; i < 6; i++) boxes[nboxes][i] = b[i];
+    nboxes++;
+  };
+  if (part == PDB200_PART_ALL) {
+    add(0, 0, 0, nt[0], nt[1], nt[2]);
+  } else {
+    int lo[3], hi[3];
+    interior_tile_box(P, TF, nt, lo, hi);
+    if (part == PDB200_PART_INTERIOR) {
+      add(lo[0], lo[1], lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+    } else {  // the complement as up to six slabs
+      add(0, 0, 0, nt[0], nt[1], lo[2]);
+      add(0, 0, hi[2], nt[0], nt[1], nt[2] - hi[2]);
+      add(0, 0, lo[2], nt[0], lo[1], hi[2] - lo[2]);
+      add(0, hi[1], lo[2], nt[0], nt[1] - hi[1], hi[2] - lo[2]);
+      add(0, lo[1], lo[2], lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+      add(hi[0], lo[1], lo[2], nt[0] - hi[0], hi[1] - lo[1], hi[2] - lo[2]);
+    }
+  }
+  int launches = 0;
 #define PDB_LAUNCH(AM, HC, WO) \
-  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F)
+  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F, TF)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \
     if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \
@@ -458,16 +551,23 @@ void launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double*
     else PDB_LAUNCH(AM, false, false);                  \
   } while (0)
   const int am = P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR ? P.a_mode : PDB200_A_DIAGONAL;
-  if (am == PDB200_A_IDENTITY) PDB_LAUNCH_A(PDB200_A_IDENTITY);
-  else if (am == PDB200_A_SCALAR) PDB_LAUNCH_A(PDB200_A_SCALAR);
-  else PDB_LAUNCH_A(PDB200_A_DIAGONAL);
+  for (int b = 0; b < nboxes; b++) {
+    for (int d = 0; d < 3; d++) TF.off[d] = boxes[b][d];
+    const dim3 grid(boxes[b][3], boxes[b][4], boxes[b][5]);
+    if (am == PDB200_A_IDENTITY) PDB_LAUNCH_A(PDB200_A_IDENTITY);
+    else if (am == PDB200_A_SCALAR) PDB_LAUNCH_A(PDB200_A_SCALAR);
+    else PDB_LAUNCH_A(PDB200_A_DIAGONAL);
+    launches++;
+  }
 #undef PDB_LAUNCH_A
 #undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
   if (!overwrite) {
     axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, P.ndofs);
     PDB_CUDA(cudaGetLastError());
+    launches++;
   }
+  return launches;
 }
 
 }  // namespace pdb

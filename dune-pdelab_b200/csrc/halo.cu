@@ -6,6 +6,9 @@
 // (dir, side) is the owned cell layer at distance 1 from that box face, and the data received
 // fills the ghost layer at distance 0.  A DG cell is n contiguous doubles, so the copy is a
 // strided block copy; consecutive threads move consecutive doubles of a cell.
+#include <cstddef>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace pdb {
@@ -47,5 +50,263 @@ void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int s
   halo_copy_kernel<<<blocks, threads, 0, s>>>(P, x, buf, dir, layer, pack ? 1 : 0, total);
   PDB_CUDA(cudaGetLastError());
 }
+
+}  // namespace pdb
+
+// ---------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange over NVLink: every rank owns a MAILBOX in device memory (receive
+// buffers for its processor sides + flags), shared with its face neighbours through CUDA IPC.
+//   push   (sender):   wait until the neighbour has consumed the previous epoch (ack), copy the owned
+//                      boundary layer of x straight into the neighbour's receive buffer with remote
+//                      stores, __threadfence_system(), then the last CTA publishes ready = epoch.
+//   unpack (receiver): spin on the local ready flag, copy the receive buffer into the ghost layer
+//                      of x, then the last CTA sends ack = epoch to the sender.
+// No NCCL call, no host round trip: two kernels per exchange regardless of the number of sides,
+// and they run on a high-priority side stream while the interior tiles are computed.
+// Replaces the CopyDataHandle communication of boilerplate/pdelab.hh:872-880 /
+// gridfunctionspace/genericdatahandle.hh on the reference's overlapping partition.
+
+namespace pdb {
+
+namespace {
+
+struct MailboxHeader {
+  unsigned long long ready[6];      // [my side] epoch of the data the neighbour across that side has delivered
+  unsigned long long ack[6];        // [my side] last epoch the neighbour across that side has consumed
+  unsigned long long buf_off[6];    // byte offset of the receive buffer of each side
+  unsigned long long layer_doubles[6];
+  unsigned long long magic;
+};
+constexpr unsigned long long MAILBOX_MAGIC = 0x70646232303068ull;  // "pdb200h"
+constexpr unsigned long long SPIN_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
+
+struct SideDesc {
+  int active, dir, layer_src, layer_dst;
+  long long total;                 // doubles in the layer
+  double* peer_buf;                // receive buffer in the NEIGHBOUR's mailbox for its side (dir, 1-side)
+  unsigned long long* peer_ready;  // neighbour's ready[(dir, 1-side)]
+  unsigned long long* peer_ack;    // neighbour's ack[(dir, 1-side)]
+  const double* my_buf;            // my receive buffer for this side
+  unsigned long long* my_ready;
+  unsigned long long* my_ack;
+};
+struct SideTable {
+  SideDesc s[6];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// thread 0 spins until *flag >= want (or the timeout expires: sets *err, never hangs the GPU)
+__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long want, int* err) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < want) {
+      if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ long long layer_dof(const DevParams& P, int dir, int layer, long long i) {
+  const long long f = i / P.n;
+  const int k = (int)(i - f * P.n);
+  int c[3] = {0, 0, 0};
+  long long ff = f;
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    if (d != dir && d < P.dim) {
+      c[d] = (int)(ff % P.N[d]);
+      ff /= P.N[d];
+    }
+  c[dir] = layer;
+  return cell_index(P.N, c[0], c[1], c[2]) * P.n + k;
+}
+
+// grid = (blocks per side, 6)
+__global__ void p2p_push_kernel(const DevParams P, const SideTable T, const double* __restrict__ x,
+                                unsigned long long epoch, unsigned int* counters, int* err) {
+  const SideDesc& S = T.s[blockIdx.y];
+  if (!S.active) return;
+  spin_until(S.my_ack, epoch - 1, err);  // the neighbour has emptied its receive buffer
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.total; i += stride)
+    S.peer_buf[i] = x[layer_dof(P, S.dir, S.layer_src, i)];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&counters[blockIdx.y], 1u);
+    if (done == gridDim.x - 1) {
+      counters[blockIdx.y] = 0;
+      __threadfence_system();
+      st_release_sys(S.peer_ready, epoch);
+    }
+  }
+}
+
+__global__ void p2p_unpack_kernel(const DevParams P, const SideTable T, double* __restrict__ x,
+                                  unsigned long long epoch, unsigned int* counters, int* err) {
+  const SideDesc& S = T.s[blockIdx.y];
+  if (!S.active) return;
+  spin_until(S.my_ready, epoch, err);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.total; i += stride)
+    x[layer_dof(P, S.dir, S.layer_dst, i)] = S.my_buf[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&counters[6 + blockIdx.y], 1u);
+    if (done == gridDim.x - 1) {
+      counters[6 + blockIdx.y] = 0;
+      st_release_sys(S.peer_ack, epoch);
+    }
+  }
+}
+
+}  // namespace
+
+struct P2PHalo {
+  unsigned char* mailbox = nullptr;  // device memory of this rank (cudaMalloc, IPC-exported)
+  size_t mailbox_bytes = 0;
+  MailboxHeader header;              // host copy
+  void* peer_base[6] = {};           // mapped mailboxes of the neighbours
+  SideTable table;
+  unsigned int* counters = nullptr;  // [12]
+  int* err = nullptr;
+  unsigned long long epoch = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {};
+  int nactive = 0;
+};
+
+P2PHalo* p2p_create(const DevParams& P, pdb200_ipc_handle* mine) {
+  if (!P.dg) throw Error("p2p halo exchange is implemented for QkDG spaces");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(pdb200_ipc_handle), "handle size");
+  P2PHalo* H = new P2PHalo;
+  std::memset(&H->header, 0, sizeof(H->header));
+  std::memset(&H->table, 0, sizeof(H->table));
+  size_t off = (sizeof(MailboxHeader) + 255) / 256 * 256;
+  for (int d = 0; d < P.dim; d++)
+    for (int s = 0; s < 2; s++) {
+      if (P.side_kind[d][s] != PDB200_SIDE_PROCESSOR) continue;
+      if (P.N[d] < 3) throw Error("halo exchange needs at least 3 cell layers in the exchange direction");
+      const unsigned long long n = (unsigned long long)(P.ncells / P.N[d]) * P.n;
+      H->header.buf_off[2 * d + s] = off;
+      H->header.layer_doubles[2 * d + s] = n;
+      off += (n * sizeof(double) + 255) / 256 * 256;
+    }
+  H->header.magic = MAILBOX_MAGIC;
+  H->mailbox_bytes = off;
+  PDB_CUDA(cudaMalloc(&H->mailbox, off));
+  PDB_CUDA(cudaMemset(H->mailbox, 0, off));
+  PDB_CUDA(cudaMemcpy(H->mailbox, &H->header, sizeof(H->header), cudaMemcpyHostToDevice));
+  PDB_CUDA(cudaMalloc(&H->counters, 12 * sizeof(unsigned int)));
+  PDB_CUDA(cudaMemset(H->counters, 0, 12 * sizeof(unsigned int)));
+  PDB_CUDA(cudaMalloc(&H->err, sizeof(int)));
+  PDB_CUDA(cudaMemset(H->err, 0, sizeof(int)));
+  int lo = 0, hi = 0;
+  PDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  PDB_CUDA(cudaStreamCreateWithPriority(&H->stream, cudaStreamNonBlocking, hi));
+  for (auto& e : H->ev) PDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaIpcMemHandle_t ih;
+  PDB_CUDA(cudaIpcGetMemHandle(&ih, H->mailbox));
+  std::memset(mine, 0, sizeof(*mine));
+  std::memcpy(mine->bytes, &ih, sizeof(ih));
+  PDB_CUDA(cudaDeviceSynchronize());
+  return H;
+}
+
+void p2p_connect(P2PHalo* H, const DevParams& P, int dir, int side, const pdb200_ipc_handle* peer) {
+  if (dir < 0 || dir >= P.dim || side < 0 || side > 1) throw Error("invalid (dir, side)");
+  if (P.side_kind[dir][side] != PDB200_SIDE_PROCESSOR) throw Error("p2p_connect: not a processor side");
+  const int s = 2 * dir + side, sp = 2 * dir + (1 - side);  // my side, the neighbour's side facing me
+  cudaIpcMemHandle_t ih;
+  std::memcpy(&ih, peer->bytes, sizeof(ih));
+  void* base = nullptr;
+  PDB_CUDA(cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess));
+  H->peer_base[s] = base;
+  MailboxHeader ph;
+  PDB_CUDA(cudaMemcpy(&ph, base, sizeof(ph), cudaMemcpyDeviceToHost));
+  if (ph.magic != MAILBOX_MAGIC) throw Error("p2p_connect: the peer handle is not a pdelab_b200 mailbox");
+  if (ph.layer_doubles[sp] != H->header.layer_doubles[s])
+    throw Error("p2p_connect: the neighbour's layer size differs (inconsistent partition)");
+  unsigned char* pb = (unsigned char*)base;
+  SideDesc& S = H->table.s[s];
+  S.active = 1;
+  S.dir = dir;
+  S.layer_src = side ? P.N[dir] - 2 : 1;
+  S.layer_dst = side ? P.N[dir] - 1 : 0;
+  S.total = (long long)H->header.layer_doubles[s];
+  S.peer_buf = (double*)(pb + ph.buf_off[sp]);
+  S.peer_ready = (unsigned long long*)(pb + offsetof(MailboxHeader, ready)) + sp;
+  S.peer_ack = (unsigned long long*)(pb + offsetof(MailboxHeader, ack)) + sp;
+  S.my_buf = (const double*)(H->mailbox + H->header.buf_off[s]);
+  S.my_ready = (unsigned long long*)(H->mailbox + offsetof(MailboxHeader, ready)) + s;
+  S.my_ack = (unsigned long long*)(H->mailbox + offsetof(MailboxHeader, ack)) + s;
+  H->nactive++;
+}
+
+void p2p_destroy(P2PHalo* H) {
+  if (!H) return;
+  cudaDeviceSynchronize();
+  for (void* b : H->peer_base)
+    if (b) cudaIpcCloseMemHandle(b);
+  if (H->mailbox) cudaFree(H->mailbox);
+  if (H->counters) cudaFree(H->counters);
+  if (H->err) cudaFree(H->err);
+  if (H->stream) cudaStreamDestroy(H->stream);
+  for (auto& e : H->ev)
+    if (e) cudaEventDestroy(e);
+  delete H;
+}
+
+static void p2p_require_connected(P2PHalo* H, const DevParams& P) {
+  int need = 0;
+  for (int d = 0; d < P.dim; d++)
+    for (int s = 0; s < 2; s++) need += P.side_kind[d][s] == PDB200_SIDE_PROCESSOR;
+  if (H->nactive != need) throw Error("p2p halo: not every processor side is connected");
+}
+
+int p2p_push(P2PHalo* H, const DevParams& P, const double* x, cudaStream_t s) {
+  p2p_require_connected(H, P);
+  if (H->nactive == 0) return 0;
+  H->epoch++;
+  p2p_push_kernel<<<dim3(24, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  PDB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int p2p_wait_unpack(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
+  if (H->nactive == 0) return 0;
+  p2p_unpack_kernel<<<dim3(24, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  PDB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+void p2p_check(P2PHalo* H) {
+  int e = 0;
+  PDB_CUDA(cudaMemcpy(&e, H->err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(H->err, 0, sizeof(int));
+    throw Error("p2p halo exchange timed out waiting for a neighbour");
+  }
+}
+
+cudaStream_t p2p_stream(P2PHalo* H) { return H->stream; }
+cudaEvent_t p2p_event(P2PHalo* H, int i) { return H->ev[i]; }
 
 }  // namespace pdb

@@ -34,6 +34,7 @@ struct pdb200_operator {
   FastPlan* fast = nullptr;
   FemPlan* fem = nullptr;
   MatrixPlan* matrix = nullptr;
+  P2PHalo* p2p = nullptr;
   uint64_t launches = 0;
   const char* last_kernel = "";
   std::vector<double> xq, wq;
@@ -47,6 +48,7 @@ struct pdb200_operator {
     dg_fast_plan_destroy(fast);
     fem_plan_destroy(fem);
     matrix_plan_destroy(matrix);
+    p2p_destroy(p2p);
   }
 };
 
@@ -102,10 +104,23 @@ void check_errflag(pdb200_operator* op) {
 enum class Mode { Residual, JacobianApply, OnTheFly };
 
 // run one vector kernel on device pointers
-void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mode) {
+void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mode, int part = PDB200_PART_ALL,
+                       cudaStream_t stream_override = nullptr) {
   const DevParams& P = op->P;
+  struct StreamGuard {  // the BOUNDARY part of apply_p2p runs on the side stream
+    pdb200_operator* op;
+    cudaStream_t saved;
+    ~StreamGuard() { op->stream = saved; }
+  } guard{op, op->stream};
+  if (stream_override) op->stream = stream_override;
   const bool residual = mode == Mode::Residual;
   const bool overwrite = mode == Mode::OnTheFly;
+  bool use_fast0 = P.dg && !residual && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
+  if (part != PDB200_PART_ALL && !use_fast0) {
+    // kernels without a tile decomposition: everything runs in the BOUNDARY phase (after the exchange)
+    if (part == PDB200_PART_INTERIOR) return;
+    part = PDB200_PART_ALL;
+  }
   if (!P.dg) {
     launch_fem_vector(op->fem, P, x, y, residual, overwrite, op->stream);
     op->last_kernel = residual ? "fem_residual" : "fem_jacobian_apply";
@@ -118,9 +133,8 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
                 "(needs QkDG k=2, dim=3, diagonal A, b=0, even cells[0], jacobian_apply)");
   if (use_fast) {
     if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
-    launch_dg_fast(op->fast, P, x, y, residual, overwrite, op->stream);
+    op->launches += launch_dg_fast(op->fast, P, x, y, residual, overwrite, part, op->stream);
     op->last_kernel = "dg_fast_q2_3d";
-    op->launches += overwrite ? 1 : 2;
   } else {
     launch_dg_generic(P, x, y, residual, overwrite, op->errflag, op->stream);
     op->last_kernel = residual ? "dg_generic_residual" : "dg_generic_jacobian_apply";
@@ -498,6 +512,64 @@ int pdb200_halo_unpack(pdb200_handle h, double* x, int dir, int side, const doub
   PDB_CATCH
 }
 
+int pdb200_onthefly_apply_part(pdb200_handle h, const double* x, double* y, int part) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (part < PDB200_PART_ALL || part > PDB200_PART_BOUNDARY) throw Error("invalid part");
+  if (!is_device_pointer(x) || !is_device_pointer(y)) throw Error("apply_part expects device pointers");
+  run_vector_device(h, x, y, Mode::OnTheFly, part);
+  PDB_CATCH
+}
+
+int pdb200_halo_p2p_create(pdb200_handle h, pdb200_ipc_handle* mine) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!mine) throw Error("null argument");
+  if (h->p2p) throw Error("p2p mailbox already created");
+  h->p2p = p2p_create(h->P, mine);
+  PDB_CATCH
+}
+int pdb200_halo_p2p_connect(pdb200_handle h, int dir, int side, const pdb200_ipc_handle* neighbour) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->p2p) throw Error("call pdb200_halo_p2p_create first");
+  if (!neighbour) throw Error("null argument");
+  p2p_connect(h->p2p, h->P, dir, side, neighbour);
+  PDB_CATCH
+}
+int pdb200_halo_exchange_p2p(pdb200_handle h, double* x) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->p2p) throw Error("call pdb200_halo_p2p_create / _connect first");
+  if (!is_device_pointer(x)) throw Error("halo_exchange_p2p expects a device pointer");
+  h->launches += p2p_push(h->p2p, h->P, x, h->stream);
+  h->launches += p2p_wait_unpack(h->p2p, h->P, x, h->stream);
+  PDB_CATCH
+}
+int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->p2p) throw Error("call pdb200_halo_p2p_create / _connect first");
+  if (!is_device_pointer(x) || !is_device_pointer(y)) throw Error("apply_p2p expects device pointers");
+  cudaStream_t side = p2p_stream(h->p2p);
+  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 0), h->stream));  // x is ready
+  PDB_CUDA(cudaStreamWaitEvent(side, p2p_event(h->p2p, 0), 0));
+  h->launches += p2p_push(h->p2p, h->P, x, side);
+  h->launches += p2p_wait_unpack(h->p2p, h->P, x, side);
+  // the boundary tiles follow the unpack on the (high-priority) side stream, so they fill in
+  // beside the last interior tiles instead of waiting for them; the outputs are disjoint
+  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_BOUNDARY, side);
+  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 1), side));
+  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_INTERIOR);
+  PDB_CUDA(cudaStreamWaitEvent(h->stream, p2p_event(h->p2p, 1), 0));
+  PDB_CATCH
+}
+
 int pdb200_set_stream(pdb200_handle h, void* stream) {
   PDB_TRY
   PDB_CHECK_HANDLE(h);
@@ -509,6 +581,7 @@ int pdb200_synchronize(pdb200_handle h) {
   PDB_CHECK_HANDLE(h);
   ensure_device(h);
   PDB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->p2p) p2p_check(h->p2p);
   PDB_CATCH
 }
 int pdb200_launch_count(pdb200_handle h, uint64_t* n) {

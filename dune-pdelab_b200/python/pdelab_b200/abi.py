@@ -15,6 +15,7 @@ A_IDENTITY, A_SCALAR, A_DIAGONAL, A_FULL = 0, 1, 2, 3
 SIDE_DOMAIN, SIDE_PROCESSOR = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 LAYOUT_CSR, LAYOUT_BCSR = 0, 1
+PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 
 
 class Problem(C.Structure):

@@ -33,6 +33,8 @@ SYMBOLS = [
     "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
     "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
+    "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
+    "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
 ]
 
@@ -67,6 +69,11 @@ def load_library():
     lib.pdb200_halo_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.pdb200_halo_unpack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.pdb200_set_stream.argtypes = [vp, vp]
+    lib.pdb200_onthefly_apply_part.argtypes = [vp, vp, vp, C.c_int]
+    lib.pdb200_halo_p2p_create.argtypes = [vp, vp]
+    lib.pdb200_halo_p2p_connect.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.pdb200_halo_exchange_p2p.argtypes = [vp, vp]
+    lib.pdb200_onthefly_apply_p2p.argtypes = [vp, vp, vp]
     lib.pdb200_cell_dof_indices.argtypes = [vp, C.c_uint64, vp]
     lib.pdb200_constrained_dofs.argtypes = [vp, u64p, vp]
     lib.pdb200_quadrature.argtypes = [vp, vp, vp]
@@ -233,6 +240,29 @@ class GridOperator:
 
     def halo_unpack(self, x, d, side, buf):
         self._chk(self.lib.pdb200_halo_unpack(self._h, _ptr(x), d, side, _ptr(buf)))
+
+    def apply_part(self, x, y, part):
+        """y = J x restricted to the INTERIOR or BOUNDARY tiles of the local box (abi.PART_*)."""
+        self._chk(self.lib.pdb200_onthefly_apply_part(self._h, _ptr(x), _ptr(y), part))
+        return y
+
+    def halo_p2p_create(self):
+        """Create this rank's mailbox; returns the 64-byte IPC handle to give to the neighbours."""
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.pdb200_halo_p2p_create(self._h, buf))
+        return buf.raw
+
+    def halo_p2p_connect(self, d, side, handle_bytes):
+        buf = C.create_string_buffer(bytes(handle_bytes), 64)
+        self._chk(self.lib.pdb200_halo_p2p_connect(self._h, d, side, buf))
+
+    def halo_exchange_p2p(self, x):
+        self._chk(self.lib.pdb200_halo_exchange_p2p(self._h, _ptr(x)))
+
+    def apply_p2p(self, x, y):
+        """y = J x on the overlapping partition, exchange hidden behind the interior tiles."""
+        self._chk(self.lib.pdb200_onthefly_apply_p2p(self._h, _ptr(x), _ptr(y)))
+        return y
 
     # misc ----------------------------------------------------------------------------------
     def set_stream(self, stream_ptr):

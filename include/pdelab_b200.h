@@ -176,6 +176,29 @@ int pdb200_halo_layer_size(pdb200_handle h, int dir, uint64_t* ndoubles);
 int pdb200_halo_pack(pdb200_handle h, const double* x, int dir, int side, double* buf);
 int pdb200_halo_unpack(pdb200_handle h, double* x, int dir, int side, const double* buf);
 
+/* Parts of the local box for overlapping communication with computation: INTERIOR = every tile
+ * of cells that reads no ghost layer (can run while the halo exchange is in flight), BOUNDARY =
+ * the rest.  INTERIOR followed by BOUNDARY equals ALL.  Device pointers only, y is overwritten. */
+enum { PDB200_PART_ALL = 0, PDB200_PART_INTERIOR = 1, PDB200_PART_BOUNDARY = 2 };
+int pdb200_onthefly_apply_part(pdb200_handle h, const double* x, double* y, int part);
+
+/* Peer-to-peer halo exchange over NVLink / NVSwitch without NCCL or host round trips (one process
+ * per GPU, CUDA IPC).  Every rank creates a MAILBOX (receive buffers for its processor sides +
+ * ready/ack flags) and hands the returned handle to its face neighbours out of band (the Python
+ * host uses one torch.distributed all_gather at set-up); each processor side is then connected
+ * to the neighbour's mailbox.  Replaces the same CopyDataHandle communication as the pack/unpack
+ * entry points above. */
+typedef struct pdb200_ipc_handle { unsigned char bytes[64]; } pdb200_ipc_handle;
+int pdb200_halo_p2p_create(pdb200_handle h, pdb200_ipc_handle* mine);
+int pdb200_halo_p2p_connect(pdb200_handle h, int dir, int side, const pdb200_ipc_handle* neighbour);
+/* owner -> ghost copy of the DEVICE vector x across all connected sides (two kernels: push into
+ * the neighbours' mailboxes, wait + unpack); asynchronous on the handle's stream */
+int pdb200_halo_exchange_p2p(pdb200_handle h, double* x);
+/* y = J x on the overlapping partition with the exchange hidden behind the interior tiles:
+ * side stream: push, wait + unpack, BOUNDARY;  main stream: INTERIOR, (join).
+ * x's ghost layers are updated as a side effect.  Device pointers only. */
+int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y);
+
 /* stream control for device-pointer calls: `stream` is a cudaStream_t */
 int pdb200_set_stream(pdb200_handle h, void* stream);
 int pdb200_synchronize(pdb200_handle h);

@@ -1,0 +1,131 @@
+"""Overlapping partition on the CUDA path: interior/boundary split of the fast kernel and the
+peer-to-peer (CUDA IPC mailbox) halo exchange, world_size 2 and 4.  All ranks share cuda:0 when the
+box has fewer GPUs than ranks (IPC between processes works on one device, NCCL would not), the
+set-up handshake runs over gloo.  Parity definition of SURVEY.md §8e: owned rows of the
+distributed result equal the single-domain oracle on the global grid to 1e-12."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from pdelab_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_interior_plus_boundary_equals_all(cuda_lib):
+    from pdelab_b200.capi import GridOperator
+    from problems import kappa_field
+    cells = (12, 10, 13)
+    nc = int(np.prod(cells))
+    for side_kind in ([[0, 0], [0, 1], [1, 1]], [[0, 0], [1, 0], [0, 1]], [[0, 0], [0, 0], [0, 0]]):
+        spec = abi.ProblemSpec(cells, degree=2, alpha=3.0, a_mode=abi.A_SCALAR, A=kappa_field(nc), side_kind=side_kind)
+        go = GridOperator(spec)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x = torch.rand(spec.num_dofs, dtype=torch.float64, device="cuda", generator=g)
+        y_all = torch.full_like(x, float("nan"))
+        y_split = torch.full_like(x, float("nan"))
+        go.apply(x, y_all)
+        go.apply_part(x, y_split, abi.PART_INTERIOR)
+        torch.cuda.synchronize()
+        n_int = int((~torch.isnan(y_split)).sum())
+        go.apply_part(x, y_split, abi.PART_BOUNDARY)
+        torch.cuda.synchronize()
+        assert go.last_kernel() == "dg_fast_q2_3d"
+        assert torch.equal(y_all, y_split)            # same kernel, same tiles: bit-identical
+        if any(any(r) for r in side_kind):
+            assert 0 < n_int < spec.num_dofs          # the interior part is a strict, non-empty subset
+        else:
+            assert n_int == spec.num_dofs
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, cells, out):
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [os.path.join(here, "..", "oracle"), here, os.path.join(here, "..", "dune-pdelab_b200", "python")]
+        import torch.distributed as dist
+        from oracle import Oracle
+        from pdelab_b200.capi import GridOperator
+        from pdelab_b200.partition import OverlappingPartition, P2PHaloExchanger
+        from problems import kappa_field, mt_vector
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ndev = torch.cuda.device_count()
+        dev = rank % ndev
+        torch.cuda.set_device(dev)
+        part = OverlappingPartition.strong(cells, world, rank)
+        n = 27
+        ncg = int(np.prod(cells))
+        zg = mt_vector(ncg * n).reshape(ncg, n)
+        kg = kappa_field(ncg)
+        gidx = part.local_cell_grid().reshape(-1)
+        own = part.owned_mask().reshape(-1)
+        z = np.full((gidx.size, n), 1e300)          # ghosts poisoned: the exchange must fill them
+        z[own] = zg[gidx[own]]
+        spec = abi.ProblemSpec(part.local_cells, degree=2, lower=part.local_lower, upper=part.local_upper, alpha=3.0,
+                               a_mode=abi.A_SCALAR, A=kg[gidx], side_kind=part.side_kind, device=dev)
+        go = GridOperator(spec)
+        halo = P2PHaloExchanger(go, part, dist)
+        zd = torch.from_numpy(z.reshape(-1)).cuda()
+        yd = torch.full_like(zd, float("nan"))
+        want = Oracle(abi.ProblemSpec(cells, degree=2, alpha=3.0, a_mode=abi.A_SCALAR, A=kg)).jacobian_apply(
+            zg.reshape(-1)).reshape(-1, n)
+        errs = []
+        for it in range(3):                          # several epochs: flags/acks must keep working
+            halo.apply(zd, yd)
+            go.synchronize()
+            y = yd.cpu().numpy().reshape(-1, n)
+            errs.append(float(np.abs(y[own] - want[gidx[own]]).max() / np.abs(want).max()))
+        # face ghosts now hold the neighbour's owned values
+        zl = zd.cpu().numpy().reshape(-1, n)
+        lc = part.local_cells
+        coords = np.unravel_index(np.arange(gidx.size), lc[::-1])   # (z, y, x)
+        outside = np.zeros(gidx.size, dtype=int)
+        for d in range(3):
+            c = coords[2 - d] + part.local_lo[d]
+            outside += ~((part.owned_lo[d] <= c) & (c < part.owned_hi[d]))
+        face_ghost = outside == 1
+        ok_ghost = bool(face_ghost.any()) and bool(np.array_equal(zl[face_ghost], zg[gidx[face_ghost]]))
+        # plain exchange entry point too
+        zd2 = torch.from_numpy(z.reshape(-1)).cuda()
+        halo.exchange(zd2)
+        go.synchronize()
+        # (edge/corner ghosts carry whatever the neighbour's own ghosts held: never read by owned rows)
+        keep = torch.from_numpy(outside <= 1).cuda()
+        same = bool(torch.equal(zd2.view(-1, n)[keep], zd.view(-1, n)[keep]))
+        out.put((rank, max(errs), ok_ghost and same, go.last_kernel(), None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out.put((rank, 1.0, False, "", traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world,cells", [(2, (8, 6, 12)), (4, (8, 12, 10))])
+def test_p2p_halo_apply_matches_global_oracle(cuda_lib, world, cells):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cells, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, ok, kern, tb in res:
+        assert tb is None, tb
+        assert err < 1e-12, (rank, err)
+        assert ok, rank
+        assert kern == "dg_fast_q2_3d"
