@@ -103,9 +103,18 @@ struct FastPlan;
 FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K);
 void dg_fast_plan_destroy(FastPlan*);
 // part: PDB200_PART_*; returns the number of kernel launches
-int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual,
+// r0 != nullptr: residual form  y += J x + r0  with r0 = R(0) (the operator is affine)
+int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0,
                    bool overwrite, int part, cudaStream_t s);
 
+
+// dg_kron.cu: Kronecker-factorised kernel for higher degree (k = 3, 4; dim = 3, diagonal A, b = 0)
+bool dg_kron_supported(const DevParams& P);
+struct KronPlan;
+KronPlan* dg_kron_plan_create(const DevParams& P, const Kron1D& K);
+void dg_kron_plan_destroy(KronPlan*);
+int launch_dg_kron(KronPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
+                   cudaStream_t s);
 
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);

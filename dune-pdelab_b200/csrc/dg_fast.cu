@@ -375,10 +375,15 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   if (tid == 0) tma_store_commit_and_wait();
 }
 
-__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ t, long long n) {
+// y += t (+ r0): accumulate semantics of the reference engines; r0 = R(0) turns J x into the residual
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ t, const double* __restrict__ r0,
+                            long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) y[i] += t[i];
+  if (r0)
+    for (; i < n; i += stride) y[i] += t[i] + r0[i];
+  else
+    for (; i < n; i += stride) y[i] += t[i];
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -497,9 +502,9 @@ static void interior_tile_box(const DevParams& P, const TileFrame& F, const int 
   }
 }
 
-int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
                    int part, cudaStream_t s) {
-  if (residual) throw Error("fast DG kernel implements jacobian_apply only");
+  if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
   if (part != PDB200_PART_ALL && !overwrite) throw Error("partial application needs the overwrite form");
   double* out = y;
   if (!overwrite) {  // accumulate semantics (y += J z) through a scratch vector
@@ -563,7 +568,7 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
 #undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
   if (!overwrite) {
-    axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, P.ndofs);
+    axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, r0, P.ndofs);
     PDB_CUDA(cudaGetLastError());
     launches++;
   }

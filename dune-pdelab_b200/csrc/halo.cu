@@ -78,11 +78,13 @@ struct MailboxHeader {
   unsigned long long magic;
 };
 constexpr unsigned long long MAILBOX_MAGIC = 0x70646232303068ull;  // "pdb200h"
+constexpr int P2P_BLOCKS = 64;  // CTAs per side
 constexpr unsigned long long SPIN_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
 
 struct SideDesc {
   int active, dir, layer_src, layer_dst;
   long long total;                 // doubles in the layer
+  long long chunk, stride;         // contiguous run and its repeat stride, in doubles (see copy_layer)
   double* peer_buf;                // receive buffer in the NEIGHBOUR's mailbox for its side (dir, 1-side)
   unsigned long long* peer_ready;  // neighbour's ready[(dir, 1-side)]
   unsigned long long* peer_ack;    // neighbour's ack[(dir, 1-side)]
@@ -122,30 +124,53 @@ __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsig
   __syncthreads();
 }
 
-__device__ __forceinline__ long long layer_dof(const DevParams& P, int dir, int layer, long long i) {
-  const long long f = i / P.n;
-  const int k = (int)(i - f * P.n);
-  int c[3] = {0, 0, 0};
-  long long ff = f;
+// A cell layer normal to `dir` is a set of contiguous chunks: the block of all lower directions
+// (chunk = n * prod_{d<dir} N_d doubles), repeated with stride chunk * N_dir.  z-layers are one
+// contiguous block, y-layers one chunk per z.  Element i of the packed layer (lexicographic
+// tangential order, lower directions fastest) lives at  layer*chunk + (i / chunk)*stride + i % chunk.
+template <typename T>
+__device__ __forceinline__ long long layer_elem(long long i, long long chunk, long long stride, long long layer_off) {
+  const long long c = i / chunk;
+  return layer_off + c * stride + (i - c * chunk);
+}
+
+template <typename T>
+__device__ __forceinline__ void copy_layer(T* __restrict__ dst, const T* __restrict__ src, long long total, long long chunk,
+                                           long long stride, long long layer_off, bool strided_src) {
+  // grid-stride, four independent loads in flight per thread
+  const long long step = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * step < total; i += 4 * step) {
+    T v[4];
 #pragma unroll
-  for (int d = 0; d < 3; d++)
-    if (d != dir && d < P.dim) {
-      c[d] = (int)(ff % P.N[d]);
-      ff /= P.N[d];
+    for (int u = 0; u < 4; u++) {
+      const long long j = i + u * step;
+      v[u] = src[strided_src ? layer_elem<T>(j, chunk, stride, layer_off) : j];
     }
-  c[dir] = layer;
-  return cell_index(P.N, c[0], c[1], c[2]) * P.n + k;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long j = i + u * step;
+      dst[strided_src ? j : layer_elem<T>(j, chunk, stride, layer_off)] = v[u];
+    }
+  }
+  for (; i < total; i += step) {
+    const T v = src[strided_src ? layer_elem<T>(i, chunk, stride, layer_off) : i];
+    dst[strided_src ? i : layer_elem<T>(i, chunk, stride, layer_off)] = v;
+  }
 }
 
 // grid = (blocks per side, 6)
+template <int VEC>
 __global__ void p2p_push_kernel(const DevParams P, const SideTable T, const double* __restrict__ x,
                                 unsigned long long epoch, unsigned int* counters, int* err) {
   const SideDesc& S = T.s[blockIdx.y];
   if (!S.active) return;
   spin_until(S.my_ack, epoch - 1, err);  // the neighbour has emptied its receive buffer
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.total; i += stride)
-    S.peer_buf[i] = x[layer_dof(P, S.dir, S.layer_src, i)];
+  if (VEC == 2)
+    copy_layer<double2>((double2*)S.peer_buf, (const double2*)x, S.total / 2, S.chunk / 2, S.stride / 2,
+                        (long long)S.layer_src * (S.chunk / 2), true);
+  else
+    copy_layer<double>(S.peer_buf, x, S.total, S.chunk, S.stride, (long long)S.layer_src * S.chunk, true);
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -158,14 +183,17 @@ __global__ void p2p_push_kernel(const DevParams P, const SideTable T, const doub
   }
 }
 
+template <int VEC>
 __global__ void p2p_unpack_kernel(const DevParams P, const SideTable T, double* __restrict__ x,
                                   unsigned long long epoch, unsigned int* counters, int* err) {
   const SideDesc& S = T.s[blockIdx.y];
   if (!S.active) return;
   spin_until(S.my_ready, epoch, err);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.total; i += stride)
-    x[layer_dof(P, S.dir, S.layer_dst, i)] = S.my_buf[i];
+  if (VEC == 2)
+    copy_layer<double2>((double2*)x, (const double2*)S.my_buf, S.total / 2, S.chunk / 2, S.stride / 2,
+                        (long long)S.layer_dst * (S.chunk / 2), false);
+  else
+    copy_layer<double>(x, S.my_buf, S.total, S.chunk, S.stride, (long long)S.layer_dst * S.chunk, false);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -191,6 +219,7 @@ struct P2PHalo {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2] = {};
   int nactive = 0;
+  bool vec2 = true;  // every chunk is an even number of doubles: 16-byte accesses
 };
 
 P2PHalo* p2p_create(const DevParams& P, pdb200_ipc_handle* mine) {
@@ -251,6 +280,10 @@ void p2p_connect(P2PHalo* H, const DevParams& P, int dir, int side, const pdb200
   S.layer_src = side ? P.N[dir] - 2 : 1;
   S.layer_dst = side ? P.N[dir] - 1 : 0;
   S.total = (long long)H->header.layer_doubles[s];
+  S.chunk = P.n;
+  for (int d = 0; d < dir; d++) S.chunk *= P.N[d];
+  S.stride = S.chunk * P.N[dir];
+  if (S.chunk % 2) H->vec2 = false;
   S.peer_buf = (double*)(pb + ph.buf_off[sp]);
   S.peer_ready = (unsigned long long*)(pb + offsetof(MailboxHeader, ready)) + sp;
   S.peer_ack = (unsigned long long*)(pb + offsetof(MailboxHeader, ack)) + sp;
@@ -285,14 +318,20 @@ int p2p_push(P2PHalo* H, const DevParams& P, const double* x, cudaStream_t s) {
   p2p_require_connected(H, P);
   if (H->nactive == 0) return 0;
   H->epoch++;
-  p2p_push_kernel<<<dim3(24, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  if (H->vec2 && (uintptr_t)x % 16 == 0)
+    p2p_push_kernel<2><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  else
+    p2p_push_kernel<1><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   PDB_CUDA(cudaGetLastError());
   return 1;
 }
 
 int p2p_wait_unpack(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
   if (H->nactive == 0) return 0;
-  p2p_unpack_kernel<<<dim3(24, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  if (H->vec2 && (uintptr_t)x % 16 == 0)
+    p2p_unpack_kernel<2><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
+  else
+    p2p_unpack_kernel<1><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   PDB_CUDA(cudaGetLastError());
   return 1;
 }

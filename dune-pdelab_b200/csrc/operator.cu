@@ -32,9 +32,12 @@ struct pdb200_operator {
   double *dx = nullptr, *dy = nullptr;
   int* errflag = nullptr;
   FastPlan* fast = nullptr;
+  KronPlan* kron = nullptr;
   FemPlan* fem = nullptr;
   MatrixPlan* matrix = nullptr;
   P2PHalo* p2p = nullptr;
+  double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
+  bool r0_valid = false;
   uint64_t launches = 0;
   const char* last_kernel = "";
   std::vector<double> xq, wq;
@@ -44,8 +47,10 @@ struct pdb200_operator {
     for (void* p : owned) cudaFree(p);
     if (dx) cudaFree(dx);
     if (dy) cudaFree(dy);
+    if (r0) cudaFree(r0);
     if (errflag) cudaFree(errflag);
     dg_fast_plan_destroy(fast);
+    dg_kron_plan_destroy(kron);
     fem_plan_destroy(fem);
     matrix_plan_destroy(matrix);
     p2p_destroy(p2p);
@@ -115,7 +120,7 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   if (stream_override) op->stream = stream_override;
   const bool residual = mode == Mode::Residual;
   const bool overwrite = mode == Mode::OnTheFly;
-  bool use_fast0 = P.dg && !residual && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
+  bool use_fast0 = P.dg && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
   if (part != PDB200_PART_ALL && !use_fast0) {
     // kernels without a tile decomposition: everything runs in the BOUNDARY phase (after the exchange)
     if (part == PDB200_PART_INTERIOR) return;
@@ -127,14 +132,39 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
     op->launches += 2;
     return;
   }
-  bool use_fast = !residual && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
-  if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast)
+  bool use_fast = use_fast0;
+  const bool use_kron = !use_fast && dg_kron_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
+  if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast && !use_kron)
     throw Error("PDB200_KERNEL_FAST requested but the configuration has no fast kernel "
-                "(needs QkDG k=2, dim=3, diagonal A, b=0, even cells[0], jacobian_apply)");
-  if (use_fast) {
-    if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
-    op->launches += launch_dg_fast(op->fast, P, x, y, residual, overwrite, part, op->stream);
-    op->last_kernel = "dg_fast_q2_3d";
+                "(needs QkDG k in {2,3,4}, dim=3, diagonal A, b=0, even cells[0])");
+  if (use_fast || use_kron) {
+    const double* r0 = nullptr;
+    if (residual) {
+      // The operator is affine: R(x) = J x + R(0).  R(0) (source term lambda_volume,
+      // convectiondiffusiondg.hh:1048-1075, and the boundary data g, j, o, :684-879) is evaluated
+      // once per coefficient set with the reference-order kernel and cached.
+      if (!op->r0_valid) {
+        if (!op->r0) PDB_CUDA(cudaMalloc(&op->r0, (size_t)P.ndofs * sizeof(double)));
+        double* zero = nullptr;
+        PDB_CUDA(cudaMalloc(&zero, (size_t)P.ndofs * sizeof(double)));
+        PDB_CUDA(cudaMemsetAsync(zero, 0, (size_t)P.ndofs * sizeof(double), op->stream));
+        launch_dg_generic(P, zero, op->r0, /*residual=*/true, /*overwrite=*/true, op->errflag, op->stream);
+        PDB_CUDA(cudaStreamSynchronize(op->stream));
+        PDB_CUDA(cudaFree(zero));
+        op->r0_valid = true;
+        op->launches += 1;
+      }
+      r0 = op->r0;
+    }
+    if (use_fast) {
+      if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
+      op->launches += launch_dg_fast(op->fast, P, x, y, r0, overwrite, part, op->stream);
+      op->last_kernel = residual ? "dg_fast_q2_3d+r0" : "dg_fast_q2_3d";
+    } else {
+      if (!op->kron) op->kron = dg_kron_plan_create(P, op->K);
+      op->launches += launch_dg_kron(op->kron, P, x, y, r0, overwrite, op->stream);
+      op->last_kernel = residual ? "dg_kron_3d+r0" : "dg_kron_3d";
+    }
   } else {
     launch_dg_generic(P, x, y, residual, overwrite, op->errflag, op->stream);
     op->last_kernel = residual ? "dg_generic_residual" : "dg_generic_jacobian_apply";
@@ -295,6 +325,7 @@ int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
   upd(P.j, p->j, (size_t)nbf * P.nfq * 8, "j");
   upd(P.o, p->o, (size_t)nbf * P.nfq * 8, "o");
   if (p->bctype) throw Error("update_coefficients: bctype changes the constraint set; create a new operator");
+  h->r0_valid = false;
   PDB_CUDA(cudaStreamSynchronize(h->stream));
   PDB_CATCH
 }

@@ -76,6 +76,61 @@ def test_fast_jacobian_apply_matches_oracle(cuda_lib, case):
     assert rel_err(y, want + y0) < TOL
 
 
+@pytest.mark.parametrize("case", [dict(cells=(8, 4, 4), a="scalar"), dict(cells=(10, 9, 7), a="diagonal", bc="mixed", with_c=True),
+                                  dict(cells=(6, 5, 3), a="scalar", extent=(1.0, 0.7, 1.3))],
+                         ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_fast_residual_matches_oracle(cuda_lib, case):
+    """residual = J x + R(0) through the Kronecker kernel, R(0) cached per coefficient set."""
+    case = dict(case, with_f=True)
+    if case.get("bc", "dirichlet") == "dirichlet":
+        case["bc"] = "dirichlet_g"
+    spec = dg_problem(degree=2, kernel=abi.KERNEL_FAST, **case)
+    go, orc = _ops(spec)
+    x = mt_vector(spec.num_dofs)
+    r0 = mt_vector(spec.num_dofs, seed=9)
+    for _ in range(2):                                        # second call uses the cached R(0)
+        r = go.residual(x, r0.copy())
+        assert go.last_kernel() == "dg_fast_q2_3d+r0"
+        assert rel_err(r, orc.residual(x, r0.copy())) < TOL
+    # new source term: the cache must be invalidated
+    f2 = np.random.default_rng(5).standard_normal(spec.arrays["f"].shape)
+    go.update_coefficients(f=f2)
+    from oracle import Oracle
+    r = go.residual(x, r0.copy())
+    assert rel_err(r, Oracle(spec.replace(f=f2)).residual(x, r0.copy())) < TOL
+
+
+KRON_CASES = [
+    dict(cells=(4, 4, 3), degree=4), dict(cells=(2, 1, 1), degree=4, a="identity"),
+    dict(cells=(6, 5, 4), degree=4, a="diagonal", with_c=True, bc="mixed"),                   # partial tiles
+    dict(cells=(4, 3, 2), degree=4, a="scalar", extent=(1.0, 0.7, 1.3), method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF, alpha=1.0),
+    dict(cells=(8, 4, 2), degree=3), dict(cells=(10, 5, 3), degree=3, a="diagonal", with_c=True, bc="mixed", method=abi.DG_IIPG),
+]
+
+
+@pytest.mark.parametrize("case", KRON_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_kron_jacobian_apply_and_residual_match_oracle(cuda_lib, case):
+    """Higher-degree Kronecker kernel (csrc/dg_kron.cu): cfg3 of BASELINE.json is k = 4."""
+    spec = dg_problem(kernel=abi.KERNEL_FAST, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    want = orc.jacobian_apply(z)
+    y = go.apply(z, np.full(spec.num_dofs, np.nan))
+    assert go.last_kernel() == "dg_kron_3d"
+    assert rel_err(y, want) < TOL
+    y0 = mt_vector(spec.num_dofs, seed=7)
+    assert rel_err(go.jacobian_apply(z, y0.copy()), want + y0) < TOL
+    # residual with source term and boundary data: J x + R(0)
+    case = dict(case, with_f=True)
+    if case.get("bc", "dirichlet") == "dirichlet":
+        case["bc"] = "dirichlet_g"
+    spec = dg_problem(kernel=abi.KERNEL_FAST, **case)
+    go, orc = _ops(spec)
+    r = go.residual(z, y0.copy())
+    assert go.last_kernel() == "dg_kron_3d+r0"
+    assert rel_err(r, orc.residual(z, y0.copy())) < TOL
+
+
 def test_fast_and_generic_agree_on_device_tensors(cuda_lib):
     import torch
     spec = dg_problem((32, 16, 12), degree=2, a="scalar")
