@@ -104,8 +104,12 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K);
 void dg_fast_plan_destroy(FastPlan*);
 // part: PDB200_PART_*; returns the number of kernel launches
 // r0 != nullptr: residual form  y += J x + r0  with r0 = R(0) (the operator is affine)
+// [ztile_lo, ztile_hi): optional window of tile layers along z (PART_ALL only), used to pipeline
+// host transfers with the computation
 int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0,
-                   bool overwrite, int part, cudaStream_t s);
+                   bool overwrite, int part, cudaStream_t s, int ztile_lo = 0, int ztile_hi = 1 << 30);
+int dg_fast_ztiles(const DevParams& P);
+void dg_fast_ztile_layers(const DevParams& P, int lo, int hi, int* z0, int* z1);
 
 
 // dg_kron.cu: Kronecker-factorised kernel for higher degree (k = 3, 4; dim = 3, diagonal A, b = 0)

@@ -502,8 +502,23 @@ static void interior_tile_box(const DevParams& P, const TileFrame& F, const int 
   }
 }
 
+// number of tile layers along z and the cell layers [z0, z1) that tile layers [lo, hi) write
+int dg_fast_ztiles(const DevParams& P) {
+  TileFrame TF;
+  int nt[3];
+  tile_frame(P, TF, nt);
+  return nt[2];
+}
+void dg_fast_ztile_layers(const DevParams& P, int lo, int hi, int* z0, int* z1) {
+  TileFrame TF;
+  int nt[3];
+  tile_frame(P, TF, nt);
+  *z0 = lo <= 0 ? 0 : TF.org[2] + lo * TZ;                     // the first window also owns the lower ghost layer
+  *z1 = hi >= nt[2] ? P.N[2] : std::min(TF.org[2] + hi * TZ, P.N[2]);  // the last one the upper ghost layer
+}
+
 int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
-                   int part, cudaStream_t s) {
+                   int part, cudaStream_t s, int ztile_lo, int ztile_hi) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
   if (part != PDB200_PART_ALL && !overwrite) throw Error("partial application needs the overwrite form");
   double* out = y;
@@ -530,7 +545,8 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
     nboxes++;
   };
   if (part == PDB200_PART_ALL) {
-    add(0, 0, 0, nt[0], nt[1], nt[2]);
+    const int zlo = std::max(0, ztile_lo), zhi = std::min(nt[2], ztile_hi);  // optional window of tile layers
+    add(0, 0, zlo, nt[0], nt[1], zhi - zlo);
   } else {
     int lo[3], hi[3];
     interior_tile_box(P, TF, nt, lo, hi);

@@ -5,6 +5,7 @@
 // the reference's GridOperator references (function-space sizes, constraints, local-operator
 // parameters) and exposes residual / jacobian_apply / jacobian / fill_pattern.
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -31,6 +32,9 @@ struct pdb200_operator {
   // staging for host-pointer calls
   double *dx = nullptr, *dy = nullptr;
   int* errflag = nullptr;
+  // host-pointer calls of the fast kernel: transfers pipelined with the computation
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t pipe_ev[2 * 16 + 1] = {};
   FastPlan* fast = nullptr;
   KronPlan* kron = nullptr;
   FemPlan* fem = nullptr;
@@ -49,6 +53,10 @@ struct pdb200_operator {
     if (dy) cudaFree(dy);
     if (r0) cudaFree(r0);
     if (errflag) cudaFree(errflag);
+    if (h2d_stream) cudaStreamDestroy(h2d_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
+    for (auto& e : pipe_ev)
+      if (e) cudaEventDestroy(e);
     dg_fast_plan_destroy(fast);
     dg_kron_plan_destroy(kron);
     fem_plan_destroy(fem);
@@ -172,11 +180,63 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   }
 }
 
+// y = J x with HOST vectors through the fast kernel: the vector is cut into windows of tile layers
+// along z; window c is computed as soon as its input layers (and one layer of window c+1) have
+// arrived, and its result travels back while the next window is computed.  PCIe is full duplex,
+// so the call costs about max(H2D, D2H) instead of H2D + kernel + D2H.
+bool run_onthefly_host_pipelined(pdb200_operator* op, const double* x, double* y) {
+  const DevParams& P = op->P;
+  if (!(P.dg && dg_fast_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC)) return false;
+  const int nzt = dg_fast_ztiles(P);
+  const int nwin = std::min(16, nzt);
+  if (nwin < 2) return false;
+  const size_t bytes = (size_t)P.ndofs * sizeof(double);
+  if (!op->dx) PDB_CUDA(cudaMalloc(&op->dx, bytes));
+  if (!op->dy) PDB_CUDA(cudaMalloc(&op->dy, bytes));
+  if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
+  if (!op->h2d_stream) {
+    PDB_CUDA(cudaStreamCreateWithFlags(&op->h2d_stream, cudaStreamNonBlocking));
+    PDB_CUDA(cudaStreamCreateWithFlags(&op->d2h_stream, cudaStreamNonBlocking));
+    for (auto& e : op->pipe_ev) PDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const size_t layer = (size_t)P.N[0] * P.N[1] * P.n;  // doubles per cell layer
+  cudaEvent_t* ev_in = op->pipe_ev;                     // [16]
+  cudaEvent_t* ev_out = op->pipe_ev + 16;               // [16]
+  cudaEvent_t ev_start = op->pipe_ev[32];
+  PDB_CUDA(cudaEventRecord(ev_start, op->stream));      // order after earlier work on the handle's stream
+  PDB_CUDA(cudaStreamWaitEvent(op->h2d_stream, ev_start, 0));
+  PDB_CUDA(cudaStreamWaitEvent(op->d2h_stream, ev_start, 0));
+  int zin0[16], zin1[16], tlo[16], thi[16];
+  for (int c = 0; c < nwin; c++) {
+    tlo[c] = (int)((long long)nzt * c / nwin);
+    thi[c] = (int)((long long)nzt * (c + 1) / nwin);
+    dg_fast_ztile_layers(P, tlo[c], thi[c], &zin0[c], &zin1[c]);
+  }
+  for (int c = 0; c < nwin; c++) {  // all uploads are queued up front: the copy engine streams them back to back
+    PDB_CUDA(cudaMemcpyAsync(op->dx + zin0[c] * layer, x + zin0[c] * layer, (zin1[c] - zin0[c]) * layer * sizeof(double),
+                             cudaMemcpyHostToDevice, op->h2d_stream));
+    PDB_CUDA(cudaEventRecord(ev_in[c], op->h2d_stream));
+  }
+  for (int c = 0; c < nwin; c++) {
+    PDB_CUDA(cudaStreamWaitEvent(op->stream, ev_in[std::min(c + 1, nwin - 1)], 0));  // needs one layer of the next window
+    op->launches += launch_dg_fast(op->fast, P, op->dx, op->dy, nullptr, true, PDB200_PART_ALL, op->stream, tlo[c], thi[c]);
+    PDB_CUDA(cudaEventRecord(ev_out[c], op->stream));
+    PDB_CUDA(cudaStreamWaitEvent(op->d2h_stream, ev_out[c], 0));
+    PDB_CUDA(cudaMemcpyAsync(y + zin0[c] * layer, op->dy + zin0[c] * layer, (zin1[c] - zin0[c]) * layer * sizeof(double),
+                             cudaMemcpyDeviceToHost, op->d2h_stream));
+  }
+  op->last_kernel = "dg_fast_q2_3d";
+  PDB_CUDA(cudaStreamSynchronize(op->d2h_stream));
+  PDB_CUDA(cudaStreamSynchronize(op->stream));
+  return true;
+}
+
 void run_vector(pdb200_operator* op, const double* x, double* y, Mode mode) {
   ensure_device(op);
   const DevParams& P = op->P;
   const bool xd = is_device_pointer(x), yd = is_device_pointer(y);
   const size_t bytes = (size_t)P.ndofs * sizeof(double);
+  if (!xd && !yd && mode == Mode::OnTheFly && run_onthefly_host_pipelined(op, x, y)) return;
   const double* xdev = x;
   double* ydev = y;
   if (!xd) {
