@@ -135,7 +135,8 @@ cudaEvent_t p2p_event(P2PHalo*, int i);
 
 // fem.cu: conforming Qk residual / jacobian_apply (coloured scatter)
 struct FemPlan;
-FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev);
+FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev, const Kron1D& K);
+void fem_plan_invalidate(FemPlan*);  // coefficients changed: drop the cached R(0)
 void fem_plan_destroy(FemPlan*);
 void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                        cudaStream_t s);

@@ -31,10 +31,19 @@
 
 namespace pdb {
 
+// exactly integrated 1-D matrices for the Kronecker form of alpha_volume (diagonal A, b = 0)
+struct FemKron {
+  double MinvK[MAX_N1 * MAX_N1];  // M^-1 K, row-major with leading dimension n1
+  double M[MAX_N1 * MAX_N1];
+};
+
 struct FemPlan {
   QkLayout L;
   uint64_t* con = nullptr;  // constrained DOFs (device)
   long long ncon = 0;
+  FemKron kron;
+  double* r0 = nullptr;     // R(0) of the affine residual (Kronecker path), cached per coefficient set
+  bool r0_valid = false;
 };
 
 namespace {
@@ -153,6 +162,70 @@ __device__ __forceinline__ void fem_cell_volume(const DevParams& P, long long ce
   }
 }
 
+// The same cell integral for a cell-wise constant DIAGONAL tensor, b = 0, without the source term:
+//   r = |K| (M (x) M (x) M) [ sum_d (A_dd / h_d^2) (M^-1 K)_d x + c x ]
+// (the (k+1)-point Gauss rule of convectiondiffusionfem.hh:93-94 integrates these polynomials exactly,
+// so this equals alpha_volume to rounding): one sweep per direction plus three mass sweeps instead
+// of 18 quadrature sweeps.
+template <int DIM, int K>
+__device__ __forceinline__ void fem_cell_volume_kron(const DevParams& P, const FemKron& Q, long long cell,
+                                                     const double (&x)[LocalSize<DIM, K + 1>::N],
+                                                     double (&r)[LocalSize<DIM, K + 1>::N]) {
+  constexpr int N1 = K + 1, N = LocalSize<DIM, N1>::N;
+  double a[3] = {1.0, 1.0, 1.0};
+  if (P.a_mode == PDB200_A_SCALAR) {
+    a[0] = a[1] = a[2] = __ldg(P.A + cell);
+  } else if (P.a_mode == PDB200_A_DIAGONAL) {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) a[d] = __ldg(P.A + cell * DIM + d);
+  }
+  const double cc = P.c ? __ldg(P.c + cell) : 0.0;
+  double t[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) t[i] = cc * x[i];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    const int S = d == 0 ? 1 : (d == 1 ? N1 : N1 * N1);
+    const double al = a[d] * P.ih[d] * P.ih[d];
+#pragma unroll
+    for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+      for (int lo = 0; lo < S; lo++) {
+        const int base = hi * S * N1 + lo;
+#pragma unroll
+        for (int o = 0; o < N1; o++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < N1; i++) acc = fma(Q.MinvK[o * N1 + i], x[base + i * S], acc);
+          t[base + o * S] = fma(al, acc, t[base + o * S]);
+        }
+      }
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    const int S = d == 0 ? 1 : (d == 1 ? N1 : N1 * N1);
+    const double sc = d == 0 ? P.vol : 1.0;
+#pragma unroll
+    for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+      for (int lo = 0; lo < S; lo++) {
+        const int base = hi * S * N1 + lo;
+        double in[N1];
+#pragma unroll
+        for (int i = 0; i < N1; i++) in[i] = t[base + i * S];
+#pragma unroll
+        for (int o = 0; o < N1; o++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < N1; i++) acc = fma(Q.M[o * N1 + i] * sc, in[i], acc);
+          t[base + o * S] = acc;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = t[i];
+}
+
 // alpha_boundary of one boundary face (convectiondiffusionfem.hh:207-275); x and r are the cell's
 // local vectors in shared memory.  Rare path (non-Dirichlet boundary cells only): plain loops.
 template <int DIM, int K, bool RESIDUAL>
@@ -203,10 +276,12 @@ __device__ __noinline__ void fem_cell_boundary(const DevParams& P, long long cel
   }
 }
 
-template <int DIM, int K, bool RESIDUAL>
+// KRON: Kronecker form of the cell integral (diagonal A, b = 0); the u-independent part of the
+// residual then comes from r0 = R(0) (the operator is affine), which is added in step 3.
+template <int DIM, int K, bool RESIDUAL, bool KRON>
 __global__ void __launch_bounds__(FEM_THREADS)
-    fem_vector_kernel(const DevParams P, const QkLayout L, const double* __restrict__ x, double* __restrict__ y,
-                      int overwrite) {
+    fem_vector_kernel(const DevParams P, const QkLayout L, const FemKron Q, const double* __restrict__ x,
+                      double* __restrict__ y, const double* __restrict__ r0, int overwrite) {
   constexpr int N1 = K + 1, N = LocalSize<DIM, N1>::N;
   constexpr int T0 = Tile<DIM>::T0, T1 = Tile<DIM>::T1, T2 = Tile<DIM>::T2;
   constexpr int C0 = T0 + 1, C1 = T1 + 1, C2 = DIM == 3 ? T2 + 1 : 1;          // cells of the box
@@ -242,11 +317,14 @@ __global__ void __launch_bounds__(FEM_THREADS)
       const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
       xl[i] = xs[(K * lc0 + i0) + Q0 * ((K * lc1 + i1) + Q1 * (K * lc2 + i2))];
     }
-    fem_cell_volume<DIM, K, RESIDUAL>(P, cell, xl, rl);
+    if (KRON)
+      fem_cell_volume_kron<DIM, K>(P, Q, cell, xl, rl);
+    else
+      fem_cell_volume<DIM, K, RESIDUAL>(P, cell, xl, rl);
 #pragma unroll
     for (int i = 0; i < N; i++) rs[ci * N + i] = rl[i];
     // boundary faces in intersection order (default/assembler.hh:156-236); needs b, j or o data
-    if (P.bctype) {
+    if (!KRON && P.bctype) {
       bool onb = false;
       for (int d = 0; d < DIM; d++) onb |= c[d] == 0 || c[d] == P.N[d] - 1;
       if (onb) {
@@ -294,6 +372,7 @@ __global__ void __launch_bounds__(FEM_THREADS)
     }
     const long long gi = qk_lattice_index(L, p);
     double v = overwrite ? 0.0 : y[gi];
+    if (KRON && r0) v += r0[gi];
     for (int a2 = 0; a2 < cnt[2]; a2++)
       for (int a1 = 0; a1 < cnt[1]; a1++)
         for (int a0 = 0; a0 < cnt[0]; a0++) {
@@ -311,9 +390,9 @@ __global__ void constrain_kernel(double* __restrict__ y, const uint64_t* __restr
   if (i < n) y[idx[i]] = 0.0;
 }
 
-template <int DIM, int K>
-void launch_fem(const FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
-                cudaStream_t s) {
+template <int DIM, int K, bool RESIDUAL, bool KRON>
+void launch_fem_variant(const FemPlan* plan, const DevParams& P, const double* x, double* y, const double* r0,
+                        bool overwrite, cudaStream_t s) {
   constexpr int N1 = K + 1, N = LocalSize<DIM, N1>::N;
   constexpr int T0 = Tile<DIM>::T0, T1 = Tile<DIM>::T1, T2 = Tile<DIM>::T2;
   constexpr int C0 = T0 + 1, C1 = T1 + 1, C2 = DIM == 3 ? T2 + 1 : 1;
@@ -322,21 +401,53 @@ void launch_fem(const FemPlan* plan, const DevParams& P, const double* x, double
   // lattice points per direction: K*N_d + 1, K*T_d owned per tile
   dim3 grid((K * P.N[0] + 1 + K * T0 - 1) / (K * T0), (K * P.N[1] + 1 + K * T1 - 1) / (K * T1),
             DIM == 3 ? (K * P.N[2] + 1 + K * T2 - 1) / (K * T2) : 1);
-  if (residual) {
-    PDB_CUDA(cudaFuncSetAttribute(fem_vector_kernel<DIM, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fem_vector_kernel<DIM, K, true><<<grid, FEM_THREADS, smem, s>>>(P, plan->L, x, y, overwrite ? 1 : 0);
-  } else {
-    PDB_CUDA(cudaFuncSetAttribute(fem_vector_kernel<DIM, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fem_vector_kernel<DIM, K, false><<<grid, FEM_THREADS, smem, s>>>(P, plan->L, x, y, overwrite ? 1 : 0);
-  }
+  PDB_CUDA(cudaFuncSetAttribute(fem_vector_kernel<DIM, K, RESIDUAL, KRON>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  fem_vector_kernel<DIM, K, RESIDUAL, KRON><<<grid, FEM_THREADS, smem, s>>>(P, plan->L, plan->kron, x, y, r0,
+                                                                             overwrite ? 1 : 0);
   PDB_CUDA(cudaGetLastError());
+}
+
+template <int DIM, int K>
+void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
+                cudaStream_t s) {
+  const bool kron = P.a_mode != PDB200_A_FULL && P.b == nullptr;
+  if (!kron) {
+    if (residual)
+      launch_fem_variant<DIM, K, true, false>(plan, P, x, y, nullptr, overwrite, s);
+    else
+      launch_fem_variant<DIM, K, false, false>(plan, P, x, y, nullptr, overwrite, s);
+    return;
+  }
+  const double* r0 = nullptr;
+  if (residual) {
+    // R(x) = J x + R(0): the source term and the Neumann / outflow data (convectiondiffusionfem.hh:134,
+    // 243-272) do not depend on x; evaluate them once with the quadrature kernel and cache
+    if (!plan->r0_valid) {
+      if (!plan->r0) PDB_CUDA(cudaMalloc(&plan->r0, (size_t)P.ndofs * sizeof(double)));
+      double* zero = nullptr;
+      PDB_CUDA(cudaMalloc(&zero, (size_t)P.ndofs * sizeof(double)));
+      PDB_CUDA(cudaMemsetAsync(zero, 0, (size_t)P.ndofs * sizeof(double), s));
+      launch_fem_variant<DIM, K, true, false>(plan, P, zero, plan->r0, nullptr, true, s);
+      PDB_CUDA(cudaStreamSynchronize(s));
+      PDB_CUDA(cudaFree(zero));
+      plan->r0_valid = true;
+    }
+    r0 = plan->r0;
+  }
+  launch_fem_variant<DIM, K, false, true>(plan, P, x, y, r0, overwrite, s);
 }
 
 }  // namespace
 
-FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev) {
+FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev, const Kron1D& K1) {
   FemPlan* plan = new FemPlan;
   plan->L = make_qk_layout(P);
+  for (int i = 0; i < P.n1; i++)
+    for (int j = 0; j < P.n1; j++) {
+      plan->kron.MinvK[i * P.n1 + j] = K1.MinvK[i * MAX_N1 + j];
+      plan->kron.M[i * P.n1 + j] = K1.M[i * MAX_N1 + j];
+    }
   std::vector<int8_t> bct;
   if (bctype_dev) {
     long long nbf = 0;
@@ -356,10 +467,14 @@ FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev) {
 void fem_plan_destroy(FemPlan* p) {
   if (!p) return;
   if (p->con) cudaFree(p->con);
+  if (p->r0) cudaFree(p->r0);
   delete p;
 }
 
 const QkLayout& fem_plan_layout(const FemPlan* p) { return p->L; }
+void fem_plan_invalidate(FemPlan* p) {
+  if (p) p->r0_valid = false;
+}
 const uint64_t* fem_plan_constrained(const FemPlan* p, long long* n) {
   *n = p->ncon;
   return p->con;

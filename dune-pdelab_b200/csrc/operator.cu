@@ -136,7 +136,8 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   }
   if (!P.dg) {
     launch_fem_vector(op->fem, P, x, y, residual, overwrite, op->stream);
-    op->last_kernel = residual ? "fem_residual" : "fem_jacobian_apply";
+    const bool kron = P.a_mode != PDB200_A_FULL && P.b == nullptr;
+    op->last_kernel = kron ? (residual ? "fem_kron+r0" : "fem_kron") : (residual ? "fem_residual" : "fem_jacobian_apply");
     op->launches += 2;
     return;
   }
@@ -355,7 +356,7 @@ int pdb200_create(const pdb200_problem* p, pdb200_handle* out) {
   P.o = upload(op.get(), p->o, (size_t)nbf * P.nfq);
   PDB_CUDA(cudaMalloc(&op->errflag, sizeof(int)));
   PDB_CUDA(cudaMemset(op->errflag, 0, sizeof(int)));
-  if (!P.dg) op->fem = fem_plan_create(P, p->bctype ? op->P.bctype : nullptr);
+  if (!P.dg) op->fem = fem_plan_create(P, p->bctype ? op->P.bctype : nullptr, op->K);
   *out = op.release();
   PDB_CATCH
 }
@@ -386,6 +387,7 @@ int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
   upd(P.o, p->o, (size_t)nbf * P.nfq * 8, "o");
   if (p->bctype) throw Error("update_coefficients: bctype changes the constraint set; create a new operator");
   h->r0_valid = false;
+  fem_plan_invalidate(h->fem);
   PDB_CUDA(cudaStreamSynchronize(h->stream));
   PDB_CATCH
 }

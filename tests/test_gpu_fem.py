@@ -42,7 +42,9 @@ def test_fem_residual_and_apply_match_oracle(cuda_lib, case):
     x = mt_vector(n)
     r0 = mt_vector(n, seed=9)
     assert rel_err(go.residual(x, r0.copy()), orc.residual(x, r0.copy())) < TOL
-    assert go.last_kernel() == "fem_residual"
+    kron = case.get("a", "scalar") != "full" and not case.get("with_b", False)   # Kronecker cell integral + cached R(0)
+    assert go.last_kernel() == ("fem_kron+r0" if kron else "fem_residual")
+    assert rel_err(go.residual(x, r0.copy()), orc.residual(x, r0.copy())) < TOL   # second call: cached R(0)
     assert rel_err(go.jacobian_apply(x, r0.copy()), orc.jacobian_apply(x, r0.copy())) < TOL
     y = go.apply(x, np.full(n, np.nan))            # OnTheFlyOperator::apply: y = J x
     assert rel_err(y, orc.jacobian_apply(x)) < TOL
