@@ -109,21 +109,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// thread 0 spins until *flag >= want (or the timeout expires: sets *err, never hangs the GPU)
-__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long want, int* err) {
-  if (threadIdx.x == 0) {
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(flag) < want) {
-      if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
-        atomicExch(err, 1);
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-  __syncthreads();
-}
-
 // A cell layer normal to `dir` is a set of contiguous chunks: the block of all lower directions
 // (chunk = n * prod_{d<dir} N_d doubles), repeated with stride chunk * N_dir.  z-layers are one
 // contiguous block, y-layers one chunk per z.  Element i of the packed layer (lexicographic
@@ -159,13 +144,31 @@ __device__ __forceinline__ void copy_layer(T* __restrict__ dst, const T* __restr
   }
 }
 
+// Waiting is done by ONE warp (lane s watches side s), in its own tiny kernel, so that no wide
+// copy kernel sits on SM resources while it spins: the copy kernels below are launched behind it
+// on the same stream and run only once the data / the free mailbox is there.
+//   which = 0: my_ack >= want (the neighbour has emptied its receive buffer), 1: my_ready >= want
+__global__ void p2p_wait_kernel(const SideTable T, int which, unsigned long long want, int* err) {
+  const int s = threadIdx.x;
+  if (s < 6 && T.s[s].active) {
+    const unsigned long long* flag = which ? T.s[s].my_ready : T.s[s].my_ack;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < want) {
+      if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+}
+
 // grid = (blocks per side, 6)
 template <int VEC>
 __global__ void p2p_push_kernel(const DevParams P, const SideTable T, const double* __restrict__ x,
                                 unsigned long long epoch, unsigned int* counters, int* err) {
   const SideDesc& S = T.s[blockIdx.y];
   if (!S.active) return;
-  spin_until(S.my_ack, epoch - 1, err);  // the neighbour has emptied its receive buffer
   if (VEC == 2)
     copy_layer<double2>((double2*)S.peer_buf, (const double2*)x, S.total / 2, S.chunk / 2, S.stride / 2,
                         (long long)S.layer_src * (S.chunk / 2), true);
@@ -188,7 +191,6 @@ __global__ void p2p_unpack_kernel(const DevParams P, const SideTable T, double* 
                                   unsigned long long epoch, unsigned int* counters, int* err) {
   const SideDesc& S = T.s[blockIdx.y];
   if (!S.active) return;
-  spin_until(S.my_ready, epoch, err);
   if (VEC == 2)
     copy_layer<double2>((double2*)x, (const double2*)S.my_buf, S.total / 2, S.chunk / 2, S.stride / 2,
                         (long long)S.layer_dst * (S.chunk / 2), false);
@@ -318,22 +320,24 @@ int p2p_push(P2PHalo* H, const DevParams& P, const double* x, cudaStream_t s) {
   p2p_require_connected(H, P);
   if (H->nactive == 0) return 0;
   H->epoch++;
+  p2p_wait_kernel<<<1, 32, 0, s>>>(H->table, 0, H->epoch - 1, H->err);
   if (H->vec2 && (uintptr_t)x % 16 == 0)
     p2p_push_kernel<2><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   else
     p2p_push_kernel<1><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   PDB_CUDA(cudaGetLastError());
-  return 1;
+  return 2;
 }
 
 int p2p_wait_unpack(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
   if (H->nactive == 0) return 0;
+  p2p_wait_kernel<<<1, 32, 0, s>>>(H->table, 1, H->epoch, H->err);
   if (H->vec2 && (uintptr_t)x % 16 == 0)
     p2p_unpack_kernel<2><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   else
     p2p_unpack_kernel<1><<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(P, H->table, x, H->epoch, H->counters, H->err);
   PDB_CUDA(cudaGetLastError());
-  return 1;
+  return 2;
 }
 
 void p2p_check(P2PHalo* H) {

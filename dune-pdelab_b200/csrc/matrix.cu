@@ -278,13 +278,14 @@ constexpr int QK_THREADS = 256;
 template <int G, typename IDX>
 __global__ void __launch_bounds__(QK_THREADS)
     qk_colidx_kernel(const QkDecode D, const QkLut* __restrict__ lut_g, const u64* __restrict__ rowptr, u64 nrows,
-                     IDX* __restrict__ colidx) {
+                     IDX* __restrict__ colidx, const uint32_t* __restrict__ rowlist) {
   __shared__ QkLut lut;
   for (int i = threadIdx.x; i < (int)(sizeof(QkLut) / 4); i += QK_THREADS) ((uint32_t*)&lut)[i] = ((const uint32_t*)lut_g)[i];
   __syncthreads();
   const int lane = threadIdx.x % G;
-  const u64 row = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
+  u64 row = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
   if (row >= nrows) return;
+  if (rowlist) row = rowlist[row];  // nrows = length of the list
   const QkRow R = qk_row(D, (uint32_t)row);
   const u64 start = rowptr[row];
   for (int slot = lane; slot < R.len; slot += G) {
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(QK_THREADS)
     qk_assemble_kernel(const DevParams P, const QkDecode D, const Mat1D T1, const QkTables Q,
                        const double* __restrict__ tables_g, const QkLut* __restrict__ lut_g,
                        const u64* __restrict__ rowptr, u64 nrows, const unsigned char* __restrict__ constrained,
-                       double* __restrict__ values, int fresh) {
+                       double* __restrict__ values, int fresh, const uint32_t* __restrict__ rowlist) {
   constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
   constexpr int MAXLEN = DIM == 3 ? (2 * K + 1) * (2 * K + 1) * (2 * K + 1) : (2 * K + 1) * (2 * K + 1);
   constexpr int ROWS_PER_CTA = QK_THREADS / G;
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(QK_THREADS)
   const u64 rstride = (u64)gridDim.x * ROWS_PER_CTA;
   const int joff = (lane % N1) + 5 * (((lane / N1) % N1) + 5 * (lane / (N1 * N1)));
   const int N0c = P.N[0], N1c = P.N[1], N2c = P.N[2];
-  for (u64 row = row0; row < nrows; row += rstride) {
+  for (u64 rix = row0; rix < nrows; rix += rstride) {
+    const u64 row = rowlist ? (u64)rowlist[rix] : rix;  // with a list, nrows is its length
     const QkRow R = qk_row(D, (uint32_t)row);
     const u64 start = rowptr[row];
     const uint8_t* o2s = off2slot + R.shape * 125;
@@ -409,6 +411,120 @@ __global__ void __launch_bounds__(QK_THREADS)
     }
     for (int s = lane; s < R.len; s += G) values[start + s] = fresh ? rb[s] : values[start + s] + rb[s];
     __syncwarp(gmask);
+  }
+}
+
+// ---- interior rows, one x-line of rows per CTA ------------------------------------------------------
+// All rows of an entity group whose lattice point is not on the boundary have the same box shape, so
+// the column offset of slot s is the same for every row: a thread keeps ONE slot and walks along the
+// x-line of rows.  Everything that depends on (group, slot) — the cells that contain both the row's
+// and the column's lattice point and the local indices (i, j) in each — is decoded once per thread;
+// per row what is left is  v = sum_k T[i_k][j_k] * kappa[cell_k]  in ascending cell order (the order of
+// the reference's scatter_jacobian, assemblerutilities.hh:449-460) and one coalesced store, or, for
+// the pattern, colidx = base + row (the column's group is fixed by the offset parity).
+// Rows on the boundary (clipped boxes, constrained rows) stay with the generic kernels above, which
+// are then driven by an explicit row list.
+// row stride of the staged coefficient rows: = 4 (mod 16) doubles, so that the four rows and the two
+// x-neighbours of a candidate set fall into distinct shared-memory banks
+__host__ __device__ inline int qk_kap_stride(int N0) { return (N0 + 11) / 16 * 16 + 4; }
+
+template <int DIM, int K, typename IDX, bool VALUES>
+__global__ void __launch_bounds__(256, 4) qk_interior_kernel(const DevParams P, const QkDecode D, int g, int L, const QkLut* __restrict__ lut_g,
+                                   const double* __restrict__ tab_g, const u64* __restrict__ rowptr,
+                                   double* __restrict__ values, IDX* __restrict__ colidx, int fresh) {
+  constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  extern __shared__ double kap[];  // [2][2][N0] coefficients of the candidate cells of this line
+  const int s = D.sbits[g];
+  const bool vt[3] = {!(s & 1), !((s >> 1) & 1), !((s >> 2) & 1)};  // vertex-type direction: two candidate cells
+  const int N0 = P.N[0], KS = qk_kap_stride(N0);
+  const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
+  const int a1 = (int)blockIdx.x + (vt[1] ? 1 : 0), a2 = DIM == 3 ? (int)blockIdx.y + (vt[2] ? 1 : 0) : 0;
+  const int lo0 = vt[0] ? 1 : 0, hi0 = N0 - 1;
+  // rows of the line are packed densely over the CTA: R = blockDim / L rows in flight, slot fixed per thread
+  const int R = (int)blockDim.x / L;
+  const int rsub = (int)threadIdx.x / L, slot = (int)threadIdx.x - rsub * L;
+  const bool active = rsub < R;
+  int shape = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) shape |= (vt[d] ? 1 : 0) << d;
+  const int off = active ? lut_g->slot2off[shape][slot] : 0;
+  const int o[3] = {off & 7, (off >> 3) & 7, off >> 6};
+  int e[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < DIM; d++) e[d] = o[d] - (vt[d] ? K : 1);
+  const u64 base = rowptr[D.start[g] + (u64)lo0 + (u64)sz0 * ((u64)a1 + (u64)sz1 * (u64)a2)];
+  if (VALUES) {
+    const int cb1 = a1 - (vt[1] ? 1 : 0), cb2 = DIM == 3 ? a2 - (vt[2] ? 1 : 0) : 0;
+    const int cn1 = vt[1] ? 2 : 1, cn2 = DIM == 3 ? (vt[2] ? 2 : 1) : 1;
+    for (int i = threadIdx.x; i < cn2 * cn1 * N0; i += blockDim.x) {
+      const int x = i % N0, j1 = (i / N0) % cn1, j2 = i / (N0 * cn1);
+      kap[(j2 * 2 + j1) * KS + x] =
+          P.a_mode == PDB200_A_IDENTITY ? 1.0 : __ldg(P.A + cell_index(P.N, x, cb1 + j1, cb2 + j2));
+    }
+    __syncthreads();
+    // per direction: candidate cell (0: lower / only, 1: upper), local row index, local column index
+    int nd[3] = {1, 1, 1}, dl[3][2] = {}, li[3][2] = {}, lj[3][2] = {};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      int n = 0;
+      if (vt[d]) {
+        if (e[d] <= 0) { dl[d][n] = 0; li[d][n] = K; lj[d][n] = e[d] + K; n++; }
+        if (e[d] >= 0) { dl[d][n] = 1; li[d][n] = 0; lj[d][n] = e[d]; n++; }
+      } else {
+        dl[d][n] = 0; li[d][n] = 1; lj[d][n] = e[d] + 1; n++;
+      }
+      nd[d] = n;
+    }
+    // the <= 2^DIM (cell, i, j) combinations in ascending cell order; a combination is evaluated only
+    // if some lane of the warp needs it (most entries couple through a single cell)
+    double coef[8];
+    int idx[8];
+    bool any[8];
+#pragma unroll
+    for (int c2 = 0; c2 < 2; c2++)
+#pragma unroll
+      for (int c1 = 0; c1 < 2; c1++)
+#pragma unroll
+        for (int c0 = 0; c0 < 2; c0++) {
+          const int k = c0 + 2 * c1 + 4 * c2;
+          const bool on = active && c0 < nd[0] && c1 < nd[1] && c2 < nd[2];
+          const int i = li[0][c0] + N1 * (li[1][c1] + N1 * (DIM == 3 ? li[2][c2] : 0));
+          const int j = lj[0][c0] + N1 * (lj[1][c1] + N1 * (DIM == 3 ? lj[2][c2] : 0));
+          coef[k] = on ? tab_g[i * N + j] : 0.0;
+          idx[k] = on ? (dl[2][c2] * 2 + dl[1][c1]) * KS + dl[0][c0] : 0;
+          any[k] = __any_sync(0xffffffffu, on);
+        }
+    if (!active) return;
+    const int xoff = vt[0] ? -1 : 0;
+    double* dst = values + base + (size_t)rsub * L + slot;
+    for (int a0 = lo0 + rsub; a0 <= hi0; a0 += R, dst += (size_t)R * L) {
+      const double* kp = kap + a0 + xoff;
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (any[k]) v = fma(coef[k], kp[idx[k]], v);  // lanes that do not need it carry coef = 0, idx = 0
+      *dst = fresh ? v : *dst + v;
+    }
+  } else {
+    if (!active) return;
+    long long col0;
+    if (K == 1) {
+      col0 = (lo0 + e[0]) + (long long)(N0 + 1) * ((a1 + e[1]) + (long long)(P.N[1] + 1) * (DIM == 3 ? a2 + e[2] : 0));
+    } else {
+      int par = 0, sh[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const int q = ((s >> d) & 1) + e[d];  // lattice offset of the column relative to 2 a_d
+        const int pb = q & 1;
+        par |= pb << d;
+        sh[d] = (q - pb) / 2;
+      }
+      const int g2 = D.group_of_s[par];
+      col0 = (long long)D.start[g2] + (lo0 + sh[0]) +
+             (long long)D.sz0[g2] * ((a1 + sh[1]) + (long long)D.sz1[g2] * (DIM == 3 ? a2 + sh[2] : 0));
+    }
+    IDX* dst = colidx + base + (size_t)rsub * L + slot;
+    for (int a0 = lo0 + rsub; a0 <= hi0; a0 += R, dst += (size_t)R * L) *dst = (IDX)(col0 + (a0 - lo0));
   }
 }
 
@@ -717,6 +833,9 @@ struct MatrixPlan {
   u64 nrows = 0, nnz = 0, nbrows = 0, nblocks = 0;
   u64* rowptr = nullptr;           // Qk: scalar CSR row pointers; DG: block row pointers (cells)
   unsigned char* flags = nullptr;  // Qk: constrained rows
+  uint32_t* brows = nullptr;       // Qk: rows whose lattice point lies on the boundary (ascending)
+  u64 nbr = 0;
+  bool interior_ok = false;        // Qk: the interior-line kernels apply (every group has interior rows)
 };
 
 static FastDiv make_fastdiv(uint32_t d) {
@@ -880,6 +999,69 @@ static void build_qk_tables(MatrixPlan* plan) {
   PDB_CUDA(cudaMemcpy(plan->tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 
+// rows handled by the generic kernels when the interior-line kernels take the rest
+static void build_qk_boundary_rows(MatrixPlan* plan) {
+  const DevParams& P = plan->P;
+  const QkDecode& D = plan->D;
+  plan->interior_ok = true;
+  for (int d = 0; d < P.dim; d++)
+    if (P.N[d] < 2) plan->interior_ok = false;  // no interior vertex in that direction
+  if ((size_t)4 * qk_kap_stride(P.N[0]) * sizeof(double) > 200 * 1024) plan->interior_ok = false;  // coefficient rows of a line in smem
+  if (!plan->interior_ok) return;
+  std::vector<uint32_t> rows;
+  for (int g = 0; g < D.ng; g++) {
+    const int s = D.sbits[g];
+    const bool vt[3] = {!(s & 1), !((s >> 1) & 1), !((s >> 2) & 1)};
+    int sz[3] = {1, 1, 1};
+    for (int d = 0; d < P.dim; d++) sz[d] = vt[d] ? P.N[d] + 1 : P.N[d];
+    for (int a2 = 0; a2 < sz[2]; a2++)
+      for (int a1 = 0; a1 < sz[1]; a1++) {
+        const bool line_b = (P.dim > 1 && vt[1] && (a1 == 0 || a1 == sz[1] - 1)) ||
+                            (P.dim > 2 && vt[2] && (a2 == 0 || a2 == sz[2] - 1));
+        const uint32_t r0 = D.start[g] + (uint32_t)sz[0] * ((uint32_t)a1 + (uint32_t)sz[1] * (uint32_t)a2);
+        if (line_b) {
+          for (int a0 = 0; a0 < sz[0]; a0++) rows.push_back(r0 + a0);
+        } else if (vt[0]) {
+          rows.push_back(r0);
+          rows.push_back(r0 + sz[0] - 1);
+        }
+      }
+  }
+  std::sort(rows.begin(), rows.end());
+  plan->nbr = rows.size();
+  if (plan->nbr) {
+    PDB_CUDA(cudaMalloc(&plan->brows, rows.size() * sizeof(uint32_t)));
+    PDB_CUDA(cudaMemcpy(plan->brows, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+}
+
+// launches the interior-line kernel for every entity group; returns the number of launches
+template <int DIM, int K, typename IDX, bool VALUES>
+static int launch_qk_interior(MatrixPlan* p, double* values, IDX* colidx, bool fresh, cudaStream_t s) {
+  const DevParams& P = p->P;
+  const QkDecode& D = p->D;
+  int launches = 0;
+  for (int g = 0; g < D.ng; g++) {
+    const int sb = D.sbits[g];
+    const bool vt[3] = {!(sb & 1), !((sb >> 1) & 1), !((sb >> 2) & 1)};
+    int L = 1;
+    for (int d = 0; d < DIM; d++) L *= vt[d] ? 2 * K + 1 : K + 1;
+    const int n1 = vt[1] ? P.N[1] - 1 : P.N[1], n2 = DIM == 3 ? (vt[2] ? P.N[2] - 1 : P.N[2]) : 1;
+    const int nrow0 = vt[0] ? P.N[0] - 1 : P.N[0];
+    if (n1 <= 0 || n2 <= 0 || nrow0 <= 0) continue;
+    const int threads = 256;
+    const size_t smem = VALUES ? (size_t)4 * qk_kap_stride(P.N[0]) * sizeof(double) : 0;
+    if (smem > 48 * 1024)
+      PDB_CUDA(cudaFuncSetAttribute(qk_interior_kernel<DIM, K, IDX, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    qk_interior_kernel<DIM, K, IDX, VALUES><<<dim3(n1, n2), threads, smem, s>>>(P, D, g, L, p->lut, p->tables, p->rowptr,
+                                                                               values, colidx, fresh ? 1 : 0);
+    PDB_CUDA(cudaGetLastError());
+    launches++;
+  }
+  return launches;
+}
+
 MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s) {
   MatrixPlan* plan = new MatrixPlan;
   plan->P = P;
@@ -927,6 +1109,7 @@ MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s)
           plan->T.C[i * n1 + j] = (double)C;
         }
       build_qk_tables(plan);
+      build_qk_boundary_rows(plan);
     }
     PDB_CUDA(cudaStreamSynchronize(s));
   } catch (...) {
@@ -940,6 +1123,7 @@ void matrix_plan_destroy(MatrixPlan* p) {
   if (!p) return;
   if (p->rowptr) cudaFree(p->rowptr);
   if (p->flags) cudaFree(p->flags);
+  if (p->brows) cudaFree(p->brows);
   if (p->tables) cudaFree(p->tables);
   if (p->lut) cudaFree(p->lut);
   delete p;
@@ -975,11 +1159,24 @@ int matrix_pattern_write(MatrixPlan* p, int layout, void* rowptr, bool rowptr_de
   } else {
     PDB_CUDA(cudaMemcpyAsync(rp, p->rowptr, (nr + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     const int G = P.n > 16 ? 32 : (P.n > 8 ? 16 : 8);
-    const u64 blocks = (nr * G + QK_THREADS - 1) / QK_THREADS;
+    // interior rows: one x-line per CTA; boundary rows (or everything on degenerate grids): generic kernel
+    const uint32_t* list = p->interior_ok ? p->brows : nullptr;
+    const u64 ngen = p->interior_ok ? p->nbr : nr;
+    if (p->interior_ok) {
+#define PDB_INT(DD, KK)                                                                                   \
+  if (P.dim == DD && P.k == KK)                                                                           \
+    launches += col32 ? launch_qk_interior<DD, KK, uint32_t, false>(p, nullptr, (uint32_t*)ci, false, s)  \
+                      : launch_qk_interior<DD, KK, u64, false>(p, nullptr, (u64*)ci, false, s);
+      PDB_INT(2, 1) PDB_INT(2, 2) PDB_INT(3, 1) PDB_INT(3, 2)
+#undef PDB_INT
+    }
+    const u64 blocks = (ngen * G + QK_THREADS - 1) / QK_THREADS;
 #define PDB_COLIDX(GG)                                                                                        \
-  if (col32) qk_colidx_kernel<GG, uint32_t><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, nr, (uint32_t*)ci); \
-  else qk_colidx_kernel<GG, u64><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, nr, (u64*)ci)
-    if (G == 32) { PDB_COLIDX(32); } else if (G == 16) { PDB_COLIDX(16); } else { PDB_COLIDX(8); }
+  if (col32) qk_colidx_kernel<GG, uint32_t><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, ngen, (uint32_t*)ci, list); \
+  else qk_colidx_kernel<GG, u64><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, ngen, (u64*)ci, list)
+    if (blocks > 0) {
+      if (G == 32) { PDB_COLIDX(32); } else if (G == 16) { PDB_COLIDX(16); } else { PDB_COLIDX(8); }
+    }
 #undef PDB_COLIDX
   }
   PDB_CUDA(cudaGetLastError());
@@ -998,7 +1195,7 @@ int matrix_pattern_write(MatrixPlan* p, int layout, void* rowptr, bool rowptr_de
 }
 
 template <int G, int DIM, int K, bool NT1, bool OUTFLOW>
-static void launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+static int launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
   constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
   constexpr int MAXLEN = DIM == 3 ? (2 * K + 1) * (2 * K + 1) * (2 * K + 1) : (2 * K + 1) * (2 * K + 1);
   constexpr int ROWS_PER_CTA = QK_THREADS / G;
@@ -1011,27 +1208,37 @@ static void launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStrea
   PDB_CUDA(cudaGetDevice(&dev));
   PDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QK_THREADS, smem));
-  const u64 want = (p->nrows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  // a single unit table and no boundary terms: interior rows go through the x-line kernel
+  int launches = 0;
+  const bool split = NT1 && !OUTFLOW && p->interior_ok;
+  if (split) launches += launch_qk_interior<DIM, K, uint32_t, true>(p, v, nullptr, fresh, s);
+  const u64 nrows = split ? p->nbr : p->nrows;
+  const uint32_t* list = split ? p->brows : nullptr;
+  const u64 want = (nrows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   const unsigned blocks = (unsigned)std::min<u64>(want, (u64)sms * std::max(per_sm, 1));
-  kern<<<blocks, QK_THREADS, smem, s>>>(p->P, p->D, p->T, p->Q, p->tables, p->lut, p->rowptr, p->nrows, p->flags, v,
-                                        fresh ? 1 : 0);
+  if (blocks > 0) {
+    kern<<<blocks, QK_THREADS, smem, s>>>(p->P, p->D, p->T, p->Q, p->tables, p->lut, p->rowptr, nrows, p->flags, v,
+                                          fresh ? 1 : 0, list);
+    launches++;
+  }
+  return launches;
 }
 
 template <int G, int DIM, int K>
-static void launch_qk_assemble_nt(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+static int launch_qk_assemble_nt(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
   const bool outflow = p->P.bctype != nullptr && p->P.b != nullptr;  // jacobian_boundary has outflow terms only
-  if (outflow) launch_qk_assemble_t<G, DIM, K, false, true>(p, v, fresh, s);
-  else if (p->Q.nt == 1) launch_qk_assemble_t<G, DIM, K, true, false>(p, v, fresh, s);
-  else launch_qk_assemble_t<G, DIM, K, false, false>(p, v, fresh, s);
+  if (outflow) return launch_qk_assemble_t<G, DIM, K, false, true>(p, v, fresh, s);
+  if (p->Q.nt == 1) return launch_qk_assemble_t<G, DIM, K, true, false>(p, v, fresh, s);
+  return launch_qk_assemble_t<G, DIM, K, false, false>(p, v, fresh, s);
 }
 
-static void launch_qk_assemble(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
+static int launch_qk_assemble(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
   const DevParams& P = p->P;
-  if (P.dim == 2 && P.k == 1) launch_qk_assemble_nt<8, 2, 1>(p, v, fresh, s);
-  else if (P.dim == 2 && P.k == 2) launch_qk_assemble_nt<16, 2, 2>(p, v, fresh, s);
-  else if (P.dim == 3 && P.k == 1) launch_qk_assemble_nt<8, 3, 1>(p, v, fresh, s);
-  else if (P.dim == 3 && P.k == 2) launch_qk_assemble_nt<32, 3, 2>(p, v, fresh, s);
-  else throw Error("conforming Jacobian: unsupported (dim, degree)");
+  if (P.dim == 2 && P.k == 1) return launch_qk_assemble_nt<8, 2, 1>(p, v, fresh, s);
+  if (P.dim == 2 && P.k == 2) return launch_qk_assemble_nt<16, 2, 2>(p, v, fresh, s);
+  if (P.dim == 3 && P.k == 1) return launch_qk_assemble_nt<8, 3, 1>(p, v, fresh, s);
+  if (P.dim == 3 && P.k == 2) return launch_qk_assemble_nt<32, 3, 2>(p, v, fresh, s);
+  throw Error("conforming Jacobian: unsupported (dim, degree)");
 }
 
 int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, bool fresh, int* errflag,
@@ -1042,10 +1249,11 @@ int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, 
     PDB_CUDA(cudaMalloc(&v, std::max<u64>(p->nnz, 1) * sizeof(double)));
     if (!fresh) PDB_CUDA(cudaMemcpyAsync(v, values, p->nnz * sizeof(double), cudaMemcpyHostToDevice, s));
   }
+  int launches = 1;
   if (P.dg) {
     dg_assemble_kernel<<<(unsigned)P.ncells, 128, 0, s>>>(P, p->rowptr, layout == PDB200_LAYOUT_BCSR, v, fresh ? 1 : 0, errflag);
   } else {
-    launch_qk_assemble(p, v, fresh, s);
+    launches = launch_qk_assemble(p, v, fresh, s);
   }
   PDB_CUDA(cudaGetLastError());
   if (!values_dev) {
@@ -1053,7 +1261,7 @@ int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, 
     PDB_CUDA(cudaStreamSynchronize(s));
     cudaFree(v);
   }
-  return 1;
+  return launches;
 }
 
 int matrix_mv(MatrixPlan* p, int layout, const double* values, const double* x, double* y, cudaStream_t s) {
