@@ -141,6 +141,9 @@ void fem_plan_destroy(FemPlan*);
 void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                        cudaStream_t s);
 struct QkLayout;  // host_tables.h
+// fem_kron.cu: Kronecker-form conforming Qk apply (diagonal A, b = 0): warp-shuffle / smem / register assembly
+void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* MinvK, const double* x, double* y,
+                     const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s);
 const QkLayout& fem_plan_layout(const FemPlan*);
 const uint64_t* fem_plan_constrained(const FemPlan*, long long* n);  // device list of constrained DOFs
 

@@ -70,6 +70,7 @@ struct TileFrame {
   int org[3];  // cell coordinate of tile (0,0,0)
   int lim[3];  // exclusive upper bound of the tiled cell range
   double* out; // the output vector (ghost rows are written with plain stores)
+  int pf;      // L2 prefetch distance in tiles of the launch's linear block order (0 = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +107,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// warms L2 with the core box of a tile that a later CTA will load (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait() {
@@ -242,7 +249,8 @@ template <int AMODE, bool HAS_C, bool WEIGHTS_ON>
 __global__ void __launch_bounds__(TX* TY* TZ, 3)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
-                         const DevParams P, const FastConst F, const TileFrame TF) {
+                         const __grid_constant__ CUtensorMap tm_pf, const DevParams P, const FastConst F,
+                         const TileFrame TF) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
@@ -261,6 +269,15 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     tma_load_4d(tile + R2, &tm_yh, 0, x0 / 2, y0 + TY, z0, &bar);
     tma_load_4d(tile + R3, &tm_zh, 0, x0 / 2, y0, z0 - 1, &bar);
     tma_load_4d(tile + R4, &tm_zh, 0, x0 / 2, y0, z0 + TZ, &bar);
+    if (TF.pf) {  // the tile TF.pf places further on in launch order: every input byte is prefetched once
+      unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
+      const unsigned px = lin % gridDim.x;
+      lin /= gridDim.x;
+      const unsigned py = lin % gridDim.y, pz = lin / gridDim.y;
+      if (pz < gridDim.z)
+        tma_prefetch_4d(&tm_pf, 0, (px + TF.off[0]) * (TX / 2), TF.org[1] + (py + TF.off[1]) * TY,
+                        TF.org[2] + (pz + TF.off[2]) * TZ);
+    }
   }
 
   // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
@@ -536,6 +553,13 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
   int nt[3];
   tile_frame(P, TF, nt);
   TF.out = out;
+  {
+    static const int pf_env = [] {
+      const char* e = getenv("PDB200_FAST_PREFETCH");
+      return e ? atoi(e) : 444;  // three tiles per SM ahead: measured 1-2 % (profiles/r01_prefetch_sweep.txt)
+    }();
+    TF.pf = pf_env;
+  }
   // boxes of tiles to launch: {offset, extent}
   int boxes[7][6], nboxes = 0;
   auto add = [&](int ox, int oy, int oz, int ex, int ey, int ez) {
@@ -563,7 +587,7 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
   }
   int launches = 0;
 #define PDB_LAUNCH(AM, HC, WO) \
-  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, plan->F, TF)
+  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, mx.core, P, plan->F, TF)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \
     if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \

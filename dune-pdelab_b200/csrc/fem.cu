@@ -44,6 +44,7 @@ struct FemPlan {
   FemKron kron;
   double* r0 = nullptr;     // R(0) of the affine residual (Kronecker path), cached per coefficient set
   bool r0_valid = false;
+  bool fused_constraints = false;  // the last launch already zeroed the constrained rows
 };
 
 namespace {
@@ -412,6 +413,7 @@ template <int DIM, int K>
 void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                 cudaStream_t s) {
   const bool kron = P.a_mode != PDB200_A_FULL && P.b == nullptr;
+  plan->fused_constraints = false;
   if (!kron) {
     if (residual)
       launch_fem_variant<DIM, K, true, false>(plan, P, x, y, nullptr, overwrite, s);
@@ -435,7 +437,9 @@ void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, b
     }
     r0 = plan->r0;
   }
-  launch_fem_variant<DIM, K, false, true>(plan, P, x, y, r0, overwrite, s);
+  // all boundary lattice points constrained (no bctype array): the kernel writes the zero rows itself
+  plan->fused_constraints = P.bctype == nullptr;
+  launch_fem_kron(P, plan->L, plan->kron.MinvK, x, y, r0, overwrite, plan->fused_constraints, s);
 }
 
 }  // namespace
@@ -489,7 +493,7 @@ void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, doubl
   else if (P.dim == 3 && P.k == 2) launch_fem<3, 2>(plan, P, x, y, residual, overwrite, s);
   else throw Error("conforming Qk kernel: unsupported (dim, degree)");
   // postAssembly: constrain_residual (residualengine.hh:228-233, jacobianapplyengine.hh:249-254)
-  if (plan->ncon) {
+  if (plan->ncon && !plan->fused_constraints) {
     constrain_kernel<<<(unsigned)((plan->ncon + 255) / 256), 256, 0, s>>>(y, plan->con, plan->ncon);
     PDB_CUDA(cudaGetLastError());
   }

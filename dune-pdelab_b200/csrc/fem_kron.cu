@@ -1,0 +1,326 @@
+// fem_kron.cu — conforming Qk (k = 1, 2; dim = 2, 3) matrix-free  y (+)= J x (+ R(0))  for
+// ConvectionDiffusionFEM with a cell-wise constant DIAGONAL tensor and b = 0: the fast path behind
+// GridOperator::residual / jacobian_apply (gridoperator/gridoperator.hh:176-197).
+//
+// What it replaces in the reference (paths relative to /root/reference/dune/pdelab/):
+//   DefaultAssembler::assemble cell loop                 gridoperator/default/assembler.hh:85-279
+//   LFSIndexCache gather / scatter                        gridfunctionspace/lfsindexcache.hh:603-633,
+//                                                         gridoperator/default/residualengine.hh:131-233
+//   ConvectionDiffusionFEM::alpha_volume                  localoperator/convectiondiffusionfem.hh:63-136
+//   constrain_residual                                    constraints/common/constraints.hh:904-915
+//
+// Cell integral.  The (k+1)-point Gauss rule of convectiondiffusionfem.hh:93-94 integrates the
+// products of 1-D polynomials exactly, so alpha_volume of cell e equals
+//     r_e = |K| (M (x) M (x) M) [ sum_d (A_dd / h_d^2) (M^-1 K)_d x_e + c_e x_e ]
+// (M, K the exact 1-D mass / stiffness matrices): one 1-D sweep per direction and three mass
+// sweeps (integer matrices 30 M resp. 6 M, scale folded into the coefficients).
+//
+// Mapping to the machine.  One thread per cell; the scatter r[ci(i)] += rl[i] of the reference is
+// turned into a race-free, atomic-free assembly along the three grid directions:
+//   x: the 32 lanes of a warp are 32 consecutive cells of an x-row; the face  i_0 = k  of a cell is
+//      handed to the right neighbour with warp shuffles;
+//   y: the warps of a CTA are consecutive x-rows; face  i_1 = k  goes to the next warp through a
+//      double-buffered shared-memory slot (one __syncthreads per step);
+//   z: a thread marches along z; face  i_2 = k  is carried in registers to the next step, and so is
+//      the plane of input values it shares with the next cell.
+// After the three hand-overs a thread holds the finished rows of the k^dim lattice points its cell
+// owns (local indices < k) and writes each exactly once; along x consecutive lanes write
+// consecutive addresses of one sub-entity group of the container (host_tables.h: QkLayout), so all
+// global traffic is coalesced.  Lane 0 / warp 0 / step 0 of a tile are the overlap cell layer
+// (their own rows are written by the neighbouring tile).  Deterministic: fixed summation order.
+// In 2-D the march runs along y and there is no shared-memory stage.
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "host_tables.h"
+
+namespace pdb {
+
+namespace {
+
+struct FemKronParams {
+  double s[3];     // |K| / D^dim / h_d^2   (D = 30 for k = 2, 6 for k = 1)
+  double sc;       // |K| / D^dim
+  double MinvK[MAX_N1 * MAX_N1];  // row-major, leading dimension n1
+  long long goff[8];              // first container index of sub-entity group s (k = 2); goff[0] = 0 for k = 1
+  int gd0[8], gd1[8];             // entities per x-row / y-column of group s
+  int N[3];
+  int chunk;       // cells per march chunk
+  int tiles_x;     // 2-D: warps of a CTA are independent x-tiles
+  int fuse_constraints;  // every boundary lattice point is constrained (no bctype array): write 0 there
+};
+
+template <int DIM, int K>
+struct KL {
+  static constexpr int N1 = K + 1;
+  static constexpr int N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  static constexpr int MD = DIM - 1;                        // march direction
+  static constexpr int SM = DIM == 3 ? N1 * N1 : N1;        // local stride of the march direction
+};
+
+// container index of local DOF (i0, i1, i2) of cell c (closed form of LFSIndexCache, host_tables.h)
+template <int DIM, int K>
+__device__ __forceinline__ long long lat_index(const FemKronParams& F, int c0, int c1, int c2, int i0, int i1, int i2) {
+  if (K == 1) {
+    const long long p1 = c1 + i1, p2 = c2 + i2;
+    return (c0 + i0) + (long long)F.gd0[0] * (p1 + (DIM == 3 ? (long long)F.gd1[0] * p2 : 0));
+  }
+  const int s = (i0 & 1) | ((i1 & 1) << 1) | (DIM == 3 ? (i2 & 1) << 2 : 0);
+  const long long q1 = c1 + (i1 >> 1), q2 = c2 + (i2 >> 1);
+  return F.goff[s] + (c0 + (i0 >> 1)) + (long long)F.gd0[s] * (q1 + (DIM == 3 ? (long long)F.gd1[s] * q2 : 0));
+}
+
+// v <- (D M along stride S) v for every line: 30 M = [[4,2,-1],[2,16,2],[-1,2,4]], 6 M = [[2,1],[1,2]]
+template <int DIM, int K, int AXIS>
+__device__ __forceinline__ void mass_sweep(double (&t)[KL<DIM, K>::N]) {
+  constexpr int N1 = K + 1, N = KL<DIM, K>::N;
+  constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
+#pragma unroll
+  for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+    for (int lo = 0; lo < S; lo++) {
+      const int base = hi * S * N1 + lo;
+      if (K == 2) {
+        const double v0 = t[base], v1 = t[base + S], v2 = t[base + 2 * S];
+        const double e = v0 + v2;
+        const double w = fma(2.0, v1, -e);
+        t[base] = fma(5.0, v0, w);
+        t[base + S] = fma(16.0, v1, e + e);
+        t[base + 2 * S] = fma(5.0, v2, w);
+      } else {
+        const double e = t[base] + t[base + S];
+        t[base] += e;
+        t[base + S] += e;
+      }
+    }
+}
+
+// t (+)= al (M^-1 K along AXIS) x
+template <int DIM, int K, int AXIS, bool ACC>
+__device__ __forceinline__ void stiff_sweep(const FemKronParams& F, double al, const double (&x)[KL<DIM, K>::N],
+                                            double (&t)[KL<DIM, K>::N]) {
+  constexpr int N1 = K + 1, N = KL<DIM, K>::N;
+  constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
+  double W[N1 * N1];
+#pragma unroll
+  for (int i = 0; i < N1 * N1; i++) W[i] = al * F.MinvK[i];
+#pragma unroll
+  for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+    for (int lo = 0; lo < S; lo++) {
+      const int base = hi * S * N1 + lo;
+#pragma unroll
+      for (int o = 0; o < N1; o++) {
+        double acc = ACC ? t[base + o * S] : 0.0;
+#pragma unroll
+        for (int i = 0; i < N1; i++) acc = fma(W[o * N1 + i], x[base + i * S], acc);
+        t[base + o * S] = acc;
+      }
+    }
+}
+
+template <int DIM, int K, int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB)
+    fem_kron_kernel(const DevParams P, const FemKronParams F, const double* __restrict__ xg, double* __restrict__ yg,
+                    const double* __restrict__ r0, int overwrite) {
+  using L = KL<DIM, K>;
+  constexpr int N1 = L::N1, N = L::N, SM = L::SM;
+  constexpr int NYX = DIM == 3 ? K * N1 : 1;  // values handed to the next warp per cell
+  __shared__ double slot[DIM == 3 ? 2 * WY * NYX * 32 : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // cell coordinates: lane 0 / warp 0 / step 0 are the overlap layer of the tile
+  int c0, c1 = 0, cm0;  // cm0: first march coordinate (overlap layer)
+  if (DIM == 3) {
+    c0 = (int)blockIdx.x * 31 - 1 + lane;
+    c1 = (int)blockIdx.y * (WY - 1) - 1 + warp;
+    cm0 = (int)blockIdx.z * F.chunk - 1;
+  } else {
+    const int tile = (int)blockIdx.x * WY + warp;
+    c0 = tile * 31 - 1 + lane;
+    cm0 = (int)blockIdx.y * F.chunk - 1;
+    if (tile >= F.tiles_x) return;  // whole warp; no block-wide barrier in 2-D
+  }
+  const int Nm = F.N[L::MD];
+  const bool vx = c0 >= 0 && c0 < F.N[0];
+  const bool vy = DIM == 3 ? (c1 >= 0 && c1 < F.N[1]) : true;
+  // rows of this thread that exist: the cell layer c_d == N_d owns only the lattice layer i_d == 0
+  const bool ownx = lane > 0 && c0 <= F.N[0];
+  const bool owny = DIM == 3 ? (warp > 0 && c1 <= F.N[1]) : true;
+
+  double x[N], t[N];
+  double carry[DIM == 3 ? K * K : K];
+#pragma unroll
+  for (int i = 0; i < (DIM == 3 ? K * K : K); i++) carry[i] = 0.0;
+  bool have_plane = false;  // x[.., i_m = k] of the previous step is this step's plane i_m = 0
+  const int steps = min(F.chunk, Nm + 1 - (cm0 + 1)) + 1;
+
+  for (int step = 0; step < steps; step++) {
+    const int cm = cm0 + step;
+    const int c2 = DIM == 3 ? cm : 0;
+    const int cy = DIM == 3 ? c1 : cm;
+    const bool valid = vx && vy && cm >= 0 && cm < Nm;
+    if (valid) {
+      // ---- gather (loadCoefficientsLFSUInside); the plane shared with the previous cell is carried
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
+        const int im = DIM == 3 ? i2 : i1;
+        if (im == 0) {
+          if (have_plane)
+            x[i] = x[i + K * SM];
+          else
+            x[i] = __ldg(xg + lat_index<DIM, K>(F, c0, cy, c2, i0, i1, i2));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
+        const int im = DIM == 3 ? i2 : i1;
+        if (im != 0) x[i] = __ldg(xg + lat_index<DIM, K>(F, c0, cy, c2, i0, i1, i2));
+      }
+      const long long cell = c0 + (long long)F.N[0] * (cy + (DIM == 3 ? (long long)F.N[1] * c2 : 0));
+      double a[3] = {1.0, 1.0, 1.0};
+      if (P.a_mode == PDB200_A_SCALAR) {
+        a[0] = a[1] = a[2] = __ldg(P.A + cell);
+      } else if (P.a_mode == PDB200_A_DIAGONAL) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) a[d] = __ldg(P.A + cell * DIM + d);
+      }
+      stiff_sweep<DIM, K, 0, false>(F, a[0] * F.s[0], x, t);
+      stiff_sweep<DIM, K, 1, true>(F, a[1] * F.s[1], x, t);
+      if (DIM == 3) stiff_sweep<DIM, K, 2, true>(F, a[2] * F.s[2], x, t);
+      if (P.c) {
+        const double cc = __ldg(P.c + cell) * F.sc;
+#pragma unroll
+        for (int i = 0; i < N; i++) t[i] = fma(cc, x[i], t[i]);
+      }
+      mass_sweep<DIM, K, 0>(t);
+      mass_sweep<DIM, K, 1>(t);
+      if (DIM == 3) mass_sweep<DIM, K, 2>(t);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++) t[i] = 0.0;
+    }
+    have_plane = valid;  // uniform along the march for a thread with vx && vy; others never load
+
+    // ---- x: face i_0 = k -> right neighbour's i_0 = 0 ------------------------------------------
+#pragma unroll
+    for (int j = 0; j < N / N1; j++) {
+      const double up = __shfl_up_sync(0xffffffffu, t[j * N1 + K], 1);
+      if (lane > 0) t[j * N1] += up;
+    }
+    // ---- y: face i_1 = k (i_0 < k) -> next warp's i_1 = 0 ---------------------------------------
+    if (DIM == 3) {
+      double* buf = slot + (step & 1) * (WY * NYX * 32);
+#pragma unroll
+      for (int i2 = 0; i2 < N1; i2++)
+#pragma unroll
+        for (int i0 = 0; i0 < K; i0++) buf[(warp * NYX + i2 * K + i0) * 32 + lane] = t[i0 + N1 * (K + N1 * i2)];
+      __syncthreads();
+      if (warp > 0) {
+#pragma unroll
+        for (int i2 = 0; i2 < N1; i2++)
+#pragma unroll
+          for (int i0 = 0; i0 < K; i0++) t[i0 + N1 * N1 * i2] += buf[((warp - 1) * NYX + i2 * K + i0) * 32 + lane];
+      }
+    }
+    // ---- march direction: face i_m = k carried to the next step ---------------------------------
+#pragma unroll
+    for (int j = 0; j < (DIM == 3 ? K * K : K); j++) {
+      const int i0 = j % K, i1 = DIM == 3 ? j / K : 0;
+      const int lo = DIM == 3 ? i0 + N1 * i1 : i0;
+      t[lo] += carry[j];
+      carry[j] = t[lo + K * SM];
+    }
+    // ---- the k^dim lattice points this cell owns are complete: write each row once --------------
+    if (step > 0 && ownx && owny) {
+      const bool lastx = c0 == F.N[0], lasty = DIM == 3 && c1 == F.N[1], lastm = cm == Nm;
+#pragma unroll
+      for (int j = 0; j < (DIM == 3 ? K * K * K : K * K); j++) {
+        const int i0 = j % K, i1 = (j / K) % K, i2 = DIM == 3 ? j / (K * K) : 0;
+        const int im = DIM == 3 ? i2 : i1;
+        if ((lastx && i0) || (lasty && i1) || (lastm && im)) continue;
+        const long long gi = lat_index<DIM, K>(F, c0, cy, c2, i0, DIM == 3 ? i1 : im, i2);
+        double v = t[i0 + N1 * (DIM == 3 ? i1 + N1 * i2 : im)];
+        if (F.fuse_constraints) {
+          // constrain_residual: all boundary lattice points are Dirichlet- or processor-constrained
+          const bool onb = (i0 == 0 && (c0 == 0 || lastx)) || (DIM == 3 && i1 == 0 && (c1 == 0 || lasty)) ||
+                           (im == 0 && (cm == 0 || lastm));
+          if (onb) {
+            yg[gi] = 0.0;
+            continue;
+          }
+        }
+        if (r0) v += __ldg(r0 + gi);
+        if (!overwrite) v += yg[gi];
+        yg[gi] = v;
+      }
+    }
+  }
+}
+
+template <int DIM, int K, int WY, int MINB>
+void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK, const double* x, double* y,
+                    const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s) {
+  FemKronParams F;
+  const double D = K == 2 ? 30.0 : 6.0;
+  double sc = P.vol;
+  for (int d = 0; d < DIM; d++) sc /= D;
+  F.sc = sc;
+  for (int d = 0; d < 3; d++) {
+    F.s[d] = d < DIM ? sc / (P.h[d] * P.h[d]) : 0.0;
+    F.N[d] = d < DIM ? P.N[d] : 1;
+  }
+  for (int i = 0; i < MAX_N1 * MAX_N1; i++) F.MinvK[i] = i < (K + 1) * (K + 1) ? MinvK[i] : 0.0;
+  for (int g = 0; g < 8; g++) {
+    int edim = 0;
+    for (int d = 0; d < DIM; d++) edim += (g >> d) & 1;
+    F.goff[g] = K == 1 ? 0 : (g < (1 << DIM) ? Lq.block_off[edim] + Lq.group_off[g] : 0);
+    F.gd0[g] = K == 1 ? P.N[0] + 1 : ((g & 1) ? P.N[0] : P.N[0] + 1);
+    F.gd1[g] = K == 1 ? P.N[1] + 1 : ((g & 2) ? P.N[1] : P.N[1] + 1);
+  }
+  F.fuse_constraints = fuse_constraints ? 1 : 0;
+  const int tiles_x = (P.N[0] + 1 + 30) / 31;
+  F.tiles_x = tiles_x;
+  const int Nm = P.N[DIM - 1] + 1;  // cell layers along the march direction incl. the closing one
+  const long long columns = DIM == 3 ? (long long)tiles_x * ((P.N[1] + 1 + WY - 2) / (WY - 1)) : (tiles_x + WY - 1) / WY;
+  // chunks along the march direction: every chunk repeats one overlap layer, and the CTAs should fill
+  // whole waves of the 148 SMs; pick the count with the least estimated time (waves x steps)
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_chunks = std::max(1, Nm / 8);
+  for (int ch = 1; ch <= max_chunks; ch++) {
+    const int len = (Nm + ch - 1) / ch;
+    const long long ctas = columns * ((Nm + len - 1) / len);
+    const double waves = (double)((ctas + 147) / 148);
+    const double cost = waves * (len + 1);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = ch;
+    }
+  }
+  F.chunk = (Nm + best - 1) / best;
+  const int chunks = (Nm + F.chunk - 1) / F.chunk;
+  dim3 grid;
+  if (DIM == 3)
+    grid = dim3(tiles_x, (P.N[1] + 1 + WY - 2) / (WY - 1), chunks);
+  else
+    grid = dim3((tiles_x + WY - 1) / WY, chunks, 1);
+  fem_kron_kernel<DIM, K, WY, MINB><<<grid, 32 * WY, 0, s>>>(P, F, x, y, r0, overwrite ? 1 : 0);
+  PDB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+// MinvK: M^-1 K of the 1-D Lagrange basis, row-major with leading dimension k+1
+void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* K1, const double* x, double* y,
+                     const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s) {
+  if (P.dim == 2 && P.k == 1) launch_variant<2, 1, 4, 8>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
+  else if (P.dim == 2 && P.k == 2) launch_variant<2, 2, 4, 4>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
+  else if (P.dim == 3 && P.k == 1) launch_variant<3, 1, 16, 2>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
+  else if (P.dim == 3 && P.k == 2) launch_variant<3, 2, 12, 1>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
+  else throw Error("conforming Qk Kronecker kernel: unsupported (dim, degree)");
+}
+
+}  // namespace pdb
