@@ -438,6 +438,10 @@ void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, b
     r0 = plan->r0;
   }
   // all boundary lattice points constrained (no bctype array): the kernel writes the zero rows itself
+  if (P.ndofs >= (1ll << 31)) {  // fem_kron.cu keeps container indices in 32 bits
+    launch_fem_variant<DIM, K, false, true>(plan, P, x, y, r0, overwrite, s);
+    return;
+  }
   plan->fused_constraints = P.bctype == nullptr;
   launch_fem_kron(P, plan->L, plan->kron.MinvK, x, y, r0, overwrite, plan->fused_constraints, s);
 }

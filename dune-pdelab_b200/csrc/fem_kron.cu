@@ -45,6 +45,7 @@ struct FemKronParams {
   double MinvK[MAX_N1 * MAX_N1];  // row-major, leading dimension n1
   long long goff[8];              // first container index of sub-entity group s (k = 2); goff[0] = 0 for k = 1
   int gd0[8], gd1[8];             // entities per x-row / y-column of group s
+  int d2[8];                      // gd0 * gd1 (3-D): index stride of the group along z
   int N[3];
   int chunk;       // cells per march chunk
   int tiles_x;     // 2-D: warps of a CTA are independent x-tiles
@@ -59,17 +60,28 @@ struct KL {
   static constexpr int SM = DIM == 3 ? N1 * N1 : N1;        // local stride of the march direction
 };
 
-// container index of local DOF (i0, i1, i2) of cell c (closed form of LFSIndexCache, host_tables.h)
+// Container indices (closed form of LFSIndexCache, host_tables.h) in 32-bit arithmetic: a thread
+// keeps one running index per sub-entity group (the index of the group entity anchored at its
+// cell); a local DOF (i0, i1, i2) is that index plus a warp-uniform delta.
 template <int DIM, int K>
-__device__ __forceinline__ long long lat_index(const FemKronParams& F, int c0, int c1, int c2, int i0, int i1, int i2) {
-  if (K == 1) {
-    const long long p1 = c1 + i1, p2 = c2 + i2;
-    return (c0 + i0) + (long long)F.gd0[0] * (p1 + (DIM == 3 ? (long long)F.gd1[0] * p2 : 0));
+struct Idx {
+  static constexpr int NG = K == 1 ? 1 : (1 << DIM);
+  int base[NG];
+  __device__ __forceinline__ void init(const FemKronParams& F, int c0, int c1, int c2) {
+#pragma unroll
+    for (int g = 0; g < NG; g++)
+      base[g] = (int)F.goff[g] + c0 + F.gd0[g] * c1 + (DIM == 3 ? F.d2[g] * c2 : 0);
   }
-  const int s = (i0 & 1) | ((i1 & 1) << 1) | (DIM == 3 ? (i2 & 1) << 2 : 0);
-  const long long q1 = c1 + (i1 >> 1), q2 = c2 + (i2 >> 1);
-  return F.goff[s] + (c0 + (i0 >> 1)) + (long long)F.gd0[s] * (q1 + (DIM == 3 ? (long long)F.gd1[s] * q2 : 0));
-}
+  __device__ __forceinline__ void advance(const FemKronParams& F) {
+#pragma unroll
+    for (int g = 0; g < NG; g++) base[g] += DIM == 3 ? F.d2[g] : F.gd0[g];
+  }
+  __device__ __forceinline__ long long at(const FemKronParams& F, int i0, int i1, int i2) const {
+    if (K == 1) return base[0] + i0 + F.gd0[0] * i1 + (DIM == 3 ? F.d2[0] * i2 : 0);
+    const int g = (i0 & 1) | ((i1 & 1) << 1) | (DIM == 3 ? (i2 & 1) << 2 : 0);
+    return base[g] + (i0 >> 1) + F.gd0[g] * (i1 >> 1) + (DIM == 3 ? F.d2[g] * (i2 >> 1) : 0);
+  }
+};
 
 // v <- (D M along stride S) v for every line: 30 M = [[4,2,-1],[2,16,2],[-1,2,4]], 6 M = [[2,1],[1,2]]
 template <int DIM, int K, int AXIS>
@@ -120,15 +132,44 @@ __device__ __forceinline__ void stiff_sweep(const FemKronParams& F, double al, c
     }
 }
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+
+template <int DIM, int K>
+struct KS {  // per-thread staging slots in shared memory (values per thread)
+  static constexpr int NLD = KL<DIM, K>::N - KL<DIM, K>::SM;  // input planes i_m = 1..k
+  static constexpr int KO = DIM == 3 ? K * K * K : K * K;      // owned lattice points
+  static constexpr int NCO = 4;                                // A_dd (<= 3) and c
+  static constexpr int PER_THREAD = NLD + NCO + 2 * KO;
+};
+
+// The loads of step s+1 (input planes, coefficients: group X; old y and R(0) of the rows to be
+// written: group Y) are issued with cp.async into per-thread shared-memory slots while step s is
+// computed, so no global-memory latency is exposed inside the march.
 template <int DIM, int K, int WY, int MINB>
 __global__ void __launch_bounds__(32 * WY, MINB)
     fem_kron_kernel(const DevParams P, const FemKronParams F, const double* __restrict__ xg, double* __restrict__ yg,
                     const double* __restrict__ r0, int overwrite) {
   using L = KL<DIM, K>;
-  constexpr int N1 = L::N1, N = L::N, SM = L::SM;
+  using S = KS<DIM, K>;
+  constexpr int N1 = L::N1, N = L::N, SM = L::SM, NT = 32 * WY;
   constexpr int NYX = DIM == 3 ? K * N1 : 1;  // values handed to the next warp per cell
-  __shared__ double slot[DIM == 3 ? 2 * WY * NYX * 32 : 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NSLOT = DIM == 3 ? 2 * WY * NYX * 32 : 0;
+  extern __shared__ double dyn[];
+  double* slot = dyn;
+  const int tid = threadIdx.x;
+  double* xs = dyn + NSLOT + tid;        // [NLD][NT]
+  double* co = xs + S::NLD * NT;         // [NCO][NT]
+  double* ys = co + S::NCO * NT;         // [KO][NT]   old y
+  double* rs = ys + S::KO * NT;          // [KO][NT]   R(0)
+  const int lane = tid & 31, warp = tid >> 5;
   // cell coordinates: lane 0 / warp 0 / step 0 are the overlap layer of the tile
   int c0, c1 = 0, cm0;  // cm0: first march coordinate (overlap layer)
   if (DIM == 3) {
@@ -147,51 +188,95 @@ __global__ void __launch_bounds__(32 * WY, MINB)
   // rows of this thread that exist: the cell layer c_d == N_d owns only the lattice layer i_d == 0
   const bool ownx = lane > 0 && c0 <= F.N[0];
   const bool owny = DIM == 3 ? (warp > 0 && c1 <= F.N[1]) : true;
+  const bool lastx = c0 == F.N[0], lasty = DIM == 3 && c1 == F.N[1];
+  const bool need_y = !overwrite, need_r = r0 != nullptr;
+  const int steps = min(F.chunk, Nm + 1 - (cm0 + 1)) + 1;
+  Idx<DIM, K> cur, nxt;  // container indices anchored at the cell of this step / the next step
+  cur.init(F, c0, DIM == 3 ? c1 : cm0, DIM == 3 ? cm0 : 0);
+  nxt = cur;
+  int cell_nxt = c0 + F.N[0] * ((DIM == 3 ? c1 : cm0) + (DIM == 3 ? F.N[1] * cm0 : 0));
+  const int cell_stride = DIM == 3 ? F.N[0] * F.N[1] : F.N[0];
+
+  // group X of a step: input planes 1..k and the coefficients of the cell
+  // (nxt / cell_nxt address the cell of `step` when these are called)
+  auto issue_x = [&](int step) {
+    const int cm = cm0 + step;
+    if (step < steps && vx && vy && cm >= 0 && cm < Nm) {
+#pragma unroll
+      for (int i = SM; i < N; i++) {
+        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
+        cp_async8(xs + (i - SM) * NT, xg + nxt.at(F, i0, i1, i2));
+      }
+      const long long cell = cell_nxt;
+      if (P.a_mode == PDB200_A_SCALAR) {
+        cp_async8(co, P.A + cell);
+      } else if (P.a_mode == PDB200_A_DIAGONAL) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) cp_async8(co + d * NT, P.A + cell * DIM + d);
+      }
+      if (P.c) cp_async8(co + 3 * NT, P.c + cell);
+    }
+    cp_async_commit();
+  };
+  // group Y of a step: old y / R(0) of the rows the step will write
+  auto issue_y = [&](int step) {
+    const int cm = cm0 + step;
+    if ((need_y || need_r) && step > 0 && step < steps && ownx && owny) {
+      const bool lastm = cm == Nm;
+#pragma unroll
+      for (int j = 0; j < S::KO; j++) {
+        const int i0 = j % K, i1 = (j / K) % K, i2 = DIM == 3 ? j / (K * K) : 0;
+        const int im = DIM == 3 ? i2 : i1;
+        if ((lastx && i0) || (lasty && i1) || (lastm && im)) continue;
+        const long long gi = nxt.at(F, i0, i1, i2);
+        if (need_y) cp_async8(ys + j * NT, yg + gi);
+        if (need_r) cp_async8(rs + j * NT, r0 + gi);
+      }
+    }
+    cp_async_commit();
+  };
 
   double x[N], t[N];
   double carry[DIM == 3 ? K * K : K];
 #pragma unroll
   for (int i = 0; i < (DIM == 3 ? K * K : K); i++) carry[i] = 0.0;
   bool have_plane = false;  // x[.., i_m = k] of the previous step is this step's plane i_m = 0
-  const int steps = min(F.chunk, Nm + 1 - (cm0 + 1)) + 1;
+  issue_x(0);
+  issue_y(0);
 
   for (int step = 0; step < steps; step++) {
     const int cm = cm0 + step;
-    const int c2 = DIM == 3 ? cm : 0;
-    const int cy = DIM == 3 ? c1 : cm;
     const bool valid = vx && vy && cm >= 0 && cm < Nm;
+    cp_async_wait<1>();  // group X of this step has landed (group Y may still be in flight)
+    double a[3] = {1.0, 1.0, 1.0}, cc = 0.0;
     if (valid) {
       // ---- gather (loadCoefficientsLFSUInside); the plane shared with the previous cell is carried
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
-        const int im = DIM == 3 ? i2 : i1;
-        if (im == 0) {
-          if (have_plane)
-            x[i] = x[i + K * SM];
-          else
-            x[i] = __ldg(xg + lat_index<DIM, K>(F, c0, cy, c2, i0, i1, i2));
-        }
+      for (int i = 0; i < SM; i++) {
+        const int i0 = i % N1, i1 = (i / N1) % N1;
+        if (have_plane)
+          x[i] = x[i + K * SM];
+        else
+          x[i] = __ldg(xg + cur.at(F, i0, DIM == 3 ? i1 : 0, 0));
       }
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
-        const int im = DIM == 3 ? i2 : i1;
-        if (im != 0) x[i] = __ldg(xg + lat_index<DIM, K>(F, c0, cy, c2, i0, i1, i2));
-      }
-      const long long cell = c0 + (long long)F.N[0] * (cy + (DIM == 3 ? (long long)F.N[1] * c2 : 0));
-      double a[3] = {1.0, 1.0, 1.0};
+      for (int i = SM; i < N; i++) x[i] = xs[(i - SM) * NT];
       if (P.a_mode == PDB200_A_SCALAR) {
-        a[0] = a[1] = a[2] = __ldg(P.A + cell);
+        a[0] = a[1] = a[2] = co[0];
       } else if (P.a_mode == PDB200_A_DIAGONAL) {
 #pragma unroll
-        for (int d = 0; d < DIM; d++) a[d] = __ldg(P.A + cell * DIM + d);
+        for (int d = 0; d < DIM; d++) a[d] = co[d * NT];
       }
+      if (P.c) cc = co[3 * NT] * F.sc;
+    }
+    nxt.advance(F);
+    cell_nxt += cell_stride;
+    issue_x(step + 1);  // the slots were just read by their only user: refill them behind the compute
+    if (valid) {
       stiff_sweep<DIM, K, 0, false>(F, a[0] * F.s[0], x, t);
       stiff_sweep<DIM, K, 1, true>(F, a[1] * F.s[1], x, t);
       if (DIM == 3) stiff_sweep<DIM, K, 2, true>(F, a[2] * F.s[2], x, t);
       if (P.c) {
-        const double cc = __ldg(P.c + cell) * F.sc;
 #pragma unroll
         for (int i = 0; i < N; i++) t[i] = fma(cc, x[i], t[i]);
       }
@@ -234,15 +319,16 @@ __global__ void __launch_bounds__(32 * WY, MINB)
       carry[j] = t[lo + K * SM];
     }
     // ---- the k^dim lattice points this cell owns are complete: write each row once --------------
+    cp_async_wait<1>();  // group Y of this step (issued one step ago) has landed
     if (step > 0 && ownx && owny) {
-      const bool lastx = c0 == F.N[0], lasty = DIM == 3 && c1 == F.N[1], lastm = cm == Nm;
+      const bool lastm = cm == Nm;
 #pragma unroll
-      for (int j = 0; j < (DIM == 3 ? K * K * K : K * K); j++) {
+      for (int j = 0; j < S::KO; j++) {
         const int i0 = j % K, i1 = (j / K) % K, i2 = DIM == 3 ? j / (K * K) : 0;
         const int im = DIM == 3 ? i2 : i1;
         if ((lastx && i0) || (lasty && i1) || (lastm && im)) continue;
-        const long long gi = lat_index<DIM, K>(F, c0, cy, c2, i0, DIM == 3 ? i1 : im, i2);
-        double v = t[i0 + N1 * (DIM == 3 ? i1 + N1 * i2 : im)];
+        const long long gi = cur.at(F, i0, i1, i2);
+        double v = t[i0 + N1 * (i1 + N1 * i2)];
         if (F.fuse_constraints) {
           // constrain_residual: all boundary lattice points are Dirichlet- or processor-constrained
           const bool onb = (i0 == 0 && (c0 == 0 || lastx)) || (DIM == 3 && i1 == 0 && (c1 == 0 || lasty)) ||
@@ -252,12 +338,15 @@ __global__ void __launch_bounds__(32 * WY, MINB)
             continue;
           }
         }
-        if (r0) v += __ldg(r0 + gi);
-        if (!overwrite) v += yg[gi];
+        if (need_r) v += rs[j * NT];
+        if (need_y) v += ys[j * NT];
         yg[gi] = v;
       }
     }
+    issue_y(step + 1);
+    cur = nxt;
   }
+  cp_async_wait<0>();
 }
 
 template <int DIM, int K, int WY, int MINB>
@@ -279,6 +368,7 @@ void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK,
     F.goff[g] = K == 1 ? 0 : (g < (1 << DIM) ? Lq.block_off[edim] + Lq.group_off[g] : 0);
     F.gd0[g] = K == 1 ? P.N[0] + 1 : ((g & 1) ? P.N[0] : P.N[0] + 1);
     F.gd1[g] = K == 1 ? P.N[1] + 1 : ((g & 2) ? P.N[1] : P.N[1] + 1);
+    F.d2[g] = F.gd0[g] * F.gd1[g];
   }
   F.fuse_constraints = fuse_constraints ? 1 : 0;
   const int tiles_x = (P.N[0] + 1 + 30) / 31;
@@ -307,7 +397,13 @@ void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK,
     grid = dim3(tiles_x, (P.N[1] + 1 + WY - 2) / (WY - 1), chunks);
   else
     grid = dim3((tiles_x + WY - 1) / WY, chunks, 1);
-  fem_kron_kernel<DIM, K, WY, MINB><<<grid, 32 * WY, 0, s>>>(P, F, x, y, r0, overwrite ? 1 : 0);
+  constexpr size_t smem = ((DIM == 3 ? 2 * WY * K * (K + 1) * 32 : 0) + (size_t)KS<DIM, K>::PER_THREAD * 32 * WY) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PDB_CUDA(cudaFuncSetAttribute(fem_kron_kernel<DIM, K, WY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  fem_kron_kernel<DIM, K, WY, MINB><<<grid, 32 * WY, smem, s>>>(P, F, x, y, r0, overwrite ? 1 : 0);
   PDB_CUDA(cudaGetLastError());
 }
 
