@@ -47,6 +47,8 @@ constexpr int R3 = R2 + TZ * TX * NLOC;           // z-halo lower  [TY][TX]
 constexpr int R4 = R3 + TY * TX * NLOC;           // z-halo upper
 constexpr int SMEM_DOUBLES = R4 + TY * TX * NLOC;
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;      // 69,120 B
+constexpr int R0TILE = TX * TY * TZ * NLOC;       // R(0) tile behind the output stage (residual form)
+static_assert((R0TILE * 8) % 128 == 0 && 2 * R0TILE <= SMEM_DOUBLES, "R(0) tile must fit behind the stage");
 static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 && (R4 * 8) % 128 == 0,
               "TMA destinations must be 128-byte aligned");
 
@@ -71,6 +73,8 @@ struct TileFrame {
   int lim[3];  // exclusive upper bound of the tiled cell range
   double* out; // the output vector (ghost rows are written with plain stores)
   int pf;      // L2 prefetch distance in tiles of the launch's linear block order (0 = off)
+  int accumulate;    // y += J x (TMA reduce-add store) instead of y = J x
+  const double* r0;  // residual form: R(0) is added to the staged tile before it leaves
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +117,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
                "r"(c2), "r"(c3)
+               : "memory");
+}
+// y += tile: the L2 performs the read-modify-write (every element is touched once per launch, so
+// the result does not depend on the order in which the tiles arrive)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait() {
@@ -249,8 +262,8 @@ template <int AMODE, bool HAS_C, bool WEIGHTS_ON>
 __global__ void __launch_bounds__(TX* TY* TZ, 3)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                          const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
-                         const __grid_constant__ CUtensorMap tm_pf, const DevParams P, const FastConst F,
-                         const TileFrame TF) {
+                         const __grid_constant__ CUtensorMap tm_pf, const __grid_constant__ CUtensorMap tm_r0,
+                         const DevParams P, const FastConst F, const TileFrame TF) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
@@ -361,15 +374,35 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     }
   }
   __syncthreads();  // every thread is done reading the input tile: reuse R0 as the output stage
+  if (TF.r0 && tid == 0) {
+    // residual form R(x) = J x + R(0) (the operator is affine): fetch the tile of the cached R(0)
+    // behind the staging area; it is added to y by a second TMA reduce, no thread touches it
+    mbar_expect_tx(&bar, TX * TY * TZ * NLOC * 8);
+    tma_load_4d(tile + R0TILE, &tm_r0, 0, x0 / 2, y0, z0, &bar);
+  }
   {  // the TMA store writes the whole box (clipped to the vector): cells of the box outside the
      // tiled range are ghost rows, which are zero
     const int dst = ((cz * TY + cy) * TX + cx) * NLOC;
 #pragma unroll
     for (int i = 0; i < NLOC; i++) tile[dst + i] = active ? t[i] : 0.0;
+    if (TF.accumulate && active && constrained) {  // constrained rows are SET to zero, not incremented
+      double* __restrict__ row = TF.out + (long long)(gx + Nx * (gy + Ny * gz)) * NLOC;
+#pragma unroll
+      for (int i = 0; i < NLOC; i++) row[i] = 0.0;
+    }
   }
   fence_proxy_async();
   __syncthreads();
-  if (tid == 0) tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+  if (tid == 0) {
+    if (TF.accumulate)
+      tma_reduce_add_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+    else
+      tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+    if (TF.r0) {  // residual form: y += R(0) tile, which has been travelling since the input tile died
+      mbar_wait(&bar, 1);
+      tma_reduce_add_4d(&tm_out, tile + R0TILE, 0, x0 / 2, y0, z0);
+    }
+  }
 
   // ---- rows of the ghost layers in y / z next to this tile := 0 (constraints/p0.hh:31-41 +
   // constrain_residual); only tiles at the ends of the tiled range take this path ----------------
@@ -538,21 +571,16 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
                    int part, cudaStream_t s, int ztile_lo, int ztile_hi) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
   if (part != PDB200_PART_ALL && !overwrite) throw Error("partial application needs the overwrite form");
-  double* out = y;
-  if (!overwrite) {  // accumulate semantics (y += J z) through a scratch vector
-    if (plan->scratch_n < P.ndofs) {
-      if (plan->scratch) cudaFree(plan->scratch);
-      PDB_CUDA(cudaMalloc(&plan->scratch, P.ndofs * sizeof(double)));
-      plan->scratch_n = P.ndofs;
-    }
-    out = plan->scratch;
-  }
+  double* out = y;  // accumulate semantics (y += J z [+ R(0)]) through the TMA reduce-add store
   const FastPlan::Maps mx = get_maps(plan, x, P);
   const FastPlan::Maps my = get_maps(plan, out, P);
+  const FastPlan::Maps mr = r0 ? get_maps(plan, r0, P) : my;
   TileFrame TF;
   int nt[3];
   tile_frame(P, TF, nt);
   TF.out = out;
+  TF.accumulate = overwrite ? 0 : 1;
+  TF.r0 = r0;
   {
     static const int pf_env = [] {
       const char* e = getenv("PDB200_FAST_PREFETCH");
@@ -587,7 +615,7 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
   }
   int launches = 0;
 #define PDB_LAUNCH(AM, HC, WO) \
-  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, mx.core, P, plan->F, TF)
+  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, mx.core, mr.core, P, plan->F, TF)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \
     if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \
@@ -607,11 +635,6 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
 #undef PDB_LAUNCH_A
 #undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
-  if (!overwrite) {
-    axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, r0, P.ndofs);
-    PDB_CUDA(cudaGetLastError());
-    launches++;
-  }
   return launches;
 }
 

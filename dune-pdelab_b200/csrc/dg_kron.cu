@@ -73,7 +73,8 @@ struct KronDims {
   static constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;
   static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 && (R4 * 8) % 128 == 0,
                 "TMA destinations must be 128-byte aligned");
-  static_assert(2 * CELLS * NLOC <= TILE_DOUBLES, "staging + scratch must fit into the input tile");
+  static_assert(3 * CELLS * NLOC <= TILE_DOUBLES, "staging + scratch + R(0) tile must fit into the input tile");
+  static_assert((2 * CELLS * NLOC * 8) % 128 == 0, "R(0) tile is a TMA destination");
 };
 
 template <int K>
@@ -113,6 +114,13 @@ __device__ __forceinline__ void k_tma_load_4d(void* dst, const CUtensorMap* map,
           k_smem_u32(dst)),
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(k_smem_u32(bar))
       : "memory");
+}
+__device__ __forceinline__ void k_tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                                    int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   map),
+               "r"(k_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void k_tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
@@ -230,7 +238,8 @@ template <int K>
 __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
     dg_kron_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
                       const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
-                      const DevParams P, const KronConst<K> C) {
+                      const __grid_constant__ CUtensorMap tm_r0, const DevParams P, const KronConst<K> C,
+                      const int accumulate, const int has_r0, double* __restrict__ yout) {
   using D = KronDims<K>;
   constexpr int N1 = D::N1, NLOC = D::NLOC, NPL = D::NPL, TX = D::TX, TY = D::TY, TZ = D::TZ, ROWX = D::ROWX;
   extern __shared__ __align__(128) double tile[];
@@ -364,6 +373,12 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
                                 ct[4], cco[5], cg[5], ct[5], 0.0, tz);
   }
   __syncthreads();  // every thread is done reading the input tile: it becomes staging + scratch
+  if (has_r0 && tid == 0) {
+    // residual form R(x) = J x + R(0): the tile of the cached R(0) travels into the third region of
+    // the dead input tile and is added to y by a second TMA reduce (no thread touches it)
+    k_mbar_expect_tx(&bar, D::CELLS * NLOC * 8);
+    k_tma_load_4d(tile + 2 * D::CELLS * NLOC, &tm_r0, 0, x0 / 2, y0, z0, &bar);
+  }
 
   double* stage = tile;                         // [CELLS][NLOC], final layout of the output tile
   double* scratch = tile + D::CELLS * NLOC;     // [CELLS][NLOC], accumulators in transit
@@ -402,6 +417,13 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
       for (int ix = 0; ix < N1; ix++)
 #pragma unroll
         for (int iz = 0; iz < N1; iz++) dst[iz * NPL + s * N1 + ix] = constrained ? 0.0 : u[ix * N1 + iz];
+      if (accumulate && constrained) {  // constrained rows are SET to zero, not incremented
+        double* __restrict__ row = yout + (long long)(gx + Nx * (gy + Ny * gz)) * NLOC;
+#pragma unroll
+        for (int ix = 0; ix < N1; ix++)
+#pragma unroll
+          for (int iz = 0; iz < N1; iz++) row[iz * NPL + s * N1 + ix] = 0.0;
+      }
     } else if (lane_on) {
       // cells of the box outside the grid: clipped by the TMA store, nothing to write
     }
@@ -409,7 +431,14 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
   k_fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
-    k_tma_store_4d(&tm_out, stage, 0, x0 / 2, y0, z0);
+    if (accumulate)  // y += tile: read-modify-write in L2, every element touched once per launch
+      k_tma_reduce_add_4d(&tm_out, stage, 0, x0 / 2, y0, z0);
+    else
+      k_tma_store_4d(&tm_out, stage, 0, x0 / 2, y0, z0);
+    if (has_r0) {
+      k_mbar_wait(&bar, 1);
+      k_tma_reduce_add_4d(&tm_out, tile + 2 * D::CELLS * NLOC, 0, x0 / 2, y0, z0);
+    }
     k_tma_store_commit_and_wait();
   }
 }
@@ -523,37 +552,26 @@ static KronPlan::Maps& kron_maps(KronPlan* plan, const void* ptr, const DevParam
 
 template <int K>
 static void kron_launch(KronPlan* plan, const KronConst<K>& C, const DevParams& P, const double* x, double* out,
-                        cudaStream_t s) {
+                        const double* r0, bool accumulate, cudaStream_t s) {
   using D = KronDims<K>;
   const KronPlan::Maps mx = kron_maps<K>(plan, x, P);
   const KronPlan::Maps my = kron_maps<K>(plan, out, P);
   dim3 grid((P.N[0] + D::TX - 1) / D::TX, (P.N[1] + D::TY - 1) / D::TY, (P.N[2] + D::TZ - 1) / D::TZ);
-  dg_kron_3d_kernel<K><<<grid, D::THREADS, D::SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, P, C);
+  const KronPlan::Maps mr = r0 ? kron_maps<K>(plan, r0, P) : my;
+  dg_kron_3d_kernel<K><<<grid, D::THREADS, D::SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, mr.core, P, C,
+                                                               accumulate ? 1 : 0, r0 ? 1 : 0, out);
   PDB_CUDA(cudaGetLastError());
 }
 
 int launch_dg_kron(KronPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
                    cudaStream_t s) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
-  double* out = y;
-  if (!overwrite) {
-    if (plan->scratch_n < P.ndofs) {
-      if (plan->scratch) cudaFree(plan->scratch);
-      PDB_CUDA(cudaMalloc(&plan->scratch, P.ndofs * sizeof(double)));
-      plan->scratch_n = P.ndofs;
-    }
-    out = plan->scratch;
-  }
+  // accumulate semantics (y += J x [+ R(0)]) through TMA reduce-add stores
   if (P.k == 4)
-    kron_launch<4>(plan, plan->C4, P, x, out, s);
+    kron_launch<4>(plan, plan->C4, P, x, y, r0, !overwrite, s);
   else
-    kron_launch<3>(plan, plan->C3, P, x, out, s);
+    kron_launch<3>(plan, plan->C3, P, x, y, r0, !overwrite, s);
   int launches = 1;
-  if (!overwrite) {
-    kron_axpy_kernel<<<148 * 8, 256, 0, s>>>(y, out, r0, P.ndofs);
-    PDB_CUDA(cudaGetLastError());
-    launches++;
-  }
   return launches;
 }
 
