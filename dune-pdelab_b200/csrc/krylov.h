@@ -1,0 +1,29 @@
+// krylov.h — device-resident Krylov solvers (krylov.cu), bound to an operator by operator.cu
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <functional>
+
+#include "../../include/pdelab_b200.h"
+
+namespace pdb {
+
+struct KrylovOps {
+  std::function<void(const double* in, double* out)> apply;  // out = A in (device pointers, overwrite)
+  const double* dinv = nullptr;                               // point-Jacobi 1 / A_ii; nullptr = Richardson(1.0)
+};
+
+struct KrylovWork;
+KrylovWork* krylov_create();
+void krylov_destroy(KrylovWork*);
+// solves A x = b (x: initial guess in, solution out; b: defect out); returns the number of launches of
+// this module's kernels (the operator's own launches are counted by the caller's apply)
+int krylov_solve(KrylovWork*, int solver, long long n, const KrylovOps& ops, double* x, double* b, double reduction,
+                 unsigned maxit, cudaStream_t s, pdb200_solve_result* res);
+double krylov_two_norm(KrylovWork*, long long n, const double* a, cudaStream_t s);
+void krylov_axpy(long long n, double a, const double* x, double* y, cudaStream_t s);  // y += a x
+void krylov_diag_inverse(long long nrows, const uint64_t* rowptr, const uint32_t* colidx, const double* values,
+                         double* dinv, cudaStream_t s);
+
+}  // namespace pdb

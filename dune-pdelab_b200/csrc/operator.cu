@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "host_tables.h"
+#include "krylov.h"
 
 using namespace pdb;
 
@@ -40,6 +41,7 @@ struct pdb200_operator {
   FemPlan* fem = nullptr;
   MatrixPlan* matrix = nullptr;
   P2PHalo* p2p = nullptr;
+  KrylovWork* krylov = nullptr;
   double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
   bool r0_valid = false;
   uint64_t launches = 0;
@@ -62,6 +64,7 @@ struct pdb200_operator {
     fem_plan_destroy(fem);
     matrix_plan_destroy(matrix);
     p2p_destroy(p2p);
+    krylov_destroy(krylov);
   }
 };
 
@@ -575,6 +578,138 @@ int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const doubl
   if (!is_device_pointer(values) || !is_device_pointer(x) || !is_device_pointer(y))
     throw Error("csr_mv expects device pointers");
   h->launches += matrix_mv(h->matrix, layout, values, x, y, h->stream);
+  PDB_CATCH
+}
+
+namespace {
+
+// device staging of a host vector for the solver entry points
+struct Staged {
+  double* dev = nullptr;
+  double* host = nullptr;
+  size_t bytes = 0;
+  bool owned = false;
+  Staged(double* p, size_t n, bool copy_in, cudaStream_t s) : host(p), bytes(n * sizeof(double)) {
+    if (is_device_pointer(p)) {
+      dev = p;
+    } else {
+      PDB_CUDA(cudaMalloc(&dev, bytes));
+      owned = true;
+      if (copy_in) PDB_CUDA(cudaMemcpyAsync(dev, p, bytes, cudaMemcpyHostToDevice, s));
+    }
+  }
+  void copy_out(cudaStream_t s) {
+    if (owned) PDB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+  }
+  ~Staged() {
+    if (owned) cudaFree(dev);
+  }
+};
+
+// binds the operator (matrix-free or assembled) and the preconditioner, then runs the Krylov loop
+void solve_device(pdb200_operator* h, int solver, int precond, const double* values, int layout, double* z, double* r,
+                  double reduction, uint32_t maxiter, pdb200_solve_result* res) {
+  const DevParams& P = h->P;
+  if (!h->krylov) h->krylov = krylov_create();
+  KrylovOps ops;
+  double* dinv = nullptr;
+  struct Free {
+    double*& p;
+    ~Free() {
+      if (p) cudaFree(p);
+    }
+  } free_dinv{dinv};
+  if (!values) {
+    if (precond != PDB200_PRECOND_NONE)
+      throw Error("pdb200_solve: the matrix-free back-end is ISTLBackend_SEQ_MatrixFree_*_Richardson (no preconditioner)");
+    ops.apply = [h](const double* in, double* out) { run_vector_device(h, in, out, Mode::OnTheFly); };
+  } else {
+    if (!is_device_pointer(values)) throw Error("pdb200_solve: matrix values must be a device pointer");
+    if (!h->matrix) h->matrix = matrix_plan_create(P, h->fem, h->stream);
+    ops.apply = [h, values, layout](const double* in, double* out) {
+      h->launches += matrix_mv(h->matrix, layout, values, in, out, h->stream);
+    };
+    if (precond == PDB200_PRECOND_JACOBI) {
+      if (layout != PDB200_LAYOUT_CSR) throw Error("pdb200_solve: Jacobi needs the scalar CSR layout");
+      uint64_t nrows = 0, nnz = 0;
+      matrix_pattern_size(h->matrix, PDB200_LAYOUT_CSR, &nrows, &nnz);
+      uint64_t* rowptr = nullptr;
+      uint32_t* colidx = nullptr;
+      PDB_CUDA(cudaMalloc(&rowptr, (nrows + 1) * sizeof(uint64_t)));
+      PDB_CUDA(cudaMalloc(&colidx, nnz * sizeof(uint32_t)));
+      PDB_CUDA(cudaMalloc(&dinv, nrows * sizeof(double)));
+      h->launches += matrix_pattern_write(h->matrix, PDB200_LAYOUT_CSR, rowptr, true, colidx, true, true, h->stream);
+      krylov_diag_inverse((long long)nrows, rowptr, colidx, values, dinv, h->stream);
+      h->launches += 1;
+      PDB_CUDA(cudaStreamSynchronize(h->stream));
+      cudaFree(rowptr);
+      cudaFree(colidx);
+      ops.dinv = dinv;
+    } else if (precond != PDB200_PRECOND_NONE) {
+      throw Error("pdb200_solve: unknown preconditioner");
+    }
+  }
+  h->launches += krylov_solve(h->krylov, solver, P.ndofs, ops, z, r, reduction, maxiter, h->stream, res);
+}
+
+}  // namespace
+
+int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
+                 double reduction, uint32_t maxiter, pdb200_solve_result* res) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!z || !r || !res) throw Error("pdb200_solve: null argument");
+  Staged zs(z, (size_t)h->P.ndofs, true, h->stream), rs(r, (size_t)h->P.ndofs, true, h->stream);
+  solve_device(h, solver, precond, values, layout, zs.dev, rs.dev, reduction, maxiter, res);
+  zs.copy_out(h->stream);
+  rs.copy_out(h->stream);
+  PDB_CUDA(cudaStreamSynchronize(h->stream));
+  check_errflag(h);
+  PDB_CATCH
+}
+
+int pdb200_solve_stationary(pdb200_handle h, int solver, int precond, int matrix_free, double* x, double reduction,
+                            double min_defect, uint32_t maxiter, pdb200_solve_result* res) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!x || !res) throw Error("pdb200_solve_stationary: null argument");
+  const DevParams& P = h->P;
+  const size_t n = (size_t)P.ndofs;
+  if (!h->krylov) h->krylov = krylov_create();
+  Staged xs(x, n, true, h->stream);
+  double *values = nullptr, *r = nullptr, *z = nullptr;
+  struct Free3 {
+    double *&a, *&b, *&c;
+    ~Free3() {
+      if (a) cudaFree(a);
+      if (b) cudaFree(b);
+      if (c) cudaFree(c);
+    }
+  } guard{values, r, z};
+  if (!matrix_free) {  // *_jacobian = 0; go.jacobian(x, *_jacobian)  (linearproblem.hh:221-226)
+    if (!h->matrix) h->matrix = matrix_plan_create(P, h->fem, h->stream);
+    uint64_t nrows = 0, nnz = 0;
+    matrix_pattern_size(h->matrix, PDB200_LAYOUT_CSR, &nrows, &nnz);
+    PDB_CUDA(cudaMalloc(&values, nnz * sizeof(double)));
+    h->launches += matrix_assemble(h->matrix, PDB200_LAYOUT_CSR, values, true, /*fresh=*/true, h->errflag, h->stream);
+  }
+  PDB_CUDA(cudaMalloc(&r, n * sizeof(double)));
+  PDB_CUDA(cudaMalloc(&z, n * sizeof(double)));
+  PDB_CUDA(cudaMemsetAsync(r, 0, n * sizeof(double), h->stream));
+  PDB_CUDA(cudaMemsetAsync(z, 0, n * sizeof(double), h->stream));
+  run_vector_device(h, xs.dev, r, Mode::Residual);  // residual is additive (:244-246)
+  const double defect = krylov_two_norm(h->krylov, P.ndofs, r, h->stream);
+  const double red = defect > 0.0 ? std::max(reduction, min_defect / defect) : reduction;
+  solve_device(h, solver, precond, values, PDB200_LAYOUT_CSR, z, r, red, maxiter, res);
+  res->first_defect = defect;
+  res->defect = defect * res->reduction;
+  krylov_axpy(P.ndofs, -1.0, z, xs.dev, h->stream);  // *_x -= z
+  h->launches += 1;
+  xs.copy_out(h->stream);
+  PDB_CUDA(cudaStreamSynchronize(h->stream));
+  check_errflag(h);
   PDB_CATCH
 }
 

@@ -32,11 +32,22 @@ SYMBOLS = [
     "pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply", "pdb200_jacobian_apply_nonlinear",
     "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
+    "pdb200_solve", "pdb200_solve_stationary",
     "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
 ]
+
+
+class SolveResult(C.Structure):
+    """pdb200_solve_result = LinearSolverResult (backend/solver.hh:28-51) + the defect norms."""
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_uint32), ("elapsed", C.c_double),
+                ("reduction", C.c_double), ("conv_rate", C.c_double), ("first_defect", C.c_double),
+                ("defect", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def load_library():
@@ -61,6 +72,10 @@ def load_library():
     lib.pdb200_jacobian.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_jacobian_fresh.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_csr_mv.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.pdb200_solve.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_uint32,
+                                 C.POINTER(SolveResult)]
+    lib.pdb200_solve_stationary.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_uint32,
+                                            C.POINTER(SolveResult)]
     lib.pdb200_pattern_size.argtypes = [vp, u64p, u64p]
     lib.pdb200_block_pattern_size.argtypes = [vp, u64p, u64p]
     for name in ("pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern"):
@@ -228,6 +243,25 @@ class GridOperator:
     def csr_mv(self, values, x, y, layout=abi.LAYOUT_CSR):
         self._chk(self.lib.pdb200_csr_mv(self._h, _ptr(values), layout, _ptr(x), _ptr(y)))
         return y
+
+    # linear solvers (device-resident Krylov loops) -----------------------------------------
+    def solve(self, z, r, reduction, solver=abi.SOLVER_BICGSTAB, precond=abi.PRECOND_NONE, values=None,
+              layout=abi.LAYOUT_CSR, maxiter=5000):
+        """Solve J z = r like the reference's ISTL back-ends (seqistlsolverbackend.hh): matrix-free
+        (values=None: ISTLBackend_SEQ_MatrixFree_BCGS_Richardson) or with the assembled matrix
+        (ISTLBackend_SEQ_BCGS_Jac / _CG_Jac).  z: initial guess in, solution out; r: defect out."""
+        res = SolveResult()
+        self._chk(self.lib.pdb200_solve(self._h, solver, precond, _ptr(values), layout, _ptr(z), _ptr(r),
+                                        float(reduction), int(maxiter), C.byref(res)))
+        return res.as_dict()
+
+    def solve_stationary(self, x, reduction=1e-10, min_defect=1e-99, solver=abi.SOLVER_BICGSTAB,
+                         precond=abi.PRECOND_NONE, matrix_free=True, maxiter=5000):
+        """StationaryLinearProblemSolver::apply (stationary/linearproblem.hh:188-302): x -= J^-1 R(x)."""
+        res = SolveResult()
+        self._chk(self.lib.pdb200_solve_stationary(self._h, solver, precond, 1 if matrix_free else 0, _ptr(x),
+                                                   float(reduction), float(min_defect), int(maxiter), C.byref(res)))
+        return res.as_dict()
 
     # halo ----------------------------------------------------------------------------------
     def halo_layer_size(self, d):

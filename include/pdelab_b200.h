@@ -167,6 +167,38 @@ int pdb200_jacobian_fresh(pdb200_handle h, const double* x, double* values, int 
  * jacobian_apply on the device. */
 int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const double* x, double* y);
 
+/* ---- linear solvers on the device (the consumers of jacobian_apply / jacobian) ---------------
+ * pdb200_solve: the reference's sequential ISTL back-ends with every vector resident on the GPU.
+ *   values == NULL : matrix-free, ISTLBackend_SEQ_MatrixFree_BCGS_Richardson
+ *                    (backend/istl/seqistlsolverbackend.hh:157-203,1039-1050): OnTheFlyOperator (:44-100)
+ *                    + Richardson(1.0) + BiCGSTAB (or CG); precond must be PDB200_PRECOND_NONE
+ *   values != NULL : assembled matrix in `layout` (MatrixAdapter), ISTLBackend_SEQ_BCGS_Jac / _CG_Jac
+ *                    (:401-416,538-553; SeqJac, one step, w = 1; scalar CSR layout only) or no
+ *                    preconditioner
+ * z: initial guess in, solution out;  r: right-hand side in, final defect out (dune-istl overwrites
+ * the right-hand side).  Host or device pointers.  Stopping rule of dune-istl:
+ * |defect| < reduction * |defect_0|  (two-norm, SequentialNorm).  Not converged within maxiter is
+ * reported through res->converged == 0, not as an error (LinearSolverResult, backend/solver.hh:28-51). */
+enum { PDB200_SOLVER_BICGSTAB = 0, PDB200_SOLVER_CG = 1 };
+enum { PDB200_PRECOND_NONE = 0, PDB200_PRECOND_JACOBI = 1 };
+typedef struct pdb200_solve_result {
+  int32_t converged;
+  uint32_t iterations;
+  double elapsed;       /* seconds, wall clock of the call */
+  double reduction;     /* achieved defect reduction */
+  double conv_rate;     /* reduction^(1/iterations) */
+  double first_defect;  /* |b - A z_0| */
+  double defect;        /* final defect norm */
+} pdb200_solve_result;
+int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
+                 double reduction, uint32_t maxiter, pdb200_solve_result* res);
+/* StationaryLinearProblemSolver::apply (stationary/linearproblem.hh:188-302):
+ *   [A = 0; jacobian(x, A)]  r = 0; residual(x, r);  red = max(reduction, min_defect / |r|);
+ *   solve J z = r to red;  x -= z.
+ * matrix_free != 0 skips the assembly (linearSolverIsMatrixFree).  x: host or device pointer. */
+int pdb200_solve_stationary(pdb200_handle h, int solver, int precond, int matrix_free, double* x, double reduction,
+                            double min_defect, uint32_t maxiter, pdb200_solve_result* res);
+
 /* Halo exchange support for the overlapping partition (replaces the AddDataHandle/CopyDataHandle
  * communication of boilerplate/pdelab.hh:872-880 + gridfunctionspace/genericdatahandle.hh).
  * pack copies the DOFs of the owned cell layer next to side (dir,side) — the layer at distance

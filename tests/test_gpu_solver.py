@@ -1,0 +1,128 @@
+"""Device-resident Krylov solvers (csrc/krylov.cu) against the host restatement of dune-istl's
+iterations and the reference's solver-level acceptance tests:
+test/matrixfree/matrix_free_linear.cc:390-393 (equal iteration counts assembled vs matrix-free,
+err^2 <= 1e-6), test/testmatrixfree.cc:175-178 (Q2, err^2 <= 1e-7)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from manufactured import GpuOps, OracleOps, bicgstab, l2_error_squared
+from pdelab_b200 import abi
+from pdelab_b200.capi import GridOperator
+from problems import dg_problem, fem_problem, mt_vector, rel_err
+from test_reference_invariants import make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def host_cg(apply, b, reduction, dinv=None, maxit=5000):
+    """dune-istl CGSolver::apply with SeqJac (w = 1) or Richardson(1.0), x0 = 0."""
+    x = np.zeros_like(b)
+    r = b.copy()
+    def0 = np.linalg.norm(r)
+    p = r * dinv if dinv is not None else r.copy()
+    rholast = p @ r
+    for i in range(1, maxit + 1):
+        q = apply(p)
+        lam = rholast / (p @ q)
+        x += lam * p
+        r -= lam * q
+        if np.linalg.norm(r) < reduction * def0:
+            return x, i
+        z = r * dinv if dinv is not None else r
+        rho = z @ r
+        p = z + (rho / rholast) * p
+        rholast = rho
+    raise RuntimeError("CG did not converge")
+
+
+def test_matrix_free_bicgstab_matches_host_restatement_and_reference_test(cuda_lib):
+    """ISTLBackend_SEQ_MatrixFree_BCGS_Richardson on matrix_free_linear.cc's problem."""
+    spec, x0, u, thr = make_case("matrix_free_linear")
+    go = GridOperator(spec)
+    r = go.residual(x0, np.zeros(spec.num_dofs))
+    z_host, it_host = bicgstab(OracleOps(spec).jacobian_apply, r, 1e-10)
+    z = np.zeros(spec.num_dofs)
+    rr = r.copy()
+    res = go.solve(z, rr, 1e-10)                      # matrix-free, on the device
+    assert res["converged"] == 1
+    assert abs(res["iterations"] - it_host) <= 1, (res, it_host)
+    assert rel_err(z, z_host) < 1e-7
+    assert res["reduction"] < 1e-10 and abs(res["first_defect"] - np.linalg.norm(r)) < 1e-12 * np.linalg.norm(r)
+    # the defect handed back in r is b - A z
+    assert np.linalg.norm(rr) <= 1.0000001 * res["defect"] + 1e-300
+    assert l2_error_squared(spec, x0 - z, u) <= thr
+    # assembled operator, same solver: same iteration count (matrix_free_linear.cc:390-393)
+    import torch
+    nr, nnz = go.pattern_size()
+    vals = torch.zeros(nnz, dtype=torch.float64, device="cuda")
+    go.jacobian(torch.zeros(nr, dtype=torch.float64, device="cuda"), vals, fresh=True)
+    z2 = np.zeros(spec.num_dofs)
+    res2 = go.solve(z2, r.copy(), 1e-10, values=vals)
+    # BiCGSTAB amplifies rounding: the assembled product (row gather) and the Kronecker kernel sum in
+    # different orders, which moves the stopping test by a few of ~60 iterations (the CPU suite, where
+    # both operators share one arithmetic, asserts equality)
+    assert res2["converged"] == 1 and abs(res2["iterations"] - res["iterations"]) <= 5
+    assert rel_err(z2, z_host) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["testconvectiondiffusiondg", "testfastdgassembler", "matrix_free_linear",
+                                  "testmatrixfree"])
+@pytest.mark.parametrize("matrix_free", [True, False])
+def test_solve_stationary_reaches_the_reference_thresholds(cuda_lib, name, matrix_free):
+    """StationaryLinearProblemSolver::apply entirely on the device."""
+    spec, x0, u, thr = make_case(name)
+    go = GridOperator(spec)
+    x = x0.copy()
+    res = go.solve_stationary(x, reduction=1e-10, matrix_free=matrix_free,
+                              precond=abi.PRECOND_NONE if matrix_free else abi.PRECOND_JACOBI)
+    assert res["converged"] == 1, res
+    err = l2_error_squared(spec, x, u)
+    assert np.isfinite(err) and err <= thr, err
+    assert res["defect"] <= 1e-10 * res["first_defect"] * 1.0000001
+
+
+def test_cg_jacobi_on_assembled_q1_poisson_matches_host_cg_and_direct_solve(cuda_lib):
+    import torch
+    spec = fem_problem((12, 10, 8), degree=1, a="scalar")
+    ops = GpuOps(spec)
+    J = ops.matrix().tocsr()
+    go = ops.go
+    n = spec.num_dofs
+    b = mt_vector(n, seed=3)
+    b[go.constrained_dofs().astype(np.int64)] = 0.0   # consistent right-hand side (constrained rows are unit rows)
+    dinv = 1.0 / J.diagonal()
+    x_host, it_host = host_cg(lambda v: J @ v, b, 1e-9, dinv)
+    vals = torch.from_numpy(np.ascontiguousarray(J.data)).cuda()
+    z = np.zeros(n)
+    res = go.solve(z, b.copy(), 1e-9, solver=abi.SOLVER_CG, precond=abi.PRECOND_JACOBI, values=vals)
+    assert res["converged"] == 1 and abs(res["iterations"] - it_host) <= 1, (res, it_host)
+    x_direct = spla.spsolve(J.tocsc(), b)
+    assert rel_err(z, x_direct) < 1e-7
+    # matrix-free CG (Richardson) on the same operator
+    z2 = np.zeros(n)
+    res2 = go.solve(z2, b.copy(), 1e-9, solver=abi.SOLVER_CG)
+    assert res2["converged"] == 1
+    assert rel_err(z2, x_direct) < 1e-6
+
+
+def test_solver_on_device_tensors_large_dg_and_not_converged_is_reported(cuda_lib):
+    """Device pointers in place; maxiter too small -> converged == 0 (no exception), like
+    InverseOperatorResult."""
+    import torch
+    spec = dg_problem((32, 16, 16), degree=2, a="scalar")
+    go = GridOperator(spec)
+    n = spec.num_dofs
+    g = torch.Generator(device="cuda").manual_seed(1)
+    b = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    z = torch.zeros_like(b)
+    res = go.solve(z, b.clone(), 1e-8, solver=abi.SOLVER_CG)     # SIPG with b = 0 is SPD
+    assert res["converged"] == 1 and go.last_kernel() == "dg_fast_q2_3d"
+    y = torch.empty_like(b)
+    go.apply(z, y)
+    assert float((y - b).norm() / b.norm()) < 2e-8
+    z.zero_()
+    res = go.solve(z, b.clone(), 1e-12, maxiter=3)
+    assert res["converged"] == 0 and res["iterations"] == 3
+    with pytest.raises(Exception, match="no preconditioner"):
+        go.solve(z, b.clone(), 1e-8, precond=abi.PRECOND_JACOBI)
