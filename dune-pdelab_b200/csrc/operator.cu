@@ -619,13 +619,22 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
       if (p) cudaFree(p);
     }
   } free_dinv{dinv};
+  double* staged_values = nullptr;
+  Free free_values{staged_values};
   if (!values) {
     if (precond != PDB200_PRECOND_NONE)
       throw Error("pdb200_solve: the matrix-free back-end is ISTLBackend_SEQ_MatrixFree_*_Richardson (no preconditioner)");
     ops.apply = [h](const double* in, double* out) { run_vector_device(h, in, out, Mode::OnTheFly); };
   } else {
-    if (!is_device_pointer(values)) throw Error("pdb200_solve: matrix values must be a device pointer");
     if (!h->matrix) h->matrix = matrix_plan_create(P, h->fem, h->stream);
+    if (!is_device_pointer(values)) {  // host container (the C++ mirror's BCRSMatrixContainer): stage it
+      uint64_t nr = 0, nnz = 0;
+      matrix_pattern_size(h->matrix, layout, &nr, &nnz);
+      const size_t count = layout == PDB200_LAYOUT_BCSR ? (size_t)nnz * P.n * P.n : (size_t)nnz;
+      PDB_CUDA(cudaMalloc(&staged_values, count * sizeof(double)));
+      PDB_CUDA(cudaMemcpyAsync(staged_values, values, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      values = staged_values;
+    }
     ops.apply = [h, values, layout](const double* in, double* out) {
       h->launches += matrix_mv(h->matrix, layout, values, in, out, h->stream);
     };

@@ -33,6 +33,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <exception>
 #include <memory>
 #include <string>
@@ -918,6 +919,145 @@ class OnTheFlyOperator {
 
  private:
   const GO& go_;
+};
+
+// ---- linear solver back-ends and the stationary problem solver -----------------------------------
+// LinearSolverResult / LinearResultStorage (backend/solver.hh:28-75)
+template <class RF>
+struct LinearSolverResult {
+  bool converged = false;
+  unsigned int iterations = 0;
+  double elapsed = 0.0;
+  RF reduction = 0.0;
+  RF conv_rate = 0.0;
+  void clear() { *this = LinearSolverResult(); }
+};
+
+namespace detail {
+// what every sequential back-end of this mirror is: a (solver, preconditioner) pair run on the device
+template <int SOLVER, int PRECOND, bool MATRIX_FREE>
+class DeviceBackend {
+ public:
+  static constexpr int solver = SOLVER, precond = PRECOND;
+  static constexpr bool matrix_free = MATRIX_FREE;
+  explicit DeviceBackend(unsigned maxiter = 5000, int verbose = 1) : maxiter_(maxiter), verbose_(verbose) {}
+  // SequentialNorm (backend/istl/seqistlsolverbackend.hh / backend/solver.hh): two-norm
+  template <class V>
+  double norm(const V& v) const {
+    return std::sqrt(v.dot(v));
+  }
+  const LinearSolverResult<double>& result() const { return res; }
+  unsigned maxiter() const { return maxiter_; }
+  void store(const pdb200_solve_result& r) {
+    res.converged = r.converged != 0;
+    res.iterations = r.iterations;
+    res.elapsed = r.elapsed;
+    res.reduction = r.reduction;
+    res.conv_rate = r.conv_rate;
+    if (verbose_ > 0)
+      std::printf("=== device Krylov: %u iterations, reduction %.3e, %.4f s\n", r.iterations, r.reduction, r.elapsed);
+  }
+
+ protected:
+  LinearSolverResult<double> res;
+  unsigned maxiter_;
+  int verbose_;
+};
+}  // namespace detail
+
+// ISTLBackend_SEQ_MatrixFree_BCGS_Richardson (seqistlsolverbackend.hh:157-203,1039-1050)
+template <class GO>
+class ISTLBackend_SEQ_MatrixFree_BCGS_Richardson
+    : public detail::DeviceBackend<PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE, true> {
+  using Base = detail::DeviceBackend<PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE, true>;
+
+ public:
+  explicit ISTLBackend_SEQ_MatrixFree_BCGS_Richardson(const GO& go, unsigned maxiter = 5000, int verbose = 1)
+      : Base(maxiter, verbose), go_(go) {}
+  // apply(z, r, reduction): solve J z = r, r := final defect (:181-192)
+  template <class V, class W>
+  void apply(V& z, W& r, double reduction) {
+    pdb200_solve_result s;
+    check(pdb200_solve(go_.handle(), solver, precond, nullptr, PDB200_LAYOUT_CSR, z.data(), r.data(), reduction,
+                       maxiter_, &s),
+          "ISTLBackend_SEQ_MatrixFree_BCGS_Richardson::apply");
+    store(s);
+  }
+  void setLinearizationPoint(const typename GO::Domain&) {}  // linear operators only
+
+ private:
+  const GO& go_;
+};
+
+namespace detail {
+template <class GO, int SOLVER, int PRECOND>
+class AssembledBackend : public DeviceBackend<SOLVER, PRECOND, false> {
+  using Base = DeviceBackend<SOLVER, PRECOND, false>;
+
+ public:
+  // the reference's assembled back-ends are constructed without the grid operator (:208-224); the
+  // device path needs its handle, so it is passed here
+  explicit AssembledBackend(const GO& go, unsigned maxiter = 5000, int verbose = 1) : Base(maxiter, verbose), go_(go) {}
+  // apply(A, z, r, reduction) (:226-248)
+  template <class M, class V, class W>
+  void apply(M& A, V& z, W& r, double reduction) {
+    pdb200_solve_result s;
+    check(pdb200_solve(go_.handle(), SOLVER, PRECOND, A.values().data(), PDB200_LAYOUT_CSR, z.data(), r.data(),
+                       reduction, this->maxiter_, &s),
+          "ISTLBackend_SEQ::apply");
+    this->store(s);
+  }
+
+ private:
+  const GO& go_;
+};
+}  // namespace detail
+// ISTLBackend_SEQ_BCGS_Jac / _CG_Jac / _BCGS_Richardson (seqistlsolverbackend.hh:385-416,538-553)
+template <class GO>
+using ISTLBackend_SEQ_BCGS_Jac = detail::AssembledBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_JACOBI>;
+template <class GO>
+using ISTLBackend_SEQ_CG_Jac = detail::AssembledBackend<GO, PDB200_SOLVER_CG, PDB200_PRECOND_JACOBI>;
+template <class GO>
+using ISTLBackend_SEQ_BCGS_Richardson = detail::AssembledBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE>;
+
+// StationaryLinearProblemSolverResult (stationary/linearproblem.hh:20-45)
+template <class RF>
+struct StationaryLinearProblemSolverResult : LinearSolverResult<RF> {
+  RF first_defect = 0.0, defect = 0.0;
+  double assembler_time = 0.0, linear_solver_time = 0.0;
+  int linear_solver_iterations = 0;
+};
+
+// StationaryLinearProblemSolver (stationary/linearproblem.hh:57-320): apply() assembles (unless the
+// back-end is matrix-free), evaluates r = R(x), solves J z = r to max(reduction, min_defect/|r|) and
+// updates x -= z — as ONE device-resident call (pdb200_solve_stationary).
+template <class GO, class LS, class V>
+class StationaryLinearProblemSolver {
+ public:
+  using Result = StationaryLinearProblemSolverResult<double>;
+  StationaryLinearProblemSolver(const GO& go, LS& ls, V& x, double reduction, double min_defect = 1e-99, int verbose = 1)
+      : go_(go), ls_(ls), x_(&x), reduction_(reduction), min_defect_(min_defect), verbose_(verbose) {}
+  void apply(bool /*reuse_matrix*/ = false) {
+    pdb200_solve_result s;
+    check(pdb200_solve_stationary(go_.handle(), LS::solver, LS::precond, LS::matrix_free ? 1 : 0, x_->data(), reduction_,
+                                  min_defect_, ls_.maxiter(), &s),
+          "StationaryLinearProblemSolver::apply");
+    ls_.store(s);
+    static_cast<LinearSolverResult<double>&>(res_) = ls_.result();
+    res_.first_defect = s.first_defect;
+    res_.defect = s.defect;
+    res_.linear_solver_time = s.elapsed;
+    res_.linear_solver_iterations = (int)s.iterations;
+  }
+  const Result& result() const { return res_; }
+
+ private:
+  const GO& go_;
+  LS& ls_;
+  V* x_;
+  double reduction_, min_defect_;
+  int verbose_;
+  Result res_;
 };
 
 // constraints(bctype, gfs, cc) (constraints/common/constraints.hh:588-687): the constrained set is
