@@ -531,13 +531,15 @@ __global__ void __launch_bounds__(256, 4) qk_interior_kernel(const DevParams P, 
 template <int G>
 __global__ void __launch_bounds__(QK_THREADS)
     qk_mv_kernel(const QkDecode D, const QkLut* __restrict__ lut_g, const u64* __restrict__ rowptr, u64 nrows,
-                 const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y) {
+                 const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y,
+                 const uint32_t* __restrict__ rowlist) {
   __shared__ QkLut lut;
   for (int i = threadIdx.x; i < (int)(sizeof(QkLut) / 4); i += QK_THREADS) ((uint32_t*)&lut)[i] = ((const uint32_t*)lut_g)[i];
   __syncthreads();
   const int lane = threadIdx.x % G;
-  const u64 row = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
-  const bool live = row < nrows;
+  const u64 rix = ((u64)blockIdx.x * QK_THREADS + threadIdx.x) / G;
+  const bool live = rix < nrows;
+  const u64 row = live && rowlist ? (u64)rowlist[rix] : rix;  // with a list, nrows is its length
   double acc = 0.0;
   if (live) {
     const QkRow R = qk_row(D, (uint32_t)row);
@@ -550,6 +552,170 @@ __global__ void __launch_bounds__(QK_THREADS)
   }
   for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
   if (live && lane == 0) y[row] = acc;
+}
+
+// y = A x for the interior rows, one x-line of rows per CTA (the SpMV twin of qk_interior_kernel):
+// for interior rows the column of slot s is  col0(s) + (a0 - lo0),  so a lane keeps the col0 of its
+// <= 4 slots (slot = lane + 32 j) in registers and the warp walks along the line: values are read
+// fully coalesced, x is read as 125 (Q2, 3-D) unit-stride streams that live in L1, colidx is not read
+// at all and nothing is decoded per entry.  One warp-shuffle reduction per row.
+template <int DIM, int K>
+__global__ void __launch_bounds__(256) qk_mv_interior_kernel(const DevParams P, const QkDecode D, int g, int L,
+                                                             const QkLut* __restrict__ lut_g,
+                                                             const u64* __restrict__ rowptr,
+                                                             const double* __restrict__ values,
+                                                             const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int MAXJ = 4;  // (2K+1)^3 = 125 <= 128 slots
+  const int s = D.sbits[g];
+  const bool vt[3] = {!(s & 1), !((s >> 1) & 1), !((s >> 2) & 1)};
+  const int N0 = P.N[0];
+  const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
+  const int a1 = (int)blockIdx.x + (vt[1] ? 1 : 0), a2 = DIM == 3 ? (int)blockIdx.y + (vt[2] ? 1 : 0) : 0;
+  const int lo0 = vt[0] ? 1 : 0, hi0 = N0 - 1;
+  int shape = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) shape |= (vt[d] ? 1 : 0) << d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  uint32_t col0[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; j++) {
+    const int slot = lane + 32 * j;
+    col0[j] = 0;
+    if (slot < L) {
+      const int off = lut_g->slot2off[shape][slot];
+      const int o[3] = {off & 7, (off >> 3) & 7, off >> 6};
+      int e[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) e[d] = o[d] - (vt[d] ? K : 1);
+      long long c;
+      if (K == 1) {
+        c = (lo0 + e[0]) + (long long)(N0 + 1) * ((a1 + e[1]) + (long long)(P.N[1] + 1) * (DIM == 3 ? a2 + e[2] : 0));
+      } else {
+        int par = 0, sh[3] = {0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          const int q = ((s >> d) & 1) + e[d];  // lattice offset of the column relative to 2 a_d
+          const int pb = q & 1;
+          par |= pb << d;
+          sh[d] = (q - pb) / 2;
+        }
+        const int g2 = D.group_of_s[par];
+        c = (long long)D.start[g2] + (lo0 + sh[0]) +
+            (long long)D.sz0[g2] * ((a1 + sh[1]) + (long long)D.sz1[g2] * (DIM == 3 ? a2 + sh[2] : 0));
+      }
+      col0[j] = (uint32_t)c;
+    }
+  }
+  const u64 row0 = (u64)D.start[g] + (u64)lo0 + (u64)sz0 * ((u64)a1 + (u64)sz1 * (u64)a2);
+  const u64 base = rowptr[row0];
+  // four rows per pass: 8 KB of values per warp in flight
+  const int nrows = hi0 - lo0 + 1;
+  constexpr int U = 4;
+  for (int r = warp; r < nrows; r += U * W) {
+    double acc[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      acc[u] = 0.0;
+      const int ru = r + u * W;
+      if (ru < nrows) {
+        const double* __restrict__ vrow = values + base + (size_t)ru * L;
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++)
+          if (lane + 32 * j < L) acc[u] = fma(vrow[lane + 32 * j], __ldg(x + col0[j] + ru), acc[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; u++) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (r + u * W < nrows) y[row0 + r + u * W] = acc[u];
+    }
+  }
+}
+
+// Short rows (L <= 32 entries: Q1, and the cell-interior group of Q2): a warp per row would idle most
+// lanes and pay a shuffle reduction per 9..27 products.  Here the values of a chunk of rows are staged
+// in shared memory with coalesced loads, then ONE THREAD PER ROW runs over its L entries: the shared
+// reads are conflict-free (row stride L is odd) and for a fixed slot consecutive threads read
+// consecutive x (col0(slot) + r), so the x gather is coalesced too.
+// PARTS > 1 (long rows, up to 125 entries): PARTS threads share a row (slots part, part + PARTS, ...), the
+// chunk holds 256 / PARTS rows so that it still fits shared memory, partial sums meet in shared memory.
+template <int DIM, int K, int PARTS>
+__global__ void __launch_bounds__(256) qk_mv_interior_short_kernel(const DevParams P, const QkDecode D, int g, int L,
+                                                                   const QkLut* __restrict__ lut_g,
+                                                                   const u64* __restrict__ rowptr,
+                                                                   const double* __restrict__ values,
+                                                                   const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int ROWS = 256 / PARTS;
+  extern __shared__ double vs[];  // [ROWS][L]
+  __shared__ uint32_t col0s[128];
+  __shared__ double part_sum[PARTS > 1 ? 256 : 1];
+  const int s = D.sbits[g];
+  const bool vt[3] = {!(s & 1), !((s >> 1) & 1), !((s >> 2) & 1)};
+  const int N0 = P.N[0];
+  const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
+  const int a1 = (int)blockIdx.x + (vt[1] ? 1 : 0), a2 = DIM == 3 ? (int)blockIdx.y + (vt[2] ? 1 : 0) : 0;
+  const int lo0 = vt[0] ? 1 : 0, hi0 = N0 - 1;
+  int shape = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) shape |= (vt[d] ? 1 : 0) << d;
+  if ((int)threadIdx.x < L) {
+    const int off = lut_g->slot2off[shape][threadIdx.x];
+    const int o[3] = {off & 7, (off >> 3) & 7, off >> 6};
+    int e[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) e[d] = o[d] - (vt[d] ? K : 1);
+    long long c;
+    if (K == 1) {
+      c = (lo0 + e[0]) + (long long)(N0 + 1) * ((a1 + e[1]) + (long long)(P.N[1] + 1) * (DIM == 3 ? a2 + e[2] : 0));
+    } else {
+      int par = 0, sh[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const int q = ((s >> d) & 1) + e[d];
+        const int pb = q & 1;
+        par |= pb << d;
+        sh[d] = (q - pb) / 2;
+      }
+      const int g2 = D.group_of_s[par];
+      c = (long long)D.start[g2] + (lo0 + sh[0]) +
+          (long long)D.sz0[g2] * ((a1 + sh[1]) + (long long)D.sz1[g2] * (DIM == 3 ? a2 + sh[2] : 0));
+    }
+    col0s[threadIdx.x] = (uint32_t)c;
+  }
+  const u64 row0 = (u64)D.start[g] + (u64)lo0 + (u64)sz0 * ((u64)a1 + (u64)sz1 * (u64)a2);
+  const u64 base = rowptr[row0];
+  const int nrows = hi0 - lo0 + 1;
+  // the line is cut into gridDim.z pieces of whole ROWS-row chunks
+  const int chunks = (nrows + ROWS - 1) / ROWS, per = (chunks + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int rl = threadIdx.x % ROWS, part = threadIdx.x / ROWS;
+  for (int ch = (int)blockIdx.z * per; ch < min(chunks, ((int)blockIdx.z + 1) * per); ch++) {
+    const int r0 = ch * ROWS, nr = min(ROWS, nrows - r0);
+    __syncthreads();  // col0s ready / previous chunk consumed
+    const double* __restrict__ src = values + base + (size_t)r0 * L;
+    for (int i = threadIdx.x; i < nr * L; i += 256) vs[i] = src[i];
+    __syncthreads();
+    double acc = 0.0;
+    if (rl < nr) {
+      const int r = r0 + rl;
+      const double* v = vs + rl * L;
+      for (int slot = part; slot < L; slot += PARTS) acc = fma(v[slot], __ldg(x + col0s[slot] + r), acc);
+    }
+    if (PARTS == 1) {
+      if (rl < nr) y[row0 + r0 + rl] = acc;
+    } else {
+      part_sum[threadIdx.x] = acc;
+      __syncthreads();
+      if (part == 0 && rl < nr) {
+#pragma unroll
+        for (int q = 1; q < PARTS; q++) acc += part_sum[q * ROWS + rl];
+        y[row0 + r0 + rl] = acc;
+      }
+    }
+  }
 }
 
 __global__ void set_flags_kernel(unsigned char* __restrict__ flags, const uint64_t* __restrict__ idx, long long n) {
@@ -1062,6 +1228,46 @@ static int launch_qk_interior(MatrixPlan* p, double* values, IDX* colidx, bool f
   return launches;
 }
 
+template <int DIM, int K>
+static int launch_qk_mv_interior(MatrixPlan* p, const double* values, const double* x, double* y, cudaStream_t s) {
+  const DevParams& P = p->P;
+  const QkDecode& D = p->D;
+  int launches = 0;
+  for (int g = 0; g < D.ng; g++) {
+    const int sb = D.sbits[g];
+    const bool vt[3] = {!(sb & 1), !((sb >> 1) & 1), !((sb >> 2) & 1)};
+    int L = 1;
+    for (int d = 0; d < DIM; d++) L *= vt[d] ? 2 * K + 1 : K + 1;
+    const int n1 = vt[1] ? P.N[1] - 1 : P.N[1], n2 = DIM == 3 ? (vt[2] ? P.N[2] - 1 : P.N[2]) : 1;
+    const int nrow0 = vt[0] ? P.N[0] - 1 : P.N[0];
+    if (n1 <= 0 || n2 <= 0 || nrow0 <= 0) continue;
+    // long lines (2-D grids) are cut along x so that the launch fills the machine
+    const long long lines = (long long)n1 * n2;
+    if (L <= 32) {
+      const size_t smem = (size_t)256 * L * sizeof(double);
+      if (smem > 48 * 1024)
+        PDB_CUDA(cudaFuncSetAttribute(qk_mv_interior_short_kernel<DIM, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+      const int chunks = (nrow0 + 255) / 256;
+      const int nz = (int)std::max<long long>(1, std::min<long long>(chunks, (148 * 8 + lines - 1) / lines));
+      qk_mv_interior_short_kernel<DIM, K, 1><<<dim3(n1, n2, nz), 256, smem, s>>>(P, D, g, L, p->lut, p->rowptr, values, x, y);
+    } else if (L > 64) {  // 75 / 125 entries: the chunk would cap the occupancy; one warp per row instead
+      qk_mv_interior_kernel<DIM, K><<<dim3(n1, n2), 256, 0, s>>>(P, D, g, L, p->lut, p->rowptr, values, x, y);
+    } else {
+      const size_t smem = (size_t)64 * L * sizeof(double);
+      if (smem > 48 * 1024)
+        PDB_CUDA(cudaFuncSetAttribute(qk_mv_interior_short_kernel<DIM, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+      const int chunks = (nrow0 + 63) / 64;
+      const int nz = (int)std::max<long long>(1, std::min<long long>(chunks, (148 * 8 + lines - 1) / lines));
+      qk_mv_interior_short_kernel<DIM, K, 4><<<dim3(n1, n2, nz), 256, smem, s>>>(P, D, g, L, p->lut, p->rowptr, values, x, y);
+    }
+    PDB_CUDA(cudaGetLastError());
+    launches++;
+  }
+  return launches;
+}
+
 MatrixPlan* matrix_plan_create(const DevParams& P, FemPlan* fem, cudaStream_t s) {
   MatrixPlan* plan = new MatrixPlan;
   plan->P = P;
@@ -1266,17 +1472,31 @@ int matrix_assemble(MatrixPlan* p, int layout, double* values, bool values_dev, 
 
 int matrix_mv(MatrixPlan* p, int layout, const double* values, const double* x, double* y, cudaStream_t s) {
   const DevParams& P = p->P;
+  int launches = 0;
   if (P.dg) {
+    launches = 1;
     dg_mv_kernel<<<(unsigned)P.ncells, 128, 0, s>>>(P, p->rowptr, layout == PDB200_LAYOUT_BCSR, values, x, y);
   } else {
     const int G = P.n > 16 ? 32 : (P.n > 8 ? 16 : 8);
-    const u64 blocks = (p->nrows * G + QK_THREADS - 1) / QK_THREADS;
-    if (G == 32) qk_mv_kernel<32><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
-    else if (G == 16) qk_mv_kernel<16><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
-    else qk_mv_kernel<8><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, p->nrows, values, x, y);
+    // interior rows: one x-line per CTA; boundary rows (or everything on degenerate grids): generic kernel
+    const uint32_t* list = p->interior_ok ? p->brows : nullptr;
+    const u64 ngen = p->interior_ok ? p->nbr : p->nrows;
+    if (p->interior_ok) {
+      if (P.dim == 2 && P.k == 1) launches += launch_qk_mv_interior<2, 1>(p, values, x, y, s);
+      else if (P.dim == 2 && P.k == 2) launches += launch_qk_mv_interior<2, 2>(p, values, x, y, s);
+      else if (P.dim == 3 && P.k == 1) launches += launch_qk_mv_interior<3, 1>(p, values, x, y, s);
+      else launches += launch_qk_mv_interior<3, 2>(p, values, x, y, s);
+    }
+    const u64 blocks = (ngen * G + QK_THREADS - 1) / QK_THREADS;
+    if (blocks > 0) {
+      if (G == 32) qk_mv_kernel<32><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, ngen, values, x, y, list);
+      else if (G == 16) qk_mv_kernel<16><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, ngen, values, x, y, list);
+      else qk_mv_kernel<8><<<(unsigned)blocks, QK_THREADS, 0, s>>>(p->D, p->lut, p->rowptr, ngen, values, x, y, list);
+      launches++;
+    }
   }
   PDB_CUDA(cudaGetLastError());
-  return 1;
+  return launches;
 }
 
 }  // namespace pdb
