@@ -120,6 +120,11 @@ void dg_kron_plan_destroy(KronPlan*);
 int launch_dg_kron(KronPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
                    cudaStream_t s);
 
+// dg_small.cu: Kronecker-factorised kernel for small cells (dim = 2 with k = 1, 2; dim = 3 with k = 1), thread per cell
+bool dg_small_supported(const DevParams& P);
+int launch_dg_small(const DevParams& P, const Kron1D& K, const double* x, double* y, const double* r0, bool overwrite,
+                    cudaStream_t s);
+
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);
 // halo.cu: peer-to-peer mailbox exchange over NVLink (CUDA IPC), see pdelab_b200.h

@@ -146,10 +146,12 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   }
   bool use_fast = use_fast0;
   const bool use_kron = !use_fast && dg_kron_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
-  if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast && !use_kron)
+  const bool use_small = !use_fast && !use_kron && dg_small_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
+  if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast && !use_kron && !use_small)
     throw Error("PDB200_KERNEL_FAST requested but the configuration has no fast kernel "
-                "(needs QkDG k in {2,3,4}, dim=3, diagonal A, b=0, even cells[0])");
-  if (use_fast || use_kron) {
+                "(needs QkDG with diagonal A and b=0: dim=3 with k in {2,3,4} and even cells[0], dim=3 with k=1, "
+                "or dim=2 with k in {1,2})");
+  if (use_fast || use_kron || use_small) {
     const double* r0 = nullptr;
     if (residual) {
       // The operator is affine: R(x) = J x + R(0).  R(0) (source term lambda_volume,
@@ -172,10 +174,13 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
       if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
       op->launches += launch_dg_fast(op->fast, P, x, y, r0, overwrite, part, op->stream);
       op->last_kernel = residual ? "dg_fast_q2_3d+r0" : "dg_fast_q2_3d";
-    } else {
+    } else if (use_kron) {
       if (!op->kron) op->kron = dg_kron_plan_create(P, op->K);
       op->launches += launch_dg_kron(op->kron, P, x, y, r0, overwrite, op->stream);
       op->last_kernel = residual ? "dg_kron_3d+r0" : "dg_kron_3d";
+    } else {
+      op->launches += launch_dg_small(P, op->K, x, y, r0, overwrite, op->stream);
+      op->last_kernel = residual ? "dg_small+r0" : "dg_small";
     }
   } else {
     launch_dg_generic(P, x, y, residual, overwrite, op->errflag, op->stream);

@@ -184,3 +184,37 @@ def test_outflow_on_inflow_throws(cuda_lib):
     z = np.ones(spec.num_dofs)
     with pytest.raises(PDELabError, match="Outflow"):
         go.jacobian_apply(z, np.zeros_like(z))
+
+
+# dg_small.cu: thread-per-cell Kronecker kernel for dim = 2 (k = 1, 2) and dim = 3 (k = 1) — the
+# configurations of the reference's own DG tests
+SMALL_CASES = [
+    dict(cells=(16, 16), degree=1), dict(cells=(7, 5), degree=2, a="diagonal", with_c=True),
+    dict(cells=(1, 1), degree=1, a="identity"), dict(cells=(9, 4), degree=2, a="scalar", extent=(1.0, 0.6)),
+    dict(cells=(6, 5, 4), degree=1, a="scalar"), dict(cells=(3, 2, 1), degree=1, a="diagonal", with_c=True, bc="mixed"),
+    dict(cells=(8, 7), degree=1, a="scalar", method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF, alpha=1.0),
+    dict(cells=(8, 7), degree=2, a="diagonal", method=abi.DG_IIPG, bc="mixed"),
+    dict(cells=(33, 17, 9), degree=1, a="scalar", extent=(1.0, 0.7, 1.3)),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_small_cell_kernel_matches_oracle(cuda_lib, case):
+    spec = dg_problem(kernel=abi.KERNEL_FAST, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    want = orc.jacobian_apply(z)
+    y = go.apply(z, np.full(spec.num_dofs, np.nan))            # overwrite form
+    assert go.last_kernel() == "dg_small"
+    assert rel_err(y, want) < TOL
+    y0 = mt_vector(spec.num_dofs, seed=7)
+    assert rel_err(go.jacobian_apply(z, y0.copy()), want + y0) < TOL   # accumulate form
+    # residual = J x + cached R(0), with source term and inhomogeneous boundary data
+    rcase = dict(case, with_f=True)
+    if rcase.get("bc", "dirichlet") == "dirichlet":
+        rcase["bc"] = "dirichlet_g"
+    spec = dg_problem(kernel=abi.KERNEL_AUTO, **rcase)
+    go, orc = _ops(spec)
+    r = go.residual(z, y0.copy())
+    assert go.last_kernel() == "dg_small+r0"
+    assert rel_err(r, orc.residual(z, y0.copy())) < TOL

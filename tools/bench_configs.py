@@ -76,7 +76,7 @@ def fem_case(name, cells, k, reps):
 def dg_case(name, cells, k, reps, residual):
     nc = int(np.prod(cells))
     kappa = 10.0 ** (2.0 * rand(nc, 42) - 1.0)
-    kw = dict(f=rand(nc * (k + 1) ** 3, 1)) if residual else {}
+    kw = dict(f=rand(nc * (k + 1) ** len(cells), 1)) if residual else {}
     spec = abi.ProblemSpec(cells, space=abi.SPACE_QKDG, degree=k, alpha=3.0, a_mode=abi.A_SCALAR, A=kappa, **kw)
     go = GridOperator(spec)
     go.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -92,7 +92,7 @@ def dg_case(name, cells, k, reps, residual):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="cfg1,fem3d,cfg3,cfg4")
+    ap.add_argument("--which", default="cfg1,fem3d,cfg3,dg2d,cfg4")
     args = ap.parse_args()
     which = args.which.split(",")
     if "cfg1" in which:
@@ -105,6 +105,9 @@ def main():
         dg_case("cfg3 DG k=4 3D 64^3", (64, 64, 64), 4, 5, True)
         dg_case("DG k=1 3D 128^3", (128, 128, 128), 1, 5, True)
         dg_case("DG k=2 3D 128^3 generic", (128, 128, 128), 2, 5, True)
+    if "dg2d" in which:  # the reference's own DG test configurations (k = 1, 2-D), at size
+        dg_case("DG k=1 2D 4096^2", (4096, 4096), 1, 10, True)
+        dg_case("DG k=2 2D 2048^2", (2048, 2048), 2, 10, True)
     if "cfg4" in which:
         fem_case("cfg4 Q2 3D 160^3", (160, 160, 160), 2, 4)
 
