@@ -125,6 +125,14 @@ bool dg_small_supported(const DevParams& P);
 int launch_dg_small(const DevParams& P, const Kron1D& K, const double* x, double* y, const double* r0, bool overwrite,
                     cudaStream_t s);
 
+// dg_blockjac.cu: exact matrix-free block-Jacobi preconditioner z = D^-1 r (fast diagonalisation of the Kronecker-sum blocks)
+struct BlockJacPlan;
+bool dg_blockjac_supported(const DevParams& P);
+BlockJacPlan* dg_blockjac_create(const DevParams& P, const Kron1D& K);
+void dg_blockjac_destroy(BlockJacPlan*);
+void dg_blockjac_invalidate(BlockJacPlan*);  // coefficients changed
+int launch_dg_blockjac(BlockJacPlan*, const DevParams& P, const Kron1D& K, const double* r, double* z, cudaStream_t s);
+
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);
 // halo.cu: peer-to-peer mailbox exchange over NVLink (CUDA IPC), see pdelab_b200.h

@@ -1,0 +1,152 @@
+// dg_face.cuh — what the thread-per-cell QkDG kernels (dg_small.cu, dg_blockjac.cu) share: the 1-D
+// constants of the Kronecker form and the face coefficients of one cell in one direction
+// (harmonic weights and penalty, localoperator/convectiondiffusiondg.hh:326-346 interior faces,
+// :717-734 Dirichlet boundary faces).
+#pragma once
+
+#include "common.cuh"
+
+namespace pdb {
+namespace dgface {
+
+template <int K>
+struct SmallConst {
+  static constexpr int N1 = K + 1;
+  double MinvK[N1 * N1], M[N1 * N1], m0[N1], mk[N1], q0[N1], q1[N1], d0[N1], d1[N1];
+  double ih2[3];
+  double alpha_pen, theta, vol;
+};
+
+template <int DIM, int K>
+struct SL {
+  static constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+};
+
+__device__ __forceinline__ double s_fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, fma(e, e, e), y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+__device__ __forceinline__ double s_load_adiag(const DevParams& P, long long cell, int d) {
+  if (P.a_mode == PDB200_A_IDENTITY) return 1.0;
+  if (P.a_mode == PDB200_A_SCALAR) return __ldg(P.A + cell);
+  if (P.a_mode == PDB200_A_DIAGONAL) return __ldg(P.A + cell * P.dim + d);
+  return __ldg(P.A + cell * P.dim * P.dim + d * (P.dim + 1));
+}
+
+// Face coefficients of cell `cell` (coordinates g) in direction d for both sides:
+//   cs = w_self a / h^2, co = w_other a_other / h^2, cg = penalty coefficient; A0 = a / h^2.
+// kind per side: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None / Neumann / Outflow with
+// b = 0, processor boundary).  Returns true if the cell touches a processor side (constrained rows).
+template <int K>
+__device__ __forceinline__ bool direction_coefs(const DevParams& P, const SmallConst<K>& C, long long cell, const int (&g)[3],
+                                                int d, const long long (&stride)[3], double& A0, double (&cs)[2],
+                                                double (&co)[2], double (&cg)[2], bool (&onb)[2]) {
+  bool constrained = false;
+  onb[0] = g[d] == 0;
+  onb[1] = g[d] == P.N[d] - 1;
+  const double a = s_load_adiag(P, cell, d);
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    int kind = onb[side] ? 1 : 0;
+    if (onb[side]) {
+      if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
+        kind = 2;
+        constrained = true;
+      } else if (P.bctype) {
+        kind = P.bctype[bface_index(P, g, d, side)] == PDB200_BC_DIRICHLET ? 1 : 2;
+      }
+    }
+    const long long other = onb[side] ? cell : cell + (side ? stride[d] : -stride[d]);
+    const double ao = s_load_adiag(P, other, d);
+    const double aih = a * C.ih2[d];
+    double csi, coi;
+    if (P.weights_on) {
+      csi = coi = aih * ao * s_fast_rcp(a + ao + 1e-20);
+    } else {
+      csi = 0.5 * aih;
+      coi = 0.5 * ao * C.ih2[d];
+    }
+    cs[side] = kind == 0 ? csi : (kind == 1 ? aih : 0.0);
+    co[side] = kind == 0 ? coi : 0.0;
+    cg[side] = P.weights_on ? C.alpha_pen * (cs[side] + co[side]) : (cs[side] != 0.0 ? C.alpha_pen * C.ih2[d] : 0.0);
+  }
+  A0 = a * C.ih2[d];
+  return constrained;
+}
+
+// own-cell 1-D matrix T = M^-1 L_own / h^2 of direction d (row-major N1 x N1), see dg_kron.cu
+template <int K>
+__device__ __forceinline__ void own_matrix(const SmallConst<K>& C, double A0, double csL, double cgL, double csR,
+                                           double cgR, double (&T)[(K + 1) * (K + 1)], double (&eL)[K + 1],
+                                           double (&eR)[K + 1]) {
+  constexpr int N1 = K + 1;
+  const double ctL = -C.theta * csL, ctR = C.theta * csR;
+#pragma unroll
+  for (int i = 0; i < N1; i++) {
+    const double m0c = C.m0[i] * csL, mkc = -C.mk[i] * csR;
+    eL[i] = fma(C.m0[i], cgL, C.q0[i] * ctL);
+    eR[i] = fma(C.mk[i], cgR, C.q1[i] * ctR);
+#pragma unroll
+    for (int j = 0; j < N1; j++) {
+      double v = fma(A0, C.MinvK[i * N1 + j], fma(m0c, C.d0[j], mkc * C.d1[j]));
+      if (j == 0) v += eL[i];
+      if (j == K) v += eR[i];
+      T[i * N1 + j] = v;
+    }
+  }
+}
+
+template <int K>
+inline void fill_small_const(SmallConst<K>& C, const DevParams& P, const Kron1D& K1) {
+  constexpr int N1 = K + 1;
+  for (int i = 0; i < N1; i++) {
+    for (int j = 0; j < N1; j++) {
+      C.MinvK[i * N1 + j] = K1.MinvK[i * MAX_N1 + j];
+      C.M[i * N1 + j] = K1.M[i * MAX_N1 + j];
+    }
+    C.m0[i] = K1.m0[i];
+    C.mk[i] = K1.mk[i];
+    C.q0[i] = K1.q0[i];
+    C.q1[i] = K1.q1[i];
+    C.d0[i] = K1.d0[i];
+    C.d1[i] = K1.d1[i];
+  }
+  for (int d = 0; d < 3; d++) C.ih2[d] = d < P.dim ? 1.0 / (P.h[d] * P.h[d]) : 0.0;
+  C.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
+  C.theta = P.theta;
+  C.vol = P.vol;
+}
+
+template <int N>
+__device__ __forceinline__ void load_cell(const double* __restrict__ p, double (&v)[N]) {
+  if (N % 2 == 0) {  // n = 4, 8: the cell is 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
+      v[2 * i] = t.x;
+      v[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = __ldg(p + i);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void store_cell(double* __restrict__ p, const double (&v)[N]) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) reinterpret_cast<double2*>(p)[i] = make_double2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = v[i];
+  }
+}
+
+}  // namespace dgface
+}  // namespace pdb

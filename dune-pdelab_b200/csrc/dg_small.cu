@@ -18,54 +18,13 @@
 // its own n results (accumulate forms read-modify-write the same addresses).
 
 #include "common.cuh"
+#include "dg_face.cuh"
 
 namespace pdb {
 
 namespace {
 
-template <int K>
-struct SmallConst {
-  static constexpr int N1 = K + 1;
-  double MinvK[N1 * N1], M[N1 * N1], m0[N1], mk[N1], q0[N1], q1[N1], d0[N1], d1[N1];
-  double ih2[3];
-  double alpha_pen, theta, vol;
-};
-
-template <int DIM, int K>
-struct SL {
-  static constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
-};
-
-__device__ __forceinline__ double s_fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, fma(e, e, e), y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
-}
-
-__device__ __forceinline__ double s_load_adiag(const DevParams& P, long long cell, int d) {
-  if (P.a_mode == PDB200_A_IDENTITY) return 1.0;
-  if (P.a_mode == PDB200_A_SCALAR) return __ldg(P.A + cell);
-  if (P.a_mode == PDB200_A_DIAGONAL) return __ldg(P.A + cell * P.dim + d);
-  return __ldg(P.A + cell * P.dim * P.dim + d * (P.dim + 1));
-}
-
-template <int N>
-__device__ __forceinline__ void load_cell(const double* __restrict__ p, double (&v)[N]) {
-  if (N % 2 == 0) {  // n = 4, 8: the cell is 16-byte aligned
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) {
-      const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
-      v[2 * i] = t.x;
-      v[2 * i + 1] = t.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i++) v[i] = __ldg(p + i);
-  }
-}
+using namespace dgface;
 
 // t (+)= M^-1 L_d / h_d^2 along direction AXIS for all lines of the cell
 template <int DIM, int K, int AXIS, bool FIRST>
@@ -75,23 +34,14 @@ __device__ __forceinline__ void small_sweep(const SmallConst<K>& C, const double
                                             double creact, double (&t)[SL<DIM, K>::N]) {
   constexpr int N1 = K + 1, N = SL<DIM, K>::N;
   constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
-  const double ctL = -C.theta * csL, ctR = C.theta * csR;
-  double T[N1 * N1], PL1[N1], PL2[N1], PR1[N1], PR2[N1];
+  double T[N1 * N1], eL[N1], eR[N1], PL1[N1], PL2[N1], PR1[N1], PR2[N1];
+  own_matrix<K>(C, A0, csL, cgL, csR, cgR, T, eL, eR);
 #pragma unroll
   for (int i = 0; i < N1; i++) {
-    const double m0c = C.m0[i] * csL, mkc = -C.mk[i] * csR;
-    const double eL = fma(C.m0[i], cgL, C.q0[i] * ctL), eR = fma(C.mk[i], cgR, C.q1[i] * ctR);
-#pragma unroll
-    for (int j = 0; j < N1; j++) {
-      double v = fma(A0, C.MinvK[i * N1 + j], fma(m0c, C.d0[j], mkc * C.d1[j]));
-      if (j == 0) v += eL;
-      if (j == K) v += eR;
-      T[i * N1 + j] = v;
-    }
     PL1[i] = C.m0[i] * coL;
-    PL2[i] = -eL;
+    PL2[i] = -eL[i];
     PR1[i] = -C.mk[i] * coR;
-    PR2[i] = -eR;
+    PR2[i] = -eR[i];
   }
 #pragma unroll
   for (int hi = 0; hi < N / (S * N1); hi++)
@@ -160,43 +110,19 @@ __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const 
   bool constrained = false;
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
-    const bool onb[2] = {g[d] == 0, g[d] == P.N[d] - 1};
-    const double a = s_load_adiag(P, cell, d);
-    double cs[2], co[2], cg[2];
+    double A0, cs[2], co[2], cg[2];
+    bool onb[2];
+    constrained |= direction_coefs<K>(P, C, cell, g, d, stride, A0, cs, co, cg, onb);
     double nb[2][N];
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-      int kind = onb[side] ? 1 : 0;
-      if (onb[side]) {
-        if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
-          kind = 2;
-          constrained = true;
-        } else if (P.bctype) {
-          kind = P.bctype[bface_index(P, g, d, side)] == PDB200_BC_DIRICHLET ? 1 : 2;
-        }
-      }
-      const long long other = onb[side] ? cell : cell + (side ? stride[d] : -stride[d]);
-      const double ao = s_load_adiag(P, other, d);
       if (!onb[side]) {
-        load_cell<N>(z + other * N, nb[side]);
+        load_cell<N>(z + (cell + (side ? stride[d] : -stride[d])) * N, nb[side]);
       } else {
 #pragma unroll
         for (int i = 0; i < N; i++) nb[side][i] = 0.0;
       }
-      // harmonic weights and penalty, convectiondiffusiondg.hh:326-346 (interior), :717-734 (boundary)
-      const double aih = a * C.ih2[d];
-      double csi, coi;
-      if (P.weights_on) {
-        csi = coi = aih * ao * s_fast_rcp(a + ao + 1e-20);
-      } else {
-        csi = 0.5 * aih;
-        coi = 0.5 * ao * C.ih2[d];
-      }
-      cs[side] = kind == 0 ? csi : (kind == 1 ? aih : 0.0);
-      co[side] = kind == 0 ? coi : 0.0;
-      cg[side] = P.weights_on ? C.alpha_pen * (cs[side] + co[side]) : (cs[side] != 0.0 ? C.alpha_pen * C.ih2[d] : 0.0);
     }
-    const double A0 = a * C.ih2[d];
     if (d == 0)
       small_sweep<DIM, K, 0, true>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], creact, t);
     else if (d == 1)
@@ -223,36 +149,14 @@ __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const 
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] += out[i];
   }
-  if (N % 2 == 0) {
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) reinterpret_cast<double2*>(out)[i] = make_double2(t[2 * i], t[2 * i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i++) out[i] = t[i];
-  }
+  store_cell<N>(out, t);
 }
 
 template <int DIM, int K>
 void launch_variant(const DevParams& P, const Kron1D& K1, const double* z, double* y, const double* r0, bool overwrite,
                     cudaStream_t s) {
   SmallConst<K> C;
-  constexpr int N1 = K + 1;
-  for (int i = 0; i < N1; i++) {
-    for (int j = 0; j < N1; j++) {
-      C.MinvK[i * N1 + j] = K1.MinvK[i * MAX_N1 + j];
-      C.M[i * N1 + j] = K1.M[i * MAX_N1 + j];
-    }
-    C.m0[i] = K1.m0[i];
-    C.mk[i] = K1.mk[i];
-    C.q0[i] = K1.q0[i];
-    C.q1[i] = K1.q1[i];
-    C.d0[i] = K1.d0[i];
-    C.d1[i] = K1.d1[i];
-  }
-  for (int d = 0; d < 3; d++) C.ih2[d] = d < DIM ? 1.0 / (P.h[d] * P.h[d]) : 0.0;
-  C.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
-  C.theta = P.theta;
-  C.vol = P.vol;
+  fill_small_const<K>(C, P, K1);
   const unsigned blocks = (unsigned)((P.ncells + 127) / 128);
   dg_small_kernel<DIM, K><<<blocks, 128, 0, s>>>(P, C, z, y, r0, overwrite ? 0 : 1);
   PDB_CUDA(cudaGetLastError());

@@ -353,10 +353,11 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
   double it = 0.0, it_done = 0.0;
   double *PA, *PB, *PC, *PD, *PE;
   if (solver == PDB200_SOLVER_BICGSTAB) {
-    ensure(w, n, dinv ? 6 : 5);
+    const bool gp = (bool)ops.prec;  // general preconditioner: y = W p / y = W r by separate launches
+    ensure(w, n, dinv || gp ? 6 : 5);
     PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB, PE = PD + NB;
     double *r = w->vec[0], *rt = w->vec[1], *p = w->vec[2], *v = w->vec[3], *t = w->vec[4];
-    double* y = dinv ? w->vec[5] : nullptr;
+    double* y = dinv || gp ? w->vec[5] : nullptr;
     // r = b - A x  (BiCGSTABSolver::apply: op.applyscaleadd(-1, x, r))
     ops.apply(x, r);
     defect_kernel<<<NB, NT, 0, s>>>(n, b, r);
@@ -367,18 +368,20 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
       for (it = 0.5; it < maxit; it += 0.5) {
         // next search direction and  v = A W p
         bcgs_direction_kernel<<<NB, NT, 0, s>>>(n, r, p, v, dinv, y, PD, w->S);
-        ops.apply(dinv ? y : p, v);
+        if (gp) ops.prec(p, y);
+        ops.apply(y ? y : p, v);
         dot_kernel<<<NB, NT, 0, s>>>(n, rt, v, PA, nullptr);
-        bcgs_half1_kernel<<<NB, NT, 0, s>>>(n, x, dinv ? y : p, r, v, dinv, y, PA, PC, w->S);
+        bcgs_half1_kernel<<<NB, NT, 0, s>>>(n, x, y ? y : p, r, v, dinv, y, PA, PC, w->S);
         launches += 3;
         def = read_norm(w, PC, s);
         it_done = it;
         if (converged(def, def0, reduction)) break;
         it += 0.5;
         // second half: t = A W r
-        ops.apply(dinv ? y : r, t);
+        if (gp) ops.prec(r, y);
+        ops.apply(y ? y : r, t);
         dot_kernel<<<NB, NT, 0, s>>>(n, t, r, PA, PB);
-        bcgs_half2_kernel<<<NB, NT, 0, s>>>(n, x, dinv ? y : r, r, t, rt, PA, PB, PC, PD, w->S);
+        bcgs_half2_kernel<<<NB, NT, 0, s>>>(n, x, y ? y : r, r, t, rt, PA, PB, PC, PD, w->S);
         launches += 2;
         def = read_norm(w, PC, s);
         it_done = it;
@@ -389,15 +392,21 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
     // dune-istl hands the defect back in the right-hand side
     PDB_CUDA(cudaMemcpyAsync(b, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   } else if (solver == PDB200_SOLVER_CG) {
-    ensure(w, n, dinv ? 4 : 3);
+    const bool gp = (bool)ops.prec;
+    ensure(w, n, dinv || gp ? 4 : 3);
     PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB, PE = PD + NB;
     (void)PE;
     double *r = w->vec[0], *p = w->vec[1], *q = w->vec[2];
-    double* z = dinv ? w->vec[3] : nullptr;
+    double* z = dinv || gp ? w->vec[3] : nullptr;
     ops.apply(x, r);
     defect_kernel<<<NB, NT, 0, s>>>(n, b, r);
     cg_init_kernel<<<NB, NT, 0, s>>>(n, r, dinv, p, PC, PD);  // PD = p.r (rholast)
     launches += 2;
+    if (gp) {  // p = W r, rholast = p.r
+      ops.prec(r, p);
+      dot_kernel<<<NB, NT, 0, s>>>(n, p, r, PD, nullptr);
+      launches++;
+    }
     def0 = def = read_norm(w, PC, s);
     if (!converged(def0, def0, reduction) && def0 > 0.0) {
       unsigned i = 1;
@@ -409,7 +418,12 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
         def = read_norm(w, PC, s);
         it = i;
         if (converged(def, def0, reduction)) break;
-        cg_direction_kernel<<<NB, NT, 0, s>>>(n, p, dinv ? z : r, PB, w->S);
+        if (gp) {  // z = W r, rho = z.r (the fused kernel computed r.r into PB: replace it)
+          ops.prec(r, z);
+          dot_kernel<<<NB, NT, 0, s>>>(n, z, r, PB, nullptr);
+          launches++;
+        }
+        cg_direction_kernel<<<NB, NT, 0, s>>>(n, p, z ? z : r, PB, w->S);
         cg_commit_kernel<<<1, 1, 0, s>>>(w->S);
         launches += 2;
       }

@@ -11,7 +11,9 @@ namespace pdb {
 
 struct KrylovOps {
   std::function<void(const double* in, double* out)> apply;  // out = A in (device pointers, overwrite)
-  const double* dinv = nullptr;                               // point-Jacobi 1 / A_ii; nullptr = Richardson(1.0)
+  const double* dinv = nullptr;                               // point-Jacobi 1 / A_ii (fused into the vector kernels)
+  std::function<void(const double* in, double* out)> prec;   // general preconditioner out = W in (e.g. block Jacobi);
+                                                              // neither set = Richardson(1.0)
 };
 
 struct KrylovWork;

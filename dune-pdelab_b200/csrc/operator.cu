@@ -42,6 +42,7 @@ struct pdb200_operator {
   MatrixPlan* matrix = nullptr;
   P2PHalo* p2p = nullptr;
   KrylovWork* krylov = nullptr;
+  BlockJacPlan* blockjac = nullptr;
   double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
   bool r0_valid = false;
   uint64_t launches = 0;
@@ -65,6 +66,7 @@ struct pdb200_operator {
     matrix_plan_destroy(matrix);
     p2p_destroy(p2p);
     krylov_destroy(krylov);
+    dg_blockjac_destroy(blockjac);
   }
 };
 
@@ -395,6 +397,7 @@ int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
   upd(P.o, p->o, (size_t)nbf * P.nfq * 8, "o");
   if (p->bctype) throw Error("update_coefficients: bctype changes the constraint set; create a new operator");
   h->r0_valid = false;
+  dg_blockjac_invalidate(h->blockjac);
   fem_plan_invalidate(h->fem);
   PDB_CUDA(cudaStreamSynchronize(h->stream));
   PDB_CATCH
@@ -627,8 +630,14 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
   double* staged_values = nullptr;
   Free free_values{staged_values};
   if (!values) {
-    if (precond != PDB200_PRECOND_NONE)
-      throw Error("pdb200_solve: the matrix-free back-end is ISTLBackend_SEQ_MatrixFree_*_Richardson (no preconditioner)");
+    if (precond == PDB200_PRECOND_BLOCK_JACOBI) {
+      if (!h->blockjac) h->blockjac = dg_blockjac_create(P, h->K);
+      ops.prec = [h](const double* in, double* out) {
+        h->launches += launch_dg_blockjac(h->blockjac, h->P, h->K, in, out, h->stream);
+      };
+    } else if (precond != PDB200_PRECOND_NONE) {
+      throw Error("pdb200_solve: the matrix-free back-ends offer no preconditioner (Richardson) or block Jacobi");
+    }
     ops.apply = [h](const double* in, double* out) { run_vector_device(h, in, out, Mode::OnTheFly); };
   } else {
     if (!h->matrix) h->matrix = matrix_plan_create(P, h->fem, h->stream);
@@ -667,6 +676,19 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
 }
 
 }  // namespace
+
+int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!r || !z) throw Error("pdb200_block_jacobi_apply: null argument");
+  if (!h->blockjac) h->blockjac = dg_blockjac_create(h->P, h->K);
+  Staged rs(const_cast<double*>(r), (size_t)h->P.ndofs, true, h->stream), zs(z, (size_t)h->P.ndofs, false, h->stream);
+  h->launches += launch_dg_blockjac(h->blockjac, h->P, h->K, rs.dev, zs.dev, h->stream);
+  zs.copy_out(h->stream);
+  if (zs.owned || rs.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
 
 int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
                  double reduction, uint32_t maxiter, pdb200_solve_result* res) {

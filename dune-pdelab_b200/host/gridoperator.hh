@@ -965,29 +965,40 @@ class DeviceBackend {
 };
 }  // namespace detail
 
-// ISTLBackend_SEQ_MatrixFree_BCGS_Richardson (seqistlsolverbackend.hh:157-203,1039-1050)
-template <class GO>
-class ISTLBackend_SEQ_MatrixFree_BCGS_Richardson
-    : public detail::DeviceBackend<PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE, true> {
-  using Base = detail::DeviceBackend<PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE, true>;
+namespace detail {
+template <class GO, int SOLVER, int PRECOND>
+class MatrixFreeBackend : public DeviceBackend<SOLVER, PRECOND, true> {
+  using Base = DeviceBackend<SOLVER, PRECOND, true>;
 
  public:
-  explicit ISTLBackend_SEQ_MatrixFree_BCGS_Richardson(const GO& go, unsigned maxiter = 5000, int verbose = 1)
-      : Base(maxiter, verbose), go_(go) {}
-  // apply(z, r, reduction): solve J z = r, r := final defect (:181-192)
+  explicit MatrixFreeBackend(const GO& go, unsigned maxiter = 5000, int verbose = 1) : Base(maxiter, verbose), go_(go) {}
+  // apply(z, r, reduction): solve J z = r, r := final defect (seqistlsolverbackend.hh:181-192)
   template <class V, class W>
   void apply(V& z, W& r, double reduction) {
     pdb200_solve_result s;
-    check(pdb200_solve(go_.handle(), solver, precond, nullptr, PDB200_LAYOUT_CSR, z.data(), r.data(), reduction,
-                       maxiter_, &s),
-          "ISTLBackend_SEQ_MatrixFree_BCGS_Richardson::apply");
-    store(s);
+    check(pdb200_solve(go_.handle(), SOLVER, PRECOND, nullptr, PDB200_LAYOUT_CSR, z.data(), r.data(), reduction,
+                       this->maxiter_, &s),
+          "ISTLBackend_SEQ_MatrixFree::apply");
+    this->store(s);
   }
   void setLinearizationPoint(const typename GO::Domain&) {}  // linear operators only
 
  private:
   const GO& go_;
 };
+}  // namespace detail
+// ISTLBackend_SEQ_MatrixFree_BCGS_Richardson (seqistlsolverbackend.hh:157-203,1039-1050)
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_BCGS_Richardson = detail::MatrixFreeBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_NONE>;
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_CG_Richardson = detail::MatrixFreeBackend<GO, PDB200_SOLVER_CG, PDB200_PRECOND_NONE>;
+// ISTLBackend_SEQ_MatrixFree_Base<GO, PrecGO, Solver> (backend/istl/matrixfree/backends.hh:62-143) with PrecGO built
+// on AssembledBlockJacobiPreconditionerLocalOperator (assembledblockjacobipreconditioner.hh:96-230): the
+// preconditioner grid operator is not a separate object here, the library applies D^-1 matrix-free
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_BCGS_BlockJacobi = detail::MatrixFreeBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_BLOCK_JACOBI>;
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_CG_BlockJacobi = detail::MatrixFreeBackend<GO, PDB200_SOLVER_CG, PDB200_PRECOND_BLOCK_JACOBI>;
 
 namespace detail {
 template <class GO, int SOLVER, int PRECOND>

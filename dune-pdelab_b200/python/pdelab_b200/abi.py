@@ -17,7 +17,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 LAYOUT_CSR, LAYOUT_BCSR = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 SOLVER_BICGSTAB, SOLVER_CG = 0, 1
-PRECOND_NONE, PRECOND_JACOBI = 0, 1
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1, 2
 
 
 class Problem(C.Structure):

@@ -32,7 +32,7 @@ SYMBOLS = [
     "pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply", "pdb200_jacobian_apply_nonlinear",
     "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
-    "pdb200_solve", "pdb200_solve_stationary",
+    "pdb200_solve", "pdb200_solve_stationary", "pdb200_block_jacobi_apply",
     "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
@@ -72,6 +72,7 @@ def load_library():
     lib.pdb200_jacobian.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_jacobian_fresh.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_csr_mv.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.pdb200_block_jacobi_apply.argtypes = [vp, vp, vp]
     lib.pdb200_solve.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_uint32,
                                  C.POINTER(SolveResult)]
     lib.pdb200_solve_stationary.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_uint32,
@@ -254,6 +255,12 @@ class GridOperator:
         self._chk(self.lib.pdb200_solve(self._h, solver, precond, _ptr(values), layout, _ptr(z), _ptr(r),
                                         float(reduction), int(maxiter), C.byref(res)))
         return res.as_dict()
+
+    def block_jacobi_apply(self, r, z):
+        """z = D^-1 r, D = block diagonal of the QkDG Jacobian (AssembledBlockJacobiPreconditionerLocalOperator,
+        backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:96-230), matrix-free."""
+        self._chk(self.lib.pdb200_block_jacobi_apply(self._h, _ptr(r), _ptr(z)))
+        return z
 
     def solve_stationary(self, x, reduction=1e-10, min_defect=1e-99, solver=abi.SOLVER_BICGSTAB,
                          precond=abi.PRECOND_NONE, matrix_free=True, maxiter=5000):

@@ -171,7 +171,11 @@ int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const doubl
  * pdb200_solve: the reference's sequential ISTL back-ends with every vector resident on the GPU.
  *   values == NULL : matrix-free, ISTLBackend_SEQ_MatrixFree_BCGS_Richardson
  *                    (backend/istl/seqistlsolverbackend.hh:157-203,1039-1050): OnTheFlyOperator (:44-100)
- *                    + Richardson(1.0) + BiCGSTAB (or CG); precond must be PDB200_PRECOND_NONE
+ *                    + Richardson(1.0) + BiCGSTAB (or CG), precond PDB200_PRECOND_NONE; or
+ *                    ISTLBackend_SEQ_MatrixFree_Base (backend/istl/matrixfree/backends.hh:62-143) with the exact
+ *                    block-Jacobi preconditioner (AssembledBlockJacobiPreconditionerLocalOperator,
+ *                    backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:96-230), precond
+ *                    PDB200_PRECOND_BLOCK_JACOBI (QkDG, k = 1, 2, SIPG, diagonal A, b = 0)
  *   values != NULL : assembled matrix in `layout` (MatrixAdapter), ISTLBackend_SEQ_BCGS_Jac / _CG_Jac
  *                    (:401-416,538-553; SeqJac, one step, w = 1; scalar CSR layout only) or no
  *                    preconditioner
@@ -180,7 +184,7 @@ int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const doubl
  * |defect| < reduction * |defect_0|  (two-norm, SequentialNorm).  Not converged within maxiter is
  * reported through res->converged == 0, not as an error (LinearSolverResult, backend/solver.hh:28-51). */
 enum { PDB200_SOLVER_BICGSTAB = 0, PDB200_SOLVER_CG = 1 };
-enum { PDB200_PRECOND_NONE = 0, PDB200_PRECOND_JACOBI = 1 };
+enum { PDB200_PRECOND_NONE = 0, PDB200_PRECOND_JACOBI = 1, PDB200_PRECOND_BLOCK_JACOBI = 2 };
 typedef struct pdb200_solve_result {
   int32_t converged;
   uint32_t iterations;
@@ -192,6 +196,13 @@ typedef struct pdb200_solve_result {
 } pdb200_solve_result;
 int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
                  double reduction, uint32_t maxiter, pdb200_solve_result* res);
+/* z = D^-1 r with D the block diagonal of the QkDG Jacobian (one n x n block per cell), the operation of
+ * AssembledBlockJacobiPreconditionerLocalOperator::jacobian_apply_volume
+ * (backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:189-230) wrapped by
+ * GridOperatorPreconditioner::apply (gridoperatorpreconditioner.hh:81-87).  Matrix-free: the blocks are
+ * Kronecker sums and are inverted by fast diagonalisation (csrc/dg_blockjac.cu).  Host or device pointers. */
+int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z);
+
 /* StationaryLinearProblemSolver::apply (stationary/linearproblem.hh:188-302):
  *   [A = 0; jacobian(x, A)]  r = 0; residual(x, r);  red = max(reduction, min_defect / |r|);
  *   solve J z = r to red;  x -= z.

@@ -283,6 +283,17 @@ void dg_case(int ncells, double alpha, double tol, const char* name, bool check_
                std::max(5, (r1.linear_solver_iterations + r2.linear_solver_iterations) / 20),
            name << ": comparable iteration counts (" << r1.linear_solver_iterations << ", " << r2.linear_solver_iterations << ")");
     EXPECT(r2.defect <= 1e-12 * r2.first_defect * 1.000001, name << ": defect reduced by 1e-12");
+    // the matrix-free back-end of matrix_free_linear.cc:338-341 proper: BiCGSTAB preconditioned with block Jacobi
+    using LSB = PDELab::ISTLBackend_SEQ_MatrixFree_BCGS_BlockJacobi<GridOperator>;
+    LSB linearSolverBlockJacobi(gridOperator, 5000, 0);
+    V c3(gridFunctionSpace, 0.0);
+    PDELab::StationaryLinearProblemSolver<GridOperator, LSB, V> solverBJ(gridOperator, linearSolverBlockJacobi, c3, 1e-12);
+    solverBJ.apply();
+    const auto r3 = solverBJ.result();
+    const double e3 = l2_error_squared(gridFunctionSpace, c3, problem, gridOperator.handle(), degree);
+    EXPECT(r3.converged && e3 <= tol && r3.linear_solver_iterations < r2.linear_solver_iterations,
+           name << ": matrix-free BiCGSTAB + block Jacobi err^2 " << e3 << ", " << r3.linear_solver_iterations
+                << " iterations (unpreconditioned: " << r2.linear_solver_iterations << ")");
   }
 }
 
