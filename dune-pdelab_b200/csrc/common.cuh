@@ -135,6 +135,8 @@ int launch_dg_blockjac(BlockJacPlan*, const DevParams& P, const Kron1D& K, const
 
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);
+void launch_gather(const double* x, const long long* idx, long long n, double* buf, cudaStream_t s);
+void launch_scatter(const double* buf, const long long* idx, long long n, double* x, cudaStream_t s);
 // halo.cu: peer-to-peer mailbox exchange over NVLink (CUDA IPC), see pdelab_b200.h
 struct P2PHalo;
 P2PHalo* p2p_create(const DevParams& P, pdb200_ipc_handle* mine);

@@ -352,4 +352,26 @@ void p2p_check(P2PHalo* H) {
 cudaStream_t p2p_stream(P2PHalo* H) { return H->stream; }
 cudaEvent_t p2p_event(P2PHalo* H, int i) { return H->ev[i]; }
 
+// index gather / scatter (pack / unpack of the conforming-Qk ghost exchange)
+__global__ void gather_kernel(const double* __restrict__ x, const long long* __restrict__ idx, long long n,
+                              double* __restrict__ buf) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    buf[i] = x[idx[i]];
+}
+__global__ void scatter_kernel(const double* __restrict__ buf, const long long* __restrict__ idx, long long n,
+                               double* __restrict__ x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[idx[i]] = buf[i];
+}
+void launch_gather(const double* x, const long long* idx, long long n, double* buf, cudaStream_t s) {
+  if (n <= 0) return;
+  gather_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(x, idx, n, buf);
+  PDB_CUDA(cudaGetLastError());
+}
+void launch_scatter(const double* buf, const long long* idx, long long n, double* x, cudaStream_t s) {
+  if (n <= 0) return;
+  scatter_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(buf, idx, n, x);
+  PDB_CUDA(cudaGetLastError());
+}
+
 }  // namespace pdb

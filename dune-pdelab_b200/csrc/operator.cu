@@ -749,6 +749,23 @@ int pdb200_solve_stationary(pdb200_handle h, int solver, int precond, int matrix
   PDB_CATCH
 }
 
+int pdb200_gather_dofs(pdb200_handle h, const double* x, const int64_t* idx, uint64_t n, double* buf) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  launch_gather(x, (const long long*)idx, (long long)n, buf, h->stream);
+  h->launches += 1;
+  PDB_CATCH
+}
+int pdb200_scatter_dofs(pdb200_handle h, const double* buf, const int64_t* idx, uint64_t n, double* x) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  launch_scatter(buf, (const long long*)idx, (long long)n, x, h->stream);
+  h->launches += 1;
+  PDB_CATCH
+}
+
 int pdb200_halo_layer_size(pdb200_handle h, int dir, uint64_t* ndoubles) {
   PDB_TRY
   PDB_CHECK_HANDLE(h);

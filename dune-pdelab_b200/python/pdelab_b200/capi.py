@@ -34,6 +34,7 @@ SYMBOLS = [
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
     "pdb200_solve", "pdb200_solve_stationary", "pdb200_block_jacobi_apply",
     "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
+    "pdb200_gather_dofs", "pdb200_scatter_dofs",
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
@@ -85,6 +86,8 @@ def load_library():
     lib.pdb200_halo_pack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.pdb200_halo_unpack.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.pdb200_set_stream.argtypes = [vp, vp]
+    lib.pdb200_gather_dofs.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.pdb200_scatter_dofs.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.pdb200_onthefly_apply_part.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_halo_p2p_create.argtypes = [vp, vp]
     lib.pdb200_halo_p2p_connect.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -286,6 +289,14 @@ class GridOperator:
         """y = J x restricted to the INTERIOR or BOUNDARY tiles of the local box (abi.PART_*)."""
         self._chk(self.lib.pdb200_onthefly_apply_part(self._h, _ptr(x), _ptr(y), part))
         return y
+
+    def gather_dofs(self, x, idx, buf):
+        """buf[i] = x[idx[i]] on the device (idx: int64 CUDA tensor)."""
+        self._chk(self.lib.pdb200_gather_dofs(self._h, _ptr(x), idx.data_ptr(), idx.numel(), _ptr(buf)))
+
+    def scatter_dofs(self, buf, idx, x):
+        """x[idx[i]] = buf[i] on the device."""
+        self._chk(self.lib.pdb200_scatter_dofs(self._h, _ptr(buf), idx.data_ptr(), idx.numel(), _ptr(x)))
 
     def halo_p2p_create(self):
         """Create this rank's mailbox; returns the 64-byte IPC handle to give to the neighbours."""

@@ -178,26 +178,164 @@ class HaloExchanger:
             self.unpack(x, d, s, self.recv[(d, s)])
 
 
+def qk_container_index(cells, k, P):
+    """Container index of the conforming Qk DOF at lattice point(s) P (int array [..., dim],
+    0 <= P_d <= k * cells_d): the closed form of csrc/host_tables.h (QkLayout, qk_lattice_index) —
+    Q1: vertex-lexicographic; Q2: vertices | edges | faces | cells blocks, sub-entities grouped by
+    extension bitset (SURVEY.md §8a "index-formula detail")."""
+    cells = tuple(int(c) for c in cells)
+    dim = len(cells)
+    P = np.asarray(P, dtype=np.int64)
+    if k == 1:
+        idx, stride = np.zeros(P.shape[:-1], dtype=np.int64), 1
+        for d in range(dim):
+            idx = idx + stride * P[..., d]
+            stride *= cells[d] + 1
+        return idx
+    assert k == 2
+    size = lambda s: int(np.prod([cells[d] if (s >> d) & 1 else cells[d] + 1 for d in range(dim)]))
+    count = [0] * (dim + 1)
+    group_off = [0] * (1 << dim)
+    for edim in range(dim + 1):
+        for s in range(1 << dim):
+            if bin(s).count("1") == edim:
+                group_off[s] = count[edim]
+                count[edim] += size(s)
+    block_off = np.concatenate([[0], np.cumsum(count)])[:dim + 1]
+    ext = P & 1
+    s = np.zeros(P.shape[:-1], dtype=np.int64)
+    for d in range(dim):
+        s |= ext[..., d] << d
+    edim = ext.sum(axis=-1)
+    idx, stride = np.zeros(P.shape[:-1], dtype=np.int64), np.ones(P.shape[:-1], dtype=np.int64)
+    for d in range(dim):
+        idx = idx + stride * (P[..., d] >> 1)
+        stride = stride * np.where(ext[..., d] == 1, cells[d], cells[d] + 1)
+    return block_off[edim] + np.asarray(group_off, dtype=np.int64)[s] + idx
+
+
+class QkHaloExchanger:
+    """Owner -> ghost copy of a conforming Qk vector on the overlapping partition (overlap = 1).
+
+    Every lattice point has one owner: the points of the interface plane between two ranks' owned
+    cells belong to the LOWER rank (the rule of genericdatahandle.hh:894-947 restricted to a
+    Cartesian partition).  Towards its upper neighbour a rank sends the k+1 lattice planes of its
+    last owned cell layer (incl. the interface) and receives the k planes beyond the interface;
+    towards its lower neighbour it sends k planes and receives k+1.  Directions are exchanged one
+    after the other over the full tangential extent, so edge and corner neighbours are reached
+    without extra messages.  After the exchange the vector is consistent on the whole extended box;
+    the operator then computes complete rows for every point of the closure of the owned cells (the
+    boundary of the extended box is constrained like a Dirichlet boundary).
+
+    gather/scatter default to the index kernels behind the C ABI (pdb200_gather_dofs / _scatter_dofs);
+    the transport is torch.distributed point-to-point."""
+
+    def __init__(self, go, part, degree, device, gather=None, scatter=None, dist=None):
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        assert part.overlap == 1
+        self.dist, self.part, self.k = dist, part, int(degree)
+        self.gather = gather or go.gather_dofs
+        self.scatter = scatter or go.scatter_dofs
+        k, lc = self.k, part.local_cells
+        self.plan = []   # per direction: list of (neighbour, send idx, recv idx, send buf, recv buf)
+        for d in range(part.dim):
+            entries = []
+            for s in range(2):
+                nbr = part.neighbour[d][s]
+                if nbr is None:
+                    continue
+                n = lc[d]
+                if s == 1:   # upper neighbour: I own the interface plane
+                    send_r, recv_r = (k * (n - 2), k * (n - 1)), (k * (n - 1) + 1, k * n)
+                else:        # lower neighbour owns the interface plane
+                    send_r, recv_r = (k + 1, 2 * k), (0, k)
+                mk = lambda r: torch.from_numpy(self._box_indices(d, r)).to(device)
+                si, ri = mk(send_r), mk(recv_r)
+                entries.append((nbr, si, ri, torch.empty(si.numel(), dtype=torch.float64, device=device),
+                                torch.empty(ri.numel(), dtype=torch.float64, device=device)))
+            if entries:
+                self.plan.append(entries)
+        self.bytes_per_exchange = sum(e[3].numel() * 8 for entries in self.plan for e in entries)
+
+    def _box_indices(self, d, rng):
+        """container indices of the lattice points with rng[0] <= p_d <= rng[1], full extent elsewhere"""
+        part, k = self.part, self.k
+        axes = [np.arange(rng[0], rng[1] + 1) if dd == d else np.arange(k * part.local_cells[dd] + 1)
+                for dd in range(part.dim)]
+        grids = np.meshgrid(*axes[::-1], indexing="ij")[::-1]
+        P = np.stack([g.reshape(-1) for g in grids], axis=-1)
+        return qk_container_index(part.local_cells, k, P).astype(np.int64)
+
+    def owned_point_mask(self):
+        """Boolean mask over the local container: lattice points this rank OWNS (each global point
+        exactly once over all ranks): points of the closure of the owned cells minus the interface
+        planes towards lower neighbours."""
+        part, k = self.part, self.k
+        axes = [np.arange(k * part.local_cells[dd] + 1) for dd in range(part.dim)]
+        grids = np.meshgrid(*axes[::-1], indexing="ij")[::-1]
+        P = np.stack([g.reshape(-1) for g in grids], axis=-1)
+        own = np.ones(P.shape[0], dtype=bool)
+        for d in range(part.dim):
+            lo = k + 1 if part.neighbour[d][0] is not None else 0
+            hi = k * (part.local_cells[d] - 1) if part.neighbour[d][1] is not None else k * part.local_cells[d]
+            own &= (P[:, d] >= lo) & (P[:, d] <= hi)
+        mask = np.zeros(P.shape[0], dtype=bool)
+        mask[qk_container_index(part.local_cells, k, P)] = own
+        return mask
+
+    def global_point_index(self, global_cells):
+        """global container index of every local DOF (array over the local container)"""
+        part, k = self.part, self.k
+        axes = [np.arange(k * part.local_cells[dd] + 1) for dd in range(part.dim)]
+        grids = np.meshgrid(*axes[::-1], indexing="ij")[::-1]
+        P = np.stack([g.reshape(-1) for g in grids], axis=-1)
+        G = P + k * np.asarray(part.local_lo, dtype=np.int64)
+        out = np.zeros(P.shape[0], dtype=np.int64)
+        out[qk_container_index(part.local_cells, k, P)] = qk_container_index(global_cells, k, G)
+        return out
+
+    def exchange(self, x):
+        dist = self.dist
+        for entries in self.plan:      # one direction after the other: corners travel in two hops
+            ops = []
+            for nbr, si, ri, sb, rb in entries:
+                self.gather(x, si, sb)
+                ops.append(dist.P2POp(dist.isend, sb, nbr))
+                ops.append(dist.P2POp(dist.irecv, rb, nbr))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            for nbr, si, ri, sb, rb in entries:
+                self.scatter(rb, ri, x)
+
+
 def exchange_cell_field(field, part, dist):
     """Owner -> ghost copy of a per-cell field (torch tensor of shape local_cells[::-1] + trailing
     dims), used once at set-up for the coefficient arrays.  Plain tensor slicing: not a hot path."""
     import torch
-    ops, recvs = [], []
-    for d, s, nbr in part.exchanges():
-        ax = part.dim - 1 - d
-        n = part.local_cells[d]
-        src = 1 if s == 0 else n - 2
-        dst = 0 if s == 0 else n - 1
-        sendbuf = field.select(ax, src).contiguous()
-        recvbuf = torch.empty_like(sendbuf)
-        ops.append(dist.P2POp(dist.isend, sendbuf, nbr))
-        ops.append(dist.P2POp(dist.irecv, recvbuf, nbr))
-        recvs.append((ax, dst, recvbuf))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    for ax, dst, buf in recvs:
-        field.select(ax, dst).copy_(buf)
+    # one direction after the other over the full tangential extent: edge and corner ghost cells (needed
+    # by the conforming spaces) are filled in two / three hops
+    for d in range(part.dim):
+        ops, recvs = [], []
+        for s in range(2):
+            nbr = part.neighbour[d][s]
+            if nbr is None:
+                continue
+            ax = part.dim - 1 - d
+            n = part.local_cells[d]
+            src = 1 if s == 0 else n - 2
+            dst = 0 if s == 0 else n - 1
+            sendbuf = field.select(ax, src).contiguous()
+            recvbuf = torch.empty_like(sendbuf)
+            ops.append(dist.P2POp(dist.isend, sendbuf, nbr))
+            ops.append(dist.P2POp(dist.irecv, recvbuf, nbr))
+            recvs.append((ax, dst, recvbuf))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for ax, dst, buf in recvs:
+            field.select(ax, dst).copy_(buf)
     return field
 
 

@@ -219,6 +219,12 @@ int pdb200_halo_layer_size(pdb200_handle h, int dir, uint64_t* ndoubles);
 int pdb200_halo_pack(pdb200_handle h, const double* x, int dir, int side, double* buf);
 int pdb200_halo_unpack(pdb200_handle h, double* x, int dir, int side, const double* buf);
 
+/* Index gather / scatter on DEVICE vectors: buf[i] = x[idx[i]] / x[idx[i]] = buf[i] (idx: int64 device
+ * array).  The pack / unpack of the conforming-Qk ghost exchange, whose lattice planes are spread over
+ * the sub-entity groups of the container (python/pdelab_b200/partition.py: QkHaloExchanger). */
+int pdb200_gather_dofs(pdb200_handle h, const double* x, const int64_t* idx, uint64_t n, double* buf);
+int pdb200_scatter_dofs(pdb200_handle h, const double* buf, const int64_t* idx, uint64_t n, double* x);
+
 /* Parts of the local box for overlapping communication with computation: INTERIOR = every tile
  * of cells that reads no ghost layer (can run while the halo exchange is in flight), BOUNDARY =
  * the rest.  INTERIOR followed by BOUNDARY equals ALL.  Device pointers only, y is overwritten. */

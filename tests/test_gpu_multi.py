@@ -129,3 +129,101 @@ def test_p2p_halo_apply_matches_global_oracle(cuda_lib, world, cells):
         assert err < 1e-12, (rank, err)
         assert ok, rank
         assert kern == "dg_fast_q2_3d"
+
+
+# ---- conforming Qk on the overlapping partition: gather / scatter kernels + QkHaloExchanger ----------
+
+class _HostStagedDist:
+    """torch.distributed look-alike that stages CUDA buffers through the host, so that several ranks can
+    share one GPU over gloo in this test (on a multi-GPU box bench/production use NCCL directly)."""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.isend, self.irecv = "isend", "irecv"
+
+    def P2POp(self, op, buf, peer):
+        return (op, buf, peer)
+
+    def batch_isend_irecv(self, ops):
+        real, back = [], []
+        for op, buf, peer in ops:
+            host = buf.cpu() if op == "isend" else torch.empty(buf.shape, dtype=buf.dtype)
+            real.append(self.dist.P2POp(self.dist.isend if op == "isend" else self.dist.irecv, host, peer))
+            if op == "irecv":
+                back.append((buf, host))
+        reqs = self.dist.batch_isend_irecv(real)
+
+        class _Done:
+            def __init__(s, r, last):
+                s.r, s.last = r, last
+
+            def wait(s):
+                s.r.wait()
+                if s.last:
+                    for buf, host in back:
+                        buf.copy_(host)
+        return [_Done(r, i == len(reqs) - 1) for i, r in enumerate(reqs)]
+
+
+def _qk_worker(rank, world, port, cells, degree, out):
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [os.path.join(here, "..", "oracle"), here, os.path.join(here, "..", "dune-pdelab_b200", "python")]
+        import torch.distributed as dist
+        from oracle import Oracle
+        from pdelab_b200.capi import GridOperator
+        from pdelab_b200.partition import OverlappingPartition, QkHaloExchanger
+        from problems import kappa_field, mt_vector
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        part = OverlappingPartition.strong(cells, world, rank)
+        ncg = int(np.prod(cells))
+        kg = kappa_field(ncg)
+        gspec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=degree, a_mode=abi.A_SCALAR, A=kg)
+        zg = mt_vector(gspec.num_dofs)
+        want = Oracle(gspec).jacobian_apply(zg)
+        gidx = part.local_cell_grid().reshape(-1)
+        spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QK, degree=degree, lower=part.local_lower,
+                               upper=part.local_upper, a_mode=abi.A_SCALAR, A=kg[gidx], side_kind=part.side_kind, device=dev)
+        go = GridOperator(spec)
+        halo = QkHaloExchanger(go, part, degree, torch.device("cuda", dev), dist=_HostStagedDist(dist))
+        own = halo.owned_point_mask()
+        gp = halo.global_point_index(cells)
+        z = np.full(own.size, 1e300)                 # everything not owned is poisoned
+        z[own] = zg[gp[own]]
+        zd = torch.from_numpy(z).cuda()
+        yd = torch.full_like(zd, float("nan"))
+        halo.exchange(zd)
+        go.apply(zd, yd)
+        go.synchronize()
+        consistent = bool(np.array_equal(zd.cpu().numpy(), zg[gp]))
+        y = yd.cpu().numpy()
+        err = float(np.abs(y[own] - want[gp[own]]).max() / np.abs(want).max())
+        out.put((rank, err, consistent, go.last_kernel(), int(own.sum()), None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out.put((rank, 1.0, False, "", 0, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world,cells,degree", [(2, (8, 6, 10), 2), (4, (6, 10, 8), 1)])
+def test_qk_halo_apply_matches_global_oracle(cuda_lib, world, cells, degree):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_qk_worker, args=(r, world, port, cells, degree, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sum(r[4] for r in res) == int(np.prod([degree * c + 1 for c in cells]))
+    for rank, err, consistent, kern, _, tb in res:
+        assert tb is None, tb
+        assert consistent, rank
+        assert err < 1e-12, (rank, err)
+        assert kern == "fem_kron"

@@ -136,3 +136,87 @@ def test_distributed_apply_matches_global_oracle(world, cells, degree):
     for rank, err, ghosts_zero, _ in res:
         assert err < 1e-12, (rank, err)
         assert ghosts_zero
+
+
+# ---- conforming Qk on the overlapping partition (QkHaloExchanger) -----------------------------------
+
+def test_qk_container_index_matches_the_library_numbering():
+    """partition.qk_container_index restates csrc/host_tables.h; the oracle restates it too
+    (cell_dof_indices): the two must agree DOF by DOF."""
+    sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "oracle")]
+    from oracle import Oracle
+    from pdelab_b200.partition import qk_container_index
+    for cells, k in (((3, 2), 1), ((3, 2), 2), ((2, 3, 2), 1), ((3, 2, 2), 2)):
+        spec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=k)
+        orc = Oracle(spec)
+        dim, n1 = len(cells), k + 1
+        for e in range(spec.ncells):
+            c = np.unravel_index(e, cells[::-1])[::-1]
+            loc = np.array(np.unravel_index(np.arange(n1 ** dim), (n1,) * dim)[::-1]).T
+            P = loc + k * np.asarray(c)
+            assert np.array_equal(qk_container_index(cells, k, P), orc.cell_dof_indices(e).astype(np.int64))
+
+
+def _qk_worker(rank, world, port, cells, degree, out):
+    sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "oracle"), os.path.dirname(__file__)]
+    from oracle import Oracle
+    from problems import kappa_field, mt_vector
+    from pdelab_b200.partition import QkHaloExchanger
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dim = len(cells)
+        part = OverlappingPartition.strong(cells, world, rank) if dim == 3 else \
+            OverlappingPartition(cells, processor_grid(world, 2, split_x=True), rank)
+        ncg = int(np.prod(cells))
+        kg = kappa_field(ncg)
+        gspec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=degree, a_mode=abi.A_SCALAR, A=kg)
+        zg = mt_vector(gspec.num_dofs)
+        want = Oracle(gspec).jacobian_apply(zg)
+        gidx = part.local_cell_grid().reshape(-1)
+        own_c = part.owned_mask().reshape(-1)
+        kap = torch.full((gidx.size,), float("nan"), dtype=torch.float64)
+        kap[own_c] = torch.from_numpy(kg[gidx[own_c]])
+        exchange_cell_field(kap.view(part.local_cells[::-1]), part, dist)
+
+        def gather(x, idx, buf):
+            buf.copy_(x[idx])
+
+        def scatter(buf, idx, x):
+            x[idx] = buf
+
+        halo = QkHaloExchanger(None, part, degree, "cpu", gather=gather, scatter=scatter, dist=dist)
+        own = halo.owned_point_mask()
+        gp = halo.global_point_index(cells)
+        # owned values from the global vector, everything else poisoned: the exchange must fill the box
+        z = torch.full((own.size,), float("nan"), dtype=torch.float64)
+        z[torch.from_numpy(own)] = torch.from_numpy(zg[gp[own]])
+        halo.exchange(z)
+        consistent = bool(np.array_equal(z.numpy(), zg[gp]))
+        kl = torch.nan_to_num(kap, nan=1.0).numpy()
+        spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QK, degree=degree, lower=part.local_lower,
+                               upper=part.local_upper, a_mode=abi.A_SCALAR, A=kl, side_kind=part.side_kind)
+        y = Oracle(spec).jacobian_apply(np.nan_to_num(z.numpy(), nan=1e300))
+        err = np.abs(y[own] - want[gp[own]]).max() / np.abs(want).max()
+        out.put((rank, float(err), consistent, int(own.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cells,degree", [(2, (4, 3, 6), 2), (4, (3, 6, 6), 1), (4, (6, 6), 2), (4, (5, 7), 1)])
+def test_distributed_qk_apply_matches_global_oracle(world, cells, degree):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_qk_worker, args=(r, world, port, cells, degree, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ndofs = int(np.prod([degree * c + 1 for c in cells]))
+    assert sum(r[3] for r in res) == ndofs          # every lattice point has exactly one owner
+    for rank, err, consistent, _ in res:
+        assert consistent, rank                      # the whole extended box carries the global values
+        assert err < 1e-12, (rank, err)
