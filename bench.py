@@ -160,7 +160,11 @@ def run_ours(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
     C = args.cells
-    part = OverlappingPartition.weak((C, C, C), world, rank, overlap=1)
+    if args.global_cells:   # strong scaling: BASELINE.json configs[4] (512^3 cells over 2/4/8 GPUs)
+        G = args.global_cells
+        part = OverlappingPartition.strong((G, G, G), world, rank, overlap=1)
+    else:
+        part = OverlappingPartition.weak((C, C, C), world, rank, overlap=1)
     ncl = int(np.prod(part.local_cells))
     # synthetic coefficient field kappa_e = 10^(2u-1), generated on the device per rank
     g = torch.Generator(device=dev).manual_seed(42 + rank)
@@ -187,6 +191,8 @@ def run_ours(args):
             halo, halo_kind = HaloExchanger(go, part, dev), "pack + NCCL send/recv + unpack, not overlapped"
     ndofs = spec.num_dofs
     owned_dofs = int(np.prod(part.owned_cells)) * 27
+    if args.global_cells:
+        C = None
     z = torch.rand(ndofs, dtype=torch.float64, device=dev, generator=g)
     y = torch.empty_like(z)
 
@@ -273,16 +279,20 @@ def run_ours(args):
         try:
             with open(prof) as f:
                 rec = json.load(f)
-            if rec.get("cells") == [C, C, C] and rec.get("kernel") == kernel_name:
+            if rec.get("cells") == list(part.local_cells) and rec.get("kernel") == kernel_name:
                 traffic = rec.get("dram_bytes_per_launch")
         except Exception:
             pass
 
     # end to end through the C ABI with HOST buffers (pinned): H2D z, apply, D2H y inside the timed region
-    e2e_steps = max(1, min(args.steps, 10))
-    zh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
-    yh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
-    zh.copy_(z)
+    e2e_steps = max(1, min(args.steps, 10 if not args.global_cells else 2))
+    if args.no_e2e:   # side runs with very large vectors (strong scaling at 512^3): no pinned host copies
+        e2e_steps = 0
+        zh = yh = None
+    else:
+        zh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+        yh = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+        zh.copy_(z)
 
     def e2e_step():
         if halo is None:
@@ -293,27 +303,31 @@ def run_ours(args):
             yh.copy_(y, non_blocking=True)
             torch.cuda.synchronize()
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_value = None
+    if e2e_steps:
         e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = owned_dofs * world / te.item()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = owned_dofs * world / te.item()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_cells else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"ConvectionDiffusionDG SIPG QkDG k=2 on 3D YaspGrid {C}^3 cells per GPU: matrix-free "
-                            "jacobian_apply (OnTheFlyOperator::apply), fp64",
-                "cells_per_gpu": [C, C, C], "global_cells": list(part.global_cells), "dofs_per_gpu": owned_dofs,
+                "workload": (f"ConvectionDiffusionDG SIPG QkDG k=2 on 3D YaspGrid {C}^3 cells per GPU" if C else
+                             f"ConvectionDiffusionDG SIPG QkDG k=2 on 3D YaspGrid {args.global_cells}^3 cells in total") +
+                            ": matrix-free jacobian_apply (OnTheFlyOperator::apply), fp64",
+                "cells_per_gpu": list(part.owned_cells), "global_cells": list(part.global_cells), "dofs_per_gpu": owned_dofs,
                 "partition": "x".join(str(v) for v in part.procs), "overlap": 1 if world > 1 else 0,
                 "coefficients": "cell-wise scalar kappa=10^(2u-1), b=0, c=0, all-Dirichlet, alpha=3",
                 "cache": f"input+output {2 * ndofs * 8 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
@@ -342,8 +356,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=128, help="cells per direction per GPU")
+    ap.add_argument("--global-cells", type=int, default=0,
+                    help="strong scaling: cells per direction of the WHOLE grid (e.g. 512), split over the ranks")
     ap.add_argument("--ref-cells", type=int, default=64, help="cells per direction of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (side runs only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost-layer exchange for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
