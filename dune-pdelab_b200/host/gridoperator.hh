@@ -500,6 +500,52 @@ class ConvectionDiffusionFEM {
   double alpha = 0.0;
 };
 
+// L2 (localoperator/l2.hh:25-230): the mass operator  alpha_volume = scaling * int u v  (no skeleton or
+// boundary terms, no constraints of its own) — the local operator of test/test-blocked-istl-ordering.cc.
+// It is the convection-diffusion operator with A = 0, b = 0, c = scaling and boundary type None, so the
+// same kernels evaluate it (for QkDG the face coefficients vanish with A).  residual / jacobian_apply
+// only: the reference's L2 pattern is block-diagonal (doPatternVolume only), which the assembled path of
+// this library does not produce.
+namespace detail {
+template <class GV, class RF>
+class L2Parameter : public ConvectionDiffusionModelProblem<GV, RF> {
+ public:
+  using Traits = ConvectionDiffusionParameterTraits<GV, RF>;
+  using BCType = ConvectionDiffusionBoundaryConditions::Type;
+  explicit L2Parameter(RF scaling) : scaling_(scaling) {}
+  template <class E, class X>
+  typename Traits::PermTensorType A(const E&, const X&) const {
+    return typename Traits::PermTensorType(RF(0));
+  }
+  template <class E, class X>
+  RF c(const E&, const X&) const {
+    return scaling_;
+  }
+  template <class I, class X>
+  BCType bctype(const I&, const X&) const {
+    return ConvectionDiffusionBoundaryConditions::None;
+  }
+
+ private:
+  RF scaling_;
+};
+}  // namespace detail
+
+template <class GV, class FEM, class RF = double>
+class L2 {
+ public:
+  using ParameterType = detail::L2Parameter<GV, RF>;
+  static constexpr bool isLinear = true;
+  explicit L2(int intorderadd = 0, double scaling = 1.0) : param_(scaling), intorderadd(intorderadd) {}  // l2.hh:241-244
+  ParameterType& parameters() const { return param_; }
+  void setTime(double) {}
+  mutable ParameterType param_;
+  int intorderadd;
+  ConvectionDiffusionDGMethod::Type method = ConvectionDiffusionDGMethod::SIPG;
+  ConvectionDiffusionDGWeights::Type weights = ConvectionDiffusionDGWeights::weightsOn;
+  double alpha = 0.0;
+};
+
 // ConvectionDiffusionBoundaryConditionAdapter (convectiondiffusionparameter.hh:217-248)
 template <class Param>
 struct ConvectionDiffusionBoundaryConditionAdapter {
@@ -858,6 +904,14 @@ class GridOperator {
   pdb200_problem p_{};
   pdb200_handle h_ = nullptr;
 };
+
+// FastDGGridOperator (gridoperator/fastdg.hh:37-230): the reference's assembler variant that skips the
+// LFSIndexCache for DG spaces with Blocking::fixed and aliases vector blocks.  Every kernel of this library
+// already addresses DG vectors as cell * n + i, so it is the same operator: same interface, same results.
+template <class GFSU, class GFSV, class LOP, class MB, class DF, class RF, class JF,
+          class CU = typename GFSU::template ConstraintsContainer<RF>::Type,
+          class CV = typename GFSV::template ConstraintsContainer<RF>::Type>
+using FastDGGridOperator = GridOperator<GFSU, GFSV, LOP, MB, DF, RF, JF, CU, CV>;
 
 // Backend::Matrix / ISTL::BCRSMatrixContainer constructed from the grid operator
 // (backend/istl/bcrsmatrix.hh:78-82 -> MB::buildPattern -> go.fill_pattern)

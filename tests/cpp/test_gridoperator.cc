@@ -379,7 +379,60 @@ void fem_case(int ncells, double tol, const char* name) {
   EXPECT(std::abs(it_mat - it_free) <= 1, name << ": CG iterations assembled/matrix-free (" << it_mat << ", " << it_free << ")");
 }
 
+// ---- test/test-blocked-istl-ordering.cc:24-72: L2 operator, QkDG k=2 on 4^3 cells, flat vs Blocking::fixed --------
+void l2_blocked_ordering_case() {
+  constexpr int dim = 3;
+  using Grid = PDELab::YaspGrid<dim>;
+  std::array<int, dim> cells;
+  cells.fill(4);
+  Grid grid(PDELab::FieldVector<double, dim>(1.0), cells);
+  using GridView = typename Grid::LeafGridView;
+  GridView gv = grid.leafGridView();
+  using FEM = PDELab::QkDGLocalFiniteElementMap<double, double, 2, dim>;
+  FEM fem;
+  using FlatBackend = PDELab::ISTL::VectorBackend<>;
+  using BlockedBackend = PDELab::ISTL::VectorBackend<PDELab::ISTL::Blocking::fixed, FEM::maxLocalSize()>;
+  using FlatGFS = PDELab::GridFunctionSpace<GridView, FEM, PDELab::NoConstraints, FlatBackend>;
+  using BlockedGFS = PDELab::GridFunctionSpace<GridView, FEM, PDELab::NoConstraints, BlockedBackend>;
+  FlatGFS flat_gfs(gv, fem);
+  BlockedGFS blocked_gfs(gv, fem);
+  using LOP = PDELab::L2<GridView, FEM>;
+  LOP lop;
+  using MB = PDELab::ISTL::BCRSMatrixBackend;
+  MB mb(1);
+  using FlatGO = PDELab::GridOperator<FlatGFS, FlatGFS, LOP, MB, double, double, double>;
+  using BlockedGO = PDELab::FastDGGridOperator<BlockedGFS, BlockedGFS, LOP, MB, double, double, double>;
+  FlatGO flat_go(flat_gfs, flat_gfs, lop, mb);
+  BlockedGO blocked_go(blocked_gfs, blocked_gfs, lop, mb);
+  typename FlatGO::Domain flat_x(flat_gfs, 0.0), flat_r(flat_gfs, 0.0);
+  typename BlockedGO::Domain blocked_x(blocked_gfs, 0.0), blocked_r(blocked_gfs, 0.0);
+  std::mt19937_64 rng;
+  std::uniform_real_distribution<double> dist(0.0, 1.0);
+  const std::size_t N = flat_gfs.size();
+  for (std::size_t i = 0; i < N; i++) blocked_x[i] = flat_x[i] = dist(rng);
+  flat_go.residual(flat_x, flat_r);
+  blocked_go.residual(blocked_x, blocked_r);
+  bool same = true;
+  for (std::size_t i = 0; i < N; i++) same = same && flat_r[i] == blocked_r[i];
+  EXPECT(same, "L2 QkDG k=2 4^3 (test-blocked-istl-ordering): flat and blocked residuals coincide");
+  // and the values are the mass operator: compare with the oracle fed with the same problem, and with
+  // the closed form  int u * 1 = sum_i r_i  = sum over cells of |K| * mean-weighted u
+  std::vector<double> want(N, 0.0);
+  if (oracle_residual(&flat_go.problem(), flat_x.data(), want.data())) std::cerr << oracle_last_error() << std::endl;
+  EXPECT(rel_err(flat_r, want) < 1e-12, "L2 residual vs oracle " << rel_err(flat_r, want) << " [" << flat_go.lastKernel() << "]");
+  // 1^T M x = int u_h: with the Q2 Lagrange weights (1/6, 4/6, 1/6) per direction
+  double sum_r = 0, integral = 0;
+  const double w1[3] = {1.0 / 6, 4.0 / 6, 1.0 / 6};
+  for (std::size_t i = 0; i < N; i++) {
+    sum_r += flat_r[i];
+    const int l = (int)(i % 27);
+    integral += flat_x[i] * w1[l % 3] * w1[(l / 3) % 3] * w1[l / 9] / 64.0;
+  }
+  EXPECT(std::abs(sum_r - integral) < 1e-13, "L2: sum of the residual equals the integral of u_h (" << sum_r << ")");
+}
+
 int main() {
+  l2_blocked_ordering_case();
   try {
     dg_case<2, 1, PoissonProblem>(16, 3.0, 1e-6, "DG k=1 2D 16^2 (testconvectiondiffusiondg)", true);
     dg_case<2, 2, LayeredProblem>(6, 3.0, 0, "DG k=2 2D 6^2 layered diagonal A + c", false);
