@@ -157,8 +157,12 @@ void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, doubl
                        cudaStream_t s);
 struct QkLayout;  // host_tables.h
 // fem_kron.cu: Kronecker-form conforming Qk apply (diagonal A, b = 0): warp-shuffle / smem / register assembly
-void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* MinvK, const double* x, double* y,
-                     const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s);
+void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* MinvK, const double* M, const double* x, double* y,
+                     const double* r0, bool overwrite, bool fuse_constraints, bool diag, cudaStream_t s);
+// fem.cu: point diagonal of the conforming Jacobian (diagonal A, b = 0), constrained rows = 1
+void launch_fem_diagonal(FemPlan* plan, const DevParams& P, double* d, cudaStream_t s);
+// dg_blockjac.cu: point diagonal of the QkDG Jacobian (same support as the block-Jacobi preconditioner)
+int launch_dg_diagonal(const DevParams& P, const Kron1D& K, double* d, cudaStream_t s);
 const QkLayout& fem_plan_layout(const FemPlan*);
 const uint64_t* fem_plan_constrained(const FemPlan*, long long* n);  // device list of constrained DOFs
 

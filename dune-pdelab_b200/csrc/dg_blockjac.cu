@@ -214,6 +214,56 @@ __global__ void __launch_bounds__(128) blockjac_apply_kernel(const DevParams P, 
   store_cell<N>(z + cell * N, t);
 }
 
+// point diagonal of the Jacobian: diag(D_e) = |K| [ sum_d (M T_d)_{i_d i_d} prod_{e != d} M_{i_e i_e} + c prod_d M_{i_d i_d} ]
+// (PointDiagonalLocalOperatorWrapper, localoperator/pointdiagonalwrapper.hh); 1 on constrained (ghost) rows
+template <int DIM, int K>
+__global__ void __launch_bounds__(128) dg_diagonal_kernel(const DevParams P, const SmallConst<K> C, double* __restrict__ dg) {
+  constexpr int N1 = K + 1, N = SL<DIM, K>::N;
+  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= P.ncells) return;
+  const int Nx = P.N[0], Ny = P.N[1];
+  int g[3];
+  g[0] = (int)(cell % Nx);
+  g[1] = (int)((cell / Nx) % Ny);
+  g[2] = DIM == 3 ? (int)(cell / ((long long)Nx * Ny)) : 0;
+  const long long stride[3] = {1, Nx, (long long)Nx * Ny};
+  double Sd[DIM][N1];
+  bool constrained = false;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    double A0, cs[2], co[2], cg[2];
+    bool onb[2];
+    constrained |= direction_coefs<K>(P, C, cell, g, d, stride, A0, cs, co, cg, onb);
+    double T[N1 * N1], eL[N1], eR[N1];
+    own_matrix<K>(C, A0, cs[0], cg[0], cs[1], cg[1], T, eL, eR);
+#pragma unroll
+    for (int i = 0; i < N1; i++) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < N1; k++) v = fma(C.M[i * N1 + k], T[k * N1 + i], v);
+      Sd[d][i] = v;
+    }
+  }
+  const double cc = P.c ? __ldg(P.c + cell) : 0.0;
+  double t[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int id[3] = {i % N1, (i / N1) % N1, i / (N1 * N1)};
+    double m = cc, v = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      double pd = Sd[d][id[d]];
+#pragma unroll
+      for (int e = 0; e < DIM; e++)
+        if (e != d) pd *= C.M[id[e] * N1 + id[e]];
+      v += pd;
+      m *= C.M[id[d] * N1 + id[d]];
+    }
+    t[i] = constrained ? 1.0 : P.vol * (v + m);
+  }
+  store_cell<N>(dg + cell * N, t);
+}
+
 template <int DIM, int K>
 void setup_variant(BlockJacPlan* plan, const DevParams& P, const Kron1D& K1, cudaStream_t s) {
   constexpr int N1 = K + 1, PER = N1 + N1 * N1;
@@ -266,6 +316,23 @@ void dg_blockjac_destroy(BlockJacPlan* plan) {
 }
 void dg_blockjac_invalidate(BlockJacPlan* plan) {
   if (plan) plan->valid = false;
+}
+
+int launch_dg_diagonal(const DevParams& P, const Kron1D& K1, double* d, cudaStream_t s) {
+  if (!(P.dg && P.b == nullptr && P.a_mode != PDB200_A_FULL && P.m >= P.k + 1 && (P.dim == 2 || P.dim == 3) &&
+        (P.k == 1 || P.k == 2)))
+    throw Error("matrix-free point diagonal: needs QkDG (k = 1, 2; dim = 2, 3), diagonal A, b = 0");
+  const unsigned blocks = (unsigned)((P.ncells + 127) / 128);
+#define PDB_DD(DD, KK)                                              \
+  if (P.dim == DD && P.k == KK) {                                   \
+    SmallConst<KK> C;                                               \
+    fill_small_const<KK>(C, P, K1);                                 \
+    dg_diagonal_kernel<DD, KK><<<blocks, 128, 0, s>>>(P, C, d);     \
+  }
+  PDB_DD(2, 1) PDB_DD(2, 2) PDB_DD(3, 1) PDB_DD(3, 2)
+#undef PDB_DD
+  PDB_CUDA(cudaGetLastError());
+  return 1;
 }
 
 // z = D^-1 r; (re)builds the per-cell eigen-decompositions if the coefficients changed.  Returns launches.

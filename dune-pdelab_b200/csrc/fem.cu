@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(FEM_THREADS)
   }
 }
 
-__global__ void constrain_kernel(double* __restrict__ y, const uint64_t* __restrict__ idx, long long n) {
+__global__ void constrain_kernel(double* __restrict__ y, const uint64_t* __restrict__ idx, long long n, double value) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[idx[i]] = 0.0;
+  if (i < n) y[idx[i]] = value;
 }
 
 template <int DIM, int K, bool RESIDUAL, bool KRON>
@@ -443,7 +443,7 @@ void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, b
     return;
   }
   plan->fused_constraints = P.bctype == nullptr;
-  launch_fem_kron(P, plan->L, plan->kron.MinvK, x, y, r0, overwrite, plan->fused_constraints, s);
+  launch_fem_kron(P, plan->L, plan->kron.MinvK, plan->kron.M, x, y, r0, overwrite, plan->fused_constraints, false, s);
 }
 
 }  // namespace
@@ -488,6 +488,20 @@ const uint64_t* fem_plan_constrained(const FemPlan* p, long long* n) {
   return p->con;
 }
 
+// d = point diagonal of the Jacobian (PointDiagonalLocalOperatorWrapper, localoperator/pointdiagonalwrapper.hh),
+// with 1 on the constrained rows (the unit rows of set_trivial_rows, assemblerutilities.hh:666-684)
+void launch_fem_diagonal(FemPlan* plan, const DevParams& P, double* d, cudaStream_t s) {
+  if (P.a_mode == PDB200_A_FULL || P.b != nullptr || P.ndofs >= (1ll << 31))
+    throw Error("matrix-free point diagonal: needs a diagonal tensor and b = 0");
+  if (P.m != P.k + 1) throw Error("conforming Qk kernel: intorderadd must be 0 or 1 (k+1 Gauss points)");
+  const bool fused = P.bctype == nullptr;
+  launch_fem_kron(P, plan->L, plan->kron.MinvK, plan->kron.M, d, d, nullptr, true, fused, true, s);
+  if (plan->ncon && !fused) {
+    constrain_kernel<<<(unsigned)((plan->ncon + 255) / 256), 256, 0, s>>>(d, plan->con, plan->ncon, 1.0);
+    PDB_CUDA(cudaGetLastError());
+  }
+}
+
 void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                        cudaStream_t s) {
   if (P.m != P.k + 1) throw Error("conforming Qk kernel: intorderadd must be 0 or 1 (k+1 Gauss points)");
@@ -498,7 +512,7 @@ void launch_fem_vector(FemPlan* plan, const DevParams& P, const double* x, doubl
   else throw Error("conforming Qk kernel: unsupported (dim, degree)");
   // postAssembly: constrain_residual (residualengine.hh:228-233, jacobianapplyengine.hh:249-254)
   if (plan->ncon && !plan->fused_constraints) {
-    constrain_kernel<<<(unsigned)((plan->ncon + 255) / 256), 256, 0, s>>>(y, plan->con, plan->ncon);
+    constrain_kernel<<<(unsigned)((plan->ncon + 255) / 256), 256, 0, s>>>(y, plan->con, plan->ncon, 0.0);
     PDB_CUDA(cudaGetLastError());
   }
 }

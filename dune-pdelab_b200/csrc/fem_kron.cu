@@ -50,6 +50,12 @@ struct FemKronParams {
   int chunk;       // cells per march chunk
   int tiles_x;     // 2-D: warps of a CTA are independent x-tiles
   int fuse_constraints;  // every boundary lattice point is constrained (no bctype array): write 0 there
+  // diag != 0: write the POINT DIAGONAL of the Jacobian instead of J x (PointDiagonalLocalOperatorWrapper,
+  // localoperator/pointdiagonalwrapper.hh): the cell contribution is the closed form
+  //   t_i = sum_d al_d (D K)_{i_d i_d} prod_{d' != d} (D M)_{i_d' i_d'} + cc prod_d (D M)_{i_d i_d},
+  // assembled over the cells by the same hand-overs; constrained rows get 1 (unit rows of the matrix)
+  int diag;
+  double DK[MAX_N1], DM[MAX_N1];  // diagonals of D K and D M (1-D stiffness / mass, D = 30 or 6)
 };
 
 template <int DIM, int K>
@@ -202,10 +208,12 @@ __global__ void __launch_bounds__(32 * WY, MINB)
   auto issue_x = [&](int step) {
     const int cm = cm0 + step;
     if (step < steps && vx && vy && cm >= 0 && cm < Nm) {
+      if (!F.diag) {
 #pragma unroll
-      for (int i = SM; i < N; i++) {
-        const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
-        cp_async8(xs + (i - SM) * NT, xg + nxt.at(F, i0, i1, i2));
+        for (int i = SM; i < N; i++) {
+          const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
+          cp_async8(xs + (i - SM) * NT, xg + nxt.at(F, i0, i1, i2));
+        }
       }
       const long long cell = cell_nxt;
       if (P.a_mode == PDB200_A_SCALAR) {
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(32 * WY, MINB)
         if (have_plane)
           x[i] = x[i + K * SM];
         else
-          x[i] = __ldg(xg + cur.at(F, i0, DIM == 3 ? i1 : 0, 0));
+          x[i] = F.diag ? 0.0 : __ldg(xg + cur.at(F, i0, DIM == 3 ? i1 : 0, 0));
       }
 #pragma unroll
       for (int i = SM; i < N; i++) x[i] = xs[(i - SM) * NT];
@@ -272,7 +280,23 @@ __global__ void __launch_bounds__(32 * WY, MINB)
     nxt.advance(F);
     cell_nxt += cell_stride;
     issue_x(step + 1);  // the slots were just read by their only user: refill them behind the compute
-    if (valid) {
+    if (valid && F.diag) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int id[3] = {i % N1, (i / N1) % N1, i / (N1 * N1)};
+        double m = cc, v = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          double pd = a[d] * F.s[d] * F.DK[id[d]];
+#pragma unroll
+          for (int e = 0; e < DIM; e++)
+            if (e != d) pd *= F.DM[id[e]];
+          v += pd;
+          m *= F.DM[id[d]];
+        }
+        t[i] = v + m;
+      }
+    } else if (valid) {
       stiff_sweep<DIM, K, 0, false>(F, a[0] * F.s[0], x, t);
       stiff_sweep<DIM, K, 1, true>(F, a[1] * F.s[1], x, t);
       if (DIM == 3) stiff_sweep<DIM, K, 2, true>(F, a[2] * F.s[2], x, t);
@@ -334,7 +358,7 @@ __global__ void __launch_bounds__(32 * WY, MINB)
           const bool onb = (i0 == 0 && (c0 == 0 || lastx)) || (DIM == 3 && i1 == 0 && (c1 == 0 || lasty)) ||
                            (im == 0 && (cm == 0 || lastm));
           if (onb) {
-            yg[gi] = 0.0;
+            yg[gi] = F.diag ? 1.0 : 0.0;
             continue;
           }
         }
@@ -350,10 +374,18 @@ __global__ void __launch_bounds__(32 * WY, MINB)
 }
 
 template <int DIM, int K, int WY, int MINB>
-void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK, const double* x, double* y,
-                    const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s) {
+void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK, const double* M1, const double* x,
+                    double* y, const double* r0, bool overwrite, bool fuse_constraints, bool diag, cudaStream_t s) {
   FemKronParams F;
   const double D = K == 2 ? 30.0 : 6.0;
+  F.diag = diag ? 1 : 0;
+  for (int i = 0; i < MAX_N1; i++) F.DK[i] = F.DM[i] = 0.0;
+  for (int i = 0; i <= K; i++) {  // (M M^-1 K)_ii = K_ii
+    double kii = 0.0;
+    for (int j = 0; j <= K; j++) kii += M1[i * (K + 1) + j] * MinvK[j * (K + 1) + i];
+    F.DK[i] = D * kii;
+    F.DM[i] = D * M1[i * (K + 1) + i];
+  }
   double sc = P.vol;
   for (int d = 0; d < DIM; d++) sc /= D;
   F.sc = sc;
@@ -410,12 +442,12 @@ void launch_variant(const DevParams& P, const QkLayout& Lq, const double* MinvK,
 }  // namespace
 
 // MinvK: M^-1 K of the 1-D Lagrange basis, row-major with leading dimension k+1
-void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* K1, const double* x, double* y,
-                     const double* r0, bool overwrite, bool fuse_constraints, cudaStream_t s) {
-  if (P.dim == 2 && P.k == 1) launch_variant<2, 1, 4, 8>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
-  else if (P.dim == 2 && P.k == 2) launch_variant<2, 2, 4, 4>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
-  else if (P.dim == 3 && P.k == 1) launch_variant<3, 1, 16, 2>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
-  else if (P.dim == 3 && P.k == 2) launch_variant<3, 2, 12, 1>(P, L, K1, x, y, r0, overwrite, fuse_constraints, s);
+void launch_fem_kron(const DevParams& P, const QkLayout& L, const double* K1, const double* M1, const double* x, double* y,
+                     const double* r0, bool overwrite, bool fuse_constraints, bool diag, cudaStream_t s) {
+  if (P.dim == 2 && P.k == 1) launch_variant<2, 1, 4, 8>(P, L, K1, M1, x, y, r0, overwrite, fuse_constraints, diag, s);
+  else if (P.dim == 2 && P.k == 2) launch_variant<2, 2, 4, 4>(P, L, K1, M1, x, y, r0, overwrite, fuse_constraints, diag, s);
+  else if (P.dim == 3 && P.k == 1) launch_variant<3, 1, 16, 2>(P, L, K1, M1, x, y, r0, overwrite, fuse_constraints, diag, s);
+  else if (P.dim == 3 && P.k == 2) launch_variant<3, 2, 12, 1>(P, L, K1, M1, x, y, r0, overwrite, fuse_constraints, diag, s);
   else throw Error("conforming Qk Kronecker kernel: unsupported (dim, degree)");
 }
 

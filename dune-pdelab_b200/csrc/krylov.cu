@@ -331,6 +331,14 @@ void krylov_axpy(long long n, double a, const double* x, double* y, cudaStream_t
   PDB_CUDA(cudaGetLastError());
 }
 
+__global__ void __launch_bounds__(NT) invert_kernel(long long n, double* __restrict__ d) {
+  GRID_LOOP(i, n) d[i] = 1.0 / d[i];
+}
+void krylov_invert(long long n, double* d, cudaStream_t s) {
+  invert_kernel<<<NB, NT, 0, s>>>(n, d);
+  PDB_CUDA(cudaGetLastError());
+}
+
 void krylov_diag_inverse(long long nrows, const uint64_t* rowptr, const uint32_t* colidx, const double* values,
                          double* dinv, cudaStream_t s) {
   diag_inv_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, values, dinv);

@@ -25,6 +25,7 @@ int krylov_solve(KrylovWork*, int solver, long long n, const KrylovOps& ops, dou
                  unsigned maxit, cudaStream_t s, pdb200_solve_result* res);
 double krylov_two_norm(KrylovWork*, long long n, const double* a, cudaStream_t s);
 void krylov_axpy(long long n, double a, const double* x, double* y, cudaStream_t s);  // y += a x
+void krylov_invert(long long n, double* d, cudaStream_t s);  // d <- 1 / d
 void krylov_diag_inverse(long long nrows, const uint64_t* rowptr, const uint32_t* colidx, const double* values,
                          double* dinv, cudaStream_t s);
 

@@ -614,6 +614,15 @@ struct Staged {
   }
 };
 
+void point_diagonal_device(pdb200_operator* h, double* d) {
+  if (h->P.dg) {
+    h->launches += launch_dg_diagonal(h->P, h->K, d, h->stream);
+  } else {
+    launch_fem_diagonal(h->fem, h->P, d, h->stream);
+    h->launches += 2;
+  }
+}
+
 // binds the operator (matrix-free or assembled) and the preconditioner, then runs the Krylov loop
 void solve_device(pdb200_operator* h, int solver, int precond, const double* values, int layout, double* z, double* r,
                   double reduction, uint32_t maxiter, pdb200_solve_result* res) {
@@ -635,8 +644,14 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
       ops.prec = [h](const double* in, double* out) {
         h->launches += launch_dg_blockjac(h->blockjac, h->P, h->K, in, out, h->stream);
       };
+    } else if (precond == PDB200_PRECOND_JACOBI) {  // point Jacobi on the matrix-free diagonal
+      PDB_CUDA(cudaMalloc(&dinv, (size_t)P.ndofs * sizeof(double)));
+      point_diagonal_device(h, dinv);
+      krylov_invert(P.ndofs, dinv, h->stream);
+      h->launches += 1;
+      ops.dinv = dinv;
     } else if (precond != PDB200_PRECOND_NONE) {
-      throw Error("pdb200_solve: the matrix-free back-ends offer no preconditioner (Richardson) or block Jacobi");
+      throw Error("pdb200_solve: unknown preconditioner");
     }
     ops.apply = [h](const double* in, double* out) { run_vector_device(h, in, out, Mode::OnTheFly); };
   } else {
@@ -676,6 +691,18 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
 }
 
 }  // namespace
+
+int pdb200_point_diagonal(pdb200_handle h, double* d) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!d) throw Error("pdb200_point_diagonal: null argument");
+  Staged ds(d, (size_t)h->P.ndofs, false, h->stream);
+  point_diagonal_device(h, ds.dev);
+  ds.copy_out(h->stream);
+  if (ds.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
 
 int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z) {
   PDB_TRY

@@ -32,7 +32,7 @@ SYMBOLS = [
     "pdb200_residual", "pdb200_jacobian_apply", "pdb200_onthefly_apply", "pdb200_jacobian_apply_nonlinear",
     "pdb200_pattern_size", "pdb200_pattern", "pdb200_pattern_i32", "pdb200_block_pattern_size",
     "pdb200_block_pattern", "pdb200_jacobian", "pdb200_jacobian_fresh", "pdb200_csr_mv",
-    "pdb200_solve", "pdb200_solve_stationary", "pdb200_block_jacobi_apply",
+    "pdb200_solve", "pdb200_solve_stationary", "pdb200_block_jacobi_apply", "pdb200_point_diagonal",
     "pdb200_halo_layer_size", "pdb200_halo_pack", "pdb200_halo_unpack", "pdb200_set_stream",
     "pdb200_gather_dofs", "pdb200_scatter_dofs",
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
@@ -74,6 +74,7 @@ def load_library():
     lib.pdb200_jacobian_fresh.argtypes = [vp, vp, vp, C.c_int]
     lib.pdb200_csr_mv.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.pdb200_block_jacobi_apply.argtypes = [vp, vp, vp]
+    lib.pdb200_point_diagonal.argtypes = [vp, vp]
     lib.pdb200_solve.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_uint32,
                                  C.POINTER(SolveResult)]
     lib.pdb200_solve_stationary.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_uint32,
@@ -264,6 +265,12 @@ class GridOperator:
         backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:96-230), matrix-free."""
         self._chk(self.lib.pdb200_block_jacobi_apply(self._h, _ptr(r), _ptr(z)))
         return z
+
+    def point_diagonal(self, d):
+        """d = diag(J), matrix-free (PointDiagonalLocalOperatorWrapper, localoperator/pointdiagonalwrapper.hh);
+        1 on constrained rows."""
+        self._chk(self.lib.pdb200_point_diagonal(self._h, _ptr(d)))
+        return d
 
     def solve_stationary(self, x, reduction=1e-10, min_defect=1e-99, solver=abi.SOLVER_BICGSTAB,
                          precond=abi.PRECOND_NONE, matrix_free=True, maxiter=5000):

@@ -175,7 +175,8 @@ int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const doubl
  *                    ISTLBackend_SEQ_MatrixFree_Base (backend/istl/matrixfree/backends.hh:62-143) with the exact
  *                    block-Jacobi preconditioner (AssembledBlockJacobiPreconditionerLocalOperator,
  *                    backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:96-230), precond
- *                    PDB200_PRECOND_BLOCK_JACOBI (QkDG, k = 1, 2, SIPG, diagonal A, b = 0)
+ *                    PDB200_PRECOND_BLOCK_JACOBI (QkDG, k = 1, 2, SIPG, diagonal A, b = 0); or point Jacobi on the
+ *                    matrix-free diagonal (pdb200_point_diagonal), precond PDB200_PRECOND_JACOBI
  *   values != NULL : assembled matrix in `layout` (MatrixAdapter), ISTLBackend_SEQ_BCGS_Jac / _CG_Jac
  *                    (:401-416,538-553; SeqJac, one step, w = 1; scalar CSR layout only) or no
  *                    preconditioner
@@ -202,6 +203,12 @@ int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values,
  * GridOperatorPreconditioner::apply (gridoperatorpreconditioner.hh:81-87).  Matrix-free: the blocks are
  * Kronecker sums and are inverted by fast diagonalisation (csrc/dg_blockjac.cu).  Host or device pointers. */
 int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z);
+
+/* d = point diagonal of the Jacobian, matrix-free (PointDiagonalLocalOperatorWrapper,
+ * localoperator/pointdiagonalwrapper.hh: the diagonal a point-Jacobi preconditioner needs without an assembled
+ * matrix); constrained rows carry 1 like the unit rows of the assembled matrix.  Conforming Qk and QkDG (k = 1, 2),
+ * diagonal A, b = 0.  Host or device pointer.  pdb200_solve with values == NULL and PDB200_PRECOND_JACOBI uses it. */
+int pdb200_point_diagonal(pdb200_handle h, double* d);
 
 /* StationaryLinearProblemSolver::apply (stationary/linearproblem.hh:188-302):
  *   [A = 0; jacobian(x, A)]  r = 0; residual(x, r);  red = max(reduction, min_defect / |r|);

@@ -124,8 +124,8 @@ def test_solver_on_device_tensors_large_dg_and_not_converged_is_reported(cuda_li
     z.zero_()
     res = go.solve(z, b.clone(), 1e-12, maxiter=3)
     assert res["converged"] == 0 and res["iterations"] == 3
-    with pytest.raises(Exception, match="no preconditioner"):
-        go.solve(z, b.clone(), 1e-8, precond=abi.PRECOND_JACOBI)
+    with pytest.raises(Exception, match="unknown preconditioner"):
+        go.solve(z, b.clone(), 1e-8, precond=7)
 
 
 BJ_CASES = [
@@ -179,3 +179,42 @@ def test_block_jacobi_preconditioned_krylov(cuda_lib):
     x = x0.copy()
     res = go.solve_stationary(x, reduction=1e-10, matrix_free=True, precond=abi.PRECOND_BLOCK_JACOBI)
     assert res["converged"] == 1 and l2_error_squared(spec, x, u) <= thr
+
+
+DIAG_CASES = [
+    ("fem", dict(cells=(7, 6), degree=1, a="scalar")), ("fem", dict(cells=(5, 4), degree=2, a="diagonal", with_c=True)),
+    ("fem", dict(cells=(5, 4, 3), degree=1, a="diagonal")), ("fem", dict(cells=(4, 3, 3), degree=2, a="scalar", with_c=True)),
+    ("fem", dict(cells=(35, 3, 14), degree=2, a="scalar")),
+    ("dg", dict(cells=(6, 5), degree=1, a="scalar")), ("dg", dict(cells=(5, 4), degree=2, a="diagonal", with_c=True)),
+    ("dg", dict(cells=(4, 3, 3), degree=1, a="diagonal", bc="mixed")), ("dg", dict(cells=(4, 4, 3), degree=2, a="scalar")),
+]
+
+
+@pytest.mark.parametrize("kind,case", DIAG_CASES, ids=lambda c: c if isinstance(c, str) else "-".join(f"{k}={v}" for k, v in c.items()))
+def test_matrix_free_point_diagonal_equals_the_assembled_diagonal(cuda_lib, kind, case):
+    """PointDiagonalLocalOperatorWrapper (localoperator/pointdiagonalwrapper.hh): diag(J) without a matrix."""
+    spec = fem_problem(**case) if kind == "fem" else dg_problem(**case)
+    ops = GpuOps(spec)
+    J = ops.matrix().tocsr()
+    d = ops.go.point_diagonal(np.zeros(spec.num_dofs))
+    assert rel_err(d, J.diagonal()) < 1e-12
+
+
+def test_matrix_free_jacobi_cg_on_the_testmatrixfree_problem(cuda_lib):
+    """Q2 conforming problem of test/testmatrixfree.cc solved matrix-free with point-Jacobi CG on the device."""
+    spec, x0, u, thr = make_case("testmatrixfree")
+    go = GridOperator(spec)
+    x_plain, x_jac = x0.copy(), x0.copy()
+    plain = go.solve_stationary(x_plain, reduction=1e-10, solver=abi.SOLVER_CG, matrix_free=True)
+    jac = go.solve_stationary(x_jac, reduction=1e-10, solver=abi.SOLVER_CG, matrix_free=True, precond=abi.PRECOND_JACOBI)
+    assert plain["converged"] == 1 and jac["converged"] == 1
+    assert l2_error_squared(spec, x_jac, u) <= thr
+    assert rel_err(x_jac, x_plain) < 1e-6
+    # heterogeneous coefficient: the diagonal scaling pays
+    spec = fem_problem((24, 20, 16), degree=1, a="scalar")
+    go = GridOperator(spec)
+    b = mt_vector(spec.num_dofs, seed=3)
+    b[go.constrained_dofs().astype(np.int64)] = 0.0
+    r1 = go.solve(np.zeros_like(b), b.copy(), 1e-8, solver=abi.SOLVER_CG)
+    r2 = go.solve(np.zeros_like(b), b.copy(), 1e-8, solver=abi.SOLVER_CG, precond=abi.PRECOND_JACOBI)
+    assert r1["converged"] == r2["converged"] == 1 and r2["iterations"] < r1["iterations"]
