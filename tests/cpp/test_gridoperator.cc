@@ -432,8 +432,8 @@ void l2_blocked_ordering_case() {
 }
 
 int main() {
-  l2_blocked_ordering_case();
   try {
+    l2_blocked_ordering_case();
     dg_case<2, 1, PoissonProblem>(16, 3.0, 1e-6, "DG k=1 2D 16^2 (testconvectiondiffusiondg)", true);
     dg_case<2, 2, LayeredProblem>(6, 3.0, 0, "DG k=2 2D 6^2 layered diagonal A + c", false);
     dg_case<3, 2, LayeredProblem>(4, 3.0, 0, "DG k=2 3D 4^3 layered diagonal A + c (Kronecker kernel)", false);
