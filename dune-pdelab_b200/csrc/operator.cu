@@ -12,63 +12,34 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
-#include "host_tables.h"
-#include "krylov.h"
-
-using namespace pdb;
+#include "operator.h"
 
 namespace {
 thread_local std::string g_last_error;
 }
+void pdb_set_last_error(const std::string& s) { g_last_error = s; }  // for onestep.cu
 
-struct pdb200_operator {
-  DevParams P;
-  Kron1D K;
-  int device = 0;
-  int kernel_choice = PDB200_KERNEL_AUTO;
-  cudaStream_t stream = nullptr;
-  // device copies of the coefficient arrays
-  std::vector<void*> owned;
-  // staging for host-pointer calls
-  double *dx = nullptr, *dy = nullptr;
-  int* errflag = nullptr;
-  // host-pointer calls of the fast kernel: transfers pipelined with the computation
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t pipe_ev[2 * 16 + 1] = {};
-  FastPlan* fast = nullptr;
-  KronPlan* kron = nullptr;
-  FemPlan* fem = nullptr;
-  MatrixPlan* matrix = nullptr;
-  P2PHalo* p2p = nullptr;
-  KrylovWork* krylov = nullptr;
-  BlockJacPlan* blockjac = nullptr;
-  double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
-  bool r0_valid = false;
-  uint64_t launches = 0;
-  const char* last_kernel = "";
-  std::vector<double> xq, wq;
+// R(0) of the affine DG residual with the reference-order kernel, cached per coefficient set (used by the
+// Kronecker kernels' residual form and, scaled, by the one-step stage operator)
+void pdb_ensure_r0(pdb200_operator* op) {
+  if (op->r0_valid) return;
+  const DevParams& P = op->P;
+  if (!op->r0) PDB_CUDA(cudaMalloc(&op->r0, (size_t)P.ndofs * sizeof(double)));
+  double* zero = nullptr;
+  PDB_CUDA(cudaMalloc(&zero, (size_t)P.ndofs * sizeof(double)));
+  PDB_CUDA(cudaMemsetAsync(zero, 0, (size_t)P.ndofs * sizeof(double), op->stream));
+  launch_dg_generic(P, zero, op->r0, /*residual=*/true, /*overwrite=*/true, op->errflag, op->stream);
+  PDB_CUDA(cudaStreamSynchronize(op->stream));
+  PDB_CUDA(cudaFree(zero));
+  op->r0_valid = true;
+  op->launches += 1;
+}
+bool pdb_uses_cached_r0(const pdb200_operator* op) {
+  const DevParams& P = op->P;
+  return P.dg && op->kernel_choice != PDB200_KERNEL_GENERIC &&
+         (dg_fast_supported(P) || dg_kron_supported(P) || dg_small_supported(P));
+}
 
-  ~pdb200_operator() {
-    cudaSetDevice(device);
-    for (void* p : owned) cudaFree(p);
-    if (dx) cudaFree(dx);
-    if (dy) cudaFree(dy);
-    if (r0) cudaFree(r0);
-    if (errflag) cudaFree(errflag);
-    if (h2d_stream) cudaStreamDestroy(h2d_stream);
-    if (d2h_stream) cudaStreamDestroy(d2h_stream);
-    for (auto& e : pipe_ev)
-      if (e) cudaEventDestroy(e);
-    dg_fast_plan_destroy(fast);
-    dg_kron_plan_destroy(kron);
-    fem_plan_destroy(fem);
-    matrix_plan_destroy(matrix);
-    p2p_destroy(p2p);
-    krylov_destroy(krylov);
-    dg_blockjac_destroy(blockjac);
-  }
-};
 
 namespace {
 
@@ -159,17 +130,7 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
       // The operator is affine: R(x) = J x + R(0).  R(0) (source term lambda_volume,
       // convectiondiffusiondg.hh:1048-1075, and the boundary data g, j, o, :684-879) is evaluated
       // once per coefficient set with the reference-order kernel and cached.
-      if (!op->r0_valid) {
-        if (!op->r0) PDB_CUDA(cudaMalloc(&op->r0, (size_t)P.ndofs * sizeof(double)));
-        double* zero = nullptr;
-        PDB_CUDA(cudaMalloc(&zero, (size_t)P.ndofs * sizeof(double)));
-        PDB_CUDA(cudaMemsetAsync(zero, 0, (size_t)P.ndofs * sizeof(double), op->stream));
-        launch_dg_generic(P, zero, op->r0, /*residual=*/true, /*overwrite=*/true, op->errflag, op->stream);
-        PDB_CUDA(cudaStreamSynchronize(op->stream));
-        PDB_CUDA(cudaFree(zero));
-        op->r0_valid = true;
-        op->launches += 1;
-      }
+      pdb_ensure_r0(op);
       r0 = op->r0;
     }
     if (use_fast) {
@@ -322,6 +283,8 @@ int pdb200_create(const pdb200_problem* p, pdb200_handle* out) {
   P.vol = 1.0;
   for (int d = 0; d < 3; d++) {
     P.N[d] = d < P.dim ? p->cells[d] : 1;
+    op->lower[d] = p->lower[d];
+    op->upper[d] = p->upper[d];
     if (P.N[d] < 1) throw Error("cells must be positive");
     P.h[d] = d < P.dim ? (p->upper[d] - p->lower[d]) / P.N[d] : 1.0;
     if (!(P.h[d] > 0.0)) throw Error("upper must be greater than lower");
@@ -397,6 +360,7 @@ int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
   upd(P.o, p->o, (size_t)nbf * P.nfq * 8, "o");
   if (p->bctype) throw Error("update_coefficients: bctype changes the constraint set; create a new operator");
   h->r0_valid = false;
+  h->coeff_version++;
   dg_blockjac_invalidate(h->blockjac);
   fem_plan_invalidate(h->fem);
   PDB_CUDA(cudaStreamSynchronize(h->stream));

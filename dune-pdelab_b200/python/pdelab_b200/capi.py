@@ -38,6 +38,12 @@ SYMBOLS = [
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
+    # OneStepGridOperator (bound in pdelab_b200.onestep)
+    "pdb200_onestep_create", "pdb200_onestep_destroy", "pdb200_onestep_set_method", "pdb200_onestep_set_dt_mode",
+    "pdb200_onestep_pre_step", "pdb200_onestep_time_at_stage", "pdb200_onestep_pre_stage",
+    "pdb200_onestep_pre_stage_begin", "pdb200_onestep_pre_stage_add", "pdb200_onestep_const_residual",
+    "pdb200_onestep_residual", "pdb200_onestep_jacobian_apply", "pdb200_onestep_onthefly_apply",
+    "pdb200_onestep_jacobian", "pdb200_onestep_stage_operator", "pdb200_onestep_launch_count",
 ]
 
 

@@ -217,6 +217,57 @@ int pdb200_point_diagonal(pdb200_handle h, double* d);
 int pdb200_solve_stationary(pdb200_handle h, int solver, int precond, int matrix_free, double* x, double reduction,
                             double min_defect, uint32_t maxiter, pdb200_solve_result* res);
 
+/* ---- OneStepGridOperator: the operator of one Runge-Kutta / fractional-step stage ----------------------------
+ * gridoperator/onestep.hh:30-308 with the engines of gridoperator/onestep/ (localassembler.hh, prestageengine.hh,
+ * residualengine.hh, jacobianengine.hh, jacobianapplyengine.hh).  go0 is the spatial operator, go1 the temporal
+ * one (L2 mass operator, localoperator/l2.hh: a handle with A = 0, c = scaling, boundary type None).  For stage r of
+ * a method with coefficients a_ri, b_ri, d_i (instationary/onestepparameter.hh:43-84; r in 1..s, i in 0..r):
+ *     preStage : const_residual = sum_{i<r}  b_ri dt_factor0 R0(x_i) [if |b_ri| > 1e-6] + a_ri dt_factor1 R1(x_i) [if |a_ri| > 1e-6]
+ *     residual : r += b_rr dt_factor0 R0(x) + dt_factor1 R1(x) + const_residual, constrained rows := 0
+ *     jacobian / jacobian_apply : the same weights on the two Jacobians
+ * On the device a stage is ONE fused operator: the weighted sum of two convection-diffusion-reaction forms is the
+ * form with the weighted coefficient fields (csrc/onestep.cu), so every call costs one pass of the same kernels as
+ * the stationary operator.  pdb200_onestep_stage_operator hands that fused operator out as an ordinary handle:
+ * pdb200_solve, pdb200_pattern, pdb200_block_jacobi_apply, ... work on it unchanged.
+ * The two operator handles are referenced, not owned (like the reference, onestep.hh:300-305); re-sample
+ * time-dependent coefficients with pdb200_update_coefficients(go0, ...) before the call that evaluates them. */
+typedef struct pdb200_onestep* pdb200_onestep_handle;
+/* OneStepLocalAssembler::DTAssemblingMode, gridoperator/onestep/localassembler.hh:140 */
+enum { PDB200_ONESTEP_DIVIDE_OPERATOR1_BY_DT = 0, PDB200_ONESTEP_MULTIPLY_OPERATOR0_BY_DT = 1,
+       PDB200_ONESTEP_DO_NOT_ASSEMBLE_DT = 2 };
+/* OneStepGridOperator(go0, go1), onestep.hh:66-76 */
+int pdb200_onestep_create(pdb200_handle go0, pdb200_handle go1, pdb200_onestep_handle* out);
+int pdb200_onestep_destroy(pdb200_onestep_handle os);
+/* setMethod, onestep.hh:245-248: a, b are s x (s+1) row-major (row r-1 holds a(r, 0..s)), d has s+1 entries;
+ * `implicit` = method.implicit() (explicit methods switch to DoNotAssembleDT, onestep.hh:74-75) */
+int pdb200_onestep_set_method(pdb200_onestep_handle os, int s, const double* a, const double* b, const double* d,
+                              int implicit);
+/* divideMassTermByDeltaT / multiplySpatialTermByDeltaT, onestep.hh:78-91 (takes effect at the next preStep) */
+int pdb200_onestep_set_dt_mode(pdb200_onestep_handle os, int mode);
+/* preStep(method, time, dt), onestep.hh:250-254 + localassembler.hh:101-130 */
+int pdb200_onestep_pre_step(pdb200_onestep_handle os, double time, double dt);
+/* LocalAssembler::timeAtStage(stage), localassembler.hh:148-151 */
+int pdb200_onestep_time_at_stage(pdb200_onestep_handle os, int stage, double* t);
+/* preStage(stage, x), onestep.hh:130-139: x[0..stage-1] are the solutions of the earlier stages (host or device).
+ * begin/add is the same call split per earlier stage, so that a host with time-dependent coefficients can
+ * re-sample them at t + d_i dt before add(i) (prestageengine.hh:208-211 sets that time per stage). */
+int pdb200_onestep_pre_stage(pdb200_onestep_handle os, int stage, const double* const* x);
+int pdb200_onestep_pre_stage_begin(pdb200_onestep_handle os, int stage);
+int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* x);
+/* copy of the constant part of the residual assembled by preStage (host or device destination) */
+int pdb200_onestep_const_residual(pdb200_onestep_handle os, double* out);
+/* residual(x, r), onestep.hh:141-149 */
+int pdb200_onestep_residual(pdb200_onestep_handle os, const double* x, double* r);
+/* jacobian_apply(update, result), onestep.hh:180-185: y += (b_rr dt_factor0 J0 + dt_factor1 J1) z */
+int pdb200_onestep_jacobian_apply(pdb200_onestep_handle os, const double* z, double* y);
+/* the same with the zeroing fused (OnTheFlyOperator::apply on the one-step operator) */
+int pdb200_onestep_onthefly_apply(pdb200_onestep_handle os, const double* x, double* y);
+/* jacobian(x, a), onestep.hh:151-159: values += b_rr dt_factor0 dR0/dx + dt_factor1 dR1/dx on go0's pattern */
+int pdb200_onestep_jacobian(pdb200_onestep_handle os, const double* x, double* values, int layout);
+/* the fused operator of the current stage (owned by `os`; valid until the weights or coefficients change) */
+int pdb200_onestep_stage_operator(pdb200_onestep_handle os, pdb200_handle* stage);
+int pdb200_onestep_launch_count(pdb200_onestep_handle os, uint64_t* n);
+
 /* Halo exchange support for the overlapping partition (replaces the AddDataHandle/CopyDataHandle
  * communication of boilerplate/pdelab.hh:872-880 + gridfunctionspace/genericdatahandle.hh).
  * pack copies the DOFs of the owned cell layer next to side (dir,side) — the layer at distance

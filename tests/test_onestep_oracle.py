@@ -1,0 +1,80 @@
+"""CPU checks of the instationary layer (no GPU): the time-stepping parameter tables and the one-step oracle
+restatement (tests/onestep_oracle.py), pinned against the reference's own instationary test
+(test/testinstationaryfastdgassembler.cc: QkDG k=1 on 8x8, SIPG alpha=2, L2 mass operator, Alexander2, one step
+dt = 0.1 from the interpolated stationary solution, squared L2 error <= 5e-6)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from manufactured import l2_error_squared, node_coordinates, sample_data
+from onestep_oracle import OneStepOracle
+from pdelab_b200 import abi, onestep as osm
+
+METHODS = [osm.ImplicitEulerParameter, lambda: osm.OneStepThetaParameter(0.5), osm.Alexander2Parameter,
+           osm.FractionalStepParameter, osm.Alexander3Parameter, osm.ExplicitEulerParameter, osm.HeunParameter,
+           osm.Shu3Parameter, osm.RK4Parameter]
+
+
+@pytest.mark.parametrize("make", METHODS)
+def test_method_tables_are_consistent(make):
+    """sum_i a_ri = 0 and sum_i a_ri d_i = sum_i b_ri (exact for u(t) = t) — holds for every table of
+    instationary/onestepparameter.hh."""
+    m = make()
+    for r in range(1, m.s() + 1):
+        a = [m.a(r, i) for i in range(r + 1)]
+        b = [m.b(r, i) for i in range(r + 1)]
+        d = [m.d(i) for i in range(r + 1)]
+        assert abs(sum(a)) < 1e-14
+        assert abs(sum(x * y for x, y in zip(a, d)) - sum(b)) < 1e-14
+        assert m.a(r, r) == 1.0          # the stage weight of the temporal operator is dt_factor1 alone
+    assert m.d(0) == 0.0 and m.d(m.s()) == 1.0
+    assert m.implicit() == any(abs(m.b(r, r)) > 0 for r in range(1, m.s() + 1))
+
+
+def u_exact(X):
+    return np.exp(-np.sum(X * X, axis=1))
+
+
+def heat_problem(cells=(8, 8), degree=1, space=abi.SPACE_QKDG):
+    """ParameterA of test/testinstationaryfastdgassembler.cc:17-104: A = I, f = (2 d - 4 |x|^2) exp(-|x|^2),
+    Dirichlet g = exp(-|x|^2)."""
+    dim = len(cells)
+    spec = abi.ProblemSpec(cells, space=space, degree=degree, method=abi.DG_SIPG, weights=abi.DG_WEIGHTS_ON, alpha=2.0)
+    return sample_data(spec, u_exact, lambda X: (2.0 * dim - 4.0 * np.sum(X * X, axis=1)) * u_exact(X))
+
+
+def oracle_time_step(spec0, method, x, time, dt):
+    """OneStepMethod::apply (instationary/implicitonestep.hh:122-262) with a direct stage solver."""
+    os_ = OneStepOracle(spec0, osm.l2_spec(spec0))
+    xs = [x]
+    os_.preStep(method, time, dt)
+    for r in range(1, method.s() + 1):
+        os_.preStage(r, xs)
+        xr = xs[r - 1].copy()
+        res = os_.residual(xr)
+        xr -= spla.spsolve(os_.matrix().tocsc(), res)
+        xs.append(xr)
+    return xs[-1]
+
+
+def test_reference_instationary_dg_test_on_the_oracle():
+    spec0 = heat_problem()
+    x = u_exact(node_coordinates(spec0))                    # interpolate(g, gfs, x)
+    x = oracle_time_step(spec0, osm.Alexander2Parameter(), x, 0.0, 0.1)
+    err2 = l2_error_squared(spec0, x, u_exact, npts=7)       # integrateGridFunction(..., 12)
+    assert err2 <= 5e-6, err2                                # testinstationaryfastdgassembler.cc:197
+
+
+def test_one_step_residual_is_affine_and_consistent():
+    """residual(x) = J x + residual(0) and J from matrix() == jacobian_apply, for a stage with a constant part."""
+    spec0 = heat_problem((4, 3))
+    os_ = OneStepOracle(spec0, osm.l2_spec(spec0, 2.0))
+    rng = np.random.default_rng(1)
+    xs = [rng.random(spec0.num_dofs) for _ in range(3)]
+    os_.preStep(osm.Alexander3Parameter(), 0.3, 0.05)
+    os_.preStage(3, xs)
+    x = rng.random(spec0.num_dofs)
+    M = os_.matrix()
+    assert np.allclose(os_.residual(x), M @ x + os_.residual(np.zeros_like(x)), rtol=0, atol=1e-11)
+    assert np.allclose(os_.jacobian_apply(x), M @ x, rtol=0, atol=1e-11)
+    assert np.abs(os_.const).max() > 0
