@@ -24,6 +24,7 @@
 // ulp, and the 1e-20 regularisation of the harmonic weights (convectiondiffusiondg.hh:330-332) acts on the
 // scaled permeability — relative effect 1e-20 / (w0 delta).
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -540,6 +541,56 @@ int pdb200_onestep_jacobian(pdb200_onestep_handle os, const double* x, double* v
   PDB_CUDA(cudaSetDevice(os->go0->device));
   combine_stage(os);
   OS_C(pdb200_jacobian(os->stage, x, values, layout));
+  OS_CATCH
+}
+
+int pdb200_onestep_solve_stationary(pdb200_onestep_handle os, int solver, int precond, int matrix_free, double* x,
+                                    double reduction, double min_defect, uint32_t maxiter, pdb200_solve_result* res) {
+  OS_TRY
+  OS_CHECK(os);
+  need_stage(os);
+  need_implicit(os, "StationaryLinearProblemSolver::apply");
+  if (!x || !res) throw Error("pdb200_onestep_solve_stationary: null argument");
+  PDB_CUDA(cudaSetDevice(os->go0->device));
+  combine_stage(os);
+  pdb200_operator* st = os->stage;
+  const long long n = st->P.ndofs;
+  cudaStream_t s = st->stream;
+  if (!st->krylov) st->krylov = krylov_create();
+  Staged X(os, &os->hx, x, true);
+  double *values = nullptr, *r = nullptr, *z = nullptr;
+  struct Free3 {
+    double *&a, *&b, *&c;
+    ~Free3() {
+      if (a) cudaFree(a);
+      if (b) cudaFree(b);
+      if (c) cudaFree(c);
+    }
+  } guard{values, r, z};
+  if (!matrix_free) {  // *_jacobian = 0; igo.jacobian(x, *_jacobian)  (linearproblem.hh:221-226 on onestep.hh:151-159)
+    uint64_t nrows = 0, nnz = 0;
+    OS_C(pdb200_pattern_size(st, &nrows, &nnz));
+    PDB_CUDA(cudaMalloc(&values, nnz * sizeof(double)));
+    OS_C(pdb200_jacobian_fresh(st, X.dev, values, PDB200_LAYOUT_CSR));
+  }
+  PDB_CUDA(cudaMalloc(&r, (size_t)n * sizeof(double)));
+  PDB_CUDA(cudaMalloc(&z, (size_t)n * sizeof(double)));
+  PDB_CUDA(cudaMemsetAsync(r, 0, (size_t)n * sizeof(double), s));
+  PDB_CUDA(cudaMemsetAsync(z, 0, (size_t)n * sizeof(double), s));
+  // r = 0; igo.residual(x, r)  (linearproblem.hh:203, 244-246)
+  OS_C(pdb200_residual(st, X.dev, r));
+  axpy_kernel<<<grid_for(n), 256, 0, s>>>(r, os->const_residual, 1.0, n);
+  os->launches++;
+  PDB_CUDA(cudaGetLastError());
+  const double defect = krylov_two_norm(st->krylov, n, r, s);
+  const double red = defect > 0.0 ? std::max(reduction, min_defect / defect) : reduction;  // :212-214
+  OS_C(pdb200_solve(st, solver, precond, values, PDB200_LAYOUT_CSR, z, r, red, maxiter, res));
+  res->first_defect = defect;
+  res->defect = defect * res->reduction;
+  krylov_axpy(n, -1.0, z, X.dev, s);  // x -= z  (:289)
+  os->launches++;
+  X.copy_back();
+  PDB_CUDA(cudaStreamSynchronize(s));
   OS_CATCH
 }
 

@@ -492,6 +492,7 @@ class ConvectionDiffusionFEM {
   explicit ConvectionDiffusionFEM(Param& param, int intorderadd = 0) : param_(&param), intorderadd(intorderadd) {}
   static constexpr bool isLinear = true;
   Param& parameters() const { return *param_; }
+  void setTime(double t) { param_->setTime(t); }
   Param* param_;
   int intorderadd;
   // members the DG operator has; unused by the conforming path
@@ -536,7 +537,10 @@ class L2 {
  public:
   using ParameterType = detail::L2Parameter<GV, RF>;
   static constexpr bool isLinear = true;
-  explicit L2(int intorderadd = 0, double scaling = 1.0) : param_(scaling), intorderadd(intorderadd) {}  // l2.hh:241-244
+  // l2.hh:241-244.  The reference's intorderadd only raises the quadrature order of an integrand that the k+1
+  // Gauss points of this library already integrate exactly (degree 2k per direction), so it is accepted and
+  // not used: same mass matrix to rounding.
+  explicit L2(int /*intorderadd*/ = 0, double scaling = 1.0) : param_(scaling), intorderadd(0) {}
   ParameterType& parameters() const { return param_; }
   void setTime(double) {}
   mutable ParameterType param_;
@@ -565,6 +569,7 @@ struct ConvectionDiffusionDirichletExtensionAdapter {
   double evaluate(const E& e, const X& x) const {
     return param->g(e, x);
   }
+  void setTime(double t) { param->setTime(t); }  // convectiondiffusionparameter.hh:291-294
   Param* param;
 };
 
@@ -738,7 +743,8 @@ class GridOperator {
     const CU& trialConstraints() const { return *cu; }
     const CV& testConstraints() const { return *cv; }
     static constexpr bool isLinear() { return true; }
-    void setTime(double) {}
+    GridOperator* go = nullptr;
+    void setTime(double t) { go->setTime(t); }  // localassembler.hh: lop.setTime(t); the call-backs are re-sampled
     void setWeight(double w) {
       if (w != 1.0) throw Exception("pdelab_b200: engine weights other than 1 are not supported");
     }
@@ -747,11 +753,13 @@ class GridOperator {
   // gridoperator.hh:76-82
   GridOperator(const GFSU& gfsu, const CU& cu, const GFSV& gfsv, const CV& cv, LOP& lop, const MB& mb = MB())
       : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&cu), cv_(&cv), la_{&lop, &cu, &cv} {
+    la_.go = this;
     init();
   }
   // gridoperator.hh:85-89 (empty constraints)
   GridOperator(const GFSU& gfsu, const GFSV& gfsv, LOP& lop, const MB& mb = MB())
       : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&empty_cu_), cv_(&empty_cv_), la_{&lop, &empty_cu_, &empty_cv_} {
+    la_.go = this;
     init();
   }
   GridOperator(const GridOperator&) = delete;
@@ -773,6 +781,43 @@ class GridOperator {
     if (h_) pdb200_destroy(h_);
     h_ = nullptr;
     init();
+  }
+
+  // LocalAssembler::setTime -> lop.setTime(t) -> param.setTime(t) (gridoperator/default/localassembler.hh): the
+  // reference re-evaluates the call-backs on every assembly; here they are re-sampled when the time changes and
+  // the device arrays are refreshed in place.  setTimeDependent(false) skips the re-sampling.
+  void setTimeDependent(bool v) { time_dependent_ = v; }
+  void setTime(double t) {
+    lop_.setTime(t);
+    if (!time_dependent_ || (time_set_ && t == time_)) return;
+    time_ = t;
+    time_set_ = true;
+    auto S = detail::sample_parameters(gfsu_.gridView(), lop_.parameters(), FEM::degree, lop_.intorderadd);
+    const bool same_layout = S.a_mode == S_.a_mode && S.has_b == S_.has_b && S.has_c == S_.has_c && S.has_f == S_.has_f &&
+                             S.has_g == S_.has_g && S.has_j == S_.has_j && S.has_o == S_.has_o && S.bctype == S_.bctype;
+    if (!same_layout) {  // a field switched on or off, or the boundary types moved: new operator (new constraint set)
+      update();
+      return;
+    }
+    S_ = std::move(S);
+    pdb200_problem q = p_;
+    q.A = S_.A.empty() ? nullptr : S_.A.data();
+    q.b = S_.has_b ? S_.b.data() : nullptr;
+    q.c = S_.has_c ? S_.c.data() : nullptr;
+    q.f = S_.has_f ? S_.f.data() : nullptr;
+    q.bctype = nullptr;
+    q.g = S_.has_g ? S_.g.data() : nullptr;
+    q.j = S_.has_j ? S_.j.data() : nullptr;
+    q.o = S_.has_o ? S_.o.data() : nullptr;
+    check(pdb200_update_coefficients(h_, &q), "setTime");
+    p_.A = q.A, p_.b = q.b, p_.c = q.c, p_.f = q.f, p_.g = q.g, p_.j = q.j, p_.o = q.o;
+    p_.bctype = S_.bctype.data();
+  }
+  // StationaryLinearProblemSolver::apply as one device-resident call (dispatch point shared with OneStepGridOperator)
+  void solveStationary(int solver, int precond, bool matrix_free, double* x, double reduction, double min_defect,
+                       unsigned maxiter, pdb200_solve_result* s) const {
+    check(pdb200_solve_stationary(h_, solver, precond, matrix_free ? 1 : 0, x, reduction, min_defect, maxiter, s),
+          "StationaryLinearProblemSolver::apply");
   }
 
   // gridoperator.hh:168-173
@@ -903,6 +948,8 @@ class GridOperator {
   detail::Sampled<dim> S_;  // sampled call-backs (kept alive: p_ points into them)
   pdb200_problem p_{};
   pdb200_handle h_ = nullptr;
+  bool time_dependent_ = true, time_set_ = false;
+  double time_ = 0.0;
 };
 
 // FastDGGridOperator (gridoperator/fastdg.hh:37-230): the reference's assembler variant that skips the
@@ -919,7 +966,8 @@ template <class GO>
 class BCRSMatrixContainer {
  public:
   using ElementType = double;
-  explicit BCRSMatrixContainer(const GO& go) {
+  template <class AnyGO>  // GridOperator or OneStepGridOperator over it (bcrsmatrix.hh:78-82)
+  explicit BCRSMatrixContainer(const AnyGO& go) {
     go.fill_pattern(p_);
     v_.assign(p_.colidx.size(), 0.0);
   }
@@ -1102,11 +1150,17 @@ class StationaryLinearProblemSolver {
   using Result = StationaryLinearProblemSolverResult<double>;
   StationaryLinearProblemSolver(const GO& go, LS& ls, V& x, double reduction, double min_defect = 1e-99, int verbose = 1)
       : go_(go), ls_(ls), x_(&x), reduction_(reduction), min_defect_(min_defect), verbose_(verbose) {}
+  // linearproblem.hh:106-118: the solution vector is handed to apply(x)
+  StationaryLinearProblemSolver(const GO& go, LS& ls, double reduction, double min_defect = 1e-99, int verbose = 1)
+      : go_(go), ls_(ls), x_(nullptr), reduction_(reduction), min_defect_(min_defect), verbose_(verbose) {}
+  void apply(V& x, bool reuse_matrix = false) {  // linearproblem.hh:180-186
+    x_ = &x;
+    apply(reuse_matrix);
+  }
   void apply(bool /*reuse_matrix*/ = false) {
+    if (!x_) throw Exception("StationaryLinearProblemSolver: no solution vector");
     pdb200_solve_result s;
-    check(pdb200_solve_stationary(go_.handle(), LS::solver, LS::precond, LS::matrix_free ? 1 : 0, x_->data(), reduction_,
-                                  min_defect_, ls_.maxiter(), &s),
-          "StationaryLinearProblemSolver::apply");
+    go_.solveStationary(LS::solver, LS::precond, LS::matrix_free, x_->data(), reduction_, min_defect_, ls_.maxiter(), &s);
     ls_.store(s);
     static_cast<LinearSolverResult<double>&>(res_) = ls_.result();
     res_.first_defect = s.first_defect;

@@ -43,7 +43,8 @@ SYMBOLS = [
     "pdb200_onestep_pre_step", "pdb200_onestep_time_at_stage", "pdb200_onestep_pre_stage",
     "pdb200_onestep_pre_stage_begin", "pdb200_onestep_pre_stage_add", "pdb200_onestep_const_residual",
     "pdb200_onestep_residual", "pdb200_onestep_jacobian_apply", "pdb200_onestep_onthefly_apply",
-    "pdb200_onestep_jacobian", "pdb200_onestep_stage_operator", "pdb200_onestep_launch_count",
+    "pdb200_onestep_jacobian", "pdb200_onestep_stage_operator", "pdb200_onestep_solve_stationary",
+    "pdb200_onestep_launch_count",
 ]
 
 

@@ -214,6 +214,8 @@ class OneStepGridOperator:
         lib.pdb200_onestep_jacobian.argtypes = [vp, vp, vp, C.c_int]
         lib.pdb200_onestep_stage_operator.argtypes = [vp, C.POINTER(vp)]
         lib.pdb200_onestep_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+        lib.pdb200_onestep_solve_stationary.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_double, C.c_double,
+                                                        C.c_uint32, C.POINTER(SolveResult)]
         OneStepGridOperator._bound = True
 
     def _chk(self, rc):
@@ -322,6 +324,15 @@ class OneStepGridOperator:
         self._chk(self.lib.pdb200_onestep_stage_operator(self._h, C.byref(h)))
         return _StageOperatorView(self.lib, h, self.go0.spec)
 
+    def solve_stationary(self, x, reduction=1e-10, min_defect=1e-99, solver=abi.SOLVER_BICGSTAB,
+                         precond=abi.PRECOND_NONE, matrix_free=True, maxiter=5000):
+        """StationaryLinearProblemSolver::apply on the one-step operator (the stage solver of OneStepMethod),
+        one device-resident call: x -= J^-1 residual(x)."""
+        res = SolveResult()
+        self._chk(self.lib.pdb200_onestep_solve_stationary(self._h, solver, precond, 1 if matrix_free else 0, _ptr(x),
+                                                           float(reduction), float(min_defect), int(maxiter), C.byref(res)))
+        return res.as_dict()
+
     def postStage(self):
         pass
 
@@ -343,8 +354,8 @@ class OneStepMethod:
     """
 
     def __init__(self, method, igos: OneStepGridOperator, reduction=1e-10, solver=abi.SOLVER_BICGSTAB,
-                 precond=abi.PRECOND_NONE, maxiter=5000, min_defect=1e-99):
-        self.method, self.igos = method, igos
+                 precond=abi.PRECOND_NONE, maxiter=5000, min_defect=1e-99, matrix_free=True):
+        self.method, self.igos, self.matrix_free = method, igos, matrix_free
         self.reduction, self.solver, self.precond, self.maxiter, self.min_defect = reduction, solver, precond, maxiter, min_defect
         self.step = 1
         self.linear_solver_iterations = 0
@@ -354,24 +365,11 @@ class OneStepMethod:
         self.method = method
 
     def _solve_stage(self, x):
-        """x -= J^-1 (R(x) + const_residual) with the one-step residual and the fused stage operator."""
-        igos = self.igos
-        import torch
-        dev = hasattr(x, "data_ptr")
-        xd = x if dev else torch.from_numpy(x).cuda()
-        r = torch.zeros_like(xd)
-        igos.residual(xd, r)                                            # linearproblem.hh:203
-        defect = float(torch.linalg.vector_norm(r))
-        if defect == 0.0:
-            return dict(converged=1, iterations=0, first_defect=0.0)
-        red = max(self.reduction, self.min_defect / defect)             # :212-214
-        z = torch.zeros_like(xd)
-        res = igos.stage_operator().solve(z, r, red, solver=self.solver, precond=self.precond, maxiter=self.maxiter)
+        """pdesolver.apply(x): x -= J^-1 (R(x) + const_residual), one device-resident call."""
+        res = self.igos.solve_stationary(x, reduction=self.reduction, min_defect=self.min_defect, solver=self.solver,
+                                         precond=self.precond, matrix_free=self.matrix_free, maxiter=self.maxiter)
         if not res["converged"]:
             raise PDELabError("OneStepMethod: linear solver did not converge")
-        xd -= z                                                         # :289
-        if not dev:
-            x[:] = xd.cpu().numpy()
         return res
 
     def apply(self, time, dt, xold, xnew):

@@ -266,6 +266,12 @@ int pdb200_onestep_onthefly_apply(pdb200_onestep_handle os, const double* x, dou
 int pdb200_onestep_jacobian(pdb200_onestep_handle os, const double* x, double* values, int layout);
 /* the fused operator of the current stage (owned by `os`; valid until the weights or coefficients change) */
 int pdb200_onestep_stage_operator(pdb200_onestep_handle os, pdb200_handle* stage);
+/* StationaryLinearProblemSolver::apply (stationary/linearproblem.hh:188-302) on the one-step operator — the stage
+ * solver of OneStepMethod::apply (instationary/implicitonestep.hh:191) for linear problems, device-resident:
+ *   [A = 0; jacobian(x, A)]  r = 0; residual(x, r);  solve J z = r to max(reduction, min_defect / |r|);  x -= z.
+ * Arguments as pdb200_solve_stationary. */
+int pdb200_onestep_solve_stationary(pdb200_onestep_handle os, int solver, int precond, int matrix_free, double* x,
+                                    double reduction, double min_defect, uint32_t maxiter, pdb200_solve_result* res);
 int pdb200_onestep_launch_count(pdb200_onestep_handle os, uint64_t* n);
 
 /* Halo exchange support for the overlapping partition (replaces the AddDataHandle/CopyDataHandle

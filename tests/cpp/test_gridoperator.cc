@@ -6,6 +6,7 @@
 //   test/testmatrixfree.cc:150-178             Q2 conforming FEM 2D 32^2, err^2 <= 1e-7, both ways
 //   test/test-blocked-istl-ordering.cc:45-72   flat and blocked DG vectors are the same bytes
 //   gridoperator/gridoperator.hh:200-205       jacobian_apply(u,z,y) throws for a linear operator
+//   test/testinstationaryfastdgassembler.cc    DG k=1 2D 8^2 + L2, Alexander2, one step dt=0.1, err^2 <= 5e-6
 // and every GPU result is compared with the CPU oracle (liboracle.so, test infrastructure) fed
 // with the very same pdb200_problem.
 #include <cmath>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "../../dune-pdelab_b200/host/gridoperator.hh"
+#include "../../dune-pdelab_b200/host/onestep.hh"
 
 extern "C" {  // oracle/pdelab_oracle.cc
 int oracle_residual(const pdb200_problem*, const double*, double*);
@@ -431,9 +433,198 @@ void l2_blocked_ordering_case() {
   EXPECT(std::abs(sum_r - integral) < 1e-13, "L2: sum of the residual equals the integral of u_h (" << sum_r << ")");
 }
 
+// ---- test/testinstationaryfastdgassembler.cc: OneStepGridOperator + OneStepMethod ------------------------
+// ParameterA of the reference test (:17-104): A = I, f = (2 d - 4 |x|^2) exp(-|x|^2), Dirichlet g = exp(-|x|^2)
+template <typename GV, typename RF>
+class ParameterA : public PDELab::ConvectionDiffusionModelProblem<GV, RF> {
+ public:
+  template <typename Element, typename Coord>
+  RF f(const Element& e, const Coord& x) const {
+    auto xg = e.geometry().global(x);
+    double norm = 0;
+    for (std::size_t i = 0; i < xg.size(); i++) norm += xg[i] * xg[i];
+    return (2.0 * xg.size() - 4.0 * norm) * std::exp(-norm);
+  }
+  template <typename Element, typename Coord>
+  RF g(const Element& e, const Coord& x) const {
+    auto xg = e.geometry().global(x);
+    double norm = 0;
+    for (std::size_t i = 0; i < xg.size(); i++) norm += xg[i] * xg[i];
+    return std::exp(-norm);
+  }
+  void setTime(RF t) { time = t; }
+  RF time = 0.0;
+};
+
+void instationary_dg_case() {
+  constexpr int dim = 2, degree = 1;
+  const char* name = "instationary DG k=1 2D 8^2 (testinstationaryfastdgassembler)";
+  using Grid = PDELab::YaspGrid<dim>;
+  std::array<int, dim> cells;
+  cells.fill(8);  // one cell, globalRefine(3)
+  Grid grid(PDELab::FieldVector<double, dim>(1.0), cells);
+  using GV = typename Grid::LeafGridView;
+  GV gv = grid.leafGridView();
+  using FEM = PDELab::QkDGLocalFiniteElementMap<double, double, degree, dim>;
+  FEM fem;
+  using VBE = PDELab::ISTL::VectorBackend<PDELab::ISTL::Blocking::fixed, FEM::maxLocalSize()>;
+  using GFS = PDELab::GridFunctionSpace<GV, FEM, PDELab::NoConstraints, VBE>;
+  GFS gfs(gv, fem);
+  using Problem = ParameterA<GV, double>;
+  Problem problem;
+  using LOP = PDELab::ConvectionDiffusionDG<Problem, FEM>;
+  LOP lop(problem, PDELab::ConvectionDiffusionDGMethod::SIPG, PDELab::ConvectionDiffusionDGWeights::weightsOn, 2.0);
+  using MLOP = PDELab::L2<GV, FEM>;
+  MLOP mlop(2 * degree);
+  using MBE = PDELab::ISTL::BCRSMatrixBackend;
+  MBE mbe(9);
+  using CC = typename GFS::template ConstraintsContainer<double>::Type;
+  CC cc;
+  using GO0 = PDELab::FastDGGridOperator<GFS, GFS, LOP, MBE, double, double, double, CC, CC>;
+  GO0 go0(gfs, cc, gfs, cc, lop, mbe);
+  using GO1 = PDELab::FastDGGridOperator<GFS, GFS, MLOP, MBE, double, double, double, CC, CC>;
+  GO1 go1(gfs, cc, gfs, cc, mlop, mbe);
+  using IGO = PDELab::OneStepGridOperator<GO0, GO1>;
+  IGO igo(go0, go1);
+  using V = typename IGO::Traits::Domain;
+  const std::size_t N = gfs.size();
+  using G = PDELab::ConvectionDiffusionDirichletExtensionAdapter<Problem>;
+  G g(gv, problem);
+  V x(gfs, 0.0);
+  go0.B200_interpolate(g, x);  // Dune::PDELab::interpolate(g, gfs, x)
+
+  // --- the one-step residual against the engines restated on the oracle (stage 1 of Alexander2:
+  //     a10 = -1, b10 = 0, b11 = alpha):  r = b11 dt R0(y) + R1(y) - R1(x)
+  PDELab::Alexander2Parameter<double> method;
+  const double dt = 0.1;
+  {
+    std::mt19937_64 rng;
+    std::uniform_real_distribution<double> dist(0, 1);
+    V y(gfs), r(gfs, 0.0);
+    for (std::size_t i = 0; i < N; i++) y[i] = dist(rng);
+    igo.preStep(method, 0.0, dt);
+    std::vector<V*> xs(1, &x);
+    igo.preStage(1, xs);
+    igo.residual(y, r);
+    std::vector<double> r0(N, 0.0), r1y(N, 0.0), r1x(N, 0.0), want(N);
+    oracle_residual(&go0.problem(), y.data(), r0.data());
+    oracle_residual(&go1.problem(), y.data(), r1y.data());
+    oracle_residual(&go1.problem(), x.data(), r1x.data());
+    for (std::size_t i = 0; i < N; i++) want[i] = method.b(1, 1) * dt * r0[i] + r1y[i] - r1x[i];
+    EXPECT(rel_err(r, want) < 1e-12, name << ": one-step residual vs oracle engines " << rel_err(r, want));
+    EXPECT(std::abs(igo.timeAtStage(1) - method.d(1) * dt) < 1e-15, name << ": timeAtStage");
+    // assembled one-step Jacobian times z == matrix-free one-step jacobian_apply
+    typename IGO::Jacobian A(igo);
+    A = 0.0;
+    igo.jacobian(y, A);
+    V Jy(gfs, 0.0), Jf(gfs, 0.0);
+    A.mv(y, Jy);
+    igo.jacobian_apply(y, Jf);
+    EXPECT(rel_err(Jf, Jy.native()) < 1e-12, name << ": one-step jacobian * z == jacobian_apply " << rel_err(Jf, Jy.native()));
+    bool threw = false;
+    try {
+      igo.jacobian_apply(y, y, r);
+    } catch (PDELab::Exception&) {
+      threw = true;
+    }
+    EXPECT(threw, name << ": non-linear jacobian_apply throws for linear operators (onestep.hh:187-192)");
+  }
+
+  // --- the time loop of the reference test, matrix-free (CG + block Jacobi) and assembled (CG + Jacobi)
+  auto run = [&](auto& ls, const char* what) {
+    using LS = std::decay_t<decltype(ls)>;
+    using PDESOLVER = PDELab::StationaryLinearProblemSolver<IGO, LS, V>;
+    PDESOLVER pdesolver(igo, ls, 1e-10);
+    PDELab::OneStepMethod<double, IGO, PDESOLVER, V, V> osm(method, igo, pdesolver);
+    osm.setVerbosityLevel(0);
+    V xt(x);
+    double time = 0.0;
+    const double T = 0.1;
+    while (time < T - 1e-10) {
+      V xnew(gfs, 0.0);
+      osm.apply(time, dt, xt, xnew);
+      xt = xnew;
+      time += dt;
+    }
+    const double err = l2_error_squared(gfs, xt, problem, go0.handle(), degree);
+    EXPECT(err <= 5e-6 && !std::isnan(err), name << ": " << what << " l2 error squared " << err << " <= 5e-6, "
+                                                 << osm.result().total.linear_solver_iterations << " linear iterations");
+    return xt;
+  };
+  PDELab::ISTLBackend_SEQ_MatrixFree_CG_BlockJacobi<IGO> ls_free(igo, 10000, 0);
+  PDELab::ISTLBackend_SEQ_CG_Jac<IGO> ls_mat(igo, 10000, 0);
+  V x_free = run(ls_free, "matrix-free CG + block Jacobi");
+  V x_mat = run(ls_mat, "assembled CG + Jacobi");
+  EXPECT(rel_err(x_free, x_mat.native()) < 1e-8, name << ": both solvers reach the same state " << rel_err(x_free, x_mat.native()));
+}
+
+// conforming Q2 with Dirichlet constraints interpolated at every stage (implicitonestep.hh:264-400)
+void instationary_fem_case() {
+  constexpr int dim = 2, degree = 2;
+  const char* name = "instationary Q2 2D 16^2, fractional step";
+  using Grid = PDELab::YaspGrid<dim>;
+  std::array<int, dim> cells;
+  cells.fill(16);
+  Grid grid(PDELab::FieldVector<double, dim>(1.0), cells);
+  using GV = typename Grid::LeafGridView;
+  GV gv = grid.leafGridView();
+  using FEM = PDELab::QkLocalFiniteElementMap<GV, double, double, degree>;
+  FEM fem(gv);
+  using GFS = PDELab::GridFunctionSpace<GV, FEM, PDELab::ConformingDirichletConstraints, PDELab::ISTL::VectorBackend<>>;
+  GFS gfs(gv, fem);
+  using Problem = ParameterA<GV, double>;
+  Problem problem;
+  using LOP = PDELab::ConvectionDiffusionFEM<Problem, FEM>;
+  LOP lop(problem);
+  using MLOP = PDELab::L2<GV, FEM>;
+  MLOP mlop;
+  using MBE = PDELab::ISTL::BCRSMatrixBackend;
+  using CC = typename GFS::template ConstraintsContainer<double>::Type;
+  CC cc;
+  using GO0 = PDELab::GridOperator<GFS, GFS, LOP, MBE, double, double, double, CC, CC>;
+  using GO1 = PDELab::GridOperator<GFS, GFS, MLOP, MBE, double, double, double, CC, CC>;
+  GO0 go0(gfs, cc, gfs, cc, lop, MBE(25));
+  GO1 go1(gfs, cc, gfs, cc, mlop, MBE(25));
+  PDELab::constraints(go0, cc);
+  using IGO = PDELab::OneStepGridOperator<GO0, GO1>;
+  IGO igo(go0, go1);
+  using V = typename IGO::Traits::Domain;
+  PDELab::ConvectionDiffusionDirichletExtensionAdapter<Problem> g(gv, problem);
+  V x(gfs, 0.0);
+  go0.B200_interpolate(g, x);
+  PDELab::set_nonconstrained_dofs(cc, 0.0, x);  // start from zero in the interior: the heat equation relaxes to exp(-|x|^2)
+  using LS = PDELab::ISTLBackend_SEQ_MatrixFree_CG_Richardson<IGO>;
+  LS ls(igo, 10000, 0);
+  using PDESOLVER = PDELab::StationaryLinearProblemSolver<IGO, LS, V>;
+  PDESOLVER pdesolver(igo, ls, 1e-10);
+  PDELab::FractionalStepParameter<double> method;
+  PDELab::OneStepMethod<double, IGO, PDESOLVER, V, V> osm(method, igo, pdesolver);
+  osm.setVerbosityLevel(0);
+  double time = 0.0;
+  const double dt = 0.05;
+  for (int step = 0; step < 40; step++) {  // T = 2: the slowest mode has decayed by exp(-2 * 2 pi^2); the scheme is only
+                                           // strongly A-stable (|R(inf)| ~ 0.7), the boundary layer needs the 40 steps
+    V xnew(x);
+    osm.apply(time, dt, x, g, xnew);
+    x = xnew;
+    time += dt;
+  }
+  const double err = l2_error_squared(gfs, x, problem, go0.handle(), degree);
+  EXPECT(err <= 1e-6 && !std::isnan(err), name << ": l2 error squared after relaxation " << err << " <= 1e-6, "
+                                               << osm.result().total.linear_solver_iterations << " linear iterations");
+  // the constrained DOFs carry the interpolated boundary values
+  V gi(gfs, 0.0);
+  go0.B200_interpolate(g, gi);
+  bool same = true;
+  for (auto i : cc.dofs) same = same && x[i] == gi[i];
+  EXPECT(same, name << ": Dirichlet DOFs hold the interpolated boundary values");
+}
+
 int main() {
   try {
     l2_blocked_ordering_case();
+    instationary_dg_case();
+    instationary_fem_case();
     dg_case<2, 1, PoissonProblem>(16, 3.0, 1e-6, "DG k=1 2D 16^2 (testconvectiondiffusiondg)", true);
     dg_case<2, 2, LayeredProblem>(6, 3.0, 0, "DG k=2 2D 6^2 layered diagonal A + c", false);
     dg_case<3, 2, LayeredProblem>(4, 3.0, 0, "DG k=2 3D 4^3 layered diagonal A + c (Kronecker kernel)", false);

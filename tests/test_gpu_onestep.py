@@ -171,8 +171,10 @@ def test_errors_like_the_reference(cuda_lib):
         osm.OneStepGridOperator(_keep[0], other)
 
 
-@pytest.mark.parametrize("solver,precond", [(abi.SOLVER_BICGSTAB, abi.PRECOND_NONE), (abi.SOLVER_CG, abi.PRECOND_BLOCK_JACOBI)])
-def test_reference_instationary_dg_test(cuda_lib, solver, precond):
+@pytest.mark.parametrize("solver,precond,matrix_free", [(abi.SOLVER_BICGSTAB, abi.PRECOND_NONE, True),
+                                                        (abi.SOLVER_CG, abi.PRECOND_BLOCK_JACOBI, True),
+                                                        (abi.SOLVER_CG, abi.PRECOND_JACOBI, False)])
+def test_reference_instationary_dg_test(cuda_lib, solver, precond, matrix_free):
     """test/testinstationaryfastdgassembler.cc on the device: QkDG k=1 on 8x8, SIPG alpha=2, L2, Alexander2, one step
     dt = 0.1 from the interpolated stationary solution; squared L2 error <= 5e-6 (:197), and the same end state as the
     oracle's time step with a direct stage solver."""
@@ -183,7 +185,7 @@ def test_reference_instationary_dg_test(cuda_lib, solver, precond):
     go0, go1 = GridOperator(spec0), GridOperator(osm.l2_spec(spec0))
     igo = osm.OneStepGridOperator(go0, go1)
     method = osm.Alexander2Parameter()
-    stepper = osm.OneStepMethod(method, igo, reduction=1e-10, solver=solver, precond=precond)
+    stepper = osm.OneStepMethod(method, igo, reduction=1e-10, solver=solver, precond=precond, matrix_free=matrix_free)
     x = u_exact(node_coordinates(spec0))
     xnew = np.zeros_like(x)
     time, dt, T = 0.0, 0.1, 0.1
