@@ -148,6 +148,17 @@ void p2p_check(P2PHalo*);  // throws if a spin-wait timed out
 cudaStream_t p2p_stream(P2PHalo*);
 cudaEvent_t p2p_event(P2PHalo*, int i);
 
+// halo.cu: all-ranks reduction of inner-product partials over peer-mapped mailboxes (overlapping solvers)
+struct PeerComm;
+PeerComm* comm_create(int rank, int size, pdb200_ipc_handle* mine);
+void comm_connect(PeerComm*, int peer_rank, const pdb200_ipc_handle* peer);
+void comm_destroy(PeerComm*);
+int comm_size(const PeerComm*);
+// in place: P1[0] = sum over ranks of sum(P1[0..nb)), P1[1..nb) = 0 (the same for P2 if given); one launch
+void comm_allreduce_partials(PeerComm*, double* P1, double* P2, int nb, cudaStream_t s);
+void comm_check(PeerComm*);  // throws if a spin-wait timed out
+int launch_halo_zero(const DevParams& P, double* x, cudaStream_t s);  // ghost layers of the processor sides := 0
+
 // fem.cu: conforming Qk residual / jacobian_apply (coloured scatter)
 struct FemPlan;
 FemPlan* fem_plan_create(const DevParams& P, const int8_t* bctype_dev, const Kron1D& K);

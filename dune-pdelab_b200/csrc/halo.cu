@@ -6,6 +6,7 @@
 // (dir, side) is the owned cell layer at distance 1 from that box face, and the data received
 // fills the ghost layer at distance 0.  A DG cell is n contiguous doubles, so the copy is a
 // strided block copy; consecutive threads move consecutive doubles of a cell.
+#include <algorithm>
 #include <cstddef>
 #include <cstring>
 
@@ -351,6 +352,197 @@ void p2p_check(P2PHalo* H) {
 
 cudaStream_t p2p_stream(P2PHalo* H) { return H->stream; }
 cudaEvent_t p2p_event(P2PHalo* H, int i) { return H->ev[i]; }
+
+// ---------------------------------------------------------------------------------------------
+// All-ranks reduction over peer-mapped mailboxes: the global sum of OverlappingScalarProduct::dot
+// (backend/istl/ovlpistlsolverbackend.hh:103-108, gridView().comm().sum) without NCCL and without a host
+// round trip.  Every rank owns a small mailbox (CUDA IPC, mapped by all peers) with one value slot and one
+// flag per rank, double-buffered by the parity of the epoch.  One kernel of one CTA per reduction:
+//   1. sum the block partials of the local inner product(s) in the fixed order every consumer uses;
+//   2. thread t stores the local sums into rank t's mailbox (remote store), fences, publishes flag = epoch;
+//   3. thread t spins on the local flag of rank t (time-out into the error flag, never a hang);
+//   4. the sums of all ranks are added in rank order — the same order on every rank, so all ranks hold
+//      bit-identical scalars — and written back as partial 0 (the other partials are zeroed), which is what
+//      the consuming vector kernels re-add.
+// A rank can run at most one reduction ahead of a peer (it needs the peer's flag of the current epoch to
+// finish), so two buffers suffice.
+namespace {
+
+constexpr int COMM_MAX_RANKS = 16;
+constexpr unsigned long long COMM_MAGIC = 0x70646232303063ull;  // "pdb200c"
+struct CommBox {
+  unsigned long long magic;
+  unsigned long long flag[2][COMM_MAX_RANKS];
+  double val[2][COMM_MAX_RANKS][2];
+};
+struct CommTable {
+  int rank, size;
+  CommBox* box[COMM_MAX_RANKS];  // box[rank] is this rank's own mailbox
+};
+
+__global__ void __launch_bounds__(256) comm_allreduce_kernel(const CommTable T, double* P1, double* P2, int nb,
+                                                             unsigned long long epoch, int* err) {
+  __shared__ double ws[2][8];
+  __shared__ double tot[2];
+  double v1 = 0.0, v2 = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) {
+    v1 += P1[i];
+    if (P2) v2 += P2[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v1 += __shfl_down_sync(0xffffffffu, v1, o);
+    v2 += __shfl_down_sync(0xffffffffu, v2, o);
+  }
+  if ((threadIdx.x & 31) == 0) ws[0][threadIdx.x >> 5] = v1, ws[1][threadIdx.x >> 5] = v2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; w++) a += ws[0][w], b += ws[1][w];
+    tot[0] = a, tot[1] = b;
+  }
+  __syncthreads();
+  const int par = (int)(epoch & 1);
+  const int t = threadIdx.x;
+  if (t < T.size) {
+    CommBox* dst = T.box[t];
+    volatile double* slot = dst->val[par][T.rank];
+    slot[0] = tot[0];
+    slot[1] = tot[1];
+    __threadfence_system();
+    st_release_sys(&dst->flag[par][T.rank], epoch);
+    const unsigned long long* flag = &T.box[T.rank]->flag[par][t];
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+      if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(50);
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const CommBox* me = T.box[T.rank];
+    double g1 = 0.0, g2 = 0.0;
+    for (int r = 0; r < T.size; r++) {
+      const volatile double* slot = me->val[par][r];
+      g1 += slot[0];
+      g2 += slot[1];
+    }
+    P1[0] = g1;
+    if (P2) P2[0] = g2;
+  }
+  for (int i = 1 + t; i < nb; i += 256) {
+    P1[i] = 0.0;
+    if (P2) P2[i] = 0.0;
+  }
+}
+
+// zero one cell layer (the ghost layer of a processor side)
+__global__ void halo_zero_kernel(double* __restrict__ x, long long total, long long chunk, long long stride, long long layer_off) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step)
+    x[layer_elem<double>(i, chunk, stride, layer_off)] = 0.0;
+}
+
+}  // namespace
+
+struct PeerComm {
+  CommBox* box = nullptr;  // own mailbox (device memory, IPC-exported)
+  CommTable table;
+  void* peer_base[COMM_MAX_RANKS] = {};
+  int connected = 1;
+  unsigned long long epoch = 0;
+  int* err = nullptr;
+};
+
+PeerComm* comm_create(int rank, int size, pdb200_ipc_handle* mine) {
+  if (size < 1 || size > COMM_MAX_RANKS || rank < 0 || rank >= size) throw Error("comm_create: rank / size out of range (at most 16 ranks)");
+  PeerComm* C = new PeerComm;
+  std::memset(&C->table, 0, sizeof(C->table));
+  PDB_CUDA(cudaMalloc(&C->box, sizeof(CommBox)));
+  PDB_CUDA(cudaMemset(C->box, 0, sizeof(CommBox)));
+  const unsigned long long magic = COMM_MAGIC;
+  PDB_CUDA(cudaMemcpy(&C->box->magic, &magic, sizeof(magic), cudaMemcpyHostToDevice));
+  PDB_CUDA(cudaMalloc(&C->err, sizeof(int)));
+  PDB_CUDA(cudaMemset(C->err, 0, sizeof(int)));
+  C->table.rank = rank;
+  C->table.size = size;
+  C->table.box[rank] = C->box;
+  cudaIpcMemHandle_t ih;
+  PDB_CUDA(cudaIpcGetMemHandle(&ih, C->box));
+  std::memset(mine, 0, sizeof(*mine));
+  std::memcpy(mine->bytes, &ih, sizeof(ih));
+  PDB_CUDA(cudaDeviceSynchronize());
+  return C;
+}
+
+void comm_connect(PeerComm* C, int peer_rank, const pdb200_ipc_handle* peer) {
+  if (peer_rank < 0 || peer_rank >= C->table.size || peer_rank == C->table.rank) throw Error("comm_connect: invalid peer rank");
+  if (C->peer_base[peer_rank]) throw Error("comm_connect: peer already connected");
+  cudaIpcMemHandle_t ih;
+  std::memcpy(&ih, peer->bytes, sizeof(ih));
+  void* base = nullptr;
+  PDB_CUDA(cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess));
+  unsigned long long magic = 0;
+  PDB_CUDA(cudaMemcpy(&magic, base, sizeof(magic), cudaMemcpyDeviceToHost));
+  if (magic != COMM_MAGIC) {
+    cudaIpcCloseMemHandle(base);
+    throw Error("comm_connect: the peer handle is not a pdelab_b200 reduction mailbox");
+  }
+  C->peer_base[peer_rank] = base;
+  C->table.box[peer_rank] = (CommBox*)base;
+  C->connected++;
+}
+
+void comm_destroy(PeerComm* C) {
+  if (!C) return;
+  cudaDeviceSynchronize();
+  for (void* b : C->peer_base)
+    if (b) cudaIpcCloseMemHandle(b);
+  if (C->box) cudaFree(C->box);
+  if (C->err) cudaFree(C->err);
+  delete C;
+}
+
+int comm_size(const PeerComm* C) { return C->table.size; }
+
+void comm_allreduce_partials(PeerComm* C, double* P1, double* P2, int nb, cudaStream_t s) {
+  if (C->connected != C->table.size) throw Error("peer reduction: not every rank is connected");
+  C->epoch++;
+  comm_allreduce_kernel<<<1, 256, 0, s>>>(C->table, P1, P2, nb, C->epoch, C->err);
+  PDB_CUDA(cudaGetLastError());
+}
+
+void comm_check(PeerComm* C) {
+  int e = 0;
+  PDB_CUDA(cudaMemcpy(&e, C->err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(C->err, 0, sizeof(int));
+    throw Error("peer reduction timed out waiting for a rank");
+  }
+}
+
+// x := 0 on the ghost layers of all processor sides (set_constrained_dofs(cc, 0.0, y) for the P0 parallel
+// constraints, backend/istl/ovlpistlsolverbackend.hh:48-49; constraints/p0.hh:31-41)
+int launch_halo_zero(const DevParams& P, double* x, cudaStream_t s) {
+  int launches = 0;
+  for (int d = 0; d < P.dim; d++)
+    for (int side = 0; side < 2; side++) {
+      if (P.side_kind[d][side] != PDB200_SIDE_PROCESSOR) continue;
+      long long chunk = P.n;
+      for (int e = 0; e < d; e++) chunk *= P.N[e];
+      const long long stride = chunk * P.N[d];
+      const long long total = (P.ncells / P.N[d]) * P.n;
+      const long long layer = side ? P.N[d] - 1 : 0;
+      const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+      halo_zero_kernel<<<blocks, 256, 0, s>>>(x, total, chunk, stride, layer * chunk);
+      launches++;
+    }
+  PDB_CUDA(cudaGetLastError());
+  return launches;
+}
 
 // index gather / scatter (pack / unpack of the conforming-Qk ghost exchange)
 __global__ void gather_kernel(const double* __restrict__ x, const long long* __restrict__ idx, long long n,

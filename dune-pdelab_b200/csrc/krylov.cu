@@ -320,11 +320,14 @@ static double read_norm(KrylovWork* w, const double* P, cudaStream_t s) {
   return w->host_norm[0];
 }
 
-double krylov_two_norm(KrylovWork* w, long long n, const double* a, cudaStream_t s) {
+double krylov_two_norm(KrylovWork* w, long long n, const double* a, cudaStream_t s,
+                       const std::function<void(double*, double*)>* allreduce) {
   ensure(w, w->n ? w->n : n, 0);
   norm2_kernel<<<NB, NT, 0, s>>>(n, a, w->partials);
+  if (allreduce && *allreduce) (*allreduce)(w->partials, nullptr);
   return read_norm(w, w->partials, s);
 }
+int krylov_partial_count() { return NB; }
 
 void krylov_axpy(long long n, double a, const double* x, double* y, cudaStream_t s) {
   axpy_kernel<<<NB, NT, 0, s>>>(n, a, x, y);
@@ -360,6 +363,13 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
   double def0 = 0.0, def = 0.0;
   double it = 0.0, it_done = 0.0;
   double *PA, *PB, *PC, *PD, *PE;
+  // global sums of the overlapping scalar product: every producer of block partials is followed by the reduction
+  auto AR = [&](double* P1, double* P2) {
+    if (ops.allreduce) {
+      ops.allreduce(P1, P2);
+      launches++;
+    }
+  };
   if (solver == PDB200_SOLVER_BICGSTAB) {
     const bool gp = (bool)ops.prec;  // general preconditioner: y = W p / y = W r by separate launches
     ensure(w, n, dinv || gp ? 6 : 5);
@@ -371,6 +381,7 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
     defect_kernel<<<NB, NT, 0, s>>>(n, b, r);
     bcgs_init_kernel<<<NB, NT, 0, s>>>(n, r, rt, p, v, PD, w->S);  // PD = rt.r = |r|^2
     launches += 2;
+    AR(PD, nullptr);
     def0 = def = read_norm(w, PD, s);
     if (!converged(def0, def0, reduction) && def0 > 0.0) {
       for (it = 0.5; it < maxit; it += 0.5) {
@@ -379,7 +390,9 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
         if (gp) ops.prec(p, y);
         ops.apply(y ? y : p, v);
         dot_kernel<<<NB, NT, 0, s>>>(n, rt, v, PA, nullptr);
+        AR(PA, nullptr);
         bcgs_half1_kernel<<<NB, NT, 0, s>>>(n, x, y ? y : p, r, v, dinv, y, PA, PC, w->S);
+        AR(PC, nullptr);
         launches += 3;
         def = read_norm(w, PC, s);
         it_done = it;
@@ -389,7 +402,9 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
         if (gp) ops.prec(r, y);
         ops.apply(y ? y : r, t);
         dot_kernel<<<NB, NT, 0, s>>>(n, t, r, PA, PB);
+        AR(PA, PB);
         bcgs_half2_kernel<<<NB, NT, 0, s>>>(n, x, y ? y : r, r, t, rt, PA, PB, PC, PD, w->S);
+        AR(PC, PD);
         launches += 2;
         def = read_norm(w, PC, s);
         it_done = it;
@@ -415,13 +430,16 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
       dot_kernel<<<NB, NT, 0, s>>>(n, p, r, PD, nullptr);
       launches++;
     }
+    AR(PC, PD);
     def0 = def = read_norm(w, PC, s);
     if (!converged(def0, def0, reduction) && def0 > 0.0) {
       unsigned i = 1;
       for (; i <= maxit; i++) {
         ops.apply(p, q);
         dot_kernel<<<NB, NT, 0, s>>>(n, p, q, PA, nullptr);
+        AR(PA, nullptr);
         cg_update_kernel<<<NB, NT, 0, s>>>(n, x, p, r, q, dinv, z, PA, PD, PC, PB, w->S, i == 1 ? 1 : 0);
+        AR(PC, PB);
         launches += 2;
         def = read_norm(w, PC, s);
         it = i;
@@ -429,6 +447,7 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
         if (gp) {  // z = W r, rho = z.r (the fused kernel computed r.r into PB: replace it)
           ops.prec(r, z);
           dot_kernel<<<NB, NT, 0, s>>>(n, z, r, PB, nullptr);
+          AR(PB, nullptr);
           launches++;
         }
         cg_direction_kernel<<<NB, NT, 0, s>>>(n, p, z ? z : r, PB, w->S);

@@ -152,6 +152,22 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   }
 }
 
+
+// y = J x on the overlapping partition: exchange of x's ghost layers hidden behind the interior tiles
+void apply_p2p_device(pdb200_operator* h, double* x, double* y) {
+  cudaStream_t side = p2p_stream(h->p2p);
+  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 0), h->stream));  // x is ready
+  PDB_CUDA(cudaStreamWaitEvent(side, p2p_event(h->p2p, 0), 0));
+  h->launches += p2p_push(h->p2p, h->P, x, side);
+  h->launches += p2p_wait_unpack(h->p2p, h->P, x, side);
+  // the boundary tiles follow the unpack on the (high-priority) side stream, so they fill in
+  // beside the last interior tiles instead of waiting for them; the outputs are disjoint
+  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_BOUNDARY, side);
+  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 1), side));
+  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_INTERIOR);
+  PDB_CUDA(cudaStreamWaitEvent(h->stream, p2p_event(h->p2p, 1), 0));
+}
+
 // y = J x with HOST vectors through the fast kernel: the vector is cut into windows of tile layers
 // along z; window c is computed as soon as its input layers (and one layer of window c+1) have
 // arrived, and its result travels back while the next window is computed.  PCIe is full duplex,
@@ -589,7 +605,7 @@ void point_diagonal_device(pdb200_operator* h, double* d) {
 
 // binds the operator (matrix-free or assembled) and the preconditioner, then runs the Krylov loop
 void solve_device(pdb200_operator* h, int solver, int precond, const double* values, int layout, double* z, double* r,
-                  double reduction, uint32_t maxiter, pdb200_solve_result* res) {
+                  double reduction, uint32_t maxiter, pdb200_solve_result* res, bool ovlp = false) {
   const DevParams& P = h->P;
   if (!h->krylov) h->krylov = krylov_create();
   KrylovOps ops;
@@ -651,7 +667,45 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
       throw Error("pdb200_solve: unknown preconditioner");
     }
   }
+  if (ovlp) {
+    // OverlappingOperator + OverlappingScalarProduct (backend/istl/ovlpistlsolverbackend.hh:40-134).  Vectors are kept
+    // in the unique representation (ghost layers zero) outside the operator: the apply makes its input consistent
+    // (owner -> ghost copy over the NVLink mailboxes, hidden behind the interior tiles), evaluates the local rows,
+    // zeroes the ghost rows of the result (set_constrained_dofs(cc, 0.0, y)) and drops the input's ghosts again, so
+    // every inner product is the disjoint dot product without a mask; the global sums go through the peer mailboxes.
+    if (!h->p2p || !h->comm)
+      throw Error("pdb200_solve_ovlp: call pdb200_halo_p2p_create / _connect and pdb200_comm_create / _connect first");
+    if (!P.dg) throw Error("pdb200_solve_ovlp: implemented for QkDG spaces (face-neighbour ghost layers)");
+    if (!values) {
+      ops.apply = [h](const double* in, double* out) {
+        apply_p2p_device(h, const_cast<double*>(in), out);
+        h->launches += launch_halo_zero(h->P, out, h->stream);
+        h->launches += launch_halo_zero(h->P, const_cast<double*>(in), h->stream);
+      };
+    } else {
+      auto mv = ops.apply;
+      ops.apply = [h, mv](const double* in, double* out) {
+        h->launches += p2p_push(h->p2p, h->P, in, h->stream);
+        h->launches += p2p_wait_unpack(h->p2p, h->P, const_cast<double*>(in), h->stream);
+        mv(in, out);
+        h->launches += launch_halo_zero(h->P, out, h->stream);
+        h->launches += launch_halo_zero(h->P, const_cast<double*>(in), h->stream);
+      };
+    }
+    ops.allreduce = [h](double* P1, double* P2) {
+      comm_allreduce_partials(h->comm, P1, P2, krylov_partial_count(), h->stream);
+    };
+    h->launches += launch_halo_zero(P, r, h->stream);
+  }
   h->launches += krylov_solve(h->krylov, solver, P.ndofs, ops, z, r, reduction, maxiter, h->stream, res);
+  if (ovlp) {
+    // hand back a consistent solution (the reference's vectors are consistent on the whole overlap)
+    h->launches += p2p_push(h->p2p, h->P, z, h->stream);
+    h->launches += p2p_wait_unpack(h->p2p, h->P, z, h->stream);
+    PDB_CUDA(cudaStreamSynchronize(h->stream));
+    p2p_check(h->p2p);
+    comm_check(h->comm);
+  }
 }
 
 }  // namespace
@@ -828,17 +882,59 @@ int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y) {
   ensure_device(h);
   if (!h->p2p) throw Error("call pdb200_halo_p2p_create / _connect first");
   if (!is_device_pointer(x) || !is_device_pointer(y)) throw Error("apply_p2p expects device pointers");
-  cudaStream_t side = p2p_stream(h->p2p);
-  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 0), h->stream));  // x is ready
-  PDB_CUDA(cudaStreamWaitEvent(side, p2p_event(h->p2p, 0), 0));
-  h->launches += p2p_push(h->p2p, h->P, x, side);
-  h->launches += p2p_wait_unpack(h->p2p, h->P, x, side);
-  // the boundary tiles follow the unpack on the (high-priority) side stream, so they fill in
-  // beside the last interior tiles instead of waiting for them; the outputs are disjoint
-  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_BOUNDARY, side);
-  PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 1), side));
-  run_vector_device(h, x, y, Mode::OnTheFly, PDB200_PART_INTERIOR);
-  PDB_CUDA(cudaStreamWaitEvent(h->stream, p2p_event(h->p2p, 1), 0));
+  apply_p2p_device(h, x, y);
+  PDB_CATCH
+}
+
+int pdb200_comm_create(pdb200_handle h, int rank, int size, pdb200_ipc_handle* mine) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!mine) throw Error("null argument");
+  if (h->comm) throw Error("reduction mailbox already created");
+  h->comm = comm_create(rank, size, mine);
+  PDB_CATCH
+}
+int pdb200_comm_connect(pdb200_handle h, int peer_rank, const pdb200_ipc_handle* peer) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->comm) throw Error("call pdb200_comm_create first");
+  comm_connect(h->comm, peer_rank, peer);
+  PDB_CATCH
+}
+int pdb200_comm_sum(pdb200_handle h, double* values, int count) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!h->comm) throw Error("call pdb200_comm_create / _connect first");
+  if (count < 1 || count > 2 || !values) throw Error("pdb200_comm_sum: one or two values");
+  const int nb = krylov_partial_count();
+  double* buf = nullptr;
+  PDB_CUDA(cudaMalloc(&buf, 2 * (size_t)nb * sizeof(double)));
+  struct F {
+    double* p;
+    ~F() { cudaFree(p); }
+  } guard{buf};
+  PDB_CUDA(cudaMemsetAsync(buf, 0, 2 * (size_t)nb * sizeof(double), h->stream));
+  PDB_CUDA(cudaMemcpyAsync(buf, values, sizeof(double), cudaMemcpyDefault, h->stream));
+  if (count == 2) PDB_CUDA(cudaMemcpyAsync(buf + nb, values + 1, sizeof(double), cudaMemcpyDefault, h->stream));
+  comm_allreduce_partials(h->comm, buf, count == 2 ? buf + nb : nullptr, nb, h->stream);
+  h->launches += 1;
+  PDB_CUDA(cudaMemcpyAsync(values, buf, sizeof(double), cudaMemcpyDefault, h->stream));
+  if (count == 2) PDB_CUDA(cudaMemcpyAsync(values + 1, buf + nb, sizeof(double), cudaMemcpyDefault, h->stream));
+  PDB_CUDA(cudaStreamSynchronize(h->stream));
+  comm_check(h->comm);
+  PDB_CATCH
+}
+int pdb200_solve_ovlp(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
+                      double reduction, uint32_t maxiter, pdb200_solve_result* res) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!z || !r || !res) throw Error("pdb200_solve_ovlp: null argument");
+  if (!is_device_pointer(z) || !is_device_pointer(r)) throw Error("pdb200_solve_ovlp expects device vectors");
+  solve_device(h, solver, precond, values, layout, z, r, reduction, maxiter, res, /*ovlp=*/true);
   PDB_CATCH
 }
 

@@ -30,6 +30,7 @@ struct pdb200_operator {
   FemPlan* fem = nullptr;
   MatrixPlan* matrix = nullptr;
   P2PHalo* p2p = nullptr;
+  PeerComm* comm = nullptr;  // all-ranks reduction mailbox of the overlapping solvers
   KrylovWork* krylov = nullptr;
   BlockJacPlan* blockjac = nullptr;
   double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
@@ -55,6 +56,7 @@ struct pdb200_operator {
     fem_plan_destroy(fem);
     matrix_plan_destroy(matrix);
     p2p_destroy(p2p);
+    comm_destroy(comm);
     krylov_destroy(krylov);
     dg_blockjac_destroy(blockjac);
   }

@@ -38,6 +38,7 @@ SYMBOLS = [
     "pdb200_onthefly_apply_part", "pdb200_halo_p2p_create", "pdb200_halo_p2p_connect",
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
+    "pdb200_comm_create", "pdb200_comm_connect", "pdb200_comm_sum", "pdb200_solve_ovlp",
     # OneStepGridOperator (bound in pdelab_b200.onestep)
     "pdb200_onestep_create", "pdb200_onestep_destroy", "pdb200_onestep_set_method", "pdb200_onestep_set_dt_mode",
     "pdb200_onestep_pre_step", "pdb200_onestep_time_at_stage", "pdb200_onestep_pre_stage",
@@ -101,6 +102,11 @@ def load_library():
     lib.pdb200_halo_p2p_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.pdb200_halo_exchange_p2p.argtypes = [vp, vp]
     lib.pdb200_onthefly_apply_p2p.argtypes = [vp, vp, vp]
+    lib.pdb200_comm_create.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.pdb200_comm_connect.argtypes = [vp, C.c_int, vp]
+    lib.pdb200_comm_sum.argtypes = [vp, vp, C.c_int]
+    lib.pdb200_solve_ovlp.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_uint32,
+                                      C.POINTER(SolveResult)]
     lib.pdb200_cell_dof_indices.argtypes = [vp, C.c_uint64, vp]
     lib.pdb200_constrained_dofs.argtypes = [vp, u64p, vp]
     lib.pdb200_quadrature.argtypes = [vp, vp, vp]
@@ -329,6 +335,31 @@ class GridOperator:
         """y = J x on the overlapping partition, exchange hidden behind the interior tiles."""
         self._chk(self.lib.pdb200_onthefly_apply_p2p(self._h, _ptr(x), _ptr(y)))
         return y
+
+    # overlapping solvers ---------------------------------------------------------------------
+    def comm_create(self, rank, size):
+        """Create this rank's reduction mailbox; returns the 64-byte IPC handle for the other ranks."""
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.pdb200_comm_create(self._h, rank, size, buf))
+        return buf.raw
+
+    def comm_connect(self, peer_rank, handle_bytes):
+        buf = C.create_string_buffer(bytes(handle_bytes), 64)
+        self._chk(self.lib.pdb200_comm_connect(self._h, peer_rank, buf))
+
+    def comm_sum(self, values):
+        """gridView().comm().sum of one or two float64 values (numpy array, in place), collective."""
+        self._chk(self.lib.pdb200_comm_sum(self._h, _ptr(values), int(values.size)))
+        return values
+
+    def solve_ovlp(self, z, r, reduction, solver=abi.SOLVER_BICGSTAB, precond=abi.PRECOND_NONE, values=None,
+                   layout=abi.LAYOUT_CSR, maxiter=5000):
+        """pdb200_solve on the overlapping partition (OverlappingOperator + OverlappingScalarProduct,
+        backend/istl/ovlpistlsolverbackend.hh:30-134): collective, device vectors, z consistent on return."""
+        res = SolveResult()
+        self._chk(self.lib.pdb200_solve_ovlp(self._h, solver, precond, _ptr(values), layout, _ptr(z), _ptr(r),
+                                             float(reduction), int(maxiter), C.byref(res)))
+        return res.as_dict()
 
     # misc ----------------------------------------------------------------------------------
     def set_stream(self, stream_ptr):

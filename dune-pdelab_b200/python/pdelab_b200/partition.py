@@ -361,3 +361,45 @@ class P2PHaloExchanger:
     def apply(self, x, y):
         """y = J x with the exchange overlapped with the interior tiles."""
         return self.go.apply_p2p(x, y)
+
+
+class OverlappingSolverBackend(P2PHaloExchanger):
+    """Krylov solvers on the overlapping partition — the role of the reference's ISTLBackend_OVLP_* classes
+    (backend/istl/ovlpistlsolverbackend.hh:477-560: OverlappingOperator + OverlappingScalarProduct + BiCGSTAB / CG)
+    with one process per GPU.  On top of the halo mailboxes every rank maps every other rank's reduction mailbox
+    (one all_gather at set-up); per solve there is no torch.distributed / NCCL call at all."""
+
+    def __init__(self, go, part, dist=None, solver=None, precond=None, maxiter=5000):
+        from . import abi
+        if dist is None:
+            import torch.distributed as dist
+        super().__init__(go, part, dist)
+        mine = go.comm_create(part.rank, part.world)
+        handles = [None] * part.world
+        dist.all_gather_object(handles, mine)
+        for r in range(part.world):
+            if r != part.rank:
+                go.comm_connect(r, handles[r])
+        dist.barrier()
+        self.solver = abi.SOLVER_BICGSTAB if solver is None else solver
+        self.precond = abi.PRECOND_NONE if precond is None else precond
+        self.maxiter = maxiter
+        self.result = None
+
+    def apply(self, *args):
+        """apply(z, r, reduction): matrix-free;  apply(values, z, r, reduction): the rank's assembled matrix
+        (the call signatures of the reference's back-ends, ovlpistlsolverbackend.hh:520-545)."""
+        if len(args) == 3:
+            z, r, reduction = args
+            values = None
+        else:
+            values, z, r, reduction = args
+        self.result = self.go.solve_ovlp(z, r, reduction, solver=self.solver, precond=self.precond, values=values,
+                                         maxiter=self.maxiter)
+        return self.result
+
+    def norm(self, v):
+        """OverlappingScalarProduct::norm of a vector in the unique representation (ghost rows zero)."""
+        import numpy as np
+        own = float((v * v).sum())
+        return float(np.sqrt(self.go.comm_sum(np.array([own]))[0]))

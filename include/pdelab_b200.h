@@ -312,6 +312,26 @@ int pdb200_halo_exchange_p2p(pdb200_handle h, double* x);
  * x's ghost layers are updated as a side effect.  Device pointers only. */
 int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y);
 
+/* ---- overlapping solvers on several GPUs --------------------------------------------------------------------
+ * OverlappingOperator, OverlappingScalarProduct and the Krylov loop of the ISTLBackend_OVLP_* back-ends
+ * (backend/istl/ovlpistlsolverbackend.hh:30-134, 477-560) with one process per GPU, device-resident:
+ *   apply : owner -> ghost copy of the input over the NVLink mailboxes (hidden behind the interior tiles), local rows,
+ *           ghost rows := 0 (set_constrained_dofs(cc, 0.0, y), :48-49)
+ *   dot   : disjoint inner product + sum over all ranks (:103-108) — the sum runs through a second set of
+ *           peer-mapped mailboxes (one kernel, no NCCL call, no host round trip; bit-identical on every rank)
+ * Set-up: every rank creates its reduction mailbox and connects every other rank's (the handles travel out of
+ * band like the halo mailboxes').  At most 16 ranks. */
+int pdb200_comm_create(pdb200_handle h, int rank, int size, pdb200_ipc_handle* mine);
+int pdb200_comm_connect(pdb200_handle h, int peer_rank, const pdb200_ipc_handle* peer);
+/* gridView().comm().sum of one or two doubles (host or device pointer), collective over all ranks */
+int pdb200_comm_sum(pdb200_handle h, double* values, int count);
+/* pdb200_solve on the overlapping partition (QkDG; needs the halo and the reduction mailboxes).  values == NULL:
+ * matrix-free operator; otherwise the local assembled matrix of the rank.  precond as pdb200_solve (block / point
+ * Jacobi are local to a cell / a row: no extra communication).  z, r: DEVICE vectors over the local box; the ghost
+ * rows of r are ignored, z is consistent (ghost layers filled) on return.  Collective: every rank calls it. */
+int pdb200_solve_ovlp(pdb200_handle h, int solver, int precond, const double* values, int layout, double* z, double* r,
+                      double reduction, uint32_t maxiter, pdb200_solve_result* res);
+
 /* stream control for device-pointer calls: `stream` is a cudaStream_t */
 int pdb200_set_stream(pdb200_handle h, void* stream);
 int pdb200_synchronize(pdb200_handle h);

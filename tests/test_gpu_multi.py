@@ -227,3 +227,117 @@ def test_qk_halo_apply_matches_global_oracle(cuda_lib, world, cells, degree):
         assert consistent, rank
         assert err < 1e-12, (rank, err)
         assert kern == "fem_kron"
+
+
+# ---- overlapping Krylov solvers: OverlappingOperator + OverlappingScalarProduct on the device ---------------
+
+def _solve_worker(rank, world, port, cells, solver, precond, assembled, out):
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [os.path.join(here, "..", "oracle"), here, os.path.join(here, "..", "dune-pdelab_b200", "python")]
+        import torch.distributed as dist
+        from oracle import Oracle
+        from pdelab_b200.capi import GridOperator
+        from pdelab_b200.partition import OverlappingPartition, OverlappingSolverBackend
+        from problems import kappa_field, mt_vector
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        part = OverlappingPartition.strong(cells, world, rank)
+        n = 27
+        ncg = int(np.prod(cells))
+        bg = mt_vector(ncg * n, seed=3).reshape(ncg, n)
+        kg = kappa_field(ncg)
+        gidx = part.local_cell_grid().reshape(-1)
+        own = part.owned_mask().reshape(-1)
+        b = np.full((gidx.size, n), 1e300)           # ghost rows of the right-hand side are ignored
+        b[own] = bg[gidx[own]]
+        spec = abi.ProblemSpec(part.local_cells, degree=2, lower=part.local_lower, upper=part.local_upper, alpha=3.0,
+                               a_mode=abi.A_SCALAR, A=kg[gidx], side_kind=part.side_kind, device=dev)
+        go = GridOperator(spec)
+        ls = OverlappingSolverBackend(go, part, dist, solver=solver, precond=precond, maxiter=2000)
+        # comm().sum: every rank contributes (rank + 1, 1)
+        s = go.comm_sum(np.array([rank + 1.0, 1.0]))
+        sum_ok = s[0] == world * (world + 1) / 2 and s[1] == world
+        bd = torch.from_numpy(b.reshape(-1)).cuda()
+        zd = torch.zeros_like(bd)
+        if assembled:
+            rowptr, colidx = go.fill_pattern()
+            values = torch.zeros(colidx.size, dtype=torch.float64, device="cuda")
+            go.jacobian(torch.zeros_like(bd), values, fresh=True)
+            res = ls.apply(values, zd, bd, 1e-9)
+        else:
+            res = ls.apply(zd, bd, 1e-9)
+        go.synchronize()
+        z = zd.cpu().numpy().reshape(-1, n)
+        # gather the owned parts into the global vector and check  J z = b  with the single-domain oracle
+        parts = [None] * world
+        dist.all_gather_object(parts, (gidx[own], z[own]))
+        zg = np.zeros((ncg, n))
+        for gi, zi in parts:
+            zg[gi] = zi
+        gspec = abi.ProblemSpec(cells, degree=2, alpha=3.0, a_mode=abi.A_SCALAR, A=kg)
+        jz = Oracle(gspec).jacobian_apply(zg.reshape(-1)).reshape(-1, n)
+        err = float(np.linalg.norm(jz - bg) / np.linalg.norm(bg))
+        # the returned solution is consistent: face ghosts hold the neighbour's owned values
+        lc = part.local_cells
+        coords = np.unravel_index(np.arange(gidx.size), lc[::-1])
+        outside = np.zeros(gidx.size, dtype=int)
+        for d in range(3):
+            c = coords[2 - d] + part.local_lo[d]
+            outside += ~((part.owned_lo[d] <= c) & (c < part.owned_hi[d]))
+        fg = outside == 1
+        consistent = bool(np.array_equal(z[fg], zg[gidx[fg]]))
+        # reference count: the same solver on the undivided grid (rank 0 only)
+        ref_it = None
+        if rank == 0:
+            gg = GridOperator(gspec.replace(device=dev))
+            zz = torch.zeros(ncg * n, dtype=torch.float64, device="cuda")
+            bb = torch.from_numpy(bg.reshape(-1).copy()).cuda()
+            vals = None
+            if assembled:
+                rp, ci = gg.fill_pattern()
+                vals = torch.zeros(ci.size, dtype=torch.float64, device="cuda")
+                gg.jacobian(torch.zeros_like(bb), vals, fresh=True)
+            ref_it = gg.solve(zz, bb, 1e-9, solver=solver, precond=precond, values=vals, maxiter=2000)["iterations"]
+        out.put((rank, err, res, sum_ok and consistent, ref_it, None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out.put((rank, 1.0, {}, False, None, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world,cells,solver,precond,assembled", [
+    (2, (8, 6, 12), abi.SOLVER_CG, abi.PRECOND_BLOCK_JACOBI, False),
+    (2, (8, 6, 12), abi.SOLVER_BICGSTAB, abi.PRECOND_NONE, False),
+    (4, (8, 12, 10), abi.SOLVER_CG, abi.PRECOND_JACOBI, False),
+    (2, (4, 4, 8), abi.SOLVER_BICGSTAB, abi.PRECOND_JACOBI, True),
+])
+def test_overlapping_solver_matches_global_problem(cuda_lib, world, cells, solver, precond, assembled):
+    """ISTLBackend_OVLP-style solve on 2 and 4 ranks: the gathered solution solves the undivided problem (oracle J),
+    every rank reports the same iteration count, and that count is the single-domain solver's (same Krylov recurrences,
+    sums in a different order)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_worker, args=(r, world, port, cells, solver, precond, assembled, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    its = set()
+    ref_it = None
+    for rank, err, r, ok, rit, tb in res:
+        assert tb is None, tb
+        assert r["converged"] == 1, (rank, r)
+        assert err < 1e-7, (rank, err)
+        assert ok, rank
+        its.add(r["iterations"])
+        ref_it = rit if rit is not None else ref_it
+    assert len(its) == 1, its
+    assert abs(its.pop() - ref_it) <= max(2, ref_it // 10), (res[0][2], ref_it)
