@@ -220,3 +220,146 @@ def test_distributed_qk_apply_matches_global_oracle(world, cells, degree):
     for rank, err, consistent, _ in res:
         assert consistent, rank                      # the whole extended box carries the global values
         assert err < 1e-12, (rank, err)
+
+
+# ---- overlapping Krylov solver: the scheme of pdb200_solve_ovlp restated on the CPU (gloo) --------------------
+# Vectors are ghost-free outside the operator: the apply makes its input consistent (halo exchange), evaluates the
+# local rows (ghost rows come out zero), and drops the input's ghosts again; every inner product is then the disjoint
+# dot product of OverlappingScalarProduct (backend/istl/ovlpistlsolverbackend.hh:103-108) plus one all_reduce.
+
+class _FakeGridOperator:
+    """Records the mailbox handshake of OverlappingSolverBackend (no device here)."""
+
+    def __init__(self, rank):
+        self.rank, self.calls = rank, []
+
+    def halo_p2p_create(self):
+        return b"H%03d" % self.rank + bytes(60)
+
+    def halo_p2p_connect(self, d, s, handle):
+        self.calls.append(("halo", d, s, bytes(handle[:4])))
+
+    def comm_create(self, rank, size):
+        self.calls.append(("comm_create", rank, size))
+        return b"C%03d" % rank + bytes(60)
+
+    def comm_connect(self, peer, handle):
+        self.calls.append(("comm", peer, bytes(handle[:4])))
+
+
+def _cg_worker(rank, world, port, cells, out):
+    sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "oracle"), os.path.dirname(__file__)]
+    from oracle import Oracle
+    from pdelab_b200.partition import OverlappingSolverBackend
+    from problems import kappa_field, mt_vector
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        degree, n = 1, 8
+        part = OverlappingPartition.strong(cells, world, rank)
+        # the set-up handshake: halo mailboxes to the face neighbours, reduction mailboxes to every other rank
+        fake = _FakeGridOperator(rank)
+        OverlappingSolverBackend(fake, part, dist)
+        want_calls = [("halo", d, s, b"H%03d" % nbr) for d, s, nbr in part.exchanges()]
+        want_calls += [("comm_create", rank, world)] + [("comm", r, b"C%03d" % r) for r in range(world) if r != rank]
+        handshake_ok = fake.calls == want_calls
+
+        ncg = int(np.prod(cells))
+        bg = mt_vector(ncg * n, seed=3).reshape(ncg, n)
+        kg = kappa_field(ncg)
+        gidx = part.local_cell_grid().reshape(-1)
+        own = part.owned_mask().reshape(-1)
+        spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QKDG, degree=degree, lower=part.local_lower,
+                               upper=part.local_upper, alpha=3.0, a_mode=abi.A_SCALAR, A=kg[gidx], side_kind=part.side_kind)
+        orc = Oracle(spec)
+
+        def pack(x, d, s, buf):
+            layer = 1 if s == 0 else part.local_cells[d] - 2
+            buf.copy_(x[torch.from_numpy(_layer_index(part, n, d, layer))])
+
+        def unpack(x, d, s, buf):
+            layer = 0 if s == 0 else part.local_cells[d] - 1
+            x[torch.from_numpy(_layer_index(part, n, d, layer))] = buf
+
+        halo = HaloExchanger(None, part, "cpu", pack=pack, unpack=unpack,
+                             layer_size=lambda d: int(np.prod(part.local_cells)) // part.local_cells[d] * n, dist=dist)
+        ghost = np.repeat(~own, n)
+
+        def apply(v):                      # OverlappingOperator::apply on a ghost-free vector
+            t = torch.from_numpy(v.copy())
+            halo.exchange(t)
+            y = orc.jacobian_apply(t.numpy())
+            assert np.all(y[ghost] == 0.0)
+            return y
+
+        def dot(a, b):                     # OverlappingScalarProduct::dot
+            s = torch.tensor([float(a @ b)], dtype=torch.float64)
+            dist.all_reduce(s)
+            return float(s)
+
+        b = np.zeros((gidx.size, n))
+        b[own] = bg[gidx[own]]
+        b = b.reshape(-1)
+        x = np.zeros_like(b)
+        r = b - apply(x)
+        p = r.copy()
+        rr = dot(r, r)
+        r0 = np.sqrt(rr)
+        its = 0
+        while np.sqrt(rr) > 1e-10 * r0 and its < 500:
+            q = apply(p)
+            lam = rr / dot(p, q)
+            x += lam * p
+            r -= lam * q
+            rr_new = dot(r, r)
+            p = r + (rr_new / rr) * p
+            rr = rr_new
+            its += 1
+        assert np.all(x[ghost] == 0.0) and np.all(r[ghost] == 0.0) and np.all(p[ghost] == 0.0)
+        out.put((rank, its, gidx[own], x.reshape(-1, n)[own], handshake_ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapping_cg_scheme_reproduces_the_undivided_solve():
+    """world_size 2 over gloo: the ghost-free CG of pdb200_solve_ovlp is the CG of the undivided problem."""
+    sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "oracle")]
+    from oracle import Oracle
+    from problems import kappa_field, mt_vector
+    world, cells, n = 2, (4, 3, 6), 8
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cg_worker, args=(r, world, port, cells, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ncg = int(np.prod(cells))
+    xg = np.zeros((ncg, n))
+    for _, _, gi, xi, ok in res:
+        xg[gi] = xi
+        assert ok
+    assert len({r[1] for r in res}) == 1
+    # the same CG on the undivided grid
+    orc = Oracle(abi.ProblemSpec(cells, space=abi.SPACE_QKDG, degree=1, alpha=3.0, a_mode=abi.A_SCALAR, A=kappa_field(ncg)))
+    b = mt_vector(ncg * n, seed=3)
+    x = np.zeros_like(b)
+    r = b.copy()
+    p = r.copy()
+    rr = r @ r
+    r0 = np.sqrt(rr)
+    its = 0
+    while np.sqrt(rr) > 1e-10 * r0 and its < 500:
+        q = orc.jacobian_apply(p)
+        lam = rr / (p @ q)
+        x += lam * p
+        r -= lam * q
+        rr_new = r @ r
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+        its += 1
+    assert abs(res[0][1] - its) <= 1, (res[0][1], its)
+    assert np.abs(xg.reshape(-1) - x).max() / np.abs(x).max() < 1e-8
