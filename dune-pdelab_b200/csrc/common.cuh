@@ -132,6 +132,11 @@ BlockJacPlan* dg_blockjac_create(const DevParams& P, const Kron1D& K);
 void dg_blockjac_destroy(BlockJacPlan*);
 void dg_blockjac_invalidate(BlockJacPlan*);  // coefficients changed
 int launch_dg_blockjac(BlockJacPlan*, const DevParams& P, const Kron1D& K, const double* r, double* z, cudaStream_t s);
+// y = D z (mode 1) or y -= D z (mode 2) with the same per-cell data
+int launch_dg_blockdiag(BlockJacPlan*, const DevParams& P, const Kron1D& K, const double* z, double* y, int mode, cudaStream_t s);
+// one block SOR sweep over hyperplane wavefronts (lexicographic = index-set order), in place
+int launch_dg_blocksor(BlockJacPlan*, const DevParams& P, const Kron1D& K, const double* d, double* v, double omega,
+                       bool backward, bool zero_start, cudaStream_t s);
 
 // halo.cu: pack / unpack one cell layer of a DG vector
 void launch_halo_copy(const DevParams& P, double* x, double* buf, int dir, int side, bool pack, cudaStream_t s);

@@ -168,9 +168,11 @@ __device__ __forceinline__ void bj_sweep(const double (&G)[(K + 1) * (K + 1)], d
     }
 }
 
-template <int DIM, int K>
+// MODE 0: z = D^-1 r;  1: z = D r;  2: z -= D r  (D = G^-1 diag(|K| den) G^-T with G^-1 = M G^T, G^-T = G M per direction)
+template <int DIM, int K, int MODE = 0>
 __global__ void __launch_bounds__(128) blockjac_apply_kernel(const DevParams P, const double* __restrict__ data,
-                                                             const double* __restrict__ r, double* __restrict__ z) {
+                                                             const double* __restrict__ r, double* __restrict__ z,
+                                                             const SmallConst<K> C = SmallConst<K>()) {
   constexpr int N1 = K + 1, N = SL<DIM, K>::N, PER = N1 + N1 * N1;
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= P.ncells) return;
@@ -198,6 +200,11 @@ __global__ void __launch_bounds__(128) blockjac_apply_kernel(const DevParams P, 
 #pragma unroll
     for (int i = 0; i < N1 * N1; i++) G[d][i] = __ldg(src + (long long)(N1 + i) * P.ncells);
   }
+  if (MODE != 0) {
+    small_mass<DIM, K, 0>(C, 1.0, t);
+    small_mass<DIM, K, 1>(C, 1.0, t);
+    if (DIM == 3) small_mass<DIM, K, 2>(C, 1.0, t);
+  }
   bj_sweep<DIM, K, 0, false>(G[0], t);
   bj_sweep<DIM, K, 1, false>(G[1], t);
   if (DIM == 3) bj_sweep<DIM, K, 2, false>(G[DIM - 1], t);
@@ -206,12 +213,118 @@ __global__ void __launch_bounds__(128) blockjac_apply_kernel(const DevParams P, 
   for (int i = 0; i < N; i++) {
     const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
     const double den = lam[0][i0] + lam[1][i1] + (DIM == 3 ? lam[DIM - 1][i2] : 0.0) + cc;
+    t[i] = MODE == 0 ? t[i] / (P.vol * den) : t[i] * (P.vol * den);
+  }
+  bj_sweep<DIM, K, 0, true>(G[0], t);
+  bj_sweep<DIM, K, 1, true>(G[1], t);
+  if (DIM == 3) bj_sweep<DIM, K, 2, true>(G[DIM - 1], t);
+  if (MODE != 0) {
+    small_mass<DIM, K, 0>(C, 1.0, t);
+    small_mass<DIM, K, 1>(C, 1.0, t);
+    if (DIM == 3) small_mass<DIM, K, 2>(C, 1.0, t);
+  }
+  if (MODE == 2) {
+    double old[N];
+    load_cell<N>(z + cell * N, old);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = old[i] - t[i];
+  }
+  store_cell<N>(z + cell * N, t);
+}
+
+// One wavefront of a block SOR sweep (BlockSORPreconditionerLocalOperator, backend/istl/matrixfree/
+// blocksorpreconditioner.hh:36-60:  for T_i in index order:  a_i = d_i - sum_{j != i} A_ij v_j,  D_i b_i = a_i,
+// v_i = (1 - omega) v_i + omega b_i,  in place).  Cells couple through faces only, so cell (i, j, k) depends on the
+// already updated (i-1, j, k), (i, j-1, k), (i, j, k-1) and on the old values of its upper neighbours: all cells of the
+// hyperplane i + j + k = s are independent and the sweep over s = 0 .. sum(N) - dim reproduces the lexicographic
+// (index-set) order of the reference exactly.  One thread per cell of the hyperplane: the cell's row of J v by the
+// Kronecker sweeps of dg_small.cu from the current v, then the exact block inverse by fast diagonalisation:
+//     v_i += omega D_i^-1 (d_i - (J v)_i)        (the same update, written with the full row).
+template <int DIM, int K>
+__global__ void __launch_bounds__(128) blocksor_wave_kernel(const DevParams P, const SmallConst<K> C,
+                                                            const double* __restrict__ data, const double* __restrict__ dvec,
+                                                            double* v, double omega, int wave) {
+  constexpr int N1 = K + 1, N = SL<DIM, K>::N, PER = N1 + N1 * N1;
+  const int Nx = P.N[0], Ny = P.N[1];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ntan = DIM == 3 ? (long long)Ny * P.N[2] : Ny;
+  if (tid >= ntan) return;
+  int g[3];
+  g[1] = (int)(tid % Ny);
+  g[2] = DIM == 3 ? (int)(tid / Ny) : 0;
+  g[0] = wave - g[1] - g[2];
+  if (g[0] < 0 || g[0] >= Nx) return;
+  const long long stride[3] = {1, Nx, (long long)Nx * Ny};
+  const long long cell = g[0] + stride[1] * g[1] + stride[2] * g[2];
+  double o[N], t[N];
+  {
+    const double* p = v + cell * N;  // plain loads: v is updated in place by earlier wavefronts
+#pragma unroll
+    for (int i = 0; i < N; i++) o[i] = p[i];
+  }
+  const double creact = P.c ? __ldg(P.c + cell) : 0.0;
+  bool constrained = false;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    double A0, cs[2], co[2], cg[2];
+    bool onb[2];
+    constrained |= direction_coefs<K>(P, C, cell, g, d, stride, A0, cs, co, cg, onb);
+    double nb[2][N];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      if (!onb[side]) {
+        const double* p = v + (cell + (side ? stride[d] : -stride[d])) * N;
+#pragma unroll
+        for (int i = 0; i < N; i++) nb[side][i] = p[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) nb[side][i] = 0.0;
+      }
+    }
+    if (d == 0)
+      small_sweep<DIM, K, 0, true>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], creact, t);
+    else if (d == 1)
+      small_sweep<DIM, K, 1, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t);
+    else
+      small_sweep<DIM, K, 2, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t);
+  }
+  if (constrained) {  // ghost cells of an overlapping partition: the correction vanishes there
+#pragma unroll
+    for (int i = 0; i < N; i++) v[cell * N + i] = 0.0;
+    return;
+  }
+  small_mass<DIM, K, 0>(C, C.vol, t);
+  small_mass<DIM, K, 1>(C, 1.0, t);
+  if (DIM == 3) small_mass<DIM, K, 2>(C, 1.0, t);
+  {
+    double dd[N];
+    load_cell<N>(dvec + cell * N, dd);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = dd[i] - t[i];
+  }
+  double lam[DIM][N1], G[DIM][N1 * N1];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    const double* src = data + (long long)d * PER * P.ncells + cell;
+#pragma unroll
+    for (int i = 0; i < N1; i++) lam[d][i] = __ldg(src + (long long)i * P.ncells);
+#pragma unroll
+    for (int i = 0; i < N1 * N1; i++) G[d][i] = __ldg(src + (long long)(N1 + i) * P.ncells);
+  }
+  bj_sweep<DIM, K, 0, false>(G[0], t);
+  bj_sweep<DIM, K, 1, false>(G[1], t);
+  if (DIM == 3) bj_sweep<DIM, K, 2, false>(G[DIM - 1], t);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int i0 = i % N1, i1 = (i / N1) % N1, i2 = i / (N1 * N1);
+    const double den = lam[0][i0] + lam[1][i1] + (DIM == 3 ? lam[DIM - 1][i2] : 0.0) + creact;
     t[i] = t[i] / (P.vol * den);
   }
   bj_sweep<DIM, K, 0, true>(G[0], t);
   bj_sweep<DIM, K, 1, true>(G[1], t);
   if (DIM == 3) bj_sweep<DIM, K, 2, true>(G[DIM - 1], t);
-  store_cell<N>(z + cell * N, t);
+#pragma unroll
+  for (int i = 0; i < N; i++) v[cell * N + i] = fma(omega, t[i], o[i]);
 }
 
 // point diagonal of the Jacobian: diag(D_e) = |K| [ sum_d (M T_d)_{i_d i_d} prod_{e != d} M_{i_e i_e} + c prod_d M_{i_d i_d} ]
@@ -353,6 +466,65 @@ int launch_dg_blockjac(BlockJacPlan* plan, const DevParams& P, const Kron1D& K1,
   }
   PDB_BJ(2, 1) PDB_BJ(2, 2) PDB_BJ(3, 1) PDB_BJ(3, 2)
 #undef PDB_BJ
+  PDB_CUDA(cudaGetLastError());
+  plan->valid = true;
+  return launches;
+}
+
+// mode 1: y = D z (BlockDiagonalLocalOperatorWrapper, localoperator/blockdiagonalwrapper.hh);  mode 2: y -= D z
+// (with y = J z before: the block off-diagonal part, localoperator/blockoffdiagonalwrapper.hh)
+int launch_dg_blockdiag(BlockJacPlan* plan, const DevParams& P, const Kron1D& K1, const double* z, double* y, int mode,
+                        cudaStream_t s) {
+  if (!dg_blockjac_supported(P))
+    throw Error("block diagonal: needs QkDG (k = 1, 2; dim = 2, 3), SIPG, diagonal A, b = 0");
+  if (mode != 1 && mode != 2) throw Error("launch_dg_blockdiag: mode");
+  int launches = 0;
+  const unsigned blocks = (unsigned)((P.ncells + 127) / 128);
+#define PDB_BD(DD, KK)                                                                              \
+  if (P.dim == DD && P.k == KK) {                                                                   \
+    if (!plan->valid) {                                                                             \
+      setup_variant<DD, KK>(plan, P, K1, s);                                                        \
+      launches++;                                                                                   \
+    }                                                                                               \
+    SmallConst<KK> C;                                                                               \
+    fill_small_const<KK>(C, P, K1);                                                                 \
+    if (mode == 1) blockjac_apply_kernel<DD, KK, 1><<<blocks, 128, 0, s>>>(P, plan->data, z, y, C); \
+    else blockjac_apply_kernel<DD, KK, 2><<<blocks, 128, 0, s>>>(P, plan->data, z, y, C);           \
+    launches++;                                                                                     \
+  }
+  PDB_BD(2, 1) PDB_BD(2, 2) PDB_BD(3, 1) PDB_BD(3, 2)
+#undef PDB_BD
+  PDB_CUDA(cudaGetLastError());
+  plan->valid = true;
+  return launches;
+}
+
+// one block SOR sweep in place: forward (index order) or backward (reverse order); zero_start: v := 0 first
+// (what a Krylov solver hands to a preconditioner).  Returns the number of launches.
+int launch_dg_blocksor(BlockJacPlan* plan, const DevParams& P, const Kron1D& K1, const double* d, double* v, double omega,
+                       bool backward, bool zero_start, cudaStream_t s) {
+  if (!dg_blockjac_supported(P))
+    throw Error("block SOR: needs QkDG (k = 1, 2; dim = 2, 3), SIPG, diagonal A, b = 0");
+  int launches = 0;
+  if (zero_start) PDB_CUDA(cudaMemsetAsync(v, 0, (size_t)P.ndofs * sizeof(double), s));
+  const long long ntan = P.dim == 3 ? (long long)P.N[1] * P.N[2] : P.N[1];
+  const unsigned blocks = (unsigned)((ntan + 127) / 128);
+  int nwaves = 1;  // hyperplanes i + j + k = 0 .. sum_d (N_d - 1)
+  for (int dd = 0; dd < P.dim; dd++) nwaves += P.N[dd] - 1;
+#define PDB_SOR(DD, KK)                                                                                      \
+  if (P.dim == DD && P.k == KK) {                                                                            \
+    if (!plan->valid) {                                                                                      \
+      setup_variant<DD, KK>(plan, P, K1, s);                                                                 \
+      launches++;                                                                                            \
+    }                                                                                                        \
+    SmallConst<KK> C;                                                                                        \
+    fill_small_const<KK>(C, P, K1);                                                                          \
+    for (int w = 0; w < nwaves; w++)                                                                         \
+      blocksor_wave_kernel<DD, KK><<<blocks, 128, 0, s>>>(P, C, plan->data, d, v, omega, backward ? nwaves - 1 - w : w); \
+    launches += nwaves;                                                                                      \
+  }
+  PDB_SOR(2, 1) PDB_SOR(2, 2) PDB_SOR(3, 1) PDB_SOR(3, 2)
+#undef PDB_SOR
   PDB_CUDA(cudaGetLastError());
   plan->valid = true;
   return launches;

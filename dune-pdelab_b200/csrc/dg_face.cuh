@@ -148,5 +148,71 @@ __device__ __forceinline__ void store_cell(double* __restrict__ p, const double 
   }
 }
 
+// ---- per-cell sweeps of the thread-per-cell kernels (dg_small.cu, block SOR in dg_blockjac.cu) -------------
+
+// t (+)= M^-1 L_d / h_d^2 along direction AXIS for all lines of the cell
+template <int DIM, int K, int AXIS, bool FIRST>
+__device__ __forceinline__ void small_sweep(const SmallConst<K>& C, const double (&o)[SL<DIM, K>::N],
+                                            const double (&l)[SL<DIM, K>::N], const double (&r)[SL<DIM, K>::N], double A0,
+                                            double csL, double coL, double cgL, double csR, double coR, double cgR,
+                                            double creact, double (&t)[SL<DIM, K>::N]) {
+  constexpr int N1 = K + 1, N = SL<DIM, K>::N;
+  constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
+  double T[N1 * N1], eL[N1], eR[N1], PL1[N1], PL2[N1], PR1[N1], PR2[N1];
+  own_matrix<K>(C, A0, csL, cgL, csR, cgR, T, eL, eR);
+#pragma unroll
+  for (int i = 0; i < N1; i++) {
+    PL1[i] = C.m0[i] * coL;
+    PL2[i] = -eL[i];
+    PR1[i] = -C.mk[i] * coR;
+    PR2[i] = -eR[i];
+  }
+#pragma unroll
+  for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+    for (int lo = 0; lo < S; lo++) {
+      const int base = hi * S * N1 + lo;
+      double dlo = 0.0, dro = 0.0;
+#pragma unroll
+      for (int j = 0; j < N1; j++) {
+        dlo = fma(C.d1[j], l[base + j * S], dlo);
+        dro = fma(C.d0[j], r[base + j * S], dro);
+      }
+#pragma unroll
+      for (int i = 0; i < N1; i++) {
+        double acc = FIRST ? creact * o[base + i * S] : t[base + i * S];
+#pragma unroll
+        for (int j = 0; j < N1; j++) acc = fma(T[i * N1 + j], o[base + j * S], acc);
+        acc = fma(PL1[i], dlo, acc);
+        acc = fma(PL2[i], l[base + K * S], acc);
+        acc = fma(PR1[i], dro, acc);
+        acc = fma(PR2[i], r[base], acc);
+        t[base + i * S] = acc;
+      }
+    }
+}
+
+template <int DIM, int K, int AXIS>
+__device__ __forceinline__ void small_mass(const SmallConst<K>& C, double s, double (&t)[SL<DIM, K>::N]) {
+  constexpr int N1 = K + 1, N = SL<DIM, K>::N;
+  constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
+#pragma unroll
+  for (int hi = 0; hi < N / (S * N1); hi++)
+#pragma unroll
+    for (int lo = 0; lo < S; lo++) {
+      const int base = hi * S * N1 + lo;
+      double in[N1];
+#pragma unroll
+      for (int j = 0; j < N1; j++) in[j] = t[base + j * S];
+#pragma unroll
+      for (int i = 0; i < N1; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < N1; j++) acc = fma(C.M[i * N1 + j] * s, in[j], acc);
+        t[base + i * S] = acc;
+      }
+    }
+}
+
 }  // namespace dgface
 }  // namespace pdb

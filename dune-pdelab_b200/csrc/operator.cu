@@ -624,6 +624,15 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
       ops.prec = [h](const double* in, double* out) {
         h->launches += launch_dg_blockjac(h->blockjac, h->P, h->K, in, out, h->stream);
       };
+    } else if (precond == PDB200_PRECOND_BLOCK_SOR || precond == PDB200_PRECOND_BLOCK_SSOR) {
+      // BlockSORPreconditionerLocalOperator (backend/istl/matrixfree/blocksorpreconditioner.hh) through
+      // GridOperatorPreconditioner::apply: v = 0, one forward sweep (SSOR: forward then backward, symmetric for CG)
+      if (!h->blockjac) h->blockjac = dg_blockjac_create(P, h->K);
+      const bool sym = precond == PDB200_PRECOND_BLOCK_SSOR;
+      ops.prec = [h, sym](const double* in, double* out) {
+        h->launches += launch_dg_blocksor(h->blockjac, h->P, h->K, in, out, h->relaxation, false, true, h->stream);
+        if (sym) h->launches += launch_dg_blocksor(h->blockjac, h->P, h->K, in, out, h->relaxation, true, false, h->stream);
+      };
     } else if (precond == PDB200_PRECOND_JACOBI) {  // point Jacobi on the matrix-free diagonal
       PDB_CUDA(cudaMalloc(&dinv, (size_t)P.ndofs * sizeof(double)));
       point_diagonal_device(h, dinv);
@@ -732,6 +741,56 @@ int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z) {
   h->launches += launch_dg_blockjac(h->blockjac, h->P, h->K, rs.dev, zs.dev, h->stream);
   zs.copy_out(h->stream);
   if (zs.owned || rs.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+
+int pdb200_block_diagonal_apply(pdb200_handle h, const double* z, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!z || !y) throw Error("pdb200_block_diagonal_apply: null argument");
+  if (!h->blockjac) h->blockjac = dg_blockjac_create(h->P, h->K);
+  Staged zs(const_cast<double*>(z), (size_t)h->P.ndofs, true, h->stream), ys(y, (size_t)h->P.ndofs, false, h->stream);
+  h->launches += launch_dg_blockdiag(h->blockjac, h->P, h->K, zs.dev, ys.dev, 1, h->stream);
+  ys.copy_out(h->stream);
+  if (zs.owned || ys.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+
+int pdb200_block_offdiagonal_apply(pdb200_handle h, const double* z, double* y) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!z || !y) throw Error("pdb200_block_offdiagonal_apply: null argument");
+  if (!h->blockjac) h->blockjac = dg_blockjac_create(h->P, h->K);
+  Staged zs(const_cast<double*>(z), (size_t)h->P.ndofs, true, h->stream), ys(y, (size_t)h->P.ndofs, false, h->stream);
+  run_vector_device(h, zs.dev, ys.dev, Mode::OnTheFly);                                          // y = J z
+  h->launches += launch_dg_blockdiag(h->blockjac, h->P, h->K, zs.dev, ys.dev, 2, h->stream);    // y -= D z
+  ys.copy_out(h->stream);
+  if (zs.owned || ys.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+
+int pdb200_block_sor_apply(pdb200_handle h, const double* d, double* v, double omega, int flags) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  ensure_device(h);
+  if (!d || !v) throw Error("pdb200_block_sor_apply: null argument");
+  if (!(omega > 0.0 && omega < 2.0)) throw Error("pdb200_block_sor_apply: omega must be in (0, 2)");
+  if (!h->blockjac) h->blockjac = dg_blockjac_create(h->P, h->K);
+  const bool backward = flags & PDB200_SOR_BACKWARD, keep = flags & PDB200_SOR_KEEP_ITERATE;
+  Staged ds(const_cast<double*>(d), (size_t)h->P.ndofs, true, h->stream), vs(v, (size_t)h->P.ndofs, keep, h->stream);
+  h->launches += launch_dg_blocksor(h->blockjac, h->P, h->K, ds.dev, vs.dev, omega, backward, !keep, h->stream);
+  vs.copy_out(h->stream);
+  if (ds.owned || vs.owned) PDB_CUDA(cudaStreamSynchronize(h->stream));
+  PDB_CATCH
+}
+
+int pdb200_set_relaxation(pdb200_handle h, double omega) {
+  PDB_TRY
+  PDB_CHECK_HANDLE(h);
+  if (!(omega > 0.0 && omega < 2.0)) throw Error("pdb200_set_relaxation: omega must be in (0, 2)");
+  h->relaxation = omega;
   PDB_CATCH
 }
 

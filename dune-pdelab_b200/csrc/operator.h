@@ -35,6 +35,7 @@ struct pdb200_operator {
   BlockJacPlan* blockjac = nullptr;
   double* r0 = nullptr;  // R(0) of the affine DG residual, cached per coefficient set (fast path)
   bool r0_valid = false;
+  double relaxation = 1.0;  // omega of the block SOR / SSOR preconditioners
   uint64_t launches = 0;
   uint64_t coeff_version = 0;  // bumped by pdb200_update_coefficients (one-step stage operators re-combine on change)
   const char* last_kernel = "";

@@ -17,7 +17,8 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 LAYOUT_CSR, LAYOUT_BCSR = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 SOLVER_BICGSTAB, SOLVER_CG = 0, 1
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1, 2
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_BLOCK_SOR, PRECOND_BLOCK_SSOR = 0, 1, 2, 3, 4
+SOR_BACKWARD, SOR_KEEP_ITERATE = 1, 2
 
 
 class Problem(C.Structure):

@@ -39,6 +39,7 @@ SYMBOLS = [
     "pdb200_halo_exchange_p2p", "pdb200_onthefly_apply_p2p",
     "pdb200_synchronize", "pdb200_launch_count", "pdb200_last_kernel", "pdb200_version",
     "pdb200_comm_create", "pdb200_comm_connect", "pdb200_comm_sum", "pdb200_solve_ovlp",
+    "pdb200_block_diagonal_apply", "pdb200_block_offdiagonal_apply", "pdb200_block_sor_apply", "pdb200_set_relaxation",
     # OneStepGridOperator (bound in pdelab_b200.onestep)
     "pdb200_onestep_create", "pdb200_onestep_destroy", "pdb200_onestep_set_method", "pdb200_onestep_set_dt_mode",
     "pdb200_onestep_pre_step", "pdb200_onestep_time_at_stage", "pdb200_onestep_pre_stage",
@@ -83,6 +84,10 @@ def load_library():
     lib.pdb200_csr_mv.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.pdb200_block_jacobi_apply.argtypes = [vp, vp, vp]
     lib.pdb200_point_diagonal.argtypes = [vp, vp]
+    lib.pdb200_block_diagonal_apply.argtypes = [vp, vp, vp]
+    lib.pdb200_block_offdiagonal_apply.argtypes = [vp, vp, vp]
+    lib.pdb200_block_sor_apply.argtypes = [vp, vp, vp, C.c_double, C.c_int]
+    lib.pdb200_set_relaxation.argtypes = [vp, C.c_double]
     lib.pdb200_solve.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_uint32,
                                  C.POINTER(SolveResult)]
     lib.pdb200_solve_stationary.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_uint32,
@@ -278,6 +283,26 @@ class GridOperator:
         backend/istl/matrixfree/assembledblockjacobipreconditioner.hh:96-230), matrix-free."""
         self._chk(self.lib.pdb200_block_jacobi_apply(self._h, _ptr(r), _ptr(z)))
         return z
+
+    def block_diagonal_apply(self, z, y):
+        """y = D z (BlockDiagonalLocalOperatorWrapper, localoperator/blockdiagonalwrapper.hh), matrix-free."""
+        self._chk(self.lib.pdb200_block_diagonal_apply(self._h, _ptr(z), _ptr(y)))
+        return y
+
+    def block_offdiagonal_apply(self, z, y):
+        """y = (J - D) z (BlockOffDiagonalLocalOperatorWrapper, localoperator/blockoffdiagonalwrapper.hh)."""
+        self._chk(self.lib.pdb200_block_offdiagonal_apply(self._h, _ptr(z), _ptr(y)))
+        return y
+
+    def block_sor_apply(self, d, v, omega=1.0, backward=False, keep_iterate=False):
+        """One block SOR sweep in index-set order (BlockSORPreconditionerLocalOperator,
+        backend/istl/matrixfree/blocksorpreconditioner.hh), matrix-free, in place in v."""
+        flags = (abi.SOR_BACKWARD if backward else 0) | (abi.SOR_KEEP_ITERATE if keep_iterate else 0)
+        self._chk(self.lib.pdb200_block_sor_apply(self._h, _ptr(d), _ptr(v), float(omega), flags))
+        return v
+
+    def set_relaxation(self, omega):
+        self._chk(self.lib.pdb200_set_relaxation(self._h, float(omega)))
 
     def point_diagonal(self, d):
         """d = diag(J), matrix-free (PointDiagonalLocalOperatorWrapper, localoperator/pointdiagonalwrapper.hh);

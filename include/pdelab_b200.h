@@ -185,7 +185,9 @@ int pdb200_csr_mv(pdb200_handle h, const double* values, int layout, const doubl
  * |defect| < reduction * |defect_0|  (two-norm, SequentialNorm).  Not converged within maxiter is
  * reported through res->converged == 0, not as an error (LinearSolverResult, backend/solver.hh:28-51). */
 enum { PDB200_SOLVER_BICGSTAB = 0, PDB200_SOLVER_CG = 1 };
-enum { PDB200_PRECOND_NONE = 0, PDB200_PRECOND_JACOBI = 1, PDB200_PRECOND_BLOCK_JACOBI = 2 };
+enum { PDB200_PRECOND_NONE = 0, PDB200_PRECOND_JACOBI = 1, PDB200_PRECOND_BLOCK_JACOBI = 2,
+       PDB200_PRECOND_BLOCK_SOR = 3,   /* one forward block SOR sweep from v = 0 (matrix-free, BiCGSTAB)           */
+       PDB200_PRECOND_BLOCK_SSOR = 4   /* forward + backward sweep: the symmetric variant a CG needs                */ };
 typedef struct pdb200_solve_result {
   int32_t converged;
   uint32_t iterations;
@@ -203,6 +205,26 @@ int pdb200_solve(pdb200_handle h, int solver, int precond, const double* values,
  * GridOperatorPreconditioner::apply (gridoperatorpreconditioner.hh:81-87).  Matrix-free: the blocks are
  * Kronecker sums and are inverted by fast diagonalisation (csrc/dg_blockjac.cu).  Host or device pointers. */
 int pdb200_block_jacobi_apply(pdb200_handle h, const double* r, double* z);
+
+/* y = D z with D the block diagonal of the QkDG Jacobian — BlockDiagonalLocalOperatorWrapper::jacobian_apply_volume /
+ * _skeleton / _boundary (localoperator/blockdiagonalwrapper.hh:100-300) — and y = (J - D) z, the block off-diagonal
+ * part — BlockOffDiagonalLocalOperatorWrapper (localoperator/blockoffdiagonalwrapper.hh:60-240).  Matrix-free from the
+ * same per-cell fast-diagonalisation data as pdb200_block_jacobi_apply.  Host or device pointers; y is overwritten. */
+int pdb200_block_diagonal_apply(pdb200_handle h, const double* z, double* y);
+int pdb200_block_offdiagonal_apply(pdb200_handle h, const double* z, double* y);
+
+/* One block SOR sweep, matrix-free — BlockSORPreconditionerLocalOperator (backend/istl/matrixfree/
+ * blocksorpreconditioner.hh:36-301) wrapped by GridOperatorPreconditioner::apply(v, d):
+ *   for every cell T_i in index-set order:  a_i = d_i - sum_{j != i} A_ij v_j;  solve D_i b_i = a_i;
+ *                                           v_i = (1 - omega) v_i + omega b_i            (in place).
+ * The sweep runs over the hyperplanes i + j + k = const of the structured grid (cells of one hyperplane are mutually
+ * independent, their lower neighbours are already updated): exactly the reference's sequential order.
+ * flags: PDB200_SOR_BACKWARD sweeps in reverse order; PDB200_SOR_KEEP_ITERATE starts from the v passed in instead of
+ * v = 0 (smoother use).  QkDG, k = 1, 2, SIPG, diagonal A, b = 0.  Host or device pointers. */
+enum { PDB200_SOR_BACKWARD = 1, PDB200_SOR_KEEP_ITERATE = 2 };
+int pdb200_block_sor_apply(pdb200_handle h, const double* d, double* v, double omega, int flags);
+/* omega of PDB200_PRECOND_BLOCK_SOR / _SSOR inside pdb200_solve (default 1.0) */
+int pdb200_set_relaxation(pdb200_handle h, double omega);
 
 /* d = point diagonal of the Jacobian, matrix-free (PointDiagonalLocalOperatorWrapper,
  * localoperator/pointdiagonalwrapper.hh: the diagonal a point-Jacobi preconditioner needs without an assembled

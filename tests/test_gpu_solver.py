@@ -218,3 +218,92 @@ def test_matrix_free_jacobi_cg_on_the_testmatrixfree_problem(cuda_lib):
     r1 = go.solve(np.zeros_like(b), b.copy(), 1e-8, solver=abi.SOLVER_CG)
     r2 = go.solve(np.zeros_like(b), b.copy(), 1e-8, solver=abi.SOLVER_CG, precond=abi.PRECOND_JACOBI)
     assert r1["converged"] == r2["converged"] == 1 and r2["iterations"] < r1["iterations"]
+
+
+# ---- block diagonal / off-diagonal wrappers and block SOR (backend/istl/matrixfree/blocksorpreconditioner.hh) -------
+
+def _dense_blocks(go, spec):
+    """Assembled Jacobian of the device path as a dense matrix (small problems) + the cell-block size."""
+    n, nd = spec.local_size, spec.num_dofs
+    rowptr, colidx = go.fill_pattern()
+    vals = go.jacobian(np.zeros(nd), np.zeros(colidx.size), fresh=True)
+    import scipy.sparse as sp
+    return sp.csr_matrix((vals, colidx.astype(np.int64), rowptr.astype(np.int64)), shape=(nd, nd)).toarray(), n
+
+
+SOR_CASES = [dict(cells=(6, 5), degree=1, a="scalar"), dict(cells=(5, 4), degree=2, a="diagonal", with_c=True),
+             dict(cells=(4, 3, 3), degree=1, a="diagonal", bc="mixed"), dict(cells=(4, 3, 2), degree=2, a="scalar"),
+             dict(cells=(3, 4, 5), degree=2, a="diagonal", with_c=True, extent=(1.0, 0.7, 1.3))]
+
+
+@pytest.mark.parametrize("case", SOR_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_block_diagonal_and_offdiagonal_wrappers(cuda_lib, case):
+    """BlockDiagonalLocalOperatorWrapper / BlockOffDiagonalLocalOperatorWrapper (localoperator/blockdiagonalwrapper.hh,
+    blockoffdiagonalwrapper.hh): D z and (J - D) z, matrix-free, against the blocks of the assembled Jacobian."""
+    spec = dg_problem(**case)
+    go = GridOperator(spec)
+    J, n = _dense_blocks(go, spec)
+    nd = spec.num_dofs
+    D = np.zeros_like(J)
+    for e in range(spec.ncells):
+        s = slice(e * n, (e + 1) * n)
+        D[s, s] = J[s, s]
+    z = mt_vector(nd, seed=8) - 0.5
+    assert rel_err(go.block_diagonal_apply(z, np.full(nd, np.nan)), D @ z) < 1e-12
+    assert rel_err(go.block_offdiagonal_apply(z, np.full(nd, np.nan)), (J - D) @ z) < 1e-12
+
+
+def _sor_reference(J, n, d, v, omega, backward=False):
+    """The algorithm of blocksorpreconditioner.hh:43-52, sequential, in index-set order."""
+    v = v.copy()
+    cells = range(J.shape[0] // n)
+    for e in (reversed(cells) if backward else cells):
+        s = slice(e * n, (e + 1) * n)
+        a = d[s] - J[s, :] @ v + J[s, s] @ v[s]
+        v[s] = (1.0 - omega) * v[s] + omega * np.linalg.solve(J[s, s], a)
+    return v
+
+
+@pytest.mark.parametrize("case", SOR_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_block_sor_sweep_is_the_sequential_sweep(cuda_lib, case):
+    """The hyperplane-wavefront sweep reproduces the reference's sequential block SOR sweep (same order of updates):
+    forward from v = 0 (preconditioner use), with relaxation, backward, and continuing from a given iterate."""
+    spec = dg_problem(**case)
+    go = GridOperator(spec)
+    J, n = _dense_blocks(go, spec)
+    nd = spec.num_dofs
+    d = mt_vector(nd, seed=9) - 0.5
+    zero = np.zeros(nd)
+    v1 = go.block_sor_apply(d, np.full(nd, np.nan))
+    assert rel_err(v1, _sor_reference(J, n, d, zero, 1.0)) < 1e-11
+    v2 = go.block_sor_apply(d, np.full(nd, np.nan), omega=1.3)
+    assert rel_err(v2, _sor_reference(J, n, d, zero, 1.3)) < 1e-11
+    v3 = go.block_sor_apply(d, v2.copy(), omega=0.9, backward=True, keep_iterate=True)
+    assert rel_err(v3, _sor_reference(J, n, d, v2, 0.9, backward=True)) < 1e-11
+    v4 = go.block_sor_apply(d, v3.copy(), omega=1.0, keep_iterate=True)
+    assert rel_err(v4, _sor_reference(J, n, d, v3, 1.0)) < 1e-11
+
+
+def test_block_sor_preconditioned_krylov(cuda_lib):
+    """ISTLBackend_SEQ_MatrixFree_Base with BlockSORPreconditionerLocalOperator (backends.hh:62-143): BiCGSTAB + block
+    SOR and CG + the symmetric sweep converge to the solution of the unpreconditioned solve in fewer iterations than
+    block Jacobi."""
+    import torch
+    spec = dg_problem((16, 12, 12), degree=2, a="scalar")
+    go = GridOperator(spec)
+    nd = spec.num_dofs
+    g = torch.Generator(device="cuda").manual_seed(4)
+    b = torch.rand(nd, dtype=torch.float64, device="cuda", generator=g)
+    z0, z1, z2, z3 = (torch.zeros_like(b) for _ in range(4))
+    bj = go.solve(z0, b.clone(), 1e-8, solver=abi.SOLVER_BICGSTAB, precond=abi.PRECOND_BLOCK_JACOBI)
+    sor = go.solve(z1, b.clone(), 1e-8, solver=abi.SOLVER_BICGSTAB, precond=abi.PRECOND_BLOCK_SOR)
+    ssor = go.solve(z2, b.clone(), 1e-8, solver=abi.SOLVER_CG, precond=abi.PRECOND_BLOCK_SSOR)
+    go.set_relaxation(1.2)
+    sor12 = go.solve(z3, b.clone(), 1e-8, solver=abi.SOLVER_BICGSTAB, precond=abi.PRECOND_BLOCK_SOR)
+    assert bj["converged"] == sor["converged"] == ssor["converged"] == sor12["converged"] == 1
+    assert sor["iterations"] < bj["iterations"], (sor, bj)
+    y = torch.empty_like(b)
+    for z in (z1, z2, z3):
+        go.apply(z, y)
+        assert float((y - b).norm() / b.norm()) < 5e-8
+        assert float((z - z0).norm() / z0.norm()) < 1e-5
