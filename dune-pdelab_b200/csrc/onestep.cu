@@ -122,6 +122,11 @@ __global__ void combine_tensor_kernel(double* __restrict__ out, int mode, int di
   }
 }
 
+__global__ void scale_kernel(double* __restrict__ y, double a, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] *= a;
+}
+
 __global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, double a, long long n) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) y[i] += a * x[i];
@@ -430,17 +435,9 @@ int pdb200_onestep_pre_stage_begin(pdb200_onestep_handle os, int stage) {
   OS_CATCH
 }
 
-int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* x) {
-  OS_TRY
-  OS_CHECK(os);
-  need_stage(os);
-  if (i < 0 || i >= os->stage_no || !x) throw Error("preStage: the solutions of stages 0..r-1 are needed");
-  PDB_CUDA(cudaSetDevice(os->go0->device));
-  // prestageengine.hh:180-186, 205-230
-  const double a = coef(os->a, os->s, os->stage_no, i), b = coef(os->b, os->s, os->stage_no, i);
-  const bool do0 = std::fabs(b) > 1e-6, do1 = std::fabs(a) > 1e-6;
-  double w0 = do0 ? b * os->dt_factor0 : 0.0, w1 = do1 ? a * os->dt_factor1 : 0.0;
-  if (!do0 && !do1) return 0;
+// const_residual += w0 R0(x) + w1 R1(x) through the fused stage operator (sign of w0 pulled out, see the header)
+static void add_weighted_residual(pdb200_onestep* os, double w0, double w1, const double* x) {
+  if (w0 == 0.0 && w1 == 0.0) return;
   const double sgn = w0 < 0.0 ? -1.0 : 1.0;
   combine(os, sgn * w0, sgn * w1);
   Staged X(os, &os->hx, x, true);
@@ -457,6 +454,65 @@ int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* 
     PDB_CUDA(cudaGetLastError());
   }
   if (X.host) PDB_CUDA(cudaStreamSynchronize(s));
+}
+
+int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* x) {
+  OS_TRY
+  OS_CHECK(os);
+  need_stage(os);
+  if (i < 0 || i >= os->stage_no || !x) throw Error("preStage: the solutions of stages 0..r-1 are needed");
+  PDB_CUDA(cudaSetDevice(os->go0->device));
+  // prestageengine.hh:180-186, 205-230
+  const double a = coef(os->a, os->s, os->stage_no, i), b = coef(os->b, os->s, os->stage_no, i);
+  const bool do0 = std::fabs(b) > 1e-6, do1 = std::fabs(a) > 1e-6;
+  add_weighted_residual(os, do0 ? b * os->dt_factor0 : 0.0, do1 ? a * os->dt_factor1 : 0.0, x);
+  OS_CATCH
+}
+
+// One stage of an EXPLICIT method (ExplicitOneStepMethod::apply, instationary/explicitonestep.hh:332-414 with
+// OneStepGridOperator::explicit_jacobian_residual, gridoperator/onestep.hh:161-178 and
+// onestep/jacobianresidualengine.hh:290-400):  D = -M,  alpha = sum_i a_ri R1(x_i),  beta = sum_i b_ri R0(x_i),
+// alpha += dt beta,  solve D x_r = alpha,  i.e.  x_r = -M^-1 (sum_{i<r} a_ri M x_i + b_ri dt R0(x_i)).
+// The mass matrix of a QkDG space is block diagonal: for k <= 2 the solve is the exact block inverse by fast
+// diagonalisation (one kernel, no Krylov loop), otherwise a CG on the mass operator to `reduction`.
+int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const double* const* x, double* xr, double reduction) {
+  OS_TRY
+  OS_CHECK(os);
+  need_method(os);
+  if (os->implicit_method) throw Error("explicit one step method called with implicit scheme");  // explicitonestep.hh:226-228
+  if (stage < 1 || stage > os->s || !x || !xr) throw Error("explicit stage: stage must be in 1..s and the vectors given");
+  pdb200_operator *g0 = os->go0, *g1 = os->go1;
+  if (!g0->P.dg)
+    throw Error("explicit one-step methods need a block-diagonal mass matrix (QkDG spaces)");
+  PDB_CUDA(cudaSetDevice(g0->device));
+  os->stage_no = stage;
+  os->stage->stream = g0->stream;
+  cudaStream_t s = os->stage->stream;
+  const long long n = g0->P.ndofs;
+  PDB_CUDA(cudaMemsetAsync(os->const_residual, 0, (size_t)n * sizeof(double), s));
+  for (int i = 0; i < stage; i++) {
+    if (!x[i]) throw Error("explicit stage: the solutions of stages 0..r-1 are needed");
+    const double a = coef(os->a, os->s, stage, i), b = coef(os->b, os->s, stage, i);
+    add_weighted_residual(os, std::fabs(b) > 1e-6 ? b * os->dt : 0.0, std::fabs(a) > 1e-6 ? a : 0.0, x[i]);
+  }
+  Staged XR(os, &os->hr, xr, true);
+  g1->stream = s;
+  if (dg_blockjac_supported(g1->P)) {
+    OS_C(pdb200_block_jacobi_apply(g1, os->const_residual, XR.dev));   // M^-1 (...)
+    scale_kernel<<<grid_for(n), 256, 0, s>>>(XR.dev, -1.0, n);
+    os->launches++;
+    PDB_CUDA(cudaGetLastError());
+  } else {
+    scale_kernel<<<grid_for(n), 256, 0, s>>>(os->const_residual, -1.0, n);
+    os->launches++;
+    PDB_CUDA(cudaGetLastError());
+    pdb200_solve_result res;
+    OS_C(pdb200_solve(g1, PDB200_SOLVER_CG, PDB200_PRECOND_NONE, nullptr, PDB200_LAYOUT_CSR, XR.dev, os->const_residual,
+                      reduction > 0.0 ? reduction : 1e-12, 5000, &res));
+    if (!res.converged) throw Error("explicit stage: the mass-matrix solve did not converge");
+  }
+  XR.copy_back();
+  PDB_CUDA(cudaStreamSynchronize(s));
   OS_CATCH
 }
 

@@ -265,6 +265,15 @@ class OneStepGridOperator {
     }
     setTime(timeAtStage((int)stage));  // residualengine.hh:155-156: the stage itself lives at t + d_r dt
   }
+  // explicit_jacobian_residual (onestep.hh:161-178) + the mass solve of ExplicitOneStepMethod::apply
+  // (instationary/explicitonestep.hh:365-407) as one device call: x_r = -M^-1 sum_i (a_ri M x_i + b_ri dt R0(x_i))
+  void explicit_stage(unsigned stage, const std::vector<Domain*>& x, Domain& xr, double reduction) {
+    if (implicit) throw Exception("This function should not be called in implicit mode");
+    if (x.size() < stage) throw Exception("explicit stage: the solutions of stages 0..r-1 are needed");
+    std::vector<const double*> ptrs(stage);
+    for (unsigned i = 0; i < stage; i++) ptrs[i] = x[i]->data();
+    check(pdb200_onestep_explicit_stage(os_, (int)stage, ptrs.data(), xr.data(), reduction), "explicit_jacobian_residual");
+  }
   // onestep.hh:141-149
   void residual(const Domain& x, Range& r) const {
     if (!implicit) throw Exception("This function should not be called in explicit mode");
@@ -442,6 +451,56 @@ class OneStepMethod {
   PDESOLVER& pdesolver_;
   int verbosity_ = 1, step_ = 1;
   Result res_;
+};
+
+// ---- instationary/explicitonestep.hh ---------------------------------------------------------------------
+// ExplicitOneStepMethod<T, IGOS, LS, TrlV, TstV, TC> (explicitonestep.hh:181-414) for QkDG spaces.  The linear solver
+// LS of the reference only ever sees the block-diagonal mass matrix; here that solve is the exact block inverse inside
+// pdb200_onestep_explicit_stage, so LS is accepted for interface parity and `reduction` is forwarded for the degrees
+// without a closed-form inverse.  The time-step controller (CFL limit) is not part of this path: dt is used as given.
+template <class T, class IGOS, class LS, class TrlV, class TstV = TrlV>
+class ExplicitOneStepMethod {
+ public:
+  ExplicitOneStepMethod(const TimeSteppingParameterInterface<T>& method, IGOS& igos, LS& ls, double ls_reduction = 0.99)
+      : method_(&method), igos_(igos), ls_(ls), reduction_(ls_reduction) {
+    if (method.implicit()) throw Exception("explicit one step method called with implicit scheme");  // :226-228
+  }
+  void setVerbosityLevel(int level) { verbosity_ = level; }
+  void setStepNumber(int newstep) { step_ = newstep; }
+  void setReduction(const double& r) { reduction_ = r; }
+  void setMethod(const TimeSteppingParameterInterface<T>& method) {
+    if (method.implicit()) throw Exception("explicit one step method called with implicit scheme");
+    method_ = &method;
+  }
+  // explicitonestep.hh:282-414
+  T apply(T time, T dt, TrlV& xold, TrlV& xnew) {
+    std::vector<TrlV*> x(1, &xold);
+    std::vector<std::unique_ptr<TrlV>> owned;
+    if (verbosity_ >= 1)
+      std::cout << "TIME STEP [" << method_->name() << "] " << std::setw(6) << step_ << " time (from): " << std::scientific
+                << time << " dt: " << dt << " time (to): " << time + dt << std::endl;
+    igos_.preStep(*method_, time, dt);
+    for (unsigned r = 1; r <= method_->s(); ++r) {
+      if (r == method_->s()) {
+        x.push_back(&xnew);
+      } else {
+        owned.emplace_back(new TrlV(igos_.trialGridFunctionSpace()));
+        x.push_back(owned.back().get());
+      }
+      igos_.explicit_stage(r, x, *x[r], reduction_ >= 0.99 ? 1e-12 : reduction_);
+      igos_.postStage();
+    }
+    igos_.postStep();
+    step_++;
+    return dt;
+  }
+
+ private:
+  const TimeSteppingParameterInterface<T>* method_;
+  IGOS& igos_;
+  LS& ls_;
+  double reduction_;
+  int verbosity_ = 1, step_ = 1;
 };
 
 }  // namespace B200

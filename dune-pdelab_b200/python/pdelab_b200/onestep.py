@@ -209,6 +209,7 @@ class OneStepGridOperator:
         lib.pdb200_onestep_pre_stage_begin.argtypes = [vp, C.c_int]
         lib.pdb200_onestep_pre_stage_add.argtypes = [vp, C.c_int, vp]
         lib.pdb200_onestep_const_residual.argtypes = [vp, vp]
+        lib.pdb200_onestep_explicit_stage.argtypes = [vp, C.c_int, C.POINTER(vp), vp, C.c_double]
         for name in ("pdb200_onestep_residual", "pdb200_onestep_jacobian_apply", "pdb200_onestep_onthefly_apply"):
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.pdb200_onestep_jacobian.argtypes = [vp, vp, vp, C.c_int]
@@ -288,6 +289,15 @@ class OneStepGridOperator:
             self._chk(self.lib.pdb200_onestep_pre_stage_add(self._h, i, _ptr(x[i])))
         self._stage = stage
         self._set_time(self.timeAtStage(stage))  # the stage operator itself lives at t + d_r dt
+
+    def explicit_stage(self, stage, x, xr, reduction=1e-12):
+        """One stage of an explicit method (explicit_jacobian_residual + the mass solve of ExplicitOneStepMethod::apply,
+        onestep.hh:161-178, instationary/explicitonestep.hh:365-407): xr = -M^-1 sum_i (a_ri M x_i + b_ri dt R0(x_i))."""
+        assert len(x) >= stage
+        ptrs = (C.c_void_p * stage)(*[_ptr(v) for v in x[:stage]])
+        self._chk(self.lib.pdb200_onestep_explicit_stage(self._h, int(stage), ptrs, _ptr(xr), float(reduction)))
+        self._stage = stage
+        return xr
 
     def const_residual(self, out):
         self._chk(self.lib.pdb200_onestep_const_residual(self._h, _ptr(out)))
@@ -392,6 +402,40 @@ class OneStepMethod:
             res = self._solve_stage(xr)                                 # :191 pdesolver.apply(*x[r])
             self.linear_solver_iterations += res["iterations"]
             self.last_results.append(res)
+            igos.postStage()
+        igos.postStep()
+        self.step += 1
+        return dt
+
+
+class ExplicitOneStepMethod:
+    """ExplicitOneStepMethod<T, IGOS, LS, TrlV, TstV, TC>::apply (instationary/explicitonestep.hh:282-414) for QkDG
+    spaces: every stage is one pass over the earlier stages plus the exact inverse of the block-diagonal mass matrix.
+    The reference's time-step controller (CFL limit from the local operator) is not part of this path: dt is used as
+    given (SimpleTimeController)."""
+
+    def __init__(self, method, igos: OneStepGridOperator, reduction=0.99):
+        if method.implicit():
+            raise PDELabError("explicit one step method called with implicit scheme")   # explicitonestep.hh:226-228
+        self.method, self.igos, self.reduction = method, igos, reduction
+        self.step = 1
+
+    def setMethod(self, method):
+        if method.implicit():
+            raise PDELabError("explicit one step method called with implicit scheme")
+        self.method = method
+
+    def setReduction(self, reduction):
+        self.reduction = reduction
+
+    def apply(self, time, dt, xold, xnew):
+        m, igos = self.method, self.igos
+        x = [xold]
+        igos.preStep(m, time, dt)
+        for r in range(1, m.s() + 1):
+            xr = xnew if r == m.s() else (xnew.clone() if hasattr(xnew, "clone") else xnew.copy())
+            igos.explicit_stage(r, x, xr, 1e-12 if self.reduction >= 0.99 else self.reduction)
+            x.append(xr)
             igos.postStage()
         igos.postStep()
         self.step += 1

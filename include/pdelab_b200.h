@@ -276,6 +276,13 @@ int pdb200_onestep_time_at_stage(pdb200_onestep_handle os, int stage, double* t)
 int pdb200_onestep_pre_stage(pdb200_onestep_handle os, int stage, const double* const* x);
 int pdb200_onestep_pre_stage_begin(pdb200_onestep_handle os, int stage);
 int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* x);
+/* One stage of an EXPLICIT method — ExplicitOneStepMethod::apply (instationary/explicitonestep.hh:332-414) with
+ * OneStepGridOperator::explicit_jacobian_residual (onestep.hh:161-178):
+ *   x_r = -M^-1 sum_{i<r} ( a_ri M x_i + b_ri dt R0(x_i; t + d_i dt) ).
+ * QkDG spaces (block-diagonal mass matrix): exact block inverse for k <= 2, CG on the mass operator to `reduction`
+ * otherwise.  x[0..stage-1]: earlier stages, xr: result (host or device).  The time-step controller of the reference
+ * (CFL limit) is the caller's business: dt is the one given to pdb200_onestep_pre_step. */
+int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const double* const* x, double* xr, double reduction);
 /* copy of the constant part of the residual assembled by preStage (host or device destination) */
 int pdb200_onestep_const_residual(pdb200_onestep_handle os, double* out);
 /* residual(x, r), onestep.hh:141-149 */

@@ -556,6 +556,43 @@ void instationary_dg_case() {
   V x_free = run(ls_free, "matrix-free CG + block Jacobi");
   V x_mat = run(ls_mat, "assembled CG + Jacobi");
   EXPECT(rel_err(x_free, x_mat.native()) < 1e-8, name << ": both solvers reach the same state " << rel_err(x_free, x_mat.native()));
+
+  // --- the same problem stepped explicitly (ExplicitOneStepMethod, instationary/explicitonestep.hh): RK4, dt well
+  // inside the diffusive stability limit; the mass solve is the exact block inverse on the device
+  {
+    using EIGO = PDELab::OneStepGridOperator<GO0, GO1, false>;
+    EIGO eigo(go0, go1);
+    PDELab::RK4Parameter<double> rk4;
+    using ELS = PDELab::ISTLBackend_SEQ_MatrixFree_CG_BlockJacobi<EIGO>;
+    ELS els(eigo, 100, 0);
+    PDELab::ExplicitOneStepMethod<double, EIGO, ELS, V, V> eosm(rk4, eigo, els);
+    eosm.setVerbosityLevel(0);
+    V xt(x);
+    double time = 0.0;
+    for (int step = 0; step < 20; step++) {
+      V xnew(gfs, 0.0);
+      eosm.apply(time, 2e-5, xt, xnew);
+      xt = xnew;
+      time += 2e-5;
+    }
+    const double err = l2_error_squared(gfs, xt, problem, go0.handle(), degree);
+    EXPECT(err <= 5e-6 && !std::isnan(err), name << ": explicit RK4, 20 steps: l2 error squared " << err << " <= 5e-6");
+    bool threw = false;
+    try {
+      V r(gfs, 0.0);
+      eigo.residual(xt, r);
+    } catch (PDELab::Exception&) {
+      threw = true;
+    }
+    EXPECT(threw, name << ": residual() of the explicit operator throws (onestep.hh:143-144)");
+    threw = false;
+    try {
+      PDELab::ExplicitOneStepMethod<double, EIGO, ELS, V, V> bad(method, eigo, els);
+    } catch (PDELab::Exception&) {
+      threw = true;
+    }
+    EXPECT(threw, name << ": explicit method with an implicit scheme throws (explicitonestep.hh:226-228)");
+  }
 }
 
 // conforming Q2 with Dirichlet constraints interpolated at every stage (implicitonestep.hh:264-400)

@@ -80,3 +80,22 @@ class OneStepOracle:
         for i in self.con:
             M.rows[i], M.data[i] = [int(i)], [1.0]
         return M.tocsr()
+
+
+def explicit_stage(spec0, spec1, method, stage, time, dt, xs):
+    """x_r = -M^-1 sum_{i<r} (a_ri M x_i + b_ri dt R0(x_i)): ExplicitOneStepMethod::apply, one stage
+    (instationary/explicitonestep.hh:365-407; D = -M by the weight -1 of onestep/jacobianresidualengine.hh:303)."""
+    import scipy.sparse.linalg as spla
+    o0, o1 = Oracle(spec0), Oracle(spec1)
+    n = spec0.num_dofs
+    alpha, beta = np.zeros(n), np.zeros(n)
+    for i in range(stage):
+        a, b = method.a(stage, i), method.b(stage, i)
+        if abs(b) > 1e-6:
+            beta += b * o0.residual(xs[i])
+        if abs(a) > 1e-6:
+            alpha += a * o1.residual(xs[i])
+    alpha += dt * beta
+    rp, ci, v = o1.jacobian()
+    M = sp.csr_matrix((v, ci.astype(np.int64), rp.astype(np.int64)), shape=(n, n))
+    return spla.spsolve((-M).tocsc(), alpha)

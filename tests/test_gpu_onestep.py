@@ -223,3 +223,52 @@ def test_fused_stage_equals_separate_operators_at_size(cuda_lib):
     want = method.b(1, 1) * dt * y0 + y1
     assert float((y - want).abs().max() / want.abs().max()) < TOL
     assert igo.stage_operator().last_kernel() == "dg_fast_q2_3d"
+
+
+EXPLICIT = {"explicit_euler": osm.ExplicitEulerParameter, "heun": osm.HeunParameter, "shu3": osm.Shu3Parameter,
+            "rk4": osm.RK4Parameter}
+
+
+@pytest.mark.parametrize("mname", list(EXPLICIT))
+@pytest.mark.parametrize("cname", ["dg_fast_scalar", "dg_small_2d_identity", "dg_kron_k3", "dg_generic_full_b"])
+def test_explicit_stages_match_the_oracle(cuda_lib, cname, mname):
+    """ExplicitOneStepMethod stage by stage (exact block mass inverse for k <= 2, CG on the mass operator for k = 3)
+    against the engines restated on the oracle with a sparse direct mass solve."""
+    from onestep_oracle import explicit_stage
+    spec0 = CASES[cname]()
+    spec1 = osm.l2_spec(spec0, 1.5)
+    method = EXPLICIT[mname]()
+    igo, _orc, _keep = _pair(spec0, scaling=1.5)
+    n = spec0.num_dofs
+    time, dt = 0.25, 1e-4
+    igo.preStep(method, time, dt)
+    xs = [mt_vector(n, seed=11 + i) - 0.5 for i in range(method.s())]
+    for r in range(1, method.s() + 1):
+        got = igo.explicit_stage(r, xs[:r], np.zeros(n))
+        want = explicit_stage(spec0, spec1, method, r, time, dt, xs[:r])
+        assert rel_err(got, want) < 1e-10, r
+    with pytest.raises(Exception, match="explicit mode"):
+        igo.residual(np.zeros(n), np.zeros(n))
+    with pytest.raises(Exception, match="implicit scheme"):
+        osm.ExplicitOneStepMethod(osm.Alexander2Parameter(), igo)
+
+
+def test_explicit_rk4_keeps_the_stationary_solution(cuda_lib):
+    """The heat problem of testinstationaryfastdgassembler.cc stepped explicitly (RK4, dt well inside the diffusive
+    stability limit of the 8x8 k=1 DG grid): 20 steps from the interpolated stationary solution stay within the
+    reference test's bound."""
+    from manufactured import l2_error_squared, node_coordinates
+    from pdelab_b200.capi import GridOperator
+    from test_onestep_oracle import heat_problem, u_exact
+    spec0 = heat_problem()
+    go0, go1 = GridOperator(spec0), GridOperator(osm.l2_spec(spec0))
+    igo = osm.OneStepGridOperator(go0, go1)
+    stepper = osm.ExplicitOneStepMethod(osm.RK4Parameter(), igo)
+    x = u_exact(node_coordinates(spec0))
+    time, dt = 0.0, 2e-5
+    for _ in range(20):
+        xnew = np.zeros_like(x)
+        stepper.apply(time, dt, x, xnew)
+        x, time = xnew, time + dt
+    assert np.all(np.isfinite(x))
+    assert l2_error_squared(spec0, x, u_exact, npts=7) <= 5e-6
