@@ -1101,6 +1101,13 @@ template <class GO>
 using ISTLBackend_SEQ_MatrixFree_BCGS_BlockJacobi = detail::MatrixFreeBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_BLOCK_JACOBI>;
 template <class GO>
 using ISTLBackend_SEQ_MatrixFree_CG_BlockJacobi = detail::MatrixFreeBackend<GO, PDB200_SOLVER_CG, PDB200_PRECOND_BLOCK_JACOBI>;
+// the same back-end with PrecGO built on BlockSORPreconditionerLocalOperator (backend/istl/matrixfree/
+// blocksorpreconditioner.hh:36-301; backends.hh:79-88 requires the FastDG grid operator for it): one matrix-free block
+// SOR sweep in index-set order per application; CG gets the symmetric (forward + backward) sweep
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_BCGS_BlockSOR = detail::MatrixFreeBackend<GO, PDB200_SOLVER_BICGSTAB, PDB200_PRECOND_BLOCK_SOR>;
+template <class GO>
+using ISTLBackend_SEQ_MatrixFree_CG_BlockSSOR = detail::MatrixFreeBackend<GO, PDB200_SOLVER_CG, PDB200_PRECOND_BLOCK_SSOR>;
 
 namespace detail {
 template <class GO, int SOLVER, int PRECOND>

@@ -296,6 +296,17 @@ void dg_case(int ncells, double alpha, double tol, const char* name, bool check_
     EXPECT(r3.converged && e3 <= tol && r3.linear_solver_iterations < r2.linear_solver_iterations,
            name << ": matrix-free BiCGSTAB + block Jacobi err^2 " << e3 << ", " << r3.linear_solver_iterations
                 << " iterations (unpreconditioned: " << r2.linear_solver_iterations << ")");
+    // and with the matrix-free block SOR preconditioner (blocksorpreconditioner.hh)
+    using LSS = PDELab::ISTLBackend_SEQ_MatrixFree_BCGS_BlockSOR<GridOperator>;
+    LSS linearSolverBlockSOR(gridOperator, 5000, 0);
+    V c4(gridFunctionSpace, 0.0);
+    PDELab::StationaryLinearProblemSolver<GridOperator, LSS, V> solverSOR(gridOperator, linearSolverBlockSOR, c4, 1e-12);
+    solverSOR.apply();
+    const auto r4 = solverSOR.result();
+    const double e4 = l2_error_squared(gridFunctionSpace, c4, problem, gridOperator.handle(), degree);
+    EXPECT(r4.converged && e4 <= tol && r4.linear_solver_iterations < r2.linear_solver_iterations,
+           name << ": matrix-free BiCGSTAB + block SOR err^2 " << e4 << ", " << r4.linear_solver_iterations
+                << " iterations (block Jacobi: " << r3.linear_solver_iterations << ")");
   }
 }
 
