@@ -272,3 +272,45 @@ def test_explicit_rk4_keeps_the_stationary_solution(cuda_lib):
         x, time = xnew, time + dt
     assert np.all(np.isfinite(x))
     assert l2_error_squared(spec0, x, u_exact, npts=7) <= 5e-6
+
+
+def test_reference_testinstationary_q2(cuda_lib):
+    """test/testinstationary.cc on the device: conforming Q2 32x32, L2, implicit Euler, dt = 0.1 to T = 1 from the
+    interpolated Dirichlet extension, squared L2 error <= 1e-7 (:193-196); testGridOperatorInterface (:7-16) on the
+    one-step operator; same end state as the oracle's time loop with a direct stage solver."""
+    import scipy.sparse.linalg as spla
+    from manufactured import l2_error_squared, node_coordinates
+    from onestep_oracle import OneStepOracle
+    from pdelab_b200.capi import GridOperator
+    from test_onestep_oracle import fem_heat_problem, u_centre
+    spec0 = fem_heat_problem()
+    spec1 = osm.l2_spec(spec0)
+    go0, go1 = GridOperator(spec0), GridOperator(spec1)
+    igo = osm.OneStepGridOperator(go0, go1)
+    method = osm.OneStepThetaParameter(1.0)
+    stepper = osm.OneStepMethod(method, igo, reduction=1e-12, solver=abi.SOLVER_CG, precond=abi.PRECOND_JACOBI)
+    x = u_centre(node_coordinates(spec0))
+    xo = x.copy()
+    orc = OneStepOracle(spec0, spec1)
+    time, dt = 0.0, 0.1
+    while time < 1.0 - 1e-8:
+        xnew = x.copy()
+        stepper.apply(time, dt, x, xnew)
+        x = xnew
+        orc.preStep(method, time, dt)
+        orc.preStage(1, [xo])
+        xo = xo - spla.spsolve(orc.matrix().tocsc(), orc.residual(xo.copy()))
+        time += dt
+    assert l2_error_squared(spec0, x, u_centre, npts=6) <= 1e-7
+    assert rel_err(x, xo) < 1e-9
+    # testGridOperatorInterface: residual, jacobian, jacobian_apply of the one-step operator on u = 0
+    n = spec0.num_dofs
+    u = np.zeros(n)
+    r = igo.residual(u, np.zeros(n))
+    rowptr, colidx = igo.fill_pattern()
+    vals = igo.jacobian(u, np.zeros(colidx.size))
+    y = igo.jacobian_apply(u, np.zeros(n))
+    assert rel_err(r, orc.residual(u)) < TOL and np.all(y == 0.0)
+    M = sp.csr_matrix((vals, colidx.astype(np.int64), rowptr.astype(np.int64)), shape=(n, n))
+    Mo = orc.matrix()
+    assert abs(M - Mo).max() / abs(Mo).max() < TOL

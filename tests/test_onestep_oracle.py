@@ -78,3 +78,35 @@ def test_one_step_residual_is_affine_and_consistent():
     assert np.allclose(os_.residual(x), M @ x + os_.residual(np.zeros_like(x)), rtol=0, atol=1e-11)
     assert np.allclose(os_.jacobian_apply(x), M @ x, rtol=0, atol=1e-11)
     assert np.abs(os_.const).max() > 0
+
+
+def u_centre(X):
+    return np.exp(-np.sum((X - 0.5) ** 2, axis=1))
+
+
+def fem_heat_problem(cells=(32, 32), degree=2):
+    """PoissonProblem of test/testinstationary.cc:19-52: f = 4 (1 - c) exp(-c), c = |x - 1/2|^2, Dirichlet g = exp(-c);
+    conforming Q2 on the 4x4 grid refined three times (:62-74)."""
+    spec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=degree)
+    return sample_data(spec, u_centre, lambda X: 4.0 * (1.0 - np.sum((X - 0.5) ** 2, axis=1)) * u_centre(X))
+
+
+def test_reference_testinstationary_on_the_oracle():
+    """test/testinstationary.cc: conforming Q2 32x32, L2 temporal operator, implicit Euler (OneStepThetaParameter(1.0)),
+    dt = 0.1 up to T = 1 from the interpolated Dirichlet extension; squared L2 error <= 1e-7 (:193-196); and the
+    grid-operator interface calls of testGridOperatorInterface (:7-16) on the one-step operator."""
+    spec0 = fem_heat_problem()
+    x = u_centre(node_coordinates(spec0))
+    method = osm.OneStepThetaParameter(1.0)
+    time, dt = 0.0, 0.1
+    os_ = OneStepOracle(spec0, osm.l2_spec(spec0))
+    while time < 1.0 - 1e-8:
+        os_.preStep(method, time, dt)
+        os_.preStage(1, [x])
+        xr = x.copy()                       # interpolate(...) leaves the (time-independent) Dirichlet values in place
+        xr -= spla.spsolve(os_.matrix().tocsc(), os_.residual(xr))
+        x, time = xr, time + dt
+    assert l2_error_squared(spec0, x, u_centre, npts=6) <= 1e-7
+    u = np.zeros(spec0.num_dofs)
+    assert np.all(np.isfinite(os_.residual(u))) and np.all(np.isfinite(os_.jacobian_apply(u)))
+    assert os_.matrix().shape == (spec0.num_dofs,) * 2
