@@ -70,3 +70,37 @@ def test_product_package_does_not_touch_the_oracle():
                 hit = re.search(r"^\s*(import|from)\s+oracle|liboracle|#\s*include\s*[<\"][^>\"]*oracle|oracle_[a-z_]+\s*\(",
                                 text, flags=re.M)
                 assert hit is None, (os.path.join(dirpath, fn), hit.group(0))
+
+
+def test_python_constants_match_the_header_enums():
+    """abi.py / onestep.py mirror the enums of include/pdelab_b200.h by value."""
+    from pdelab_b200 import onestep as osm
+    text = open(os.path.join(ROOT, "include", "pdelab_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = {}
+    for body in re.findall(r"enum\s*\{(.*?)\}", text, flags=re.S):
+        for name, val in re.findall(r"(PDB200_[A-Z0-9_]+)\s*=\s*(-?\d+)", body):
+            enums[name] = int(val)
+    assert len(enums) >= 35
+    want = {
+        "PDB200_SPACE_QKDG": abi.SPACE_QKDG, "PDB200_SPACE_QK": abi.SPACE_QK,
+        "PDB200_DG_NIPG": abi.DG_NIPG, "PDB200_DG_SIPG": abi.DG_SIPG, "PDB200_DG_IIPG": abi.DG_IIPG,
+        "PDB200_DG_WEIGHTS_ON": abi.DG_WEIGHTS_ON, "PDB200_DG_WEIGHTS_OFF": abi.DG_WEIGHTS_OFF,
+        "PDB200_BC_DIRICHLET": abi.BC_DIRICHLET, "PDB200_BC_NEUMANN": abi.BC_NEUMANN, "PDB200_BC_OUTFLOW": abi.BC_OUTFLOW,
+        "PDB200_BC_NONE": abi.BC_NONE,
+        "PDB200_A_IDENTITY": abi.A_IDENTITY, "PDB200_A_SCALAR": abi.A_SCALAR, "PDB200_A_DIAGONAL": abi.A_DIAGONAL,
+        "PDB200_A_FULL": abi.A_FULL,
+        "PDB200_SIDE_DOMAIN": abi.SIDE_DOMAIN, "PDB200_SIDE_PROCESSOR": abi.SIDE_PROCESSOR,
+        "PDB200_KERNEL_AUTO": abi.KERNEL_AUTO, "PDB200_KERNEL_GENERIC": abi.KERNEL_GENERIC, "PDB200_KERNEL_FAST": abi.KERNEL_FAST,
+        "PDB200_LAYOUT_CSR": abi.LAYOUT_CSR, "PDB200_LAYOUT_BCSR": abi.LAYOUT_BCSR,
+        "PDB200_PART_ALL": abi.PART_ALL, "PDB200_PART_INTERIOR": abi.PART_INTERIOR, "PDB200_PART_BOUNDARY": abi.PART_BOUNDARY,
+        "PDB200_SOLVER_BICGSTAB": abi.SOLVER_BICGSTAB, "PDB200_SOLVER_CG": abi.SOLVER_CG,
+        "PDB200_PRECOND_NONE": abi.PRECOND_NONE, "PDB200_PRECOND_JACOBI": abi.PRECOND_JACOBI,
+        "PDB200_PRECOND_BLOCK_JACOBI": abi.PRECOND_BLOCK_JACOBI, "PDB200_PRECOND_BLOCK_SOR": abi.PRECOND_BLOCK_SOR,
+        "PDB200_PRECOND_BLOCK_SSOR": abi.PRECOND_BLOCK_SSOR,
+        "PDB200_SOR_BACKWARD": abi.SOR_BACKWARD, "PDB200_SOR_KEEP_ITERATE": abi.SOR_KEEP_ITERATE,
+        "PDB200_ONESTEP_DIVIDE_OPERATOR1_BY_DT": osm.OneStepGridOperator.DivideOperator1ByDT,
+        "PDB200_ONESTEP_MULTIPLY_OPERATOR0_BY_DT": osm.OneStepGridOperator.MultiplyOperator0ByDT,
+        "PDB200_ONESTEP_DO_NOT_ASSEMBLE_DT": osm.OneStepGridOperator.DoNotAssembleDT,
+    }
+    assert enums == want
