@@ -329,6 +329,25 @@ class OneStepGridOperator:
     def fill_pattern(self, **kw):
         return self.go0.fill_pattern(**kw)
 
+    # onestep.hh:194-211
+    def interpolate(self, stage, xold, f, x):
+        """x = interpolation of f(t_stage) on the constrained DOFs, xold elsewhere.  f: call-back t -> vector of nodal
+        values in container order (what Dune::PDELab::interpolate(f, gfs, x) produces for Lagrange spaces)."""
+        t = self.timeAtStage(stage)
+        self._set_time(t)
+        if x is not xold:
+            x[:] = xold
+        con = self.go0.constrained_dofs().astype(np.int64)
+        if con.size:
+            vals = np.asarray(f(t), dtype=np.float64)
+            if hasattr(x, "data_ptr"):
+                import torch
+                idx = torch.from_numpy(con).to(x.device)
+                x[idx] = torch.from_numpy(vals[con]).to(x.device)
+            else:
+                x[con] = vals[con]
+        return x
+
     def stage_operator(self):
         h = C.c_void_p()
         self._chk(self.lib.pdb200_onestep_stage_operator(self._h, C.byref(h)))
@@ -382,22 +401,22 @@ class OneStepMethod:
             raise PDELabError("OneStepMethod: linear solver did not converge")
         return res
 
-    def apply(self, time, dt, xold, xnew):
-        """One step from xold (time) to xnew (time + dt); returns dt.  xnew holds the initial guess."""
+    def apply(self, time, dt, xold, xnew, f=None):
+        """One step from xold (time) to xnew (time + dt); returns dt.  xnew holds the initial guess.
+        With f (a call-back t -> vector of nodal values) the constrained DOFs of every stage are interpolated from f at
+        the stage time before the solve — the second overload of the reference (implicitonestep.hh:264-400)."""
         m, igos = self.method, self.igos
         x = [xold]
         igos.preStep(m, time, dt)                                       # :159
         self.last_results = []
         for r in range(1, m.s() + 1):
             igos.preStage(r, x)                                         # :174
-            if r == m.s():
-                xr = xnew
-                if r > 1:
-                    xr[:] = x[r - 1]
-            else:
-                xr = xnew.clone() if hasattr(xnew, "clone") else xnew.copy()
-                if r > 1:
-                    xr[:] = x[r - 1]
+            xr = xnew if r == m.s() else (xnew.clone() if hasattr(xnew, "clone") else xnew.copy())
+            init_guess = xnew if r == 1 else x[r - 1]
+            if xr is not init_guess:
+                xr[:] = init_guess
+            if f is not None:
+                igos.interpolate(r, init_guess, f, xr)                  # :351-352
             x.append(xr)
             res = self._solve_stage(xr)                                 # :191 pdesolver.apply(*x[r])
             self.linear_solver_iterations += res["iterations"]

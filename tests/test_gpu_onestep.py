@@ -314,3 +314,23 @@ def test_reference_testinstationary_q2(cuda_lib):
     M = sp.csr_matrix((vals, colidx.astype(np.int64), rowptr.astype(np.int64)), shape=(n, n))
     Mo = orc.matrix()
     assert abs(M - Mo).max() / abs(Mo).max() < TOL
+
+
+def test_reference_time_dependent_boundary(cuda_lib):
+    """test/testtimedependentboundary_ovlpqk.cc (one rank) on the device: Q1 32 x 32, f = 1, g = t, implicit Euler with
+    dt = 0.01 to T = 1, boundary values interpolated at every stage; sum (v - T)^2 <= 1e-18 (:206-216)."""
+    from pdelab_b200.capi import GridOperator
+    from test_onestep_oracle import time_boundary_problem
+    spec0 = time_boundary_problem()
+    go0, go1 = GridOperator(spec0), GridOperator(osm.l2_spec(spec0))
+    igo = osm.OneStepGridOperator(go0, go1)
+    stepper = osm.OneStepMethod(osm.OneStepThetaParameter(1.0), igo, reduction=1e-11, solver=abi.SOLVER_CG,
+                                precond=abi.PRECOND_JACOBI)
+    n = spec0.num_dofs
+    x = np.zeros(n)
+    time, dt = 0.0, 0.01
+    while time < 1.0 - 1e-8:
+        xnew = x.copy()
+        stepper.apply(time, dt, x, xnew, f=lambda t: np.full(n, t))
+        x, time = xnew, time + dt
+    assert float(np.sum((x - time) ** 2)) <= 1e-18

@@ -110,3 +110,87 @@ def test_reference_testinstationary_on_the_oracle():
     u = np.zeros(spec0.num_dofs)
     assert np.all(np.isfinite(os_.residual(u))) and np.all(np.isfinite(os_.jacobian_apply(u)))
     assert os_.matrix().shape == (spec0.num_dofs,) * 2
+
+
+def time_boundary_problem(cells=(32, 32)):
+    """ConvectionDiffusionModelProblem of test/testtimedependentboundary_ovlpqk.cc:25-115: A = I, f = 1, Dirichlet
+    g(x, t) = t everywhere, conforming Q1 on 32 x 32 (:228-247); the solution is u = t."""
+    spec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=1)
+    return spec.replace(f=np.ones((spec.ncells, spec.nq)))
+
+
+def test_reference_time_dependent_boundary_on_the_oracle():
+    """test/testtimedependentboundary_ovlpqk.cc (sequential): implicit Euler, dt = 0.01 to T = 1, the Dirichlet values
+    g = t interpolated at every stage (OneStepMethod::apply with f, implicitonestep.hh:264-400); sum (v - T)^2 <= 1e-18
+    (:206-216)."""
+    spec0 = time_boundary_problem()
+    os_ = OneStepOracle(spec0, osm.l2_spec(spec0))
+    method = osm.OneStepThetaParameter(1.0)
+    n = spec0.num_dofs
+    x = np.zeros(n)                                   # interpolate(gf, gfs, zs) at t = 0
+    time, dt = 0.0, 0.01
+    lu = None
+    while time < 1.0 - 1e-8:
+        os_.preStep(method, time, dt)
+        os_.preStage(1, [x])
+        xr = x.copy()
+        xr[os_.con] = time + dt                       # igos.interpolate(r, init_guess, gf, x[r])
+        if lu is None:
+            lu = spla.splu(os_.matrix().tocsc())      # the stage matrix does not change from step to step
+        xr -= lu.solve(os_.residual(xr))
+        x, time = xr, time + dt
+    assert float(np.sum((x - time) ** 2)) <= 1e-18
+
+
+class _OracleBackedIGO(osm.OneStepGridOperator):
+    """The host-side mirror (OneStepGridOperator / OneStepMethod of pdelab_b200.onestep) with the device calls replaced
+    by the oracle restatement, so that the HOST logic (stage loop, initial guesses, boundary interpolation) runs in
+    the CPU suite.  Only the methods that cross the C ABI are overridden."""
+
+    def __init__(self, spec0, spec1):  # noqa: D401 — no library, no device
+        self.orc = OneStepOracle(spec0, spec1)
+        self._time_dependent = None
+        self._sampled_time = None
+
+        class _GO0:
+            def constrained_dofs(_self):
+                return self.orc.con.astype(np.uint64)
+        self.go0 = _GO0()
+
+    def __del__(self):
+        pass
+
+    def preStep(self, method, time, dt):
+        self._m, self._t, self._dt = method, time, dt
+        self.orc.preStep(method, time, dt)
+
+    def timeAtStage(self, stage):
+        return self._t + self._m.d(stage) * self._dt
+
+    def preStage(self, stage, x):
+        self.orc.preStage(stage, [np.asarray(v) for v in x[:stage]])
+
+    def solve_stationary(self, x, **kw):
+        x -= spla.spsolve(self.orc.matrix().tocsc(), self.orc.residual(x.copy()))
+        return dict(converged=1, iterations=1)
+
+
+def test_host_mirror_stage_loop_with_boundary_interpolation():
+    """OneStepMethod.apply(time, dt, xold, xnew, f) of the Python mirror (implicitonestep.hh:264-400) on the
+    time-dependent boundary problem, two-stage method: the interpolated Dirichlet values follow g = t at the stage times
+    and the exact solution u = t is reproduced."""
+    spec0 = time_boundary_problem((8, 8))
+    igo = _OracleBackedIGO(spec0, osm.l2_spec(spec0))
+    stepper = osm.OneStepMethod(osm.Alexander2Parameter(), igo)
+    n = spec0.num_dofs
+    x = np.zeros(n)
+    time, dt = 0.0, 0.05
+    seen = []
+    for _ in range(4):
+        xnew = x.copy()
+        stepper.apply(time, dt, x, xnew, f=lambda t: (seen.append(t), np.full(n, t))[1])
+        x, time = xnew, time + dt
+    assert float(np.sum((x - time) ** 2)) <= 1e-20
+    m = osm.Alexander2Parameter()
+    assert np.allclose(seen[:2], [m.d(1) * dt, dt]) and len(seen) == 8
+    assert stepper.linear_solver_iterations == 8 and stepper.step == 5
