@@ -1,0 +1,60 @@
+"""The C++ host partition (dune-pdelab_b200/host/partition.hh) against the Python one (pdelab_b200/partition.py), rank by
+rank: processor grids, owned / local boxes, processor sides, neighbours, local -> global cell maps and owned masks.
+CPU only (pure index arithmetic); the same program instantiates the C++ halo exchanger and overlapping solver back-end
+so that they stay compile-checked against the C ABI."""
+import json
+import os
+import subprocess
+
+import numpy as np
+
+from pdelab_b200.partition import OverlappingPartition, processor_grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_partition.cc")
+EXE = os.path.join(ROOT, "tests", "cpp", "_build", "test_partition")
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _build():
+    from pdelab_b200 import capi
+    capi.load_library()
+    deps = [SRC, os.path.join(ROOT, "dune-pdelab_b200", "host", "partition.hh"),
+            os.path.join(ROOT, "dune-pdelab_b200", "host", "gridoperator.hh"), os.path.join(ROOT, "include", "pdelab_b200.h")]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return EXE
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.run([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", EXE, SRC,
+                    "-L", os.path.join(ROOT, "dune-pdelab_b200", "lib"), "-lpdelab_b200",
+                    "-Wl,-rpath,$ORIGIN/../../../dune-pdelab_b200/lib"], check=True)
+    return EXE
+
+
+def test_cpp_partition_equals_python_partition():
+    out = subprocess.run([_build()], capture_output=True, text=True, check=True).stdout
+    recs = [json.loads(line) for line in out.splitlines()]
+    assert len(recs) > 100
+    checked = 0
+    for r in recs:
+        if r.get("split_x"):
+            assert tuple(r["procs"]) == processor_grid(r["world"], 3, split_x=True) + (1,) * 0
+            continue
+        cells, world, rank = tuple(r["cells"]), r["world"], r["rank"]
+        p = OverlappingPartition.weak(cells, world, rank) if r["weak"] else OverlappingPartition.strong(cells, world, rank)
+        dim = r["dim"]
+        assert tuple(r["procs"][:dim]) == p.procs[:dim] and all(v == 1 for v in r["procs"][dim:])
+        for key in ("global_cells", "coords", "owned_lo", "owned_hi", "local_lo", "local_hi", "local_cells"):
+            assert tuple(r[key]) == tuple(getattr(p, key)), (key, r, getattr(p, key))
+        assert [list(s) for s in r["side_kind"]] == [list(s) for s in p.side_kind]
+        assert [tuple(e) for e in r["exchanges"]] == p.exchanges()
+        assert np.allclose(r["local_lower"], p.local_lower, rtol=0, atol=0) and np.allclose(r["local_upper"], p.local_upper, rtol=0, atol=0)
+        g = p.local_cell_grid().reshape(-1).astype(np.uint64)
+        own = p.owned_mask().reshape(-1)
+        c = np.arange(g.size, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            h = int(((c + np.uint64(1)) * (g + np.uint64(7))).sum(dtype=np.uint64))
+            ho = int(((c[own] + np.uint64(3)) * (g[own] + np.uint64(1))).sum(dtype=np.uint64))
+        assert int(r["map_hash"]) == h and int(r["owned_hash"]) == ho and r["owned"] == int(own.sum())
+        assert r["grid_cells0"] == p.local_cells[0]
+        checked += 1
+    assert checked == 3 * sum((1, 2, 3, 4, 6, 8, 12))
