@@ -58,3 +58,24 @@ def test_cpp_partition_equals_python_partition():
         assert r["grid_cells0"] == p.local_cells[0]
         checked += 1
     assert checked == 3 * sum((1, 2, 3, 4, 6, 8, 12))
+
+
+def test_cpp_time_stepping_tables_equal_the_python_tables():
+    """host/onestep.hh and pdelab_b200/onestep.py restate instationary/onestepparameter.hh independently: same entries."""
+    from pdelab_b200 import capi, onestep as osm
+    capi.load_library()
+    src = os.path.join(ROOT, "tests", "cpp", "test_tables.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_tables")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, src,
+                    "-L", os.path.join(ROOT, "dune-pdelab_b200", "lib"), "-lpdelab_b200",
+                    "-Wl,-rpath,$ORIGIN/../../../dune-pdelab_b200/lib"], check=True)
+    recs = [json.loads(line) for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()]
+    assert len(recs) == 9
+    for r in recs:
+        m = osm.OneStepThetaParameter(0.5) if r["class"].startswith("OneStepTheta") else getattr(osm, r["class"])()
+        assert m.s() == r["s"] and m.implicit() == r["implicit"] and m.name() == r["name"], r["class"]
+        for k in range(1, m.s() + 1):
+            assert [m.a(k, i) for i in range(k + 1)] == r["a"][k - 1], (r["class"], "a", k)
+            assert [m.b(k, i) for i in range(k + 1)] == r["b"][k - 1], (r["class"], "b", k)
+        assert [m.d(i) for i in range(m.s() + 1)] == r["d"], r["class"]
