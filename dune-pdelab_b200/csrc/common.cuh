@@ -26,6 +26,7 @@ struct DevParams {
   double h[3], ih[3], area[3], vol;
   double theta, alpha;
   int weights_on, a_mode, dg;
+  int basis;  // PDB200_BASIS_* of the QkDG space (the Kronecker kernels are written for the Lagrange basis)
   int side_kind[3][2];
   long long bf_off[3][2];
   const double *A, *b, *c, *f, *g, *j, *o;

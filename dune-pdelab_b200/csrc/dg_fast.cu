@@ -455,7 +455,7 @@ struct FastPlan {
 };
 
 bool dg_fast_supported(const DevParams& P) {
-  return P.dg && P.dim == 3 && P.k == 2 && P.m >= 3 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && P.k == 2 && P.m >= 3 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
          P.N[0] % 2 == 0;
 }
 

@@ -474,7 +474,7 @@ struct KronPlan {
 };
 
 bool dg_kron_supported(const DevParams& P) {
-  return P.dg && P.dim == 3 && (P.k == 4 || P.k == 3) && P.m >= P.k + 1 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && (P.k == 4 || P.k == 3) && P.m >= P.k + 1 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
          P.N[0] % 2 == 0;
 }
 

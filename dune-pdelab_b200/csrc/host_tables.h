@@ -52,6 +52,63 @@ inline long double host_lagrange_dp_ld(int k, int i, long double x) {
   return r;
 }
 
+// shifted Legendre polynomials P_n(2x - 1) and derivatives (finiteelement/qkdglegendre.hh:76-139)
+inline void host_legendre_ld(int k, long double x, long double* v, long double* dv) {
+  v[0] = 1;
+  dv[0] = 0;
+  if (k >= 1) {
+    v[1] = 2 * x - 1;
+    dv[1] = 2;
+  }
+  for (int n = 2; n <= k; n++) {
+    v[n] = ((2 * n - 1) * (2 * x - 1) * v[n - 1] - (n - 1) * v[n - 2]) / n;
+    dv[n] = (2 * x - 1) * dv[n - 1] + 2 * n * v[n - 1];
+  }
+}
+// Gauss-Lobatto points on [0,1], ascending (finiteelement/qkdglobatto.hh:28-66 sorts dune-geometry's GaussLobatto rule
+// so that the lower half lies below 1/2; closed forms of the roots of P_k' for k <= 4)
+inline void host_lobatto_points(int k, long double* xi) {
+  long double t[5] = {0, 0, 0, 0, 0};
+  switch (k) {
+    case 1: t[0] = -1, t[1] = 1; break;
+    case 2: t[0] = -1, t[1] = 0, t[2] = 1; break;
+    case 3: t[0] = -1, t[1] = -sqrtl(0.2L), t[2] = sqrtl(0.2L), t[3] = 1; break;
+    default: t[0] = -1, t[1] = -sqrtl(3.0L / 7.0L), t[2] = 0, t[3] = sqrtl(3.0L / 7.0L), t[4] = 1; break;
+  }
+  for (int i = 0; i <= k; i++) xi[i] = (1 + t[i]) / 2;
+}
+inline long double host_nodal_p_ld(int k, const long double* xi, int i, long double x) {
+  long double r = 1;
+  for (int j = 0; j <= k; j++)
+    if (j != i) r *= (x - xi[j]) / (xi[i] - xi[j]);
+  return r;
+}
+inline long double host_nodal_dp_ld(int k, const long double* xi, int i, long double x) {
+  long double r = 0;
+  for (int j = 0; j <= k; j++)
+    if (j != i) {
+      long double prod = 1 / (xi[i] - xi[j]);
+      for (int l = 0; l <= k; l++)
+        if (l != i && l != j) prod *= (x - xi[l]) / (xi[i] - xi[l]);
+      r += prod;
+    }
+  return r;
+}
+// value / derivative of 1-D basis function i of the QkDG space (basis != Lagrange)
+inline void host_basis_ld(int basis, int k, int i, long double x, long double* p, long double* dp) {
+  if (basis == PDB200_BASIS_LEGENDRE) {
+    long double v[MAX_N1], dv[MAX_N1];
+    host_legendre_ld(k, x, v, dv);
+    *p = v[i];
+    *dp = dv[i];
+  } else {
+    long double xi[MAX_N1];
+    host_lobatto_points(k, xi);
+    *p = host_nodal_p_ld(k, xi, i, x);
+    *dp = host_nodal_dp_ld(k, xi, i, x);
+  }
+}
+
 // m-point Gauss-Legendre rule on [0,1], ascending (dune-geometry QuadratureRules, GaussLegendre)
 inline void host_gauss(int m, std::vector<long double>& x, std::vector<long double>& w) {
   x.assign(m, 0);
@@ -97,8 +154,15 @@ inline void host_fill_tables(DevParams& P, Kron1D& K, std::vector<double>& xq, s
   for (int pt = 0; pt < m + 2; pt++) {
     const double x = pt < m ? xq[pt] : (pt == m ? 0.0 : 1.0);
     for (int i = 0; i < n1; i++) {
-      P.P[pt * n1 + i] = host_lagrange_p(k, i, x);
-      P.DP[pt * n1 + i] = host_lagrange_dp(k, i, x);
+      if (P.basis == PDB200_BASIS_LAGRANGE) {
+        P.P[pt * n1 + i] = host_lagrange_p(k, i, x);
+        P.DP[pt * n1 + i] = host_lagrange_dp(k, i, x);
+      } else {  // the points are long double where they exist (Gauss points), exact 0 / 1 otherwise
+        long double p, dp;
+        host_basis_ld(P.basis, k, i, pt < m ? gx[pt] : (long double)x, &p, &dp);
+        P.P[pt * n1 + i] = (double)p;
+        P.DP[pt * n1 + i] = (double)dp;
+      }
     }
   }
   // exact 1-D matrices in long double (Gauss rule with k+1 points is exact for degree 2k+1)

@@ -139,7 +139,8 @@ unsigned grid_for(long long n) { return (unsigned)((n + 255) / 256); }
 void check_compatible(const pdb200_operator* g0, const pdb200_operator* g1) {
   const DevParams &P0 = g0->P, &P1 = g1->P;
   if (g0->device != g1->device) throw Error("OneStepGridOperator: both operators must live on the same device");
-  if (P0.dim != P1.dim || P0.k != P1.k || P0.dg != P1.dg || P0.ncells != P1.ncells || P0.ndofs != P1.ndofs)
+  if (P0.dim != P1.dim || P0.k != P1.k || P0.dg != P1.dg || P0.basis != P1.basis || P0.ncells != P1.ncells ||
+      P0.ndofs != P1.ndofs)
     throw Error("OneStepGridOperator: the two grid operators need the same grid and function space "
                 "(gridoperator/onestep/localassembler.hh:65-84)");
   for (int d = 0; d < 3; d++) {
@@ -196,6 +197,7 @@ void build_stage_operator(pdb200_onestep* os) {
   p.o = P0.o ? dalloc((size_t)nbf * P0.nfq) : nullptr;
   p.device = g0->device;
   p.kernel = g0->kernel_choice;
+  p.basis = P0.basis;
   pdb200_handle st = nullptr;
   OS_C(pdb200_create(&p, &st));
   os->stage = st;

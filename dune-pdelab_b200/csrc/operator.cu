@@ -293,6 +293,10 @@ int pdb200_create(const pdb200_problem* p, pdb200_handle* out) {
   P.k = p->degree;
   P.n1 = P.k + 1;
   P.dg = p->space == PDB200_SPACE_QKDG;
+  P.basis = p->basis;
+  if (P.basis < PDB200_BASIS_LAGRANGE || P.basis > PDB200_BASIS_LOBATTO) throw Error("unknown QkDG basis");
+  if (!P.dg && P.basis != PDB200_BASIS_LAGRANGE)
+    throw Error("conforming Qk spaces use the Lagrange basis (finiteelementmap/qkfem.hh)");
   P.m = (2 * P.k + p->intorderadd) / 2 + 1;  // convectiondiffusiondg.hh:139, convectiondiffusionfem.hh:93
   P.n = P.nq = P.nfq = 1;
   P.ncells = 1;

@@ -246,10 +246,13 @@ inline YaspGridView<dim_> YaspGrid<dim_>::leafGridView() const {
 }
 
 // ---- finite element maps and function spaces ------------------------------------------------------
-// QkDGLocalFiniteElementMap<D,R,k,d> (finiteelementmap/qkdg.hh:36-76, Lagrange basis)
-template <class D, class R, int k, int d>
+// QkDGBasisPolynomial (finiteelementmap/qkdg.hh:15; l2orthonormal needs dune-localfunctions' OPB machinery: not mirrored)
+enum class QkDGBasisPolynomial { lagrange = PDB200_BASIS_LAGRANGE, legendre = PDB200_BASIS_LEGENDRE, lobatto = PDB200_BASIS_LOBATTO };
+// QkDGLocalFiniteElementMap<D,R,k,d,p> (finiteelementmap/qkdg.hh:17-200): Lagrange (default), Legendre, Gauss-Lobatto
+template <class D, class R, int k, int d, QkDGBasisPolynomial p = QkDGBasisPolynomial::lagrange>
 struct QkDGLocalFiniteElementMap {
-  static constexpr int degree = k, dimension = d, space = PDB200_SPACE_QKDG;
+  static constexpr int degree = k, dimension = d, space = PDB200_SPACE_QKDG, basis = (int)p;
+  static constexpr QkDGBasisPolynomial polynomial() { return p; }
   static constexpr std::size_t maxLocalSize() {
     std::size_t n = 1;
     for (int i = 0; i < d; i++) n *= k + 1;
@@ -259,7 +262,7 @@ struct QkDGLocalFiniteElementMap {
 // QkLocalFiniteElementMap<GV,D,R,k> (finiteelementmap/qkfem.hh:17-78)
 template <class GV, class D, class R, int k>
 struct QkLocalFiniteElementMap {
-  static constexpr int degree = k, dimension = GV::dimension, space = PDB200_SPACE_QK;
+  static constexpr int degree = k, dimension = GV::dimension, space = PDB200_SPACE_QK, basis = PDB200_BASIS_LAGRANGE;
   explicit QkLocalFiniteElementMap(const GV&) {}
   QkLocalFiniteElementMap() = default;
   static constexpr std::size_t maxLocalSize() {
@@ -864,6 +867,9 @@ class GridOperator {
   // Lagrange interpolation of f (evaluate(cell, xlocal)) at the nodes j/k of every cell
   template <class F>
   void B200_interpolate(F& f, Domain& x) const {
+    if (FEM::basis != PDB200_BASIS_LAGRANGE)
+      throw Exception("interpolate: nodal interpolation at j/k is the Lagrange basis' (use an L2 projection for the "
+                      "Legendre / Gauss-Lobatto QkDG bases)");
     const auto& gv = gfsu_.gridView();
     constexpr int k = FEM::degree;
     const int n = (int)FEM::maxLocalSize();
@@ -916,6 +922,7 @@ class GridOperator {
     }
     p.space = FEM::space;
     p.degree = FEM::degree;
+    p.basis = FEM::basis;
     p.dg_method = lop_.method == ConvectionDiffusionDGMethod::SIPG   ? PDB200_DG_SIPG
                   : lop_.method == ConvectionDiffusionDGMethod::NIPG ? PDB200_DG_NIPG
                                                                      : PDB200_DG_IIPG;

@@ -14,6 +14,7 @@ BC_DIRICHLET, BC_NEUMANN, BC_OUTFLOW, BC_NONE = 1, -1, -2, -3
 A_IDENTITY, A_SCALAR, A_DIAGONAL, A_FULL = 0, 1, 2, 3
 SIDE_DOMAIN, SIDE_PROCESSOR = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
+BASIS_LAGRANGE, BASIS_LEGENDRE, BASIS_LOBATTO = 0, 1, 2
 LAYOUT_CSR, LAYOUT_BCSR = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 SOLVER_BICGSTAB, SOLVER_CG = 0, 1
@@ -47,6 +48,7 @@ class Problem(C.Structure):
         ("side_kind", (C.c_int32 * 2) * 3),
         ("device", C.c_int32),
         ("kernel", C.c_int32),
+        ("basis", C.c_int32),
     ]
 
 
@@ -71,7 +73,7 @@ class ProblemSpec:
     def __init__(self, cells, space=SPACE_QKDG, degree=2, lower=None, upper=None,
                  method=DG_SIPG, weights=DG_WEIGHTS_ON, alpha=1.0, intorderadd=0,
                  a_mode=A_IDENTITY, A=None, b=None, c=None, f=None, bctype=None, g=None, j=None,
-                 o=None, side_kind=None, device=0, kernel=KERNEL_AUTO):
+                 o=None, side_kind=None, device=0, kernel=KERNEL_AUTO, basis=BASIS_LAGRANGE):
         self.cells = tuple(int(v) for v in cells)
         self.dim = len(self.cells)
         assert self.dim in (2, 3)
@@ -88,6 +90,7 @@ class ProblemSpec:
                 self.arrays[k] = np.ascontiguousarray(v, dtype=want)
         self.side_kind = side_kind if side_kind is not None else [[SIDE_DOMAIN] * 2 for _ in range(3)]
         self.device, self.kernel = int(device), int(kernel)
+        self.basis = int(basis)
 
     # sizes -------------------------------------------------------------------------------
     @property
@@ -156,4 +159,5 @@ class ProblemSpec:
         for k, v in self.arrays.items():
             setattr(p, k, _ptr(v))
         p.device, p.kernel = self.device, self.kernel
+        p.basis = getattr(self, "basis", BASIS_LAGRANGE)
         return p

@@ -60,6 +60,12 @@ enum { PDB200_SIDE_DOMAIN = 0,     /* physical boundary: alpha_boundary is integ
                                       touch it are constrained (constraints/p0.hh:31-41)          */ };
 /* kernel selection */
 enum { PDB200_KERNEL_AUTO = 0, PDB200_KERNEL_GENERIC = 1, PDB200_KERNEL_FAST = 2 };
+/* QkDGBasisPolynomial, finiteelementmap/qkdg.hh:15 — the 1-D polynomials of the QkDG tensor-product basis:
+ *   LAGRANGE  equidistant nodes j/k                         finiteelement/qkdglagrange.hh:55-79
+ *   LEGENDRE  shifted Legendre polynomials P_n(2x - 1)      finiteelement/qkdglegendre.hh:76-139 (not normalised)
+ *   LOBATTO   Lagrange polynomials on the Gauss-Lobatto points of [0,1], ascending   finiteelement/qkdglobatto.hh:20-105
+ * Local DOF i <-> multi-index (i mod (k+1), ...), x fastest, for all three.  Conforming Qk spaces are Lagrange. */
+enum { PDB200_BASIS_LAGRANGE = 0, PDB200_BASIS_LEGENDRE = 1, PDB200_BASIS_LOBATTO = 2 };
 
 typedef struct pdb200_problem {
   int32_t dim;            /* 2 or 3                                                              */
@@ -84,6 +90,7 @@ typedef struct pdb200_problem {
   int32_t side_kind[3][2];/* PDB200_SIDE_* for (direction, lower/upper)                          */
   int32_t device;         /* CUDA device ordinal                                                 */
   int32_t kernel;         /* PDB200_KERNEL_*                                                     */
+  int32_t basis;          /* PDB200_BASIS_* (QkDG only; 0 = Lagrange)                            */
 } pdb200_problem;
 
 typedef struct pdb200_operator* pdb200_handle;

@@ -65,6 +65,52 @@ double lagrange_dp(int k, int i, double x) {
   return result;
 }
 
+// finiteelement/qkdglegendre.hh:76-139: shifted Legendre polynomials by the three-term recurrence, values and
+// derivatives of all polynomials up to degree k (LegendrePolynomials1d::pdp; k = 0, 1 are the specialisations :142-253)
+void legendre_pdp(int k, double x, double* value, double* derivative) {
+  value[0] = 1;
+  derivative[0] = 0.0;
+  if (k < 1) return;
+  value[1] = 2 * x - 1;
+  derivative[1] = 2.0;
+  for (int n = 2; n <= k; n++) {
+    value[n] = ((2 * n - 1) * (2 * x - 1) * value[n - 1] - (n - 1) * value[n - 2]) / n;
+    derivative[n] = (2 * x - 1) * derivative[n - 1] + 2 * n * value[n - 1];
+  }
+}
+// finiteelement/qkdglobatto.hh:28-66: the k+1 Gauss-Lobatto points of [0,1] (dune-geometry GaussLobatto rule, un-vendored:
+// the mathematically unique point set, taken in ASCENDING order — the constructor re-sorts the rule's point pairs so
+// that the lower half lies below 1/2; the order inside a half is the rule's, assumed outermost pair first.  Parity of the
+// DOF order is unpinned for k >= 3).
+void lobatto_points(int k, double* xi) {
+  double t[5] = {0, 0, 0, 0, 0};
+  switch (k) {
+    case 1: t[0] = -1, t[1] = 1; break;
+    case 2: t[0] = -1, t[1] = 0, t[2] = 1; break;
+    case 3: t[0] = -1, t[1] = -std::sqrt(0.2), t[2] = std::sqrt(0.2), t[3] = 1; break;
+    default: t[0] = -1, t[1] = -std::sqrt(3.0 / 7.0), t[2] = 0, t[3] = std::sqrt(3.0 / 7.0), t[4] = 1; break;
+  }
+  for (int i = 0; i <= k; i++) xi[i] = (1 + t[i]) / 2;
+}
+// qkdglobatto.hh:69-93: Lagrange polynomials through the Gauss-Lobatto points
+double lobatto_p(int k, const double* xi, int i, double x) {
+  double result = 1.0;
+  for (int j = 0; j <= k; j++)
+    if (j != i) result *= (x - xi[j]) / (xi[i] - xi[j]);
+  return result;
+}
+double lobatto_dp(int k, const double* xi, int i, double x) {
+  double result = 0.0;
+  for (int j = 0; j <= k; j++)
+    if (j != i) {
+      double prod = 1.0 / (xi[i] - xi[j]);
+      for (int l = 0; l <= k; l++)
+        if (l != i && l != j) prod *= (x - xi[l]) / (xi[i] - xi[l]);
+      result += prod;
+    }
+  return result;
+}
+
 // Gauss-Legendre rule with m points on [0,1], ascending abscissae (dune-geometry tabulates the
 // same mathematically unique rule; restated with Newton iteration in long double).
 void gauss_legendre(int m, std::vector<double>& x, std::vector<double>& w) {
@@ -110,7 +156,7 @@ struct Tables {
   double dp(int pt, int i) const { return DP[pt * n1 + i]; }
 };
 
-Tables make_tables(int k, int intorder) {
+Tables make_tables(int k, int intorder, int basis = PDB200_BASIS_LAGRANGE) {
   Tables T;
   T.k = k;
   T.n1 = k + 1;
@@ -121,9 +167,20 @@ Tables make_tables(int k, int intorder) {
   T.DP.resize(T.npts * T.n1);
   for (int pt = 0; pt < T.npts; pt++) {
     double x = pt < T.m ? T.xq[pt] : (pt == T.m ? 0.0 : 1.0);
+    double lv[10], ld[10], xi[10];
+    if (basis == PDB200_BASIS_LEGENDRE) legendre_pdp(k, x, lv, ld);
+    if (basis == PDB200_BASIS_LOBATTO) lobatto_points(k, xi);
     for (int i = 0; i < T.n1; i++) {
-      T.P[pt * T.n1 + i] = lagrange_p(k, i, x);
-      T.DP[pt * T.n1 + i] = lagrange_dp(k, i, x);
+      if (basis == PDB200_BASIS_LEGENDRE) {
+        T.P[pt * T.n1 + i] = lv[i];
+        T.DP[pt * T.n1 + i] = ld[i];
+      } else if (basis == PDB200_BASIS_LOBATTO) {
+        T.P[pt * T.n1 + i] = lobatto_p(k, xi, i, x);
+        T.DP[pt * T.n1 + i] = lobatto_dp(k, xi, i, x);
+      } else {
+        T.P[pt * T.n1 + i] = lagrange_p(k, i, x);
+        T.DP[pt * T.n1 + i] = lagrange_dp(k, i, x);
+      }
     }
   }
   return T;
@@ -170,7 +227,10 @@ struct Ctx {
     }
     // convectiondiffusiondg.hh:139 intorder = intorderadd + quadrature_factor*order (factor 2);
     // convectiondiffusionfem.hh:93 intorder = intorderadd + 2*order
-    T = make_tables(k, p->intorderadd + 2 * k);
+    if (p->basis < PDB200_BASIS_LAGRANGE || p->basis > PDB200_BASIS_LOBATTO) throw std::runtime_error("unknown QkDG basis");
+    if (!dg && p->basis != PDB200_BASIS_LAGRANGE) throw std::runtime_error("conforming Qk spaces use the Lagrange basis");
+    if (p->basis == PDB200_BASIS_LOBATTO && k > 4) throw std::runtime_error("Gauss-Lobatto points are tabulated for k <= 4");
+    T = make_tables(k, p->intorderadd + 2 * k, p->basis);
     nq = 1;
     nfq = 1;
     for (int d = 0; d < dim; d++) nq *= T.m;

@@ -44,6 +44,37 @@ def lagrange_tables(k, pts):
     return V, D
 
 
+def basis_tables(k, pts, basis=0):
+    """1-D basis of the QkDG space as power-basis polynomials (independent of the oracle's recurrences / closed forms):
+    0 Lagrange on j/k, 1 shifted Legendre P_n(2x-1) via numpy.polynomial.legendre, 2 Lagrange on the Gauss-Lobatto points
+    (end points + roots of P_k' found numerically), ascending."""
+    if basis == 0:
+        return lagrange_tables(k, pts)
+    from numpy.polynomial import legendre as Lg
+    pts = np.asarray(pts)
+    V = np.zeros((len(pts), k + 1))
+    D = np.zeros((len(pts), k + 1))
+    if basis == 1:
+        for n in range(k + 1):
+            c = np.zeros(n + 1)
+            c[n] = 1.0
+            V[:, n] = Lg.legval(2.0 * pts - 1.0, c)
+            D[:, n] = 2.0 * Lg.legval(2.0 * pts - 1.0, Lg.legder(c)) if n > 0 else 0.0
+        return V, D
+    c = np.zeros(k + 1)
+    c[k] = 1.0
+    inner = np.sort(Lg.legroots(Lg.legder(c))) if k > 1 else np.array([])
+    nodes = (1.0 + np.concatenate([[-1.0], inner, [1.0]])) / 2.0
+    for i in range(k + 1):
+        c = np.array([1.0])
+        for j in range(k + 1):
+            if j != i:
+                c = Pl.polymul(c, np.array([-nodes[j], 1.0]) / (nodes[i] - nodes[j]))
+        V[:, i] = Pl.polyval(pts, c)
+        D[:, i] = Pl.polyval(pts, Pl.polyder(c))
+    return V, D
+
+
 class Grid:
     def __init__(self, spec):
         self.spec = spec
@@ -108,7 +139,7 @@ class Grid:
 
     # basis on a point set given per direction: returns phi[P, n], grad[P, n, dim] (physical)
     def basis(self, pts_per_dir):
-        tabs = [lagrange_tables(self.k, p) for p in pts_per_dir]
+        tabs = [basis_tables(self.k, p, getattr(self.spec, "basis", 0)) for p in pts_per_dir]
         # tensor over points: point index p = p0 + m0*(p1 + m1*p2) (x fastest), same for basis index
         dim = self.dim
         shapes = [len(p) for p in pts_per_dir]

@@ -72,7 +72,7 @@ def kappa_field(ncells, seed=42):
 
 def dg_problem(cells, degree=2, extent=None, a="scalar", with_b=False, with_c=False, with_f=False,
                bc="dirichlet", method=abi.DG_SIPG, weights=abi.DG_WEIGHTS_ON, alpha=3.0, seed=42,
-               kernel=abi.KERNEL_AUTO, intorderadd=0):
+               kernel=abi.KERNEL_AUTO, intorderadd=0, basis=abi.BASIS_LAGRANGE):
     """QkDG ConvectionDiffusionDG problem (SIPG, weightsOn, alpha=3: test/matrixfree/
     matrix_free_linear.cc:105-108) with synthetic coefficient fields."""
     cells = tuple(cells)
@@ -94,7 +94,7 @@ def dg_problem(cells, degree=2, extent=None, a="scalar", with_b=False, with_c=Fa
     else:
         raise ValueError(a)
     spec = ProblemSpec(cells, space=abi.SPACE_QKDG, degree=degree, upper=extent, method=method,
-                       weights=weights, alpha=alpha, intorderadd=intorderadd, kernel=kernel, **kw)
+                       weights=weights, alpha=alpha, intorderadd=intorderadd, kernel=kernel, basis=basis, **kw)
     extra = {}
     if with_b:
         extra["b"] = rng.standard_normal((nc, dim))

@@ -79,3 +79,26 @@ def test_cpp_time_stepping_tables_equal_the_python_tables():
             assert [m.a(k, i) for i in range(k + 1)] == r["a"][k - 1], (r["class"], "a", k)
             assert [m.b(k, i) for i in range(k + 1)] == r["b"][k - 1], (r["class"], "b", k)
         assert [m.d(i) for i in range(m.s() + 1)] == r["d"], r["class"]
+
+
+def test_product_basis_tables_match_independent_numpy_evaluation():
+    """The basis-specific part of the CUDA path is its 1-D tables (the generic QkDG kernels are table-driven):
+    host_fill_tables of csrc/host_tables.h for Lagrange / Legendre / Gauss-Lobatto, k = 1..4, at the Gauss points and at
+    the cell ends, against numpy.polynomial (tests/numpy_assembly.py: basis_tables)."""
+    import shutil
+    from numpy_assembly import basis_tables
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(ROOT, "tests", "cpp", "test_host_tables.cu")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_host_tables")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-o", exe, src], check=True)
+    recs = [json.loads(line) for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()]
+    assert len(recs) == 12
+    for r in recs:
+        k, n1 = r["k"], r["k"] + 1
+        pts = np.array(r["xq"] + [0.0, 1.0])
+        V, D = basis_tables(k, pts, r["basis"])
+        P = np.array(r["P"]).reshape(len(pts), n1)
+        DP = np.array(r["DP"]).reshape(len(pts), n1)
+        assert np.abs(P - V).max() < 1e-13 * max(1.0, np.abs(V).max()), (r["basis"], k)
+        assert np.abs(DP - D).max() < 1e-12 * max(1.0, np.abs(D).max()), (r["basis"], k)

@@ -152,3 +152,47 @@ def test_quadrature_matches_numpy_leggauss():
             x, w = Oracle(spec).quadrature()
             xr, wr = np.polynomial.legendre.leggauss(spec.m)
             assert np.abs(x - 0.5 * (xr + 1)).max() < 1e-15 and np.abs(w - 0.5 * wr).max() < 1e-15
+
+
+# ---- other QkDG bases (finiteelementmap/qkdg.hh:15: QkDGBasisPolynomial legendre / lobatto) -------------------------
+BASIS_CASES = [
+    dict(cells=(3, 2), degree=1, a="scalar", basis=abi.BASIS_LEGENDRE),
+    dict(cells=(3, 2), degree=2, a="full", with_b=True, with_c=True, basis=abi.BASIS_LEGENDRE),
+    dict(cells=(2, 2), degree=3, a="diagonal", with_b=True, basis=abi.BASIS_LEGENDRE),
+    dict(cells=(2, 2, 2), degree=2, a="full", with_b=True, with_c=True, basis=abi.BASIS_LEGENDRE),
+    dict(cells=(3, 2, 2), degree=2, a="scalar", bc="mixed", with_b=True, basis=abi.BASIS_LEGENDRE),
+    dict(cells=(2, 2), degree=4, a="scalar", basis=abi.BASIS_LEGENDRE),
+    dict(cells=(3, 2), degree=2, a="full", with_b=True, with_c=True, basis=abi.BASIS_LOBATTO),
+    dict(cells=(2, 2), degree=3, a="diagonal", with_b=True, basis=abi.BASIS_LOBATTO),
+    dict(cells=(2, 2, 1), degree=3, a="scalar", bc="mixed", basis=abi.BASIS_LOBATTO),
+    dict(cells=(2, 2), degree=4, a="scalar", basis=abi.BASIS_LOBATTO),
+]
+
+
+@pytest.mark.parametrize("case", BASIS_CASES, ids=_id)
+def test_dg_oracle_matches_numpy_assembly_in_other_bases(case):
+    """Legendre (finiteelement/qkdglegendre.hh) and Gauss-Lobatto Lagrange (finiteelement/qkdglobatto.hh) QkDG bases:
+    the oracle's recurrences / closed-form nodes against numpy.polynomial (independent) through the dense assembly."""
+    _check(dg_problem(with_f=True, **case))
+
+
+def test_lobatto_equals_lagrange_up_to_degree_two_and_legendre_spans_the_same_space():
+    """k <= 2: the Gauss-Lobatto points are the equidistant ones, so the two nodal bases coincide.  Any k: a change of
+    basis C (Legendre coefficients -> Lagrange coefficients, cell-wise Kronecker) maps the Legendre operator onto the
+    Lagrange one:  J_leg = C^T J_lag C."""
+    base = dict(cells=(3, 2), a="diagonal", with_c=True, with_f=True)
+    for k in (1, 2):
+        lag = Oracle(dg_problem(degree=k, **base))
+        lob = Oracle(dg_problem(degree=k, basis=abi.BASIS_LOBATTO, **base))
+        z = mt_vector(lag.num_dofs)
+        assert rel_err(lob.jacobian_apply(z), lag.jacobian_apply(z)) < 1e-13
+        assert rel_err(lob.residual(z), lag.residual(z)) < 1e-13
+    from numpy.polynomial import legendre as Lg
+    k = 3
+    lag = Oracle(dg_problem(degree=k, **base))
+    leg = Oracle(dg_problem(degree=k, basis=abi.BASIS_LEGENDRE, **base))
+    nodes = np.arange(k + 1) / k
+    C1 = np.array([[Lg.legval(2 * x - 1, np.eye(k + 1)[n]) for n in range(k + 1)] for x in nodes])   # nodal values of P_n
+    C = np.kron(np.eye(6), np.kron(C1, C1))                                                             # y (x) x per cell
+    zl = mt_vector(leg.num_dofs) - 0.5
+    assert rel_err(leg.jacobian_apply(zl), C.T @ lag.jacobian_apply(C @ zl)) < 1e-11
