@@ -88,6 +88,15 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def host_threads():
+    """All host threads this process may use.  Deliberately NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU arm into a one-core run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(cells, threads=None):
     """The oracle port timed on the host cores on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -100,7 +109,7 @@ def cpu_baseline(cells, threads=None):
     except Exception:
         orc = Oracle(spec, native=False)
         build = "g++ -O2 -fopenmp"
-    threads = threads or max(1, min(orc.max_threads(), os.cpu_count() or 1))
+    threads = threads or host_threads()   # passed explicitly (omp num_threads clause), see host_threads()
     z = np.random.default_rng(0).random(spec.num_dofs)
     y = np.zeros_like(z)
     orc.jacobian_apply(z[:], y, threads=threads)  # warm-up (page faults)
@@ -113,6 +122,152 @@ def cpu_baseline(cells, threads=None):
     return {"value": spec.num_dofs / best, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"one jacobian_apply on {cells}^3 cells ({spec.num_dofs} DOFs), same operator and "
                       f"coefficients family, {build}, best of 2, {best:.3f} s"}
+
+
+FP64_PEAK_TFLOPS = 34.75   # measured DFMA peak of this pool's B200 (profiles/r01_fp64_peak.txt); DMMA shares the pipe
+
+
+def _time_events(torch, fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def other_configs(torch, dev, peak):
+    """BASELINE.json configs[0], [2], [3] (cfg1, cfg3, cfg4 of SURVEY.md §8d) on one GPU, timed like the headline:
+    CUDA events on the launching stream, vectors / matrices resident, warm-up first.  Algorithmic bytes per entry
+    point as in SURVEY.md §8d / DESIGN.md §5 (stated in each record)."""
+    from pdelab_b200 import abi
+    from pdelab_b200.capi import GridOperator
+
+    def rand(n, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        return torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+
+    def rec(ms, alg_bytes, units, unit, kernel, note, flops=None):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        r = {"ms": ms, "value": units / (ms * 1e-3), "unit": unit, "kernel": kernel,
+             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                          "algorithmic_bytes_per_launch": alg_bytes}, "note": note}
+        if flops is not None:
+            tf = flops / (ms * 1e-3) / 1e12
+            r["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": tf / FP64_PEAK_TFLOPS, "flops_per_launch": flops,
+                                  "note": "canonical sum-factorised count of SURVEY.md 8d (357 flop/DOF at k=4), "
+                                          "peak = measured DFMA rate (profiles/r01_fp64_peak.txt)"}
+        return r
+
+    out = {}
+
+    def fem(cells, k, reps):
+        nc = int(np.prod(cells))
+        nq = (k + 1) ** len(cells)
+        kappa = 10.0 ** (2.0 * rand(nc, 42) - 1.0)
+        spec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=k, a_mode=abi.A_SCALAR, A=kappa, f=rand(nc * nq, 1))
+        go = GridOperator(spec)
+        go.set_stream(torch.cuda.current_stream().cuda_stream)
+        n = spec.num_dofs
+        x, r = rand(n, 2), torch.zeros(n, dtype=torch.float64, device=dev)
+        res = {"dofs": n, "cells": list(cells)}
+        ms = _time_events(torch, lambda: go.residual(x, r), reps)
+        res["residual"] = rec(ms, 32.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(),
+                              "r += R(x): read x, read+write r, read cached R(0) (32 B/DOF) + kappa per cell")
+        ms = _time_events(torch, lambda: go.apply(x, r), reps)
+        res["jacobian_apply"] = rec(ms, 16.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(), "y = J x: 16 B/DOF + kappa")
+        nr, nnz = go.pattern_size()
+        res["nnz"] = nnz
+        rowptr = torch.empty(nr + 1, dtype=torch.int64, device=dev)
+        colidx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        mreps = max(2, reps // 4)
+        ms = _time_events(torch, lambda: go.fill_pattern(rowptr=rowptr, colidx=colidx, index32=True), mreps, warm=1)
+        res["fill_pattern"] = rec(ms, 4.0 * nnz + 8.0 * (nr + 1), nnz, "nnz/s", "qk_interior_kernel<pattern> + row-gather kernels",
+                                  "u32 colidx + u64 rowptr written once")
+        vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+        ms = _time_events(torch, lambda: go.jacobian(x, vals, fresh=True), mreps, warm=1)
+        res["jacobian"] = rec(ms, 8.0 * nnz + 8.0 * nc, nnz, "nnz/s", "qk_interior_kernel + qk_assemble_kernel",
+                              "A = 0; jacobian(x, A): 8 B per stored non-zero + kappa")
+        y = torch.empty(n, dtype=torch.float64, device=dev)
+        ms = _time_events(torch, lambda: go.csr_mv(vals, x, y), mreps, warm=1)
+        res["spmv"] = rec(ms, 8.0 * nnz + 16.0 * n, nnz, "nnz/s", "qk_mv_interior + qk_mv_kernel",
+                          "y = A x: 8 B per non-zero (colidx is decoded arithmetically, never read) + vectors")
+        del go, vals, colidx, rowptr
+        torch.cuda.empty_cache()
+        return res
+
+    out["cfg1_q1_2d_256"] = fem((256, 256), 1, 200)
+    out["cfg1_q1_2d_256"]["note"] = ("0.5 MB working set: L2-resident and launch-latency bound by construction "
+                                     "(the reference's own CPU-runnable case)")
+    # cfg3: DG k=4 64^3 sum-factorised residual
+    cells, k = (64, 64, 64), 4
+    nc, nloc = 64 ** 3, 125
+    kappa = 10.0 ** (2.0 * rand(nc, 42) - 1.0)
+    spec = abi.ProblemSpec(cells, space=abi.SPACE_QKDG, degree=k, alpha=ALPHA, a_mode=abi.A_SCALAR, A=kappa,
+                           f=rand(nc * nloc, 1))
+    go = GridOperator(spec)
+    go.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = spec.num_dofs
+    x, r = rand(n, 2), torch.zeros(n, dtype=torch.float64, device=dev)
+    c3 = {"dofs": n, "cells": list(cells)}
+    ms = _time_events(torch, lambda: go.residual(x, r), 20)
+    c3["residual"] = rec(ms, 32.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(),
+                         "r += R(x) = J x + cached R(0): 32 B/DOF + kappa; compute-bound config", flops=357.0 * n)
+    ms = _time_events(torch, lambda: go.apply(x, r), 20)
+    c3["jacobian_apply"] = rec(ms, 16.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(), "y = J x: 16 B/DOF + kappa",
+                               flops=357.0 * n)
+    out["cfg3_dg_k4_3d_64"] = c3
+    del go, x, r
+    torch.cuda.empty_cache()
+    out["cfg4_q2_3d_160"] = fem((160, 160, 160), 2, 8)
+    return out
+
+
+def strong_512(torch, dist, dev, world, rank, local_rank, steps=10):
+    """BASELINE.json configs[4]: DG k=2 on 512^3 cells in total, split over the ranks (strong scaling)."""
+    from pdelab_b200 import abi
+    from pdelab_b200.capi import GridOperator
+    from pdelab_b200.partition import OverlappingPartition, P2PHaloExchanger, exchange_cell_field
+    G = 512
+    part = OverlappingPartition.strong((G, G, G), world, rank, overlap=1)
+    ncl = int(np.prod(part.local_cells))
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    kappa = 10.0 ** (2.0 * torch.rand(ncl, dtype=torch.float64, device=dev, generator=g) - 1.0)
+    exchange_cell_field(kappa.view(part.local_cells[::-1]), part, dist)
+    spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QKDG, degree=2, lower=part.local_lower,
+                           upper=part.local_upper, method=abi.DG_SIPG, weights=abi.DG_WEIGHTS_ON, alpha=ALPHA,
+                           a_mode=abi.A_SCALAR, A=kappa, side_kind=part.side_kind, device=local_rank)
+    go = GridOperator(spec)
+    go.set_stream(torch.cuda.current_stream().cuda_stream)
+    halo = P2PHaloExchanger(go, part, dist)
+    z = torch.rand(spec.num_dofs, dtype=torch.float64, device=dev, generator=g)
+    y = torch.empty_like(z)
+    for _ in range(3):
+        halo.apply(z, y)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        halo.apply(z, y)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    go.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dofs = G ** 3 * 27
+    res = {"global_cells": [G] * 3, "dofs": dofs, "partition": "x".join(str(v) for v in part.procs),
+           "cells_per_gpu": list(part.owned_cells), "ms_per_step": t.item(), "value": dofs / (t.item() * 1e-3),
+           "unit": UNIT, "steps": steps, "scaling": "strong", "kernel": go.last_kernel()}
+    del halo, go, z, y, kappa
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
@@ -317,6 +472,25 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = owned_dofs * world / te.item()
 
+    # the other BASELINE.json configurations ride in the same line (N = 1: cfg1, cfg3, cfg4; N > 1: cfg5 strong)
+    configs = strong = None
+    if not args.no_configs and not args.global_cells:
+        del zh, yh
+        try:
+            if world == 1:
+                del z, y, go
+                torch.cuda.empty_cache()
+                configs = other_configs(torch, dev, peak)
+            elif isinstance(halo, P2PHaloExchanger):
+                del z, y
+                torch.cuda.empty_cache()
+                strong = strong_512(torch, dist, dev, world, rank, local_rank)
+        except Exception as e:  # noqa: BLE001  (the headline line must survive a failure of the side measurements)
+            if world == 1:
+                configs = {"error": repr(e)}
+            else:
+                strong = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -344,6 +518,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.ref_cells)
+        if configs is not None:
+            line["configs"] = configs
+        if strong is not None:
+            line["strong_512"] = strong
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -360,6 +538,7 @@ def main():
                     help="strong scaling: cells per direction of the WHOLE grid (e.g. 512), split over the ranks")
     ap.add_argument("--ref-cells", type=int, default=64, help="cells per direction of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1/cfg3/cfg4 (N=1) and strong 512^3 (N>1) records")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (side runs only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="ghost-layer exchange for N > 1")
     args = ap.parse_args()

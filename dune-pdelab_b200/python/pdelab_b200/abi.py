@@ -20,6 +20,7 @@ PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 SOLVER_BICGSTAB, SOLVER_CG = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_BLOCK_SOR, PRECOND_BLOCK_SSOR = 0, 1, 2, 3, 4
 SOR_BACKWARD, SOR_KEEP_ITERATE = 1, 2
+POINTWISE_A, POINTWISE_B, POINTWISE_C, POINTWISE_BCTYPE = 1, 2, 4, 8
 
 
 class Problem(C.Structure):
@@ -49,6 +50,7 @@ class Problem(C.Structure):
         ("device", C.c_int32),
         ("kernel", C.c_int32),
         ("basis", C.c_int32),
+        ("pointwise", C.c_int32),
     ]
 
 
@@ -73,7 +75,7 @@ class ProblemSpec:
     def __init__(self, cells, space=SPACE_QKDG, degree=2, lower=None, upper=None,
                  method=DG_SIPG, weights=DG_WEIGHTS_ON, alpha=1.0, intorderadd=0,
                  a_mode=A_IDENTITY, A=None, b=None, c=None, f=None, bctype=None, g=None, j=None,
-                 o=None, side_kind=None, device=0, kernel=KERNEL_AUTO, basis=BASIS_LAGRANGE):
+                 o=None, side_kind=None, device=0, kernel=KERNEL_AUTO, basis=BASIS_LAGRANGE, pointwise=0):
         self.cells = tuple(int(v) for v in cells)
         self.dim = len(self.cells)
         assert self.dim in (2, 3)
@@ -91,6 +93,7 @@ class ProblemSpec:
         self.side_kind = side_kind if side_kind is not None else [[SIDE_DOMAIN] * 2 for _ in range(3)]
         self.device, self.kernel = int(device), int(kernel)
         self.basis = int(basis)
+        self.pointwise = int(pointwise)  # POINTWISE_* bits: A, b, c, bctype sampled per quadrature point
 
     # sizes -------------------------------------------------------------------------------
     @property
@@ -112,6 +115,14 @@ class ProblemSpec:
     @property
     def nfq(self):
         return self.m ** (self.dim - 1)
+
+    @property
+    def points_per_cell(self):
+        """NP of the point-wise layouts: volume points, then the face points of the 2 dim faces."""
+        return self.nq + 2 * self.dim * self.nfq
+
+    def face_point(self, d, side, q):
+        return self.nq + (2 * d + side) * self.nfq + q
 
     @property
     def num_boundary_faces(self):
@@ -160,4 +171,5 @@ class ProblemSpec:
             setattr(p, k, _ptr(v))
         p.device, p.kernel = self.device, self.kernel
         p.basis = getattr(self, "basis", BASIS_LAGRANGE)
+        p.pointwise = getattr(self, "pointwise", 0)
         return p

@@ -19,12 +19,31 @@
  *  - there is no CPU fallback: every compute entry point fails if no CUDA device is usable.
  *
  * Data model of the coefficient fields.  The reference takes a C++ parameter class with call-backs
- * (localoperator/convectiondiffusionparameter.hh:135-209).  Across a C ABI these become arrays,
- * sampled exactly where the reference evaluates the call-backs:
+ * (localoperator/convectiondiffusionparameter.hh:135-209).  Across a C ABI these become arrays.
+ * Two layouts exist per field, selected by the bits of pdb200_problem::pointwise:
+ *
+ * (1) cell-/face-wise layout (bit clear) — for fields that are constant on every cell / boundary face, which is
+ *     what the Kronecker fast paths need:
  *   A       per cell (cell centre; permeabilityIsConstantPerCell()==true, :139-142)
- *   b, c    per cell (cell-wise constant fields)
- *   f       per cell and volume quadrature point  f[cell*nq + q],  q = q0 + m*(q1 + m*q2)
+ *   b, c    per cell (cell-wise constant fields: the value the call-back returns at EVERY point of the cell)
  *   bctype  per boundary face (int8: Dirichlet=1, Neumann=-1, Outflow=-2, None=-3, :111-115)
+ * (2) point-wise layout (bit set) — sampled exactly where the reference evaluates the call-backs.  A cell has
+ *     NP = nq + 2*dim*nfq sample points: first its nq = m^dim volume quadrature points, then for every face
+ *     (dir, side) in the order 0:-x 1:+x 2:-y 3:+y 4:-z 5:+z its nfq = m^(dim-1) face quadrature points,
+ *         pt = q                                 volume point   (convectiondiffusiondg.hh:143-146,178,181)
+ *         pt = nq + (2*dir + side)*nfq + q       face point, in the local coordinates of THIS cell
+ *                                                (geo_in_inside / geo_in_outside.global(ip), :370-371,426,755,797)
+ *   A       A[(cell*NP + pt) * {1, dim, dim*dim}]   permeabilityIsConstantPerCell()==false: volume points, and on
+ *                                                   every face the points seen from both adjacent cells
+ *   b       b[(cell*NP + pt) * dim]                 volume points; face points of the lower faces (the assembler
+ *                                                   visits an interior face from the larger-index cell, :426) and
+ *                                                   of boundary faces; the other slots are never read
+ *   c       c[cell*nq + q]                          volume points
+ *   bctype  bctype[bface*nfq + q]                   QkDG only (:763,979); ConvectionDiffusionFEM evaluates the
+ *                                                   type at the face centre (convectiondiffusionfem.hh:226-229)
+ *     Point-wise fields run through the reference-order kernels (no Kronecker form exists for them).
+ * Always per point:
+ *   f       per cell and volume quadrature point  f[cell*nq + q],  q = q0 + m*(q1 + m*q2)
  *   g,j,o   per boundary face and face quadrature point  g[bface*nfq + q], q = t0 + m*t1 over the
  *           tangential directions in increasing order
  * with m = (2*degree+intorderadd)/2 + 1 Gauss-Legendre points per direction in ascending order
@@ -66,6 +85,8 @@ enum { PDB200_KERNEL_AUTO = 0, PDB200_KERNEL_GENERIC = 1, PDB200_KERNEL_FAST = 2
  *   LOBATTO   Lagrange polynomials on the Gauss-Lobatto points of [0,1], ascending   finiteelement/qkdglobatto.hh:20-105
  * Local DOF i <-> multi-index (i mod (k+1), ...), x fastest, for all three.  Conforming Qk spaces are Lagrange. */
 enum { PDB200_BASIS_LAGRANGE = 0, PDB200_BASIS_LEGENDRE = 1, PDB200_BASIS_LOBATTO = 2 };
+/* pdb200_problem::pointwise — which coefficient arrays use the point-wise layout (header comment, layout (2)) */
+enum { PDB200_POINTWISE_A = 1, PDB200_POINTWISE_B = 2, PDB200_POINTWISE_C = 4, PDB200_POINTWISE_BCTYPE = 8 };
 
 typedef struct pdb200_problem {
   int32_t dim;            /* 2 or 3                                                              */
@@ -79,11 +100,11 @@ typedef struct pdb200_problem {
   double  dg_alpha;       /* penalty constant alpha                                              */
   int32_t intorderadd;    /* extra quadrature order                                              */
   int32_t a_mode;         /* PDB200_A_*                                                          */
-  const double* A;        /* [cells * {1, dim, dim*dim}] (row-major tensor) or NULL              */
-  const double* b;        /* [cells * dim] or NULL (= 0)                                         */
-  const double* c;        /* [cells] or NULL (= 0)                                               */
+  const double* A;        /* [cells * {1, dim, dim*dim}] (row-major tensor) or NULL; point-wise: [cells * NP * ...] */
+  const double* b;        /* [cells * dim] or NULL (= 0); point-wise: [cells * NP * dim]          */
+  const double* c;        /* [cells] or NULL (= 0); point-wise: [cells * m^dim]                   */
   const double* f;        /* [cells * m^dim] or NULL (= 0)                                       */
-  const int8_t* bctype;   /* [boundary faces] or NULL (= all Dirichlet)                          */
+  const int8_t* bctype;   /* [boundary faces] or NULL (= all Dirichlet); point-wise: [faces * m^(dim-1)] */
   const double* g;        /* [boundary faces * m^(dim-1)] or NULL (= 0)                          */
   const double* j;        /* same layout, Neumann flux, or NULL                                  */
   const double* o;        /* same layout, outflow flux, or NULL                                  */
@@ -91,6 +112,7 @@ typedef struct pdb200_problem {
   int32_t device;         /* CUDA device ordinal                                                 */
   int32_t kernel;         /* PDB200_KERNEL_*                                                     */
   int32_t basis;          /* PDB200_BASIS_* (QkDG only; 0 = Lagrange)                            */
+  int32_t pointwise;      /* bit mask of PDB200_POINTWISE_*: arrays in the point-wise layout     */
 } pdb200_problem;
 
 typedef struct pdb200_operator* pdb200_handle;

@@ -101,6 +101,20 @@ class Oracle:
                                           _dp(rowptr.ctypes.data), _dp(colidx.ctypes.data)))
         return rowptr, colidx
 
+    def jacobian_rows(self, rows, threads=1):
+        """Pattern and Jacobian of the sampled rows: list of (sorted column indices, values) per row,
+        bit-identical to the corresponding rows of jacobian()."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        s = self.spec
+        maxlen = (2 * s.dim + 1) * s.local_size if s.space == 0 else (2 * s.degree + 1) ** s.dim
+        rowlen = np.zeros(rows.size, dtype=np.uint64)
+        colidx = np.zeros((rows.size, maxlen), dtype=np.uint64)
+        values = np.zeros((rows.size, maxlen))
+        self._chk(self.lib.oracle_jacobian_rows(C.byref(self.p), _dp(rows.ctypes.data), C.c_uint64(rows.size),
+                                                C.c_int(threads), C.c_uint64(maxlen), _dp(rowlen.ctypes.data),
+                                                _dp(colidx.ctypes.data), _dp(values.ctypes.data)))
+        return rowlen.astype(np.int64), colidx, values
+
     def jacobian(self, x=None, values=None):
         rowptr, colidx = self.pattern()
         values = np.zeros(colidx.size) if values is None else values

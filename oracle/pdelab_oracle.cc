@@ -200,6 +200,8 @@ struct Ctx {
   long bf_off[3][2];     // first boundary face of (dir, side)
   Tables T;
   int nq, nfq;           // volume / face quadrature points
+  int np;                // sample points per cell of the point-wise coefficient layouts: nq + 2 dim nfq
+  bool pwA, pwB, pwC, pwBC;  // which coefficient call-backs are sampled per quadrature point (pdelab_b200.h)
   double theta;
   double vol;            // |K|
   bool dg;
@@ -241,6 +243,13 @@ struct Ctx {
         bf_off[d][s] = nbf;
         nbf += ncells / N[d];
       }
+    np = nq + 2 * dim * nfq;
+    pwA = (p->pointwise & PDB200_POINTWISE_A) && p->a_mode != PDB200_A_IDENTITY;
+    pwB = (p->pointwise & PDB200_POINTWISE_B) && p->b;
+    pwC = (p->pointwise & PDB200_POINTWISE_C) && p->c;
+    pwBC = (p->pointwise & PDB200_POINTWISE_BCTYPE) && p->bctype;
+    if (pwBC && !dg)
+      throw std::runtime_error("ConvectionDiffusionFEM evaluates bctype at the face centre (convectiondiffusionfem.hh:226-229)");
     // convectiondiffusiondg.hh:99-101
     theta = 1.0;
     if (p->dg_method == PDB200_DG_SIPG) theta = -1.0;
@@ -264,7 +273,9 @@ struct Ctx {
       }
     return bf_off[dir][side] + idx;
   }
-  void A(long cell, double out[3][3]) const {
+  // sample-point number (inside its cell) of face quadrature point q of face (dir, side): pdelab_b200.h
+  int face_pt(int dir, int side, int q) const { return nq + (2 * dir + side) * nfq + q; }
+  void A_entry(long e, double out[3][3]) const {
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) out[i][j] = 0.0;
     switch (p->a_mode) {
@@ -272,22 +283,34 @@ struct Ctx {
         for (int i = 0; i < dim; i++) out[i][i] = 1.0;
         break;
       case PDB200_A_SCALAR:
-        for (int i = 0; i < dim; i++) out[i][i] = p->A[cell];
+        for (int i = 0; i < dim; i++) out[i][i] = p->A[e];
         break;
       case PDB200_A_DIAGONAL:
-        for (int i = 0; i < dim; i++) out[i][i] = p->A[cell * dim + i];
+        for (int i = 0; i < dim; i++) out[i][i] = p->A[e * dim + i];
         break;
       default:
         for (int i = 0; i < dim; i++)
-          for (int j = 0; j < dim; j++) out[i][j] = p->A[cell * dim * dim + i * dim + j];
+          for (int j = 0; j < dim; j++) out[i][j] = p->A[e * dim * dim + i * dim + j];
     }
   }
-  void b(long cell, double out[3]) const {
-    for (int d = 0; d < 3; d++) out[d] = (p->b && d < dim) ? p->b[cell * dim + d] : 0.0;
+  // param.A(cell, localcenter) — with permeabilityIsConstantPerCell() == false the value is replaced at every
+  // quadrature point before it is used (convectiondiffusiondg.hh:143-146, 367-382, 752-760), so the point-wise
+  // layout holds no centre sample: sample point 0 stands in for it
+  void A(long cell, double out[3][3]) const { A_entry(pwA ? cell * np : cell, out); }
+  // param.A(cell, x_pt) for sample point pt of the cell (point-wise layout only)
+  void A_at(long cell, int pt, double out[3][3]) const { A_entry(cell * np + pt, out); }
+  // param.b(cell, x_pt): cell-wise constant field or the sample at point pt
+  void b(long cell, int pt, double out[3]) const {
+    const long e = pwB ? cell * np + pt : cell;
+    for (int d = 0; d < 3; d++) out[d] = (p->b && d < dim) ? p->b[e * dim + d] : 0.0;
   }
-  double c(long cell) const { return p->c ? p->c[cell] : 0.0; }
+  // param.c(cell, x_q) at volume point q
+  double c(long cell, int q) const { return p->c ? p->c[pwC ? cell * nq + q : cell] : 0.0; }
   double f(long cell, int q) const { return p->f ? p->f[cell * nq + q] : 0.0; }
-  int bctype(long bf) const { return p->bctype ? (int)p->bctype[bf] : (int)PDB200_BC_DIRICHLET; }
+  // param.bctype(intersection, x_q): per face or per face quadrature point
+  int bctype(long bf, int q = 0) const {
+    return p->bctype ? (int)p->bctype[pwBC ? bf * nfq + q : bf] : (int)PDB200_BC_DIRICHLET;
+  }
   double g(long bf, int q) const { return p->g ? p->g[bf * nfq + q] : 0.0; }
   double j(long bf, int q) const { return p->j ? p->j[bf * nfq + q] : 0.0; }
   double o(long bf, int q) const { return p->o ? p->o[bf * nfq + q] : 0.0; }
@@ -389,6 +412,7 @@ void alpha_volume(const Ctx& C, long cell, const double* x, double* r, Scratch& 
   for (int q = 0; q < C.nq; q++) {
     int pt[3];
     double weight = C.vol_point(q, pt);
+    if (C.pwA) C.A_at(cell, q, A);  // !permeabilityIsConstantPerCell: :143-146 / convectiondiffusionfem.hh:97-100
     C.eval_basis(pt, phi, gradphi);
     double u = 0.0;
     for (int i = 0; i < C.n; i++) u += x[i] * phi[i];
@@ -396,8 +420,8 @@ void alpha_volume(const Ctx& C, long cell, const double* x, double* r, Scratch& 
     for (int i = 0; i < C.n; i++)
       for (int d = 0; d < C.dim; d++) gradu[d] += x[i] * gradphi[i * 3 + d];
     matvec3(A, gradu, Agradu, C.dim);
-    C.b(cell, b);
-    double c = C.c(cell);
+    C.b(cell, q, b);          // param.b(cell, ip.position()), :178
+    double c = C.c(cell, q);  // param.c(cell, ip.position()), :181
     double factor = weight * C.vol;
     if (with_f) {
       double f = C.f(cell, q);
@@ -413,7 +437,9 @@ void alpha_volume(const Ctx& C, long cell, const double* x, double* r, Scratch& 
 }
 
 // jacobian_volume, convectiondiffusiondg.hh:199-266 / convectiondiffusionfem.hh:140-203
-void jacobian_volume(const Ctx& C, long cell, LocalMatrix& mat, Scratch& S) {
+// only_row >= 0 restricts the accumulation to that test function (row) — every entry has its own accumulation
+// sequence, so the kept row is bit-identical to the full local matrix's (used by the sampled-row Jacobian)
+void jacobian_volume(const Ctx& C, long cell, LocalMatrix& mat, Scratch& S, int only_row = -1) {
   double A[3][3], b[3];
   C.A(cell, A);
   double* phi = S.phi_s.data();
@@ -422,15 +448,18 @@ void jacobian_volume(const Ctx& C, long cell, LocalMatrix& mat, Scratch& S) {
   for (int q = 0; q < C.nq; q++) {
     int pt[3];
     double weight = C.vol_point(q, pt);
+    if (C.pwA) C.A_at(cell, q, A);  // :234-237
     C.eval_basis(pt, phi, gradphi);
     for (int i = 0; i < C.n; i++) matvec3(A, &gradphi[i * 3], &Agradphi[i * 3], C.dim);
-    C.b(cell, b);
-    double c = C.c(cell);
+    C.b(cell, q, b);          // :255
+    double c = C.c(cell, q);  // :258
     double factor = weight * C.vol;
     for (int j = 0; j < C.n; j++)
-      for (int i = 0; i < C.n; i++)
+      for (int i = 0; i < C.n; i++) {
+        if (only_row >= 0 && i != only_row) continue;
         mat.accumulate(i, j, (dot3(&Agradphi[j * 3], &gradphi[i * 3], C.dim) -
                               phi[j] * dot3(b, &gradphi[i * 3], C.dim) + c * phi[j] * phi[i]) * factor);
+      }
   }
 }
 
@@ -480,6 +509,28 @@ FaceCoef skeleton_coef(const Ctx& C, long cell_s, long cell_n, int dir) {
   return F;
 }
 
+// "update all variables dependent on A if A is not cell-wise constant", convectiondiffusiondg.hh:367-382 (alpha_skeleton)
+// and :575-590 (jacobian_skeleton): A_s, A_n at face quadrature point q; the weights and the penalty factor only
+// with weightsOn
+void skeleton_coef_at_point(const Ctx& C, FaceCoef& F, long cell_s, long cell_n, int dir, int q) {
+  double A_s[3][3], A_n[3][3];
+  C.A_at(cell_s, C.face_pt(dir, 0, q), A_s);  // geo_in_inside.global(ip): lower face of the inside cell
+  C.A_at(cell_n, C.face_pt(dir, 1, q), A_n);  // geo_in_outside.global(ip): upper face of the outside cell
+  matvec3(A_s, F.nF, F.An_s, C.dim);
+  matvec3(A_n, F.nF, F.An_n, C.dim);
+  if (C.p->dg_weights == PDB200_DG_WEIGHTS_ON) {
+    double area = C.face_area(dir);
+    double h_F = std::min(C.vol, C.vol) / area;
+    double delta_s = dot3(F.An_s, F.nF, C.dim);
+    double delta_n = dot3(F.An_n, F.nF, C.dim);
+    F.omega_s = delta_n / (delta_s + delta_n + 1e-20);
+    F.omega_n = delta_s / (delta_s + delta_n + 1e-20);
+    double harmonic_average = 2.0 * delta_s * delta_n / (delta_s + delta_n + 1e-20);
+    int degree = C.k;
+    F.penalty = (C.p->dg_alpha / h_F) * harmonic_average * degree * (degree + C.dim - 1);
+  }
+}
+
 // alpha_skeleton, convectiondiffusiondg.hh:271-471.  Face between the inside cell cell_s and
 // cell_n = cell_s - e_dir (the assembler visits a face from the cell with the larger index,
 // gridoperator/default/assembler.hh:178-184).
@@ -493,6 +544,7 @@ void dg_alpha_skeleton(const Ctx& C, long cell_s, long cell_n, int dir, const do
   for (int q = 0; q < C.nfq; q++) {
     int pt_s[3], pt_n[3];
     double weight = C.face_point(q, dir, pt_s);
+    if (C.pwA) skeleton_coef_at_point(C, F, cell_s, cell_n, dir, q);  // :367-382
     for (int d = 0; d < 3; d++) pt_n[d] = pt_s[d];
     pt_s[dir] = C.T.m;      // xi_dir = 0 in the inside cell
     pt_n[dir] = C.T.m + 1;  // xi_dir = 1 in the outside cell
@@ -506,7 +558,7 @@ void dg_alpha_skeleton(const Ctx& C, long cell_s, long cell_n, int dir, const do
       for (int d = 0; d < C.dim; d++) gradu_s[d] += x_s[i] * tg_s[i * 3 + d];
     for (int i = 0; i < C.n; i++)
       for (int d = 0; d < C.dim; d++) gradu_n[d] += x_n[i] * tg_n[i * 3 + d];
-    C.b(cell_s, b);
+    C.b(cell_s, C.face_pt(dir, 0, q), b);  // param.b(cell_inside, iplocal_s), :426
     double normalflux = dot3(b, F.nF, C.dim);
     double omegaup_s, omegaup_n;
     if (normalflux >= 0.0) {
@@ -544,12 +596,13 @@ void dg_jacobian_skeleton(const Ctx& C, long cell_s, long cell_n, int dir, Local
   for (int q = 0; q < C.nfq; q++) {
     int pt_s[3], pt_n[3];
     double weight = C.face_point(q, dir, pt_s);
+    if (C.pwA) skeleton_coef_at_point(C, F, cell_s, cell_n, dir, q);  // :575-590
     for (int d = 0; d < 3; d++) pt_n[d] = pt_s[d];
     pt_s[dir] = C.T.m;
     pt_n[dir] = C.T.m + 1;
     C.eval_basis(pt_s, phi_s, tg_s);
     C.eval_basis(pt_n, phi_n, tg_n);
-    C.b(cell_s, b);
+    C.b(cell_s, C.face_pt(dir, 0, q), b);  // :613
     double normalflux = dot3(b, F.nF, C.dim);
     double omegaup_s = normalflux >= 0.0 ? 1.0 : 0.0;
     double omegaup_n = normalflux >= 0.0 ? 0.0 : 1.0;
@@ -613,6 +666,19 @@ BndCoef boundary_coef(const Ctx& C, long cell, int dir, int side) {
   return F;
 }
 
+// :752-760 (residual_boundary_integral) and :967-977 (jacobian_boundary): A_s at face quadrature point q
+void boundary_coef_at_point(const Ctx& C, BndCoef& F, long cell, int dir, int side, int q) {
+  double A_s[3][3];
+  C.A_at(cell, C.face_pt(dir, side, q), A_s);
+  matvec3(A_s, F.nF, F.An_s, C.dim);
+  if (C.p->dg_weights == PDB200_DG_WEIGHTS_ON) {
+    double h_F = C.vol / C.face_area(dir);
+    double harmonic_average = dot3(F.An_s, F.nF, C.dim);
+    int degree = C.k;
+    F.penalty = (C.p->dg_alpha / h_F) * harmonic_average * degree * (degree + C.dim - 1);
+  }
+}
+
 // residual_boundary_integral, convectiondiffusiondg.hh:684-879 (alpha_boundary :884-889,
 // jacobian_apply_boundary :893-899 with jacobian_apply=true).  Returns non-zero on the
 // "Outflow boundary condition on inflow" exception (:802-806).
@@ -624,8 +690,9 @@ int dg_boundary(const Ctx& C, long cell, const int cc[3], int dir, int side, con
   double b[3];
   double* phi_s = S.phi_s.data();
   double* tg_s = S.grad_s.data();
-  int bctype = C.bctype(bf);  // constant on the face in this data model
   for (int q = 0; q < C.nfq; q++) {
+    if (C.pwA) boundary_coef_at_point(C, F, cell, dir, side, q);  // :752-760
+    int bctype = C.bctype(bf, q);  // param.bctype(ig.intersection(), ip.position()), :763
     if (bctype == PDB200_BC_NONE) continue;
     int pt[3];
     double weight = C.face_point(q, dir, pt);
@@ -641,7 +708,7 @@ int dg_boundary(const Ctx& C, long cell, const int cc[3], int dir, int side, con
     }
     double u_s = 0.0;
     for (int i = 0; i < C.n; i++) u_s += x_s[i] * phi_s[i];
-    C.b(cell, b);
+    C.b(cell, C.face_pt(dir, side, q), b);  // param.b(cell_inside, iplocal_s), :797
     double normalflux = dot3(b, F.nF, C.dim);
     if (bctype == PDB200_BC_OUTFLOW) {
       if (normalflux < -1e-30) {
@@ -690,15 +757,16 @@ int dg_jacobian_boundary(const Ctx& C, long cell, const int cc[3], int dir, int 
   double b[3];
   double* phi_s = S.phi_s.data();
   double* tg_s = S.grad_s.data();
-  int bctype = C.bctype(bf);
   for (int q = 0; q < C.nfq; q++) {
+    if (C.pwA) boundary_coef_at_point(C, F, cell, dir, side, q);  // :967-977
+    int bctype = C.bctype(bf, q);  // :979
     if (bctype == PDB200_BC_NONE || bctype == PDB200_BC_NEUMANN) continue;
     int pt[3];
     double weight = C.face_point(q, dir, pt);
     pt[dir] = side ? C.T.m + 1 : C.T.m;
     C.eval_basis(pt, phi_s, tg_s);
     double factor = weight * area;
-    C.b(cell, b);
+    C.b(cell, C.face_pt(dir, side, q), b);  // :995
     double normalflux = dot3(b, F.nF, C.dim);
     if (bctype == PDB200_BC_OUTFLOW) {
       if (normalflux < -1e-30) {
@@ -752,7 +820,7 @@ void fem_alpha_boundary(const Ctx& C, long cell, const int cc[3], int dir, int s
     if (bctype == PDB200_BC_OUTFLOW) {
       double u = 0.0;
       for (int i = 0; i < C.n; i++) u += x_s[i] * phi[i];
-      C.b(cell, b);
+      C.b(cell, C.face_pt(dir, side, q), b);  // param.b(cell_inside, local), convectiondiffusionfem.hh:254
       double o = linear_only ? 0.0 : C.o(bf, q);
       double factor = weight * area;
       for (int i = 0; i < C.n; i++) r_s[i] += (dot3(b, nF, C.dim) * u + o) * phi[i] * factor;
@@ -777,7 +845,7 @@ void fem_jacobian_boundary(const Ctx& C, long cell, const int cc[3], int dir, in
     double weight = C.face_point(q, dir, pt);
     pt[dir] = side ? C.T.m + 1 : C.T.m;
     C.eval_basis(pt, phi, grad);
-    C.b(cell, b);
+    C.b(cell, C.face_pt(dir, side, q), b);  // convectiondiffusionfem.hh:314
     double factor = weight * area;
     if (bctype == PDB200_BC_OUTFLOW) {
       for (int j = 0; j < C.n; j++)
@@ -1098,6 +1166,201 @@ int assemble_jacobian(const Ctx& C, const DofMap& M, const Csr& P, double* value
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sampled rows of pattern + Jacobian: the SAME visits in the SAME order as build_pattern / assemble_jacobian,
+// restricted to the cells that contribute to one row, so that a parity test at BASELINE sizes (cfg4: 2.1e9 non-zeros)
+// can check 1e5 rows without the 17 GB matrix.  Bit-identical to the rows of oracle_jacobian (checked on small
+// grids by tests/test_oracle_rows.py).
+// ---------------------------------------------------------------------------------------------
+
+// inverse of DofMap::index for the conforming spaces: lattice coordinates (k N_d + 1 points per direction) of DOF r
+void lattice_of_dof(const Ctx& C, const DofMap& M, long r, int lat[3]) {
+  lat[0] = lat[1] = lat[2] = 0;
+  if (C.k == 1) {
+    for (int d = 0; d < C.dim; d++) {
+      lat[d] = (int)(r % (C.N[d] + 1));
+      r /= C.N[d] + 1;
+    }
+    return;
+  }
+  int edim = C.dim;
+  while (edim > 0 && r < M.codim_block_off[edim]) edim--;
+  r -= M.codim_block_off[edim];
+  int sbest = -1;
+  for (int s = 0; s < (1 << C.dim); s++)
+    if (__builtin_popcount(s) == edim && M.group_off[s] <= r && (sbest < 0 || M.group_off[s] > M.group_off[sbest])) sbest = s;
+  r -= M.group_off[sbest];
+  for (int d = 0; d < C.dim; d++) {
+    int ext = (sbest >> d) & 1;
+    long sz = ext ? C.N[d] : C.N[d] + 1;
+    lat[d] = 2 * (int)(r % sz) + ext;
+    r /= sz;
+  }
+}
+
+struct RowAcc {
+  std::vector<uint64_t> cols;  // ascending
+  std::vector<double> vals;
+  void add(uint64_t col, double v) {
+    if (v == 0.0) return;  // scatter_jacobian drops exact zeros, assemblerutilities.hh:434,456
+    auto it = std::lower_bound(cols.begin(), cols.end(), col);
+    if (it == cols.end() || *it != col) throw std::runtime_error("entry not in pattern");
+    vals[it - cols.begin()] += v;
+  }
+};
+
+void jacobian_row(const Ctx& C, const DofMap& M, long r, bool constrained, RowAcc& R) {
+  Scratch S(C.n);
+  LocalMatrix al, al_sn, al_ns, al_nn;
+  std::vector<long> idx_s(C.n), idx_n(C.n);
+  R.cols.clear();
+  if (C.dg) {
+    const long e = r / C.n;
+    const int i = (int)(r % C.n);
+    int c[3];
+    C.cell_coord(e, c);
+    // pattern: FullVolumePattern + FullSkeletonPattern (both directions) -> own cell and all face neighbours
+    for (int j = 0; j < C.n; j++) R.cols.push_back(e * C.n + j);
+    for (int dir = 0; dir < C.dim; dir++)
+      for (int side = 0; side < 2; side++) {
+        if (side ? c[dir] == C.N[dir] - 1 : c[dir] == 0) continue;
+        int cn[3] = {c[0], c[1], c[2]};
+        cn[dir] += side ? 1 : -1;
+        long en = C.cell_index(cn);
+        for (int j = 0; j < C.n; j++) R.cols.push_back(en * C.n + j);
+      }
+    std::sort(R.cols.begin(), R.cols.end());
+    R.vals.assign(R.cols.size(), 0.0);
+    // visit of cell e (assemble_jacobian): volume, lower interior faces (e is the inside cell), boundary faces
+    for (int ii = 0; ii < C.n; ii++) idx_s[ii] = e * C.n + ii;
+    al.assign(C.n, C.n);
+    jacobian_volume(C, e, al, S);
+    for (int dir = 0; dir < C.dim; dir++)
+      for (int side = 0; side < 2; side++) {
+        bool onb = side ? c[dir] == C.N[dir] - 1 : c[dir] == 0;
+        if (!onb) {
+          if (side == 1) continue;
+          int cn[3] = {c[0], c[1], c[2]};
+          cn[dir] -= 1;
+          long celln = C.cell_index(cn);
+          al_sn.assign(C.n, C.n);
+          al_ns.assign(C.n, C.n);
+          al_nn.assign(C.n, C.n);
+          dg_jacobian_skeleton(C, e, celln, dir, al, al_sn, al_ns, al_nn, S);
+          for (int j = 0; j < C.n; j++) R.add(celln * C.n + j, al_sn(i, j));
+        } else {
+          if (C.p->side_kind[dir][side] == PDB200_SIDE_PROCESSOR) continue;
+          if (dg_jacobian_boundary(C, e, c, dir, side, al, S)) throw std::runtime_error(g_err);
+        }
+      }
+    for (int j = 0; j < C.n; j++) R.add(e * C.n + j, al(i, j));
+    // visits of the upper neighbours u = e + e_dir (ascending): e is their outside cell
+    for (int dir = 0; dir < C.dim; dir++) {
+      if (c[dir] == C.N[dir] - 1) continue;
+      int cu[3] = {c[0], c[1], c[2]};
+      cu[dir] += 1;
+      long u = C.cell_index(cu);
+      LocalMatrix scratch_ss;
+      scratch_ss.assign(C.n, C.n);
+      al_sn.assign(C.n, C.n);
+      al_ns.assign(C.n, C.n);
+      al_nn.assign(C.n, C.n);
+      dg_jacobian_skeleton(C, u, e, dir, scratch_ss, al_sn, al_ns, al_nn, S);
+      for (int j = 0; j < C.n; j++) R.add(u * C.n + j, al_ns(i, j));
+      for (int j = 0; j < C.n; j++) R.add(e * C.n + j, al_nn(i, j));
+    }
+  } else {
+    int lat[3];
+    lattice_of_dof(C, M, r, lat);
+    // cells whose closure holds the lattice point, ascending cell index
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < C.dim; d++) {
+      if (lat[d] % C.k != 0) {
+        lo[d] = hi[d] = lat[d] / C.k;
+      } else {
+        lo[d] = std::max(0, lat[d] / C.k - 1);
+        hi[d] = std::min(C.N[d] - 1, lat[d] / C.k);
+      }
+    }
+    std::vector<long> cells;
+    for (int z = lo[2]; z <= hi[2]; z++)
+      for (int y = lo[1]; y <= hi[1]; y++)
+        for (int x = lo[0]; x <= hi[0]; x++) {
+          int cc[3] = {x, y, z};
+          cells.push_back(C.cell_index(cc));
+        }
+    for (long cell : cells) {
+      int c[3];
+      C.cell_coord(cell, c);
+      for (int j = 0; j < C.n; j++) R.cols.push_back(M.index(c, cell, j));
+    }
+    std::sort(R.cols.begin(), R.cols.end());
+    R.cols.erase(std::unique(R.cols.begin(), R.cols.end()), R.cols.end());
+    R.vals.assign(R.cols.size(), 0.0);
+    for (long cell : cells) {
+      int c[3];
+      C.cell_coord(cell, c);
+      int i = -1;
+      for (int j = 0; j < C.n; j++) {
+        idx_s[j] = M.index(c, cell, j);
+        if (idx_s[j] == r) i = j;
+      }
+      if (i < 0) throw std::runtime_error("row not found in an adjacent cell");
+      al.assign(C.n, C.n);
+      jacobian_volume(C, cell, al, S, i);
+      for (int dir = 0; dir < C.dim; dir++)
+        for (int side = 0; side < 2; side++) {
+          bool onb = side ? c[dir] == C.N[dir] - 1 : c[dir] == 0;
+          if (!onb || C.p->side_kind[dir][side] == PDB200_SIDE_PROCESSOR) continue;
+          fem_jacobian_boundary(C, cell, c, dir, side, al, S);
+        }
+      for (int j = 0; j < C.n; j++) R.add(idx_s[j], al(i, j));
+    }
+  }
+  if (constrained)  // set_trivial_rows, assemblerutilities.hh:666-684
+    for (size_t e = 0; e < R.cols.size(); e++) R.vals[e] = R.cols[e] == (uint64_t)r ? 1.0 : 0.0;
+}
+
+// is DOF r constrained?  (constrained_flags for one DOF, without the O(N) flag vector)
+bool dof_constrained(const Ctx& C, const DofMap& M, long r) {
+  if (C.dg) {
+    int c[3];
+    C.cell_coord(r / C.n, c);
+    for (int dir = 0; dir < C.dim; dir++)
+      for (int side = 0; side < 2; side++)
+        if ((side ? c[dir] == C.N[dir] - 1 : c[dir] == 0) && C.p->side_kind[dir][side] == PDB200_SIDE_PROCESSOR) return true;
+    return false;
+  }
+  int lat[3];
+  lattice_of_dof(C, M, r, lat);
+  // a DOF is constrained iff it lies in the closure of a Dirichlet (or processor) boundary face
+  for (int dir = 0; dir < C.dim; dir++)
+    for (int side = 0; side < 2; side++) {
+      if (lat[dir] != (side ? C.k * C.N[dir] : 0)) continue;
+      if (C.p->side_kind[dir][side] == PDB200_SIDE_PROCESSOR) return true;
+      // boundary faces (cells of the layer) whose closure holds the point
+      int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      for (int d = 0; d < C.dim; d++) {
+        if (d == dir) {
+          lo[d] = hi[d] = side ? C.N[d] - 1 : 0;
+        } else if (lat[d] % C.k != 0) {
+          lo[d] = hi[d] = lat[d] / C.k;
+        } else {
+          lo[d] = std::max(0, lat[d] / C.k - 1);
+          hi[d] = std::min(C.N[d] - 1, lat[d] / C.k);
+        }
+      }
+      for (int z = lo[2]; z <= hi[2]; z++)
+        for (int y = lo[1]; y <= hi[1]; y++)
+          for (int x = lo[0]; x <= hi[0]; x++) {
+            int cc[3] = {x, y, z};
+            if (C.bctype(C.bface(cc, dir, side)) == PDB200_BC_DIRICHLET) return true;
+          }
+    }
+  return false;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1264,6 +1527,36 @@ int oracle_jacobian(const pdb200_problem* p, const double* x, double* values) {
   DofMap M(C);
   Csr P = build_pattern(C, M);
   if (assemble_jacobian(C, M, P, values)) return 1;
+  ORACLE_CATCH
+}
+
+// rows of fill_pattern + jacobian for the listed DOFs: rowlen[s] entries per sampled row s, padded to maxlen in
+// colidx / values (row s at offset s * maxlen); maxlen >= (2k+1)^dim (conforming) or (2 dim + 1) n (QkDG)
+int oracle_jacobian_rows(const pdb200_problem* p, const uint64_t* rows, uint64_t nrows, int nthreads, uint64_t maxlen,
+                         uint64_t* rowlen, uint64_t* colidx, double* values) {
+  ORACLE_TRY
+  Ctx C(p);
+  DofMap M(C);
+  std::string err;
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(dynamic, 64)
+  for (long s = 0; s < (long)nrows; s++) {
+    try {
+      RowAcc R;
+      long r = (long)rows[s];
+      if (r < 0 || r >= M.ndofs) throw std::runtime_error("row out of range");
+      jacobian_row(C, M, r, dof_constrained(C, M, r), R);
+      if (R.cols.size() > maxlen) throw std::runtime_error("maxlen too small");
+      rowlen[s] = R.cols.size();
+      for (size_t e = 0; e < R.cols.size(); e++) {
+        colidx[s * maxlen + e] = R.cols[e];
+        values[s * maxlen + e] = R.vals[e];
+      }
+    } catch (std::exception& ex) {
+#pragma omp critical
+      err = ex.what();
+    }
+  }
+  if (!err.empty()) throw std::runtime_error(err);
   ORACLE_CATCH
 }
 

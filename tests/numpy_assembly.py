@@ -15,6 +15,10 @@ with [v] = v_s - v_n, n pointing from s to n, {q}_w = w_s q_s + w_n q_n, using
     entities one by one instead of using the closed-form index formula.
 It yields a dense matrix J and a vector r0 with  residual(x) = J x + r0  (before constraints),
 against which tests/test_oracle_vs_numpy.py checks the C++ oracle.
+
+Spatially varying coefficients: a spec made by problems.pointwise_problem carries the analytic fields as Python
+call-backs (spec.fns: A(x, cell), b(x, cell), c(x, cell), bctype(x)); this assembly EVALUATES THEM at its own physical quadrature
+points and never reads the point-wise arrays, so it also checks the sample-point layout of pdelab_b200.h.
 """
 import itertools
 
@@ -133,6 +137,43 @@ class Grid:
         c = self.spec.arrays["c"]
         return 0.0 if c is None else float(np.asarray(c).reshape(-1)[cell])
 
+    # ---- coefficient fields at physical points X [P, dim] of cell e (call-backs if the spec has them) ----
+    def fn(self, name):
+        return (getattr(self.spec, "fns", None) or {}).get(name)
+
+    def A_at(self, e, X):
+        f = self.fn("A")
+        if f is None:
+            return np.broadcast_to(self.A(e), (len(X), self.dim, self.dim))
+        return np.stack([np.asarray(f(x, e), dtype=float).reshape(self.dim, self.dim) for x in X])
+
+    def b_at(self, e, X):
+        f = self.fn("b")
+        if f is None:
+            return np.broadcast_to(self.b(e), (len(X), self.dim))
+        return np.stack([np.asarray(f(x, e), dtype=float) for x in X])
+
+    def c_at(self, e, X):
+        f = self.fn("c")
+        if f is None:
+            return np.full(len(X), self.c(e))
+        return np.array([float(f(x, e)) for x in X])
+
+    def vol_points(self, c):
+        """physical volume quadrature points of cell c, x fastest"""
+        idx = np.array(list(itertools.product(*[range(self.m)] * self.dim)))[:, ::-1]
+        return np.stack([self.spec.lower[d] + (c[d] + self.xq[idx[:, d]]) * self.h[d] for d in range(self.dim)], axis=1)
+
+    def face_points(self, c, dirn, side):
+        """physical quadrature points of face (dirn, side) of cell c, tangential directions increasing, first fastest"""
+        tang = [d for d in range(self.dim) if d != dirn]
+        idx = np.array(list(itertools.product(*[range(self.m)] * len(tang))))[:, ::-1].reshape(-1, len(tang))
+        X = np.zeros((len(idx), self.dim))
+        X[:, dirn] = self.spec.lower[dirn] + (c[dirn] + side) * self.h[dirn]
+        for t, d in enumerate(tang):
+            X[:, d] = self.spec.lower[d] + (c[d] + self.xq[idx[:, t]]) * self.h[d]
+        return X
+
     def arr(self, name, shape):
         a = self.spec.arrays[name]
         return None if a is None else np.asarray(a).reshape(shape)
@@ -230,12 +271,13 @@ def assemble(spec):
             trace[(d, side)] = G.basis(pts)
     for c in G.cells():
         e = G.cell_index(c)
-        A, b, cc = G.A(e), G.b(e), G.c(e)
+        XV = G.vol_points(c)
+        Aq, bq, cq = G.A_at(e, XV), G.b_at(e, XV), G.c_at(e, XV)
         ids = dmap[e]
-        Agrad = np.einsum("ab,pjb->pja", A, grad)
+        Agrad = np.einsum("pab,pjb->pja", Aq, grad)
         Kloc = np.einsum("p,pja,pia->ij", wv, Agrad, grad)
-        Kloc -= np.einsum("p,pj,a,pia->ij", wv, phi, b, grad)
-        Kloc += cc * np.einsum("p,pj,pi->ij", wv, phi, phi)
+        Kloc -= np.einsum("p,pj,pa,pia->ij", wv, phi, bq, grad)
+        Kloc += np.einsum("p,p,pj,pi->ij", wv, cq, phi, phi)
         J[np.ix_(ids, ids)] += Kloc
         if f is not None:
             r0[ids] -= np.einsum("p,p,pi->i", wv, f[e], phi)
@@ -254,26 +296,28 @@ def assemble(spec):
                     cn[d] -= 1
                     en = G.cell_index(cn)
                     idn = dmap[en]
-                    An = G.A(en)
+                    XF = G.face_points(c, d, side)
+                    As, An = G.A_at(e, XF), G.A_at(en, XF)            # both traces of A at the face points
                     pn, gn = trace[(d, 1)]
-                    ds, dn = nrm @ A @ nrm, nrm @ An @ nrm
+                    ds, dn = np.einsum("a,pab,b->p", nrm, As, nrm), np.einsum("a,pab,b->p", nrm, An, nrm)
                     if spec.weights == abi.DG_WEIGHTS_ON:
                         ws, wn = dn / (ds + dn + 1e-20), ds / (ds + dn + 1e-20)
                         harm = 2 * ds * dn / (ds + dn + 1e-20)
                     else:
-                        ws = wn = 0.5
-                        harm = 1.0
+                        ws = wn = np.full(len(XF), 0.5)
+                        harm = np.ones(len(XF))
                     gamma = spec.alpha / G.h[d] * harm * pen_k
-                    beta = float(b @ nrm)        # velocity of the inside (larger-index) cell
+                    beta = G.b_at(e, XF) @ nrm     # velocity of the inside (larger-index) cell
                     # jump and average operators as row vectors over the 2n local DOFs [s | n]
                     jump = np.concatenate([ps, -pn], axis=1)                       # [P, 2n]
-                    flux = np.concatenate([ws * np.einsum("pja,ab,b->pj", gs, A.T, nrm) * 1.0,
-                                           wn * np.einsum("pja,ab,b->pj", gn, An.T, nrm)], axis=1)
-                    up = np.concatenate([ps, 0 * pn], axis=1) if beta >= 0 else np.concatenate([0 * ps, pn], axis=1)
-                    B = (beta * np.einsum("p,pj,pi->ij", wf, up, jump)
+                    flux = np.concatenate([ws[:, None] * np.einsum("pja,pba,b->pj", gs, As, nrm),
+                                           wn[:, None] * np.einsum("pja,pba,b->pj", gn, An, nrm)], axis=1)
+                    ups = (beta >= 0)[:, None]
+                    up = np.concatenate([np.where(ups, ps, 0.0), np.where(ups, 0.0, pn)], axis=1)
+                    B = (np.einsum("p,p,pj,pi->ij", wf, beta, up, jump)
                          - np.einsum("p,pj,pi->ij", wf, flux, jump)
                          + theta * np.einsum("p,pj,pi->ij", wf, jump, flux)
-                         + gamma * np.einsum("p,pj,pi->ij", wf, jump, jump))
+                         + np.einsum("p,p,pj,pi->ij", wf, gamma, jump, jump))
                     both = np.concatenate([ids, idn])
                     J[np.ix_(both, both)] += B
                     continue
@@ -284,45 +328,50 @@ def assemble(spec):
                         con[ids[np.abs(ps).sum(axis=0) > 1e-14]] = True
                     continue
                 bf = G.bface_index(c, d, side)
-                bt = abi.BC_DIRICHLET if bct is None else int(bct[bf])
-                beta = float(b @ nrm)
+                XF = G.face_points(c, d, side)
+                beta = G.b_at(e, XF) @ nrm
                 if not dg:
+                    bt = abi.BC_DIRICHLET if bct is None else int(bct[bf])   # the type at the face centre
                     if bt == abi.BC_DIRICHLET:
                         con[ids[np.abs(ps).sum(axis=0) > 1e-14]] = True
                     elif bt == abi.BC_NEUMANN:
                         if jq is not None:
                             r0[ids] += np.einsum("p,p,pi->i", wf, jq[bf], ps)
                     elif bt == abi.BC_OUTFLOW:
-                        J[np.ix_(ids, ids)] += beta * np.einsum("p,pj,pi->ij", wf, ps, ps)
+                        J[np.ix_(ids, ids)] += np.einsum("p,p,pj,pi->ij", wf, beta, ps, ps)
                         if oq is not None:
                             r0[ids] += np.einsum("p,p,pi->i", wf, oq[bf], ps)
                     continue
-                if bt == abi.BC_NONE:
-                    continue
-                if bt == abi.BC_NEUMANN:
-                    if jq is not None:
-                        r0[ids] += np.einsum("p,p,pi->i", wf, jq[bf], ps)
-                    continue
-                if bt == abi.BC_OUTFLOW:
-                    J[np.ix_(ids, ids)] += beta * np.einsum("p,pj,pi->ij", wf, ps, ps)
-                    if oq is not None:
-                        r0[ids] += np.einsum("p,p,pi->i", wf, oq[bf], ps)
-                    continue
-                # Dirichlet
-                ds = nrm @ A @ nrm
-                harm = ds if spec.weights == abi.DG_WEIGHTS_ON else 1.0
+                # DG: the boundary type is a function of the face point
+                if G.fn("bctype") is not None:
+                    btp = np.array([int(G.fn("bctype")(x)) for x in XF])
+                else:
+                    btp = np.full(len(XF), abi.BC_DIRICHLET if bct is None else int(bct[bf]))
+                As = G.A_at(e, XF)
+                ds = np.einsum("a,pab,b->p", nrm, As, nrm)
+                harm = ds if spec.weights == abi.DG_WEIGHTS_ON else np.ones(len(XF))
                 gamma = spec.alpha / G.h[d] * harm * pen_k
-                fl = np.einsum("pja,ab,b->pj", gs, A.T, nrm)
-                B = (-np.einsum("p,pj,pi->ij", wf, fl, ps) + theta * np.einsum("p,pj,pi->ij", wf, ps, fl)
-                     + gamma * np.einsum("p,pj,pi->ij", wf, ps, ps))
-                if beta >= 0:
-                    B += beta * np.einsum("p,pj,pi->ij", wf, ps, ps)
-                J[np.ix_(ids, ids)] += B
-                if gq is not None:
-                    g = gq[bf]
-                    r0[ids] -= theta * np.einsum("p,p,pi->i", wf, g, fl) + gamma * np.einsum("p,p,pi->i", wf, g, ps)
-                    if beta < 0:
-                        r0[ids] += beta * np.einsum("p,p,pi->i", wf, g, ps)
+                fl = np.einsum("pja,pba,b->pj", gs, As, nrm)
+                for kind in (abi.BC_NEUMANN, abi.BC_OUTFLOW, abi.BC_DIRICHLET):
+                    w = np.where(btp == kind, wf, 0.0)   # quadrature restricted to the points of this type
+                    if not w.any():
+                        continue
+                    if kind == abi.BC_NEUMANN:
+                        if jq is not None:
+                            r0[ids] += np.einsum("p,p,pi->i", w, jq[bf], ps)
+                    elif kind == abi.BC_OUTFLOW:
+                        J[np.ix_(ids, ids)] += np.einsum("p,p,pj,pi->ij", w, beta, ps, ps)
+                        if oq is not None:
+                            r0[ids] += np.einsum("p,p,pi->i", w, oq[bf], ps)
+                    else:
+                        B = (-np.einsum("p,pj,pi->ij", w, fl, ps) + theta * np.einsum("p,pj,pi->ij", w, ps, fl)
+                             + np.einsum("p,p,pj,pi->ij", w, gamma, ps, ps))
+                        B += np.einsum("p,p,pj,pi->ij", w, np.where(beta >= 0, beta, 0.0), ps, ps)
+                        J[np.ix_(ids, ids)] += B
+                        if gq is not None:
+                            g = gq[bf]
+                            r0[ids] -= theta * np.einsum("p,p,pi->i", w, g, fl) + np.einsum("p,p,p,pi->i", w, gamma, g, ps)
+                            r0[ids] += np.einsum("p,p,p,pi->i", w, np.where(beta < 0, beta, 0.0), g, ps)
     return J, r0, con
 
 

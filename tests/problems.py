@@ -151,6 +151,117 @@ def fem_problem(cells, degree=1, extent=None, a="scalar", with_b=False, with_c=F
     return spec.replace(**extra)
 
 
+def pointwise_problem(spec, which=("A", "b", "c", "bctype"), seed=7):
+    """Turns `spec` into a problem with spatially varying coefficient call-backs, sampled into the point-wise layouts
+    of include/pdelab_b200.h (layout (2)): A(x) non-constant per cell (permeabilityIsConstantPerCell() == false), a
+    rotating velocity b(x) = (-y, x, ...), c(x) varying inside the cells, and for QkDG a boundary type that changes
+    INSIDE boundary faces.  The fields also depend on the cell number (discontinuous across cells), so that a kernel
+    reading the wrong cell's face trace is caught.  The call-backs stay on the spec (spec.fns) for
+    tests/numpy_assembly.py, which evaluates them at its own quadrature points."""
+    dim, N = spec.dim, spec.cells
+    h = [(spec.upper[d] - spec.lower[d]) / N[d] for d in range(dim)]
+    x1, _ = np.polynomial.legendre.leggauss(spec.m)
+    xq = 0.5 * (x1 + 1.0)
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((dim, dim)) * 0.2
+
+    def A_fn(x, e):
+        s = (1.0 + 0.5 * np.sin(3.0 * x[0] + 2.0 * x[1])) * (1.0 + 0.1 * (e % 3))
+        if spec.a_mode == abi.A_SCALAR:
+            return s * np.eye(dim)
+        if spec.a_mode == abi.A_DIAGONAL:
+            return np.diag([s * (1.0 + 0.3 * d + 0.2 * x[d]) for d in range(dim)])
+        M = np.eye(dim) * s + (R @ R.T) * (1.0 + x[0])
+        return M
+
+    def b_fn(x, e):
+        v = np.zeros(dim)
+        v[0], v[1] = -(x[1] - 0.5), x[0] - 0.5
+        if dim == 3:
+            v[2] = 0.3 + 0.2 * x[2]
+        return v * (1.0 + 0.05 * (e % 2))
+
+    def c_fn(x, e):
+        return 1.0 + x[0] * x[1] + 0.1 * (e % 4)
+
+    def bc_fn(x):
+        # changes type in the middle of boundary faces (never Outflow: the rotating b has inflow parts)
+        s = np.sin(7.0 * x[0] + 5.0 * x[1] + (3.0 * x[2] if dim == 3 else 0.0))
+        return abi.BC_DIRICHLET if s > 0.2 else (abi.BC_NEUMANN if s > -0.4 else abi.BC_NONE)
+
+    nc, nq, nfq, NP = spec.ncells, spec.nq, spec.nfq, spec.points_per_cell
+    # physical coordinates of the NP sample points of every cell
+    X = np.zeros((nc, NP, dim))
+    tang = [[t for t in range(dim) if t != d] for d in range(dim)]
+    for e in range(nc):
+        c, r = [], e
+        for d in range(dim):
+            c.append(r % N[d])
+            r //= N[d]
+        x0 = np.array([spec.lower[d] + c[d] * h[d] for d in range(dim)])
+        for q in range(nq):
+            qq = q
+            for d in range(dim):
+                X[e, q, d] = x0[d] + xq[qq % spec.m] * h[d]
+                qq //= spec.m
+        for d in range(dim):
+            for side in range(2):
+                for q in range(nfq):
+                    pt, qq = spec.face_point(d, side, q), q
+                    X[e, pt, d] = x0[d] + side * h[d]
+                    for t in tang[d]:
+                        X[e, pt, t] = x0[t] + xq[qq % spec.m] * h[t]
+                        qq //= spec.m
+    kw, fns, mask = {}, {}, 0
+    if "A" in which and spec.a_mode != abi.A_IDENTITY:
+        full = np.array([[A_fn(X[e, p], e) for p in range(NP)] for e in range(nc)])
+        if spec.a_mode == abi.A_SCALAR:
+            kw["A"] = np.ascontiguousarray(full[:, :, 0, 0])
+        elif spec.a_mode == abi.A_DIAGONAL:
+            kw["A"] = np.ascontiguousarray(np.einsum("epii->epi", full))
+        else:
+            kw["A"] = np.ascontiguousarray(full)
+        fns["A"] = A_fn
+        mask |= abi.POINTWISE_A
+    if "b" in which:
+        kw["b"] = np.array([[b_fn(X[e, p], e) for p in range(NP)] for e in range(nc)])
+        fns["b"] = b_fn
+        mask |= abi.POINTWISE_B
+    if "c" in which:
+        kw["c"] = np.array([[c_fn(X[e, q], e) for q in range(nq)] for e in range(nc)])
+        fns["c"] = c_fn
+        mask |= abi.POINTWISE_C
+    if "bctype" in which and spec.space == abi.SPACE_QKDG:
+        bct = np.zeros((spec.num_boundary_faces, nfq), dtype=np.int8)
+        for d in range(dim):
+            for side in range(2):
+                off = spec.boundary_face_offset(d, side)
+                for e in range(nc):
+                    c, r = [], e
+                    for dd in range(dim):
+                        c.append(r % N[dd])
+                        r //= N[dd]
+                    if c[d] != (N[d] - 1 if side else 0):
+                        continue
+                    idx, stride = 0, 1
+                    for dd in range(dim):
+                        if dd != d:
+                            idx += stride * c[dd]
+                            stride *= N[dd]
+                    for q in range(nfq):
+                        bct[off + idx, q] = bc_fn(X[e, spec.face_point(d, side, q)])
+        kw["bctype"] = bct
+        rng2 = np.random.default_rng(seed + 1)
+        for nm in ("g", "j"):
+            if spec.arrays.get(nm) is None:
+                kw[nm] = rng2.standard_normal((spec.num_boundary_faces, nfq))
+        fns["bctype"] = bc_fn
+        mask |= abi.POINTWISE_BCTYPE
+    out = spec.replace(pointwise=mask, **kw)
+    out.fns = fns
+    return out
+
+
 def rel_err(a, b):
     """Norm-relative error  ||a-b||_inf / ||b||_inf  (entry-wise relative error is
     meaningless where cancellation gives ~0)."""

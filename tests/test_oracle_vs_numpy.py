@@ -196,3 +196,55 @@ def test_lobatto_equals_lagrange_up_to_degree_two_and_legendre_spans_the_same_sp
     C = np.kron(np.eye(6), np.kron(C1, C1))                                                             # y (x) x per cell
     zl = mt_vector(leg.num_dofs) - 0.5
     assert rel_err(leg.jacobian_apply(zl), C.T @ lag.jacobian_apply(C @ zl)) < 1e-11
+
+
+# ---- spatially varying coefficients: A, b, c (and the DG boundary type) evaluated per quadrature point -------------
+# (convectiondiffusiondg.hh:143-146,178,181,367-382,426,752-763; convectiondiffusionfem.hh:97-100,127-129,254)
+from problems import pointwise_problem  # noqa: E402
+
+PW_DG_CASES = [
+    dict(cells=(3, 2), degree=1, a="scalar"),
+    dict(cells=(3, 3), degree=2, a="full", which=("A", "b", "c")),
+    dict(cells=(2, 3), degree=2, a="diagonal", weights=abi.DG_WEIGHTS_OFF, method=abi.DG_NIPG),
+    dict(cells=(2, 2, 2), degree=1, a="full"),
+    dict(cells=(2, 2, 2), degree=2, a="scalar", which=("b", "c")),
+    dict(cells=(3, 2, 2), degree=2, a="diagonal", which=("A", "bctype")),
+    dict(cells=(2, 1, 2), degree=3, a="scalar", which=("A", "b", "c", "bctype")),
+]
+PW_FEM_CASES = [
+    dict(cells=(4, 3), degree=1, a="scalar"),
+    dict(cells=(3, 3), degree=2, a="full"),
+    dict(cells=(2, 2, 2), degree=1, a="diagonal", bc="mixed", with_b=True),
+    dict(cells=(2, 2, 2), degree=2, a="scalar", which=("b", "c")),
+]
+
+
+@pytest.mark.parametrize("case", PW_DG_CASES, ids=_id)
+def test_dg_oracle_pointwise_coefficients_match_numpy_assembly(case):
+    kw = dict(case)
+    which = kw.pop("which", ("A", "b", "c", "bctype"))
+    spec = pointwise_problem(dg_problem(with_f=True, bc="dirichlet_g", **kw), which)
+    _check(spec)
+
+
+@pytest.mark.parametrize("case", PW_FEM_CASES, ids=_id)
+def test_fem_oracle_pointwise_coefficients_match_numpy_assembly(case):
+    kw = dict(case)
+    which = kw.pop("which", ("A", "b", "c"))
+    spec = pointwise_problem(fem_problem(**kw), which)
+    _check(spec)
+
+
+def test_pointwise_layout_with_cellwise_constant_fields_equals_the_cellwise_layout():
+    """Filling the point-wise arrays with a cell-wise constant field must reproduce the cell-wise path bit for bit."""
+    base = dg_problem((3, 2, 2), degree=2, a="full", with_b=True, with_c=True, with_f=True, bc="mixed")
+    NP, nq, nfq = base.points_per_cell, base.nq, base.nfq
+    A, b, c, bct = (base.arrays[k] for k in ("A", "b", "c", "bctype"))
+    pw = base.replace(A=np.repeat(A[:, None], NP, axis=1), b=np.repeat(b[:, None], NP, axis=1),
+                      c=np.repeat(c[:, None], nq, axis=1), bctype=np.repeat(bct[:, None], nfq, axis=1),
+                      pointwise=abi.POINTWISE_A | abi.POINTWISE_B | abi.POINTWISE_C | abi.POINTWISE_BCTYPE)
+    z = mt_vector(base.num_dofs)
+    o0, o1 = Oracle(base), Oracle(pw)
+    assert np.array_equal(o0.residual(z), o1.residual(z))
+    assert np.array_equal(o0.jacobian_apply(z), o1.jacobian_apply(z))
+    assert np.array_equal(o0.jacobian()[2], o1.jacobian()[2])
