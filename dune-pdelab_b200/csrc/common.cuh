@@ -27,6 +27,8 @@ struct DevParams {
   double theta, alpha;
   int weights_on, a_mode, dg;
   int basis;  // PDB200_BASIS_* of the QkDG space (the Kronecker kernels are written for the Lagrange basis)
+  int pw;     // PDB200_POINTWISE_* bits: A / b / c / bctype in the point-wise layout of pdelab_b200.h
+  int np;     // sample points per cell of that layout: nq + 2 dim nfq
   int side_kind[3][2];
   long long bf_off[3][2];
   const double *A, *b, *c, *f, *g, *j, *o;
@@ -71,7 +73,8 @@ __host__ __device__ inline long long bface_index(const DevParams& P, const int c
   return P.bf_off[dir][side] + idx;
 }
 
-__device__ inline void load_A(const DevParams& P, long long cell, double A[3][3]) {
+// entry e of the tensor array: e = cell (cell-wise layout) or cell * np + pt (point-wise layout)
+__device__ inline void load_A(const DevParams& P, long long e, double A[3][3]) {
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) A[i][j] = 0.0;
   switch (P.a_mode) {
@@ -79,17 +82,60 @@ __device__ inline void load_A(const DevParams& P, long long cell, double A[3][3]
       for (int i = 0; i < P.dim; i++) A[i][i] = 1.0;
       break;
     case PDB200_A_SCALAR: {
-      double v = __ldg(P.A + cell);
+      double v = __ldg(P.A + e);
       for (int i = 0; i < P.dim; i++) A[i][i] = v;
     } break;
     case PDB200_A_DIAGONAL:
-      for (int i = 0; i < P.dim; i++) A[i][i] = __ldg(P.A + cell * P.dim + i);
+      for (int i = 0; i < P.dim; i++) A[i][i] = __ldg(P.A + e * P.dim + i);
       break;
     default:
       for (int i = 0; i < P.dim; i++)
-        for (int j = 0; j < P.dim; j++) A[i][j] = __ldg(P.A + cell * P.dim * P.dim + i * P.dim + j);
+        for (int j = 0; j < P.dim; j++) A[i][j] = __ldg(P.A + e * P.dim * P.dim + i * P.dim + j);
   }
 }
+
+// ---- the coefficient call-backs of the reference's parameter class, in either layout of pdelab_b200.h ----------
+// sample-point number of face quadrature point q of face (dir, side) inside its cell
+__device__ __forceinline__ int face_pt(const DevParams& P, int dir, int side, int q) {
+  return P.nq + (2 * dir + side) * P.nfq + q;
+}
+__device__ __forceinline__ bool pw_A(const DevParams& P) { return (P.pw & PDB200_POINTWISE_A) != 0; }
+// param.A(cell, x_pt), point-wise layout only (permeabilityIsConstantPerCell() == false)
+__device__ inline void load_A_at(const DevParams& P, long long cell, int pt, double A[3][3]) {
+  load_A(P, cell * P.np + pt, A);
+}
+// param.A(cell, centre); in the point-wise layout every use is preceded by load_A_at, sample 0 stands in
+__device__ inline void load_A_cell(const DevParams& P, long long cell, double A[3][3]) {
+  load_A(P, pw_A(P) ? cell * P.np : cell, A);
+}
+// param.b(cell, x_pt)
+__device__ inline void load_b(const DevParams& P, long long cell, int pt, double b[3]) {
+  b[0] = b[1] = b[2] = 0.0;
+  if (!P.b) return;
+  const long long e = (P.pw & PDB200_POINTWISE_B) ? cell * P.np + pt : cell;
+  for (int d = 0; d < P.dim; d++) b[d] = __ldg(P.b + e * P.dim + d);
+}
+// param.c(cell, x_q) at volume point q
+__device__ __forceinline__ double load_c(const DevParams& P, long long cell, int q) {
+  if (!P.c) return 0.0;
+  return __ldg(P.c + ((P.pw & PDB200_POINTWISE_C) ? cell * P.nq + q : cell));
+}
+// param.bctype(intersection, x_q): per face or per face quadrature point (QkDG, convectiondiffusiondg.hh:763)
+__device__ __forceinline__ int load_bctype(const DevParams& P, long long bf, int q) {
+  if (!P.bctype) return (int)PDB200_BC_DIRICHLET;
+  return (int)P.bctype[(P.pw & PDB200_POINTWISE_BCTYPE) ? bf * P.nfq + q : bf];
+}
+
+// weightsOff penalty of the Kronecker kernels: alpha/h_F k(k+d-1) on every interior and Dirichlet face REGARDLESS of A
+// (harmonic_average = 1, convectiondiffusiondg.hh:334-338, 724-727), none on faces without a u-dependent term.  The face
+// set-up marks the latter by cs = -0.0 (cs >= +0 everywhere else), so that a cell with A == 0 keeps its penalty.
+#ifdef __CUDACC__
+__device__ __forceinline__ bool face_has_penalty(double cs) { return __double2hiint(cs) >= 0; }
+#endif
+
+// The Kronecker fast paths need cell-wise constant DIAGONAL A, no convection and per-face boundary types; anything
+// sampled per quadrature point (P.pw) runs through the reference-order kernels.
+inline bool kron_coefficients(const DevParams& P) { return P.pw == 0 && P.b == nullptr && P.a_mode != PDB200_A_FULL; }
 
 // ---- launchers implemented in the .cu files ------------------------------------------------
 

@@ -392,7 +392,7 @@ void setup_variant(BlockJacPlan* plan, const DevParams& P, const Kron1D& K1, cud
 }  // namespace
 
 bool dg_blockjac_supported(const DevParams& P) {
-  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.b == nullptr && P.a_mode != PDB200_A_FULL && P.m >= P.k + 1 && P.theta == -1.0 &&
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && kron_coefficients(P) && P.m >= P.k + 1 && P.theta == -1.0 &&
          (P.dim == 2 || P.dim == 3) && (P.k == 1 || P.k == 2);
 }
 
@@ -432,7 +432,7 @@ void dg_blockjac_invalidate(BlockJacPlan* plan) {
 }
 
 int launch_dg_diagonal(const DevParams& P, const Kron1D& K1, double* d, cudaStream_t s) {
-  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.b == nullptr && P.a_mode != PDB200_A_FULL && P.m >= P.k + 1 &&
+  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && kron_coefficients(P) && P.m >= P.k + 1 &&
         (P.dim == 2 || P.dim == 3) && (P.k == 1 || P.k == 2)))
     throw Error("matrix-free point diagonal: needs QkDG in the Lagrange basis (k = 1, 2; dim = 2, 3), diagonal A, b = 0");
   const unsigned blocks = (unsigned)((P.ncells + 127) / 128);

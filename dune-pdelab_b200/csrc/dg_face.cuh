@@ -73,7 +73,8 @@ __device__ __forceinline__ bool direction_coefs(const DevParams& P, const SmallC
     }
     cs[side] = kind == 0 ? csi : (kind == 1 ? aih : 0.0);
     co[side] = kind == 0 ? coi : 0.0;
-    cg[side] = P.weights_on ? C.alpha_pen * (cs[side] + co[side]) : (cs[side] != 0.0 ? C.alpha_pen * C.ih2[d] : 0.0);
+    // weightsOff: the penalty does not depend on A (harmonic_average = 1): selected by the kind of face
+    cg[side] = P.weights_on ? C.alpha_pen * (cs[side] + co[side]) : (kind != 2 ? C.alpha_pen * C.ih2[d] : 0.0);
   }
   A0 = a * C.ih2[d];
   return constrained;

@@ -161,7 +161,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // Branch-free (selects only) so that the six reciprocal chains of a cell interleave.  The penalty
 // coefficient is not returned: cg = alpha_pen (cs + co) with weights on (interior: 2 alpha_pen hh,
-// Dirichlet: alpha_pen a / h^2), alpha_pen / h^2 wherever cs != 0 with weights off (penalty_coef).
+// Dirichlet: alpha_pen a / h^2), alpha_pen / h^2 on every interior / Dirichlet face with weights off (penalty_coef).
 template <bool WEIGHTS_ON>
 __device__ __forceinline__ void face_coef(int kind, double a, double ao, double ih2, double& cs, double& co) {
   const double aih = a * ih2;
@@ -173,13 +173,14 @@ __device__ __forceinline__ void face_coef(int kind, double a, double ao, double 
     csi = 0.5 * aih;
     coi = 0.5 * ao * ih2;
   }
-  cs = kind == 0 ? csi : (kind == 1 ? aih : 0.0);  // Dirichlet boundary: w_self = 1
+  // Dirichlet boundary: w_self = 1; faces without u-dependent terms: -0.0 marks "no penalty" for penalty_coef
+  cs = kind == 0 ? csi : (kind == 1 ? aih : (WEIGHTS_ON ? 0.0 : -0.0));
   co = kind == 0 ? coi : 0.0;
 }
 template <bool WEIGHTS_ON>
 __device__ __forceinline__ double penalty_coef(double cs, double co, double ih2, double alpha_pen) {
   if (WEIGHTS_ON) return alpha_pen * (cs + co);
-  return cs != 0.0 ? alpha_pen * ih2 : 0.0;
+  return face_has_penalty(cs) ? alpha_pen * ih2 : 0.0;
 }
 
 // Adds (1/h_d) M^-1 L_d(l, o, r) for the nine lines of a cell along direction S-stride.
@@ -455,7 +456,7 @@ struct FastPlan {
 };
 
 bool dg_fast_supported(const DevParams& P) {
-  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && P.k == 2 && P.m >= 3 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && P.k == 2 && P.m >= 3 && kron_coefficients(P) &&
          P.N[0] % 2 == 0;
 }
 

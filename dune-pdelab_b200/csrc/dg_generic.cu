@@ -119,11 +119,9 @@ __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, cons
     xs[i] = x[cell * N + i];
     r[i] = 0.0;
   }
-  double A_s[3][3], b_s[3] = {0, 0, 0};
-  load_A(P, cell, A_s);
-  if (P.b)
-    for (int d = 0; d < DIM; d++) b_s[d] = P.b[cell * DIM + d];
-  const double c_s = P.c ? P.c[cell] : 0.0;
+  double A_s[3][3], b_s[3];
+  load_A_cell(P, cell, A_s);
+  const bool pwA = pw_A(P);  // permeabilityIsConstantPerCell() == false: A re-evaluated at every point
   const int m = P.m;
 
   double pv[3][K + 1], dv[3][K + 1];
@@ -140,6 +138,9 @@ __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, cons
       }
     }
     point_tables<DIM, K>(P, pt, pv, dv);
+    if (pwA) load_A_at(P, cell, q, A_s);  // :143-146
+    load_b(P, cell, q, b_s);              // param.b(cell, ip.position()), :178
+    const double c_s = load_c(P, cell, q);  // :181
     double u, gu[3];
     interp<DIM, K>(xs, pv, dv, u, gu);
     double Agu[3];
@@ -161,19 +162,18 @@ __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, cons
       const bool onb = side ? c[dir] == P.N[dir] - 1 : c[dir] == 0;
       const double nsign = side ? 1.0 : -1.0;
       double An_s[3];
+      if (pwA) load_A_cell(P, cell, A_s);  // the volume loop left the last point's tensor behind
       for (int d = 0; d < 3; d++) An_s[d] = A_s[d][dir] * nsign;
       const double area = P.area[dir];
       if (!onb) {
         // interior face, this cell's side of alpha_skeleton
         const long long other = cell + (side ? stride[dir] : -stride[dir]);
         for (int i = 0; i < N; i++) xo[i] = x[other * N + i];
-        double A_o[3][3], An_o[3], b_F[3] = {0, 0, 0};
-        load_A(P, other, A_o);
+        double A_o[3][3], An_o[3], b_F[3];
+        load_A_cell(P, other, A_o);
         for (int d = 0; d < 3; d++) An_o[d] = A_o[d][dir] * nsign;
-        if (P.b) {
-          const long long bc = side ? other : cell;  // velocity of the larger-index cell (:426)
-          for (int d = 0; d < DIM; d++) b_F[d] = P.b[bc * DIM + d];
-        }
+        const long long bc = side ? other : cell;  // velocity of the larger-index cell (:426) ...
+        const int bside = 0;                       // ... evaluated on ITS lower face (geo_in_inside)
         const double h_F = fmin(P.vol, P.vol) / area;  // :313
         double omega_s, omega_o, harmonic_average;
         if (P.weights_on) {  // :326-338
@@ -185,13 +185,29 @@ __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, cons
           omega_s = omega_o = 0.5;
           harmonic_average = 1.0;
         }
-        const double penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);  // :346
-        const double betan = b_F[dir] * nsign;
-        // upwinding (:429-438): the reference tests (b.n_ref >= 0) with n_ref the normal of the
-        // larger-index cell
-        const bool take_self = side == 0 ? (betan >= 0.0) : !((-betan) >= 0.0);
+        double penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);  // :346
         double po[3][K + 1], dvo[3][K + 1];
         for (int q = 0; q < P.nfq; q++) {
+          if (pwA) {  // :367-382: both tensors at the face point, weights and penalty only with weightsOn
+            load_A_at(P, cell, face_pt(P, dir, side, q), A_s);
+            load_A_at(P, other, face_pt(P, dir, 1 - side, q), A_o);
+            for (int d = 0; d < 3; d++) {
+              An_s[d] = A_s[d][dir] * nsign;
+              An_o[d] = A_o[d][dir] * nsign;
+            }
+            if (P.weights_on) {
+              const double delta_s = An_s[dir] * nsign, delta_o = An_o[dir] * nsign;
+              omega_s = delta_o / (delta_s + delta_o + 1e-20);
+              omega_o = delta_s / (delta_s + delta_o + 1e-20);
+              harmonic_average = 2.0 * delta_s * delta_o / (delta_s + delta_o + 1e-20);
+              penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);
+            }
+          }
+          load_b(P, bc, face_pt(P, dir, bside, q), b_F);  // param.b(cell_inside, iplocal_s), :426
+          const double betan = b_F[dir] * nsign;
+          // upwinding (:429-438): the reference tests (b.n_ref >= 0) with n_ref the normal of the
+          // larger-index cell
+          const bool take_self = side == 0 ? (betan >= 0.0) : !((-betan) >= 0.0);
           int pt_s[3] = {0, 0, 0}, pt_o[3];
           double weight = 1.0;
           {
@@ -224,13 +240,22 @@ __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, cons
       } else {
         // residual_boundary_integral, :684-879
         const long long bf = bface_index(P, c, dir, side);
-        const int bctype = P.bctype ? (int)P.bctype[bf] : (int)PDB200_BC_DIRICHLET;
-        if (bctype == PDB200_BC_NONE) continue;
-        const double h_F = P.vol / area;                                                          // :717
-        const double harmonic_average = P.weights_on ? An_s[dir] * nsign : 1.0;                   // :724-727
-        const double penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);  // :734
-        const double betan = b_s[dir] * nsign;
+        const double h_F = P.vol / area;                                                    // :717
+        double harmonic_average = P.weights_on ? An_s[dir] * nsign : 1.0;                   // :724-727
+        double penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);  // :734
         for (int q = 0; q < P.nfq; q++) {
+          if (pwA) {  // :752-760
+            load_A_at(P, cell, face_pt(P, dir, side, q), A_s);
+            for (int d = 0; d < 3; d++) An_s[d] = A_s[d][dir] * nsign;
+            if (P.weights_on) {
+              harmonic_average = An_s[dir] * nsign;
+              penalty = (P.alpha / h_F) * harmonic_average * degree * (degree + DIM - 1);
+            }
+          }
+          const int bctype = load_bctype(P, bf, q);  // param.bctype(ig.intersection(), ip.position()), :763
+          if (bctype == PDB200_BC_NONE) continue;
+          load_b(P, cell, face_pt(P, dir, side, q), b_s);  // param.b(cell_inside, iplocal_s), :797
+          const double betan = b_s[dir] * nsign;
           int pt[3] = {0, 0, 0};
           double weight = 1.0;
           {

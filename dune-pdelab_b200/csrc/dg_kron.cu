@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
         csi = 0.5 * aih;
         coi = 0.5 * ao * C.ih2[d];
       }
-      ccs[f] = kind == 0 ? csi : (kind == 1 ? aih : 0.0);
+      ccs[f] = kind == 0 ? csi : (kind == 1 ? aih : -0.0);  // -0.0: no u-dependent term (face_has_penalty)
       cco[f] = kind == 0 ? coi : 0.0;
       if (side == 0) cA0[d] = aih;
     }
@@ -321,8 +321,8 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       const double A0 = cA0[d], csL = ccs[2 * d], coL = cco[2 * d], csR = ccs[2 * d + 1], coR = cco[2 * d + 1];
-      const double cgL = P.weights_on ? C.alpha_pen * (csL + coL) : (csL != 0.0 ? C.alpha_pen * C.ih2[d] : 0.0);
-      const double cgR = P.weights_on ? C.alpha_pen * (csR + coR) : (csR != 0.0 ? C.alpha_pen * C.ih2[d] : 0.0);
+      const double cgL = P.weights_on ? C.alpha_pen * (csL + coL) : (face_has_penalty(csL) ? C.alpha_pen * C.ih2[d] : 0.0);
+      const double cgR = P.weights_on ? C.alpha_pen * (csR + coR) : (face_has_penalty(csR) ? C.alpha_pen * C.ih2[d] : 0.0);
       const double ctL = -C.theta * csL, ctR = C.theta * csR;
       const double m0c = C.m0[s] * csL, mkc = -C.mk[s] * csR;
 #pragma unroll
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
     double cg[6], ct[6];
 #pragma unroll
     for (int f = 0; f < 6; f++) {
-      cg[f] = P.weights_on ? C.alpha_pen * (ccs[f] + cco[f]) : (ccs[f] != 0.0 ? C.alpha_pen * C.ih2[f >> 1] : 0.0);
+      cg[f] = P.weights_on ? C.alpha_pen * (ccs[f] + cco[f]) : (face_has_penalty(ccs[f]) ? C.alpha_pen * C.ih2[f >> 1] : 0.0);
       ct[f] = (f & 1) ? C.theta * ccs[f] : -C.theta * ccs[f];
     }
     // z-plane layout: plane iz = s; index in plane = iy * N1 + ix
@@ -474,7 +474,7 @@ struct KronPlan {
 };
 
 bool dg_kron_supported(const DevParams& P) {
-  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && (P.k == 4 || P.k == 3) && P.m >= P.k + 1 && P.b == nullptr && P.a_mode != PDB200_A_FULL &&
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && (P.k == 4 || P.k == 3) && P.m >= P.k + 1 && kron_coefficients(P) &&
          P.N[0] % 2 == 0;
 }
 

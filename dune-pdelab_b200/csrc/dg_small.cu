@@ -101,7 +101,7 @@ void launch_variant(const DevParams& P, const Kron1D& K1, const double* z, doubl
 }  // namespace
 
 bool dg_small_supported(const DevParams& P) {
-  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.b == nullptr && P.a_mode != PDB200_A_FULL && P.m >= P.k + 1)) return false;
+  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && kron_coefficients(P) && P.m >= P.k + 1)) return false;
   return (P.dim == 2 && (P.k == 1 || P.k == 2)) || (P.dim == 3 && P.k == 1);
 }
 

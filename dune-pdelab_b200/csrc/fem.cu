@@ -99,11 +99,9 @@ __device__ __forceinline__ void fem_cell_volume(const DevParams& P, long long ce
   const double* B = P.P;   // B[q*N1 + i] = p_i(x_q)
   const double* D = P.DP;  // D[q*N1 + i] = p_i'(x_q)
   double A[3][3];
-  load_A(P, cell, A);
-  double bv[3] = {0.0, 0.0, 0.0};
-  if (P.b)
-    for (int d = 0; d < DIM; d++) bv[d] = __ldg(P.b + cell * DIM + d);
-  const double cc = P.c ? __ldg(P.c + cell) : 0.0;
+  load_A_cell(P, cell, A);
+  const bool pwA = pw_A(P);
+  double bv[3];
   double u[N], gx[N], gy[N], gz[N];
   if (DIM == 3) {
     double t1[N], d1[N], t2[N], t2y[N], d2[N];
@@ -131,6 +129,9 @@ __device__ __forceinline__ void fem_cell_volume(const DevParams& P, long long ce
     double w = P.wq[q0] * P.wq[q1];
     if (DIM == 3) w *= P.wq[q2];
     const double factor = w * P.vol;
+    if (pwA) load_A_at(P, cell, q, A);      // !permeabilityIsConstantPerCell, convectiondiffusionfem.hh:97-100
+    load_b(P, cell, q, bv);                 // param.b / param.c at the quadrature point, :127-128
+    const double cc = load_c(P, cell, q);
     double g[3] = {gx[q] * P.ih[0], gy[q] * P.ih[1], DIM == 3 ? gz[q] * P.ih[2] : 0.0};
     double s = cc * u[q];
     if (RESIDUAL && P.f) s -= __ldg(P.f + cell * N + q);
@@ -239,8 +240,10 @@ __device__ __noinline__ void fem_cell_boundary(const DevParams& P, long long cel
   if (bctype == PDB200_BC_NEUMANN && !(RESIDUAL && P.j)) return;
   const int m = P.m;
   const double area = P.area[dir];
-  const double bn = P.b ? P.b[cell * DIM + dir] * (side ? 1.0 : -1.0) : 0.0;
   for (int q = 0; q < P.nfq; q++) {
+    double bv[3];
+    load_b(P, cell, face_pt(P, dir, side, q), bv);  // param.b(cell_inside, local), :254
+    const double bn = bv[dir] * (side ? 1.0 : -1.0);
     int pt[3] = {0, 0, 0};
     double weight = 1.0;
     {
@@ -412,7 +415,7 @@ void launch_fem_variant(const FemPlan* plan, const DevParams& P, const double* x
 template <int DIM, int K>
 void launch_fem(FemPlan* plan, const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                 cudaStream_t s) {
-  const bool kron = P.a_mode != PDB200_A_FULL && P.b == nullptr;
+  const bool kron = kron_coefficients(P);
   plan->fused_constraints = false;
   if (!kron) {
     if (residual)
@@ -491,7 +494,7 @@ const uint64_t* fem_plan_constrained(const FemPlan* p, long long* n) {
 // d = point diagonal of the Jacobian (PointDiagonalLocalOperatorWrapper, localoperator/pointdiagonalwrapper.hh),
 // with 1 on the constrained rows (the unit rows of set_trivial_rows, assemblerutilities.hh:666-684)
 void launch_fem_diagonal(FemPlan* plan, const DevParams& P, double* d, cudaStream_t s) {
-  if (P.a_mode == PDB200_A_FULL || P.b != nullptr || P.ndofs >= (1ll << 31))
+  if (!kron_coefficients(P) || P.ndofs >= (1ll << 31))
     throw Error("matrix-free point diagonal: needs a diagonal tensor and b = 0");
   if (P.m != P.k + 1) throw Error("conforming Qk kernel: intorderadd must be 0 or 1 (k+1 Gauss points)");
   const bool fused = P.bctype == nullptr;

@@ -310,9 +310,84 @@ __device__ __forceinline__ double qk_outflow_entry(const DevParams& P, const Mat
   return qk_boundary_entry(P, T1, cell_index(P.N, c0, c1, c2), c, li, lj);
 }
 
+// Local Jacobian entry (i, j) of one cell with coefficients in the point-wise layout (P.pw != 0): the quadrature
+// loops of jacobian_volume (convectiondiffusionfem.hh:140-203, A / b / c at every point) and, on outflow faces, of
+// jacobian_boundary (:279-325, b at the face points), in the reference's order.  Parity path.
+template <int DIM, int K>
+__device__ double qk_pw_entry(const DevParams& P, int c0, int c1, int c2, int i, int j, bool outflow) {
+  constexpr int N1 = K + 1;
+  const int c[3] = {c0, c1, c2};
+  const long long cell = cell_index(P.N, c0, c1, c2);
+  const int li[3] = {i % N1, (i / N1) % N1, i / (N1 * N1)};
+  const int lj[3] = {j % N1, (j / N1) % N1, j / (N1 * N1)};
+  const int m = P.m;
+  double A[3][3], b[3];
+  load_A_cell(P, cell, A);
+  const bool pwA = pw_A(P);
+  double v = 0.0;
+  for (int q = 0; q < P.nq; q++) {
+    int pt[3] = {0, 0, 0};
+    double w = 1.0;
+    {
+      int qq = q;
+      for (int d = 0; d < DIM; d++) {
+        pt[d] = qq % m;
+        qq /= m;
+        w *= P.wq[pt[d]];
+      }
+    }
+    if (pwA) load_A_at(P, cell, q, A);
+    load_b(P, cell, q, b);
+    const double cc = load_c(P, cell, q);
+    double phi_i = 1.0, phi_j = 1.0, gi[3] = {0, 0, 0}, gj[3] = {0, 0, 0};
+    for (int d = 0; d < DIM; d++) {
+      phi_i *= P.P[pt[d] * N1 + li[d]];
+      phi_j *= P.P[pt[d] * N1 + lj[d]];
+    }
+    for (int d = 0; d < DIM; d++) {
+      double a = P.ih[d] * P.DP[pt[d] * N1 + li[d]], bb = P.ih[d] * P.DP[pt[d] * N1 + lj[d]];
+      for (int l = 0; l < DIM; l++)
+        if (l != d) {
+          a *= P.P[pt[l] * N1 + li[l]];
+          bb *= P.P[pt[l] * N1 + lj[l]];
+        }
+      gi[d] = a;
+      gj[d] = bb;
+    }
+    double Agj[3];
+    for (int a = 0; a < 3; a++) Agj[a] = A[a][0] * gj[0] + A[a][1] * gj[1] + A[a][2] * gj[2];
+    const double adv = b[0] * gi[0] + b[1] * gi[1] + b[2] * gi[2];
+    v += (Agj[0] * gi[0] + Agj[1] * gi[1] + Agj[2] * gi[2] - phi_j * adv + cc * phi_j * phi_i) * (w * P.vol);
+  }
+  if (outflow)
+    for (int dir = 0; dir < DIM; dir++)
+      for (int side = 0; side < 2; side++) {
+        const bool on = side ? c[dir] == P.N[dir] - 1 : c[dir] == 0;
+        if (!on || P.side_kind[dir][side] == PDB200_SIDE_PROCESSOR) continue;
+        const int node = side ? K : 0;
+        if (li[dir] != node || lj[dir] != node) continue;  // p_i(xi) = delta at the face
+        if (P.bctype[bface_index(P, c, dir, side)] != PDB200_BC_OUTFLOW) continue;  // type at the face centre
+        for (int q = 0; q < P.nfq; q++) {
+          double w = 1.0, pij = 1.0;
+          int qq = q;
+          for (int d = 0; d < DIM; d++)
+            if (d != dir) {
+              const int ptd = qq % m;
+              qq /= m;
+              w *= P.wq[ptd];
+              pij *= P.P[ptd * N1 + li[d]] * P.P[ptd * N1 + lj[d]];
+            }
+          load_b(P, cell, face_pt(P, dir, side, q), b);
+          v += b[dir] * (side ? 1.0 : -1.0) * pij * (w * P.area[dir]);
+        }
+      }
+  return v;
+}
+
 // NT1: a single unit table (scalar or identity diffusion, no b, no c) — the cell weights then
-// travel by warp shuffle; otherwise they are staged in shared memory.
-template <int G, int DIM, int K, bool NT1, bool OUTFLOW>
+// travel by warp shuffle; otherwise they are staged in shared memory.  PW: coefficients in the point-wise layout,
+// entries by quadrature (qk_pw_entry) instead of unit tables.
+template <int G, int DIM, int K, bool NT1, bool OUTFLOW, bool PW = false>
 __global__ void __launch_bounds__(QK_THREADS)
     qk_assemble_kernel(const DevParams P, const QkDecode D, const Mat1D T1, const QkTables Q,
                        const double* __restrict__ tables_g, const QkLut* __restrict__ lut_g,
@@ -323,7 +398,7 @@ __global__ void __launch_bounds__(QK_THREADS)
   constexpr int ROWS_PER_CTA = QK_THREADS / G;
   constexpr int NCAND = DIM == 3 ? 8 : 4;
   extern __shared__ double sm[];
-  const int nt = NT1 ? 1 : Q.nt;
+  const int nt = PW ? 0 : (NT1 ? 1 : Q.nt);
   double* tab = sm;                                    // [nt][N*N]
   double* buf = tab + nt * N * N;                      // [ROWS_PER_CTA][MAXLEN]
   double* wbuf = buf + ROWS_PER_CTA * MAXLEN;          // [ROWS_PER_CTA][NCAND][nt]   (unused if NT1)
@@ -398,13 +473,15 @@ __global__ void __launch_bounds__(QK_THREADS)
       const int pbase = (K * c0 - R.lo[0]) + 5 * ((K * c1 - R.lo[1]) + 5 * (DIM == 3 ? K * c2 - R.lo[2] : 0));
       if (lane < N) {
         double v;
-        if (NT1) {
+        if (PW) {
+          v = qk_pw_entry<DIM, K>(P, c0, c1, c2, i, lane, OUTFLOW);
+        } else if (NT1) {
           v = w1 * tab[i * N + lane];
         } else {
           v = 0.0;
           for (int t = 0; t < nt; t++) v = fma(wb[ci * nt + t], tab[(t * N + i) * N + lane], v);
         }
-        if (OUTFLOW) v += qk_outflow_entry<DIM, K>(P, T1, c0, c1, c2, i, lane);
+        if (OUTFLOW && !PW) v += qk_outflow_entry<DIM, K>(P, T1, c0, c1, c2, i, lane);
         rb[o2s[pbase + joff]] += v;
       }
       __syncwarp(gmask);
@@ -820,16 +897,17 @@ __device__ __forceinline__ double dot3d(const double* a, const double* b) { retu
 // Entry (i = test DOF of cell e, j = trial DOF of the column cell) of the block with face code `face`.
 __device__ double dg_entry(const DevParams& P, long long e, const int c[3], int face, int i, int j, int* errflag) {
   const int m = P.m, dim = P.dim;
-  double A_s[3][3], b_s[3] = {0, 0, 0};
-  load_A(P, e, A_s);
-  if (P.b)
-    for (int d = 0; d < dim; d++) b_s[d] = P.b[e * dim + d];
+  double A_s[3][3], b_s[3];
+  load_A_cell(P, e, A_s);
+  const bool pwA = pw_A(P);  // permeabilityIsConstantPerCell() == false
   const long long stride[3] = {1, (long long)P.N[0], (long long)P.N[0] * P.N[1]};
   double v = 0.0;
   if (face < 0) {
     // jacobian_volume, convectiondiffusiondg.hh:199-266
-    const double c_s = P.c ? P.c[e] : 0.0;
     for (int q = 0; q < P.nq; q++) {
+      if (pwA) load_A_at(P, e, q, A_s);       // :234-237
+      load_b(P, e, q, b_s);                   // :255
+      const double c_s = load_c(P, e, q);     // :258
       int pt[3] = {0, 0, 0}, qq = q;
       double w = 1.0;
       for (int d = 0; d < dim; d++) {
@@ -850,19 +928,17 @@ __device__ double dg_entry(const DevParams& P, long long e, const int c[3], int 
       const bool onb = side ? c[dir] == P.N[dir] - 1 : c[dir] == 0;
       const double nsign = side ? 1.0 : -1.0;
       double An_s[3];
+      if (pwA) load_A_cell(P, e, A_s);
       for (int d = 0; d < 3; d++) An_s[d] = A_s[d][dir] * nsign;
       const double area = P.area[dir];
       if (!onb) {
         // jacobian_skeleton, :484-669, this cell's rows (ss / sn when it is the inside cell,
         // nn / ns when it is the outside cell)
         const long long other = e + (side ? stride[dir] : -stride[dir]);
-        double A_o[3][3], An_o[3], b_F[3] = {0, 0, 0};
-        load_A(P, other, A_o);
+        double A_o[3][3], An_o[3], b_F[3];
+        load_A_cell(P, other, A_o);
         for (int d = 0; d < 3; d++) An_o[d] = A_o[d][dir] * nsign;
-        if (P.b) {
-          const long long bc = side ? other : e;
-          for (int d = 0; d < dim; d++) b_F[d] = P.b[bc * dim + d];
-        }
+        const long long bc = side ? other : e;  // velocity of the larger-index cell on its lower face (:613)
         const double h_F = fmin(P.vol, P.vol) / area;
         double omega_s, omega_o, harm;
         if (P.weights_on) {
@@ -874,10 +950,26 @@ __device__ double dg_entry(const DevParams& P, long long e, const int c[3], int 
           omega_s = omega_o = 0.5;
           harm = 1.0;
         }
-        const double penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
-        const double betan = b_F[dir] * nsign;
-        const bool take_self = side == 0 ? (betan >= 0.0) : !((-betan) >= 0.0);
+        double penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
         for (int q = 0; q < P.nfq; q++) {
+          if (pwA) {  // :575-590
+            load_A_at(P, e, face_pt(P, dir, side, q), A_s);
+            load_A_at(P, other, face_pt(P, dir, 1 - side, q), A_o);
+            for (int d = 0; d < 3; d++) {
+              An_s[d] = A_s[d][dir] * nsign;
+              An_o[d] = A_o[d][dir] * nsign;
+            }
+            if (P.weights_on) {
+              const double ds = An_s[dir] * nsign, dn = An_o[dir] * nsign;
+              omega_s = dn / (ds + dn + 1e-20);
+              omega_o = ds / (ds + dn + 1e-20);
+              harm = 2.0 * ds * dn / (ds + dn + 1e-20);
+              penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
+            }
+          }
+          load_b(P, bc, face_pt(P, dir, 0, q), b_F);
+          const double betan = b_F[dir] * nsign;
+          const bool take_self = side == 0 ? (betan >= 0.0) : !((-betan) >= 0.0);
           int pt_s[3] = {0, 0, 0}, pt_o[3], qq = q;
           double w = 1.0;
           for (int d = 0; d < dim; d++)
@@ -905,17 +997,26 @@ __device__ double dg_entry(const DevParams& P, long long e, const int c[3], int 
       } else if (face < 0 && P.side_kind[dir][side] != PDB200_SIDE_PROCESSOR) {
         // jacobian_boundary, :902-1044
         const long long bf = bface_index(P, c, dir, side);
-        const int bctype = P.bctype ? (int)P.bctype[bf] : (int)PDB200_BC_DIRICHLET;
-        if (bctype == PDB200_BC_NONE || bctype == PDB200_BC_NEUMANN) continue;
         const double h_F = P.vol / area;
-        const double harm = P.weights_on ? An_s[dir] * nsign : 1.0;
-        const double penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
-        const double betan = b_s[dir] * nsign;
-        if (bctype == PDB200_BC_OUTFLOW && betan < -1e-30) {
-          *errflag = 1;
-          continue;
-        }
+        double harm = P.weights_on ? An_s[dir] * nsign : 1.0;
+        double penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
         for (int q = 0; q < P.nfq; q++) {
+          if (pwA) {  // :967-977
+            load_A_at(P, e, face_pt(P, dir, side, q), A_s);
+            for (int d = 0; d < 3; d++) An_s[d] = A_s[d][dir] * nsign;
+            if (P.weights_on) {
+              harm = An_s[dir] * nsign;
+              penalty = (P.alpha / h_F) * harm * P.k * (P.k + dim - 1);
+            }
+          }
+          const int bctype = load_bctype(P, bf, q);  // :979
+          if (bctype == PDB200_BC_NONE || bctype == PDB200_BC_NEUMANN) continue;
+          load_b(P, e, face_pt(P, dir, side, q), b_s);  // :995
+          const double betan = b_s[dir] * nsign;
+          if (bctype == PDB200_BC_OUTFLOW && betan < -1e-30) {
+            *errflag = 1;
+            continue;
+          }
           int pt[3] = {0, 0, 0}, qq = q;
           double w = 1.0;
           for (int d = 0; d < dim; d++)
@@ -1400,15 +1501,15 @@ int matrix_pattern_write(MatrixPlan* p, int layout, void* rowptr, bool rowptr_de
   return launches;
 }
 
-template <int G, int DIM, int K, bool NT1, bool OUTFLOW>
+template <int G, int DIM, int K, bool NT1, bool OUTFLOW, bool PW = false>
 static int launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
   constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
   constexpr int MAXLEN = DIM == 3 ? (2 * K + 1) * (2 * K + 1) * (2 * K + 1) : (2 * K + 1) * (2 * K + 1);
   constexpr int ROWS_PER_CTA = QK_THREADS / G;
   constexpr int NCAND = DIM == 3 ? 8 : 4;
-  const int nt = NT1 ? 1 : p->Q.nt;
+  const int nt = PW ? 0 : (NT1 ? 1 : p->Q.nt);
   const size_t smem = ((size_t)nt * N * N + (size_t)ROWS_PER_CTA * MAXLEN + (NT1 ? 0 : (size_t)ROWS_PER_CTA * NCAND * nt)) * sizeof(double) + 1000;
-  auto kern = qk_assemble_kernel<G, DIM, K, NT1, OUTFLOW>;
+  auto kern = qk_assemble_kernel<G, DIM, K, NT1, OUTFLOW, PW>;
   PDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148, per_sm = 1;
   PDB_CUDA(cudaGetDevice(&dev));
@@ -1433,6 +1534,9 @@ static int launch_qk_assemble_t(MatrixPlan* p, double* v, bool fresh, cudaStream
 template <int G, int DIM, int K>
 static int launch_qk_assemble_nt(MatrixPlan* p, double* v, bool fresh, cudaStream_t s) {
   const bool outflow = p->P.bctype != nullptr && p->P.b != nullptr;  // jacobian_boundary has outflow terms only
+  if (p->P.pw)  // coefficients sampled per quadrature point
+    return outflow ? launch_qk_assemble_t<G, DIM, K, false, true, true>(p, v, fresh, s)
+                   : launch_qk_assemble_t<G, DIM, K, false, false, true>(p, v, fresh, s);
   if (outflow) return launch_qk_assemble_t<G, DIM, K, false, true>(p, v, fresh, s);
   if (p->Q.nt == 1) return launch_qk_assemble_t<G, DIM, K, true, false>(p, v, fresh, s);
   return launch_qk_assemble_t<G, DIM, K, false, false>(p, v, fresh, s);

@@ -152,6 +152,37 @@ void check_compatible(const pdb200_operator* g0, const pdb200_operator* g1) {
     throw Error("OneStepGridOperator: the spatial operator's quadrature must be at least as fine as the temporal one's");
   if (P1.b || P1.g || P1.j || P1.o || (P1.f && P1.m != P0.m))
     throw Error("OneStepGridOperator: the temporal operator may only carry A, c and f (on the same quadrature)");
+  if (P0.pw || P1.pw)
+    throw Error("OneStepGridOperator: the stage operator combines cell-wise coefficient fields; the point-wise layouts "
+                "(pdb200_problem::pointwise) are not supported here");
+  if (P0.dg) {
+    // The fused operator w0 go0 + w1 go1 is evaluated with go0's face terms on the COMBINED tensor: with a diffusion
+    // tensor in go1 the harmonic weights and the penalty (non-linear in A) and go0's Dirichlet / Neumann terms would see
+    // it too, which is not w0 R0 + w1 R1.  A QkDG temporal operator must be a pure reaction form without face terms
+    // (L2, localoperator/l2.hh): A == 0 and no boundary integrals.
+    if (P1.a_mode != PDB200_A_IDENTITY && P1.A) {
+      std::vector<double> a1(a_len(P1, P1.a_mode));
+      PDB_CUDA(cudaMemcpy(a1.data(), P1.A, a1.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (double v : a1)
+        if (v != 0.0) throw Error("OneStepGridOperator: on QkDG spaces the temporal operator must be an L2 mass operator (A == 0)");
+    } else if (P1.a_mode == PDB200_A_IDENTITY) {
+      throw Error("OneStepGridOperator: on QkDG spaces the temporal operator must be an L2 mass operator (A == 0, not the identity)");
+    }
+    bool none = P1.bctype != nullptr;
+    if (none) {
+      long long nbf1 = 0;
+      for (int d = 0; d < P1.dim; d++) nbf1 += 2 * (P1.ncells / P1.N[d]);
+      std::vector<int8_t> bt((size_t)nbf1);
+      PDB_CUDA(cudaMemcpy(bt.data(), P1.bctype, bt.size(), cudaMemcpyDeviceToHost));
+      for (int8_t v : bt) none = none && v == PDB200_BC_NONE;
+    }
+    bool has_domain_side = false;
+    for (int d = 0; d < P1.dim; d++)
+      for (int sd = 0; sd < 2; sd++) has_domain_side |= P1.side_kind[d][sd] == PDB200_SIDE_DOMAIN;
+    if (has_domain_side && !none)
+      throw Error("OneStepGridOperator: on QkDG spaces the temporal operator must carry boundary type None on every face "
+                  "(an L2 mass operator has no boundary integrals)");
+  }
 }
 
 void build_stage_operator(pdb200_onestep* os) {
@@ -377,8 +408,9 @@ int pdb200_onestep_set_method(pdb200_onestep_handle os, int stages, const double
   os->b.assign(b, b + (size_t)stages * (stages + 1));
   os->d.assign(d, d + stages + 1);
   os->implicit_method = implicit != 0;
-  // OneStepGridOperator's constructor: explicit methods never assemble dt (onestep.hh:74-75)
-  if (!os->implicit_method) os->dt_mode = PDB200_ONESTEP_DO_NOT_ASSEMBLE_DT;
+  // OneStepGridOperator's constructor: explicit methods never assemble dt (onestep.hh:74-75).  In the reference
+  // `implicit` is a template parameter of the grid operator; here one handle may see both kinds of method, so the
+  // user's mode (dt_mode) is kept and the EFFECTIVE mode is derived from the method in pre_step.
   os->stage_no = 0;
   OS_CATCH
 }
@@ -401,10 +433,11 @@ int pdb200_onestep_pre_step(pdb200_onestep_handle os, double time, double dt) {
   os->time = time;
   os->dt = dt;
   // onestep/localassembler.hh:101-130
-  if (os->dt_mode == PDB200_ONESTEP_DIVIDE_OPERATOR1_BY_DT) {
+  const int mode = os->implicit_method ? os->dt_mode : PDB200_ONESTEP_DO_NOT_ASSEMBLE_DT;
+  if (mode == PDB200_ONESTEP_DIVIDE_OPERATOR1_BY_DT) {
     os->dt_factor0 = 1.0;
     os->dt_factor1 = 1.0 / dt;
-  } else if (os->dt_mode == PDB200_ONESTEP_MULTIPLY_OPERATOR0_BY_DT) {
+  } else if (mode == PDB200_ONESTEP_MULTIPLY_OPERATOR0_BY_DT) {
     os->dt_factor0 = dt;
     os->dt_factor1 = 1.0;
   } else {
@@ -477,26 +510,47 @@ int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* 
 // alpha += dt beta,  solve D x_r = alpha,  i.e.  x_r = -M^-1 (sum_{i<r} a_ri M x_i + b_ri dt R0(x_i)).
 // The mass matrix of a QkDG space is block diagonal: for k <= 2 the solve is the exact block inverse by fast
 // diagonalisation (one kernel, no Krylov loop), otherwise a CG on the mass operator to `reduction`.
-int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const double* const* x, double* xr, double reduction) {
+// The stage is split like preStage so that a host with time-dependent coefficients can re-sample them at
+// t + d_i dt before add(i): the jacobian-residual engine delegates to the pre-stage engine, which sets
+// la0.setTime(time + d[s] dt) for every earlier stage s (jacobianresidualengine.hh, prestageengine.hh:208-211).
+int pdb200_onestep_explicit_stage_begin(pdb200_onestep_handle os, int stage) {
   OS_TRY
   OS_CHECK(os);
   need_method(os);
   if (os->implicit_method) throw Error("explicit one step method called with implicit scheme");  // explicitonestep.hh:226-228
-  if (stage < 1 || stage > os->s || !x || !xr) throw Error("explicit stage: stage must be in 1..s and the vectors given");
-  pdb200_operator *g0 = os->go0, *g1 = os->go1;
+  if (stage < 1 || stage > os->s) throw Error("explicit stage: stage must be in 1..s");
+  pdb200_operator* g0 = os->go0;
   if (!g0->P.dg)
     throw Error("explicit one-step methods need a block-diagonal mass matrix (QkDG spaces)");
   PDB_CUDA(cudaSetDevice(g0->device));
   os->stage_no = stage;
   os->stage->stream = g0->stream;
+  PDB_CUDA(cudaMemsetAsync(os->const_residual, 0, (size_t)g0->P.ndofs * sizeof(double), os->stage->stream));
+  OS_CATCH
+}
+
+int pdb200_onestep_explicit_stage_add(pdb200_onestep_handle os, int i, const double* x) {
+  OS_TRY
+  OS_CHECK(os);
+  need_stage(os);
+  if (os->implicit_method) throw Error("explicit one step method called with implicit scheme");
+  if (i < 0 || i >= os->stage_no || !x) throw Error("explicit stage: the solutions of stages 0..r-1 are needed");
+  PDB_CUDA(cudaSetDevice(os->go0->device));
+  const double a = coef(os->a, os->s, os->stage_no, i), b = coef(os->b, os->s, os->stage_no, i);
+  add_weighted_residual(os, std::fabs(b) > 1e-6 ? b * os->dt : 0.0, std::fabs(a) > 1e-6 ? a : 0.0, x);
+  OS_CATCH
+}
+
+int pdb200_onestep_explicit_stage_finish(pdb200_onestep_handle os, double* xr, double reduction) {
+  OS_TRY
+  OS_CHECK(os);
+  need_stage(os);
+  if (os->implicit_method) throw Error("explicit one step method called with implicit scheme");
+  if (!xr) throw Error("explicit stage: null result vector");
+  pdb200_operator *g0 = os->go0, *g1 = os->go1;
+  PDB_CUDA(cudaSetDevice(g0->device));
   cudaStream_t s = os->stage->stream;
   const long long n = g0->P.ndofs;
-  PDB_CUDA(cudaMemsetAsync(os->const_residual, 0, (size_t)n * sizeof(double), s));
-  for (int i = 0; i < stage; i++) {
-    if (!x[i]) throw Error("explicit stage: the solutions of stages 0..r-1 are needed");
-    const double a = coef(os->a, os->s, stage, i), b = coef(os->b, os->s, stage, i);
-    add_weighted_residual(os, std::fabs(b) > 1e-6 ? b * os->dt : 0.0, std::fabs(a) > 1e-6 ? a : 0.0, x[i]);
-  }
   Staged XR(os, &os->hr, xr, true);
   g1->stream = s;
   if (dg_blockjac_supported(g1->P)) {
@@ -516,6 +570,17 @@ int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const dou
   XR.copy_back();
   PDB_CUDA(cudaStreamSynchronize(s));
   OS_CATCH
+}
+
+int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const double* const* x, double* xr, double reduction) {
+  if (!x || !xr) {
+    pdb_set_last_error("explicit stage: stage must be in 1..s and the vectors given");
+    return 1;
+  }
+  if (int rc = pdb200_onestep_explicit_stage_begin(os, stage)) return rc;
+  for (int i = 0; i < stage; i++)
+    if (int rc = pdb200_onestep_explicit_stage_add(os, i, x[i])) return rc;
+  return pdb200_onestep_explicit_stage_finish(os, xr, reduction);
 }
 
 int pdb200_onestep_pre_stage(pdb200_onestep_handle os, int stage, const double* const* x) {

@@ -63,14 +63,18 @@ const T* upload(pdb200_operator* op, const T* src, size_t count) {
   return d;
 }
 
+// array lengths in the cell-wise or point-wise layout (header of pdelab_b200.h)
 size_t a_count(const DevParams& P) {
+  const size_t e = (size_t)P.ncells * ((P.pw & PDB200_POINTWISE_A) ? P.np : 1);
   switch (P.a_mode) {
     case PDB200_A_IDENTITY: return 0;
-    case PDB200_A_SCALAR: return (size_t)P.ncells;
-    case PDB200_A_DIAGONAL: return (size_t)P.ncells * P.dim;
-    default: return (size_t)P.ncells * P.dim * P.dim;
+    case PDB200_A_SCALAR: return e;
+    case PDB200_A_DIAGONAL: return e * P.dim;
+    default: return e * P.dim * P.dim;
   }
 }
+size_t b_count(const DevParams& P) { return (size_t)P.ncells * ((P.pw & PDB200_POINTWISE_B) ? P.np : 1) * P.dim; }
+size_t c_count(const DevParams& P) { return (size_t)P.ncells * ((P.pw & PDB200_POINTWISE_C) ? P.nq : 1); }
 
 long long num_bfaces(const DevParams& P) {
   long long n = 0;
@@ -112,7 +116,7 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   }
   if (!P.dg) {
     launch_fem_vector(op->fem, P, x, y, residual, overwrite, op->stream);
-    const bool kron = P.a_mode != PDB200_A_FULL && P.b == nullptr;
+    const bool kron = kron_coefficients(P);
     op->last_kernel = kron ? (residual ? "fem_kron+r0" : "fem_kron") : (residual ? "fem_residual" : "fem_jacobian_apply");
     op->launches += 2;
     return;
@@ -339,11 +343,25 @@ int pdb200_create(const pdb200_problem* p, pdb200_handle* out) {
   if (P.a_mode < 0 || P.a_mode > 3) throw Error("invalid a_mode");
   if (P.a_mode != PDB200_A_IDENTITY && !p->A) throw Error("a_mode needs the array A");
   host_fill_tables(P, op->K, op->xq, op->wq);
+  P.np = P.nq + 2 * P.dim * P.nfq;
+  // point-wise layouts only for arrays that are present (a bit without its array means nothing)
+  P.pw = 0;
+  if ((p->pointwise & PDB200_POINTWISE_A) && P.a_mode != PDB200_A_IDENTITY) P.pw |= PDB200_POINTWISE_A;
+  if ((p->pointwise & PDB200_POINTWISE_B) && p->b) P.pw |= PDB200_POINTWISE_B;
+  if ((p->pointwise & PDB200_POINTWISE_C) && p->c) P.pw |= PDB200_POINTWISE_C;
+  if ((p->pointwise & PDB200_POINTWISE_BCTYPE) && p->bctype) {
+    if (!P.dg)
+      throw Error("ConvectionDiffusionFEM evaluates bctype at the face centre (convectiondiffusionfem.hh:226-229): "
+                  "PDB200_POINTWISE_BCTYPE is a QkDG layout");
+    P.pw |= PDB200_POINTWISE_BCTYPE;
+  }
+  if (p->pointwise & ~(PDB200_POINTWISE_A | PDB200_POINTWISE_B | PDB200_POINTWISE_C | PDB200_POINTWISE_BCTYPE))
+    throw Error("unknown bits in pdb200_problem::pointwise");
   P.A = upload(op.get(), p->A, a_count(P));
-  P.b = upload(op.get(), p->b, (size_t)P.ncells * P.dim);
-  P.c = upload(op.get(), p->c, (size_t)P.ncells);
+  P.b = upload(op.get(), p->b, b_count(P));
+  P.c = upload(op.get(), p->c, c_count(P));
   P.f = upload(op.get(), p->f, (size_t)P.ncells * P.nq);
-  P.bctype = upload(op.get(), p->bctype, (size_t)nbf);
+  P.bctype = upload(op.get(), p->bctype, (size_t)nbf * ((P.pw & PDB200_POINTWISE_BCTYPE) ? P.nfq : 1));
   P.g = upload(op.get(), p->g, (size_t)nbf * P.nfq);
   P.j = upload(op.get(), p->j, (size_t)nbf * P.nfq);
   P.o = upload(op.get(), p->o, (size_t)nbf * P.nfq);
@@ -372,8 +390,8 @@ int pdb200_update_coefficients(pdb200_handle h, const pdb200_problem* p) {
     PDB_CUDA(cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyDefault, h->stream));
   };
   upd(P.A, p->A, a_count(P) * 8, "A");
-  upd(P.b, p->b, (size_t)P.ncells * P.dim * 8, "b");
-  upd(P.c, p->c, (size_t)P.ncells * 8, "c");
+  upd(P.b, p->b, b_count(P) * 8, "b");
+  upd(P.c, p->c, c_count(P) * 8, "c");
   upd(P.f, p->f, (size_t)P.ncells * P.nq * 8, "f");
   upd(P.g, p->g, (size_t)nbf * P.nfq * 8, "g");
   upd(P.j, p->j, (size_t)nbf * P.nfq * 8, "j");

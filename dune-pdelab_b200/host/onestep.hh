@@ -270,9 +270,13 @@ class OneStepGridOperator {
   void explicit_stage(unsigned stage, const std::vector<Domain*>& x, Domain& xr, double reduction) {
     if (implicit) throw Exception("This function should not be called in implicit mode");
     if (x.size() < stage) throw Exception("explicit stage: the solutions of stages 0..r-1 are needed");
-    std::vector<const double*> ptrs(stage);
-    for (unsigned i = 0; i < stage; i++) ptrs[i] = x[i]->data();
-    check(pdb200_onestep_explicit_stage(os_, (int)stage, ptrs.data(), xr.data(), reduction), "explicit_jacobian_residual");
+    // split per earlier stage: R0(x_i) is evaluated with the coefficients at t + d_i dt (prestageengine.hh:208-211)
+    check(pdb200_onestep_explicit_stage_begin(os_, (int)stage), "explicit_jacobian_residual");
+    for (unsigned i = 0; i < stage; i++) {
+      setTime(timeAtStage((int)i));
+      check(pdb200_onestep_explicit_stage_add(os_, (int)i, x[i]->data()), "explicit_jacobian_residual");
+    }
+    check(pdb200_onestep_explicit_stage_finish(os_, xr.data(), reduction), "explicit_jacobian_residual");
   }
   // onestep.hh:141-149
   void residual(const Domain& x, Range& r) const {

@@ -44,7 +44,8 @@ SYMBOLS = [
     "pdb200_onestep_create", "pdb200_onestep_destroy", "pdb200_onestep_set_method", "pdb200_onestep_set_dt_mode",
     "pdb200_onestep_pre_step", "pdb200_onestep_time_at_stage", "pdb200_onestep_pre_stage",
     "pdb200_onestep_pre_stage_begin", "pdb200_onestep_pre_stage_add", "pdb200_onestep_const_residual",
-    "pdb200_onestep_explicit_stage",
+    "pdb200_onestep_explicit_stage", "pdb200_onestep_explicit_stage_begin", "pdb200_onestep_explicit_stage_add",
+    "pdb200_onestep_explicit_stage_finish",
     "pdb200_onestep_residual", "pdb200_onestep_jacobian_apply", "pdb200_onestep_onthefly_apply",
     "pdb200_onestep_jacobian", "pdb200_onestep_stage_operator", "pdb200_onestep_solve_stationary",
     "pdb200_onestep_launch_count",

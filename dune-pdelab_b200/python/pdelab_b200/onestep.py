@@ -210,6 +210,9 @@ class OneStepGridOperator:
         lib.pdb200_onestep_pre_stage_add.argtypes = [vp, C.c_int, vp]
         lib.pdb200_onestep_const_residual.argtypes = [vp, vp]
         lib.pdb200_onestep_explicit_stage.argtypes = [vp, C.c_int, C.POINTER(vp), vp, C.c_double]
+        lib.pdb200_onestep_explicit_stage_begin.argtypes = [vp, C.c_int]
+        lib.pdb200_onestep_explicit_stage_add.argtypes = [vp, C.c_int, vp]
+        lib.pdb200_onestep_explicit_stage_finish.argtypes = [vp, vp, C.c_double]
         for name in ("pdb200_onestep_residual", "pdb200_onestep_jacobian_apply", "pdb200_onestep_onthefly_apply"):
             getattr(lib, name).argtypes = [vp, vp, vp]
         lib.pdb200_onestep_jacobian.argtypes = [vp, vp, vp, C.c_int]
@@ -294,8 +297,13 @@ class OneStepGridOperator:
         """One stage of an explicit method (explicit_jacobian_residual + the mass solve of ExplicitOneStepMethod::apply,
         onestep.hh:161-178, instationary/explicitonestep.hh:365-407): xr = -M^-1 sum_i (a_ri M x_i + b_ri dt R0(x_i))."""
         assert len(x) >= stage
-        ptrs = (C.c_void_p * stage)(*[_ptr(v) for v in x[:stage]])
-        self._chk(self.lib.pdb200_onestep_explicit_stage(self._h, int(stage), ptrs, _ptr(xr), float(reduction)))
+        # split per earlier stage: every R0(x_i) is evaluated with the coefficients at t + d_i dt (the explicit engine
+        # delegates to the pre-stage engine, prestageengine.hh:208-211)
+        self._chk(self.lib.pdb200_onestep_explicit_stage_begin(self._h, int(stage)))
+        for i in range(stage):
+            self._set_time(self.timeAtStage(i))
+            self._chk(self.lib.pdb200_onestep_explicit_stage_add(self._h, i, _ptr(x[i])))
+        self._chk(self.lib.pdb200_onestep_explicit_stage_finish(self._h, _ptr(xr), float(reduction)))
         self._stage = stage
         return xr
 

@@ -312,6 +312,13 @@ int pdb200_onestep_pre_stage_add(pdb200_onestep_handle os, int i, const double* 
  * otherwise.  x[0..stage-1]: earlier stages, xr: result (host or device).  The time-step controller of the reference
  * (CFL limit) is the caller's business: dt is the one given to pdb200_onestep_pre_step. */
 int pdb200_onestep_explicit_stage(pdb200_onestep_handle os, int stage, const double* const* x, double* xr, double reduction);
+/* The same stage split per earlier stage (begin, add(0) .. add(stage-1), finish = the mass solve), so that a host with
+ * time-dependent coefficients can re-sample them at t + d_i dt before add(i): the explicit engine delegates to the
+ * pre-stage engine, which sets the time of every earlier stage (onestep/jacobianresidualengine.hh,
+ * prestageengine.hh:208-211). */
+int pdb200_onestep_explicit_stage_begin(pdb200_onestep_handle os, int stage);
+int pdb200_onestep_explicit_stage_add(pdb200_onestep_handle os, int i, const double* x);
+int pdb200_onestep_explicit_stage_finish(pdb200_onestep_handle os, double* xr, double reduction);
 /* copy of the constant part of the residual assembled by preStage (host or device destination) */
 int pdb200_onestep_const_residual(pdb200_onestep_handle os, double* out);
 /* residual(x, r), onestep.hh:141-149 */

@@ -82,15 +82,19 @@ class OneStepOracle:
         return M.tocsr()
 
 
-def explicit_stage(spec0, spec1, method, stage, time, dt, xs):
-    """x_r = -M^-1 sum_{i<r} (a_ri M x_i + b_ri dt R0(x_i)): ExplicitOneStepMethod::apply, one stage
-    (instationary/explicitonestep.hh:365-407; D = -M by the weight -1 of onestep/jacobianresidualengine.hh:303)."""
+def explicit_stage(spec0, spec1, method, stage, time, dt, xs, spec0_at=None):
+    """x_r = -M^-1 sum_{i<r} (a_ri M x_i + b_ri dt R0(x_i; t + d_i dt)): ExplicitOneStepMethod::apply, one stage
+    (instationary/explicitonestep.hh:365-407; D = -M by the weight -1 of onestep/jacobianresidualengine.hh:303; the
+    engine delegates to the pre-stage engine, which evaluates stage i at its own time, prestageengine.hh:208-211).
+    spec0_at(t): the spatial problem with its coefficients sampled at time t."""
     import scipy.sparse.linalg as spla
     o0, o1 = Oracle(spec0), Oracle(spec1)
     n = spec0.num_dofs
     alpha, beta = np.zeros(n), np.zeros(n)
     for i in range(stage):
         a, b = method.a(stage, i), method.b(stage, i)
+        if spec0_at is not None:
+            o0 = Oracle(spec0_at(time + method.d(i) * dt))
         if abs(b) > 1e-6:
             beta += b * o0.residual(xs[i])
         if abs(a) > 1e-6:

@@ -94,6 +94,8 @@ def test_python_constants_match_the_header_enums():
         "PDB200_KERNEL_AUTO": abi.KERNEL_AUTO, "PDB200_KERNEL_GENERIC": abi.KERNEL_GENERIC, "PDB200_KERNEL_FAST": abi.KERNEL_FAST,
         "PDB200_BASIS_LAGRANGE": abi.BASIS_LAGRANGE, "PDB200_BASIS_LEGENDRE": abi.BASIS_LEGENDRE,
         "PDB200_BASIS_LOBATTO": abi.BASIS_LOBATTO,
+        "PDB200_POINTWISE_A": abi.POINTWISE_A, "PDB200_POINTWISE_B": abi.POINTWISE_B,
+        "PDB200_POINTWISE_C": abi.POINTWISE_C, "PDB200_POINTWISE_BCTYPE": abi.POINTWISE_BCTYPE,
         "PDB200_LAYOUT_CSR": abi.LAYOUT_CSR, "PDB200_LAYOUT_BCSR": abi.LAYOUT_BCSR,
         "PDB200_PART_ALL": abi.PART_ALL, "PDB200_PART_INTERIOR": abi.PART_INTERIOR, "PDB200_PART_BOUNDARY": abi.PART_BOUNDARY,
         "PDB200_SOLVER_BICGSTAB": abi.SOLVER_BICGSTAB, "PDB200_SOLVER_CG": abi.SOLVER_CG,

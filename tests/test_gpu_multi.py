@@ -131,6 +131,85 @@ def test_p2p_halo_apply_matches_global_oracle(cuda_lib, world, cells):
         assert kern == "dg_fast_q2_3d"
 
 
+# ---- BASELINE-scale partition: 256^3 cells in total over 4 ranks against the UNDIVIDED oracle ----------
+
+def _worker_big(rank, world, port, cells, tmpdir, out):
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [here, os.path.join(here, "..", "dune-pdelab_b200", "python")]
+        import torch.distributed as dist
+        from pdelab_b200.capi import GridOperator
+        from pdelab_b200.partition import OverlappingPartition, P2PHaloExchanger
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        part = OverlappingPartition.strong(cells, world, rank)
+        n = 27
+        zg = np.load(os.path.join(tmpdir, "z.npy"), mmap_mode="r")        # [ncells, 27]
+        kg = np.load(os.path.join(tmpdir, "kappa.npy"), mmap_mode="r")
+        want = np.load(os.path.join(tmpdir, "want.npy"), mmap_mode="r")
+        gidx = part.local_cell_grid().reshape(-1)
+        own = part.owned_mask().reshape(-1)
+        z = np.full((gidx.size, n), 1e300)          # ghosts poisoned: the exchange must fill them
+        z[own] = zg[gidx[own]]
+        spec = abi.ProblemSpec(part.local_cells, degree=2, lower=part.local_lower, upper=part.local_upper, alpha=3.0,
+                               a_mode=abi.A_SCALAR, A=np.ascontiguousarray(kg[gidx]), side_kind=part.side_kind, device=dev)
+        go = GridOperator(spec)
+        halo = P2PHaloExchanger(go, part, dist)
+        zd = torch.from_numpy(z.reshape(-1)).cuda()
+        del z
+        yd = torch.full_like(zd, float("nan"))
+        halo.apply(zd, yd)
+        go.synchronize()
+        y = yd.cpu().numpy().reshape(-1, n)
+        w = want[gidx[own]]
+        err = float(np.abs(y[own] - w).max() / np.abs(w).max())
+        out.put((rank, err, go.last_kernel(), int(own.sum()), None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        import traceback
+        out.put((rank, 1.0, "", 0, traceback.format_exc()))
+
+
+def test_256_cubed_over_four_ranks_matches_the_undivided_oracle(cuda_lib, tmp_path):
+    """SURVEY 8e parity definition at BASELINE scale: DG k=2 on 256^3 cells (453 M DOFs) split 1x2x2 with one ghost
+    layer; the owned rows of every rank equal the single-domain oracle on the global grid to 1e-12."""
+    import torch.multiprocessing as mp
+    from oracle import Oracle
+    from problems import kappa_field, mt_vector
+    cells, world = (256, 256, 256), 4
+    ncg = int(np.prod(cells))
+    zg = mt_vector(ncg * 27)
+    kg = kappa_field(ncg)
+    try:
+        threads = max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    want = Oracle(abi.ProblemSpec(cells, degree=2, alpha=3.0, a_mode=abi.A_SCALAR, A=kg)).jacobian_apply(zg, threads=threads)
+    np.save(tmp_path / "z.npy", zg.reshape(ncg, 27))
+    np.save(tmp_path / "kappa.npy", kg)
+    np.save(tmp_path / "want.npy", want.reshape(ncg, 27))
+    del zg, want
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_big, args=(r, world, port, cells, str(tmp_path), out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=900) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    owned = 0
+    for rank, err, kern, nown, tb in res:
+        assert tb is None, tb
+        assert err < 1e-12, (rank, err)
+        assert kern == "dg_fast_q2_3d"
+        owned += nown
+    assert owned == ncg          # every cell has exactly one owner
+
+
 # ---- conforming Qk on the overlapping partition: gather / scatter kernels + QkHaloExchanger ----------
 
 class _HostStagedDist:

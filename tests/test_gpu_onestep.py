@@ -253,6 +253,53 @@ def test_explicit_stages_match_the_oracle(cuda_lib, cname, mname):
         osm.ExplicitOneStepMethod(osm.Alexander2Parameter(), igo)
 
 
+@pytest.mark.parametrize("mname", ["heun", "shu3", "rk4"])
+def test_explicit_stages_resample_time_dependent_coefficients(cuda_lib, mname):
+    """Every R0(x_i) of an explicit stage is evaluated with the coefficients at t + d_i dt (the explicit engine
+    delegates to the pre-stage engine, prestageengine.hh:208-211) — f(t) and g(t) vary strongly over one step."""
+    from onestep_oracle import explicit_stage
+    from pdelab_b200.capi import GridOperator
+    base = dg_problem((6, 4, 4), degree=2, a="scalar", with_f=True, bc="dirichlet_g")
+    f, g = base.arrays["f"], base.arrays["g"]
+
+    def at(t):
+        return base.replace(f=(1.0 + 40.0 * t) * f, g=np.cos(30.0 * t) * g)
+
+    spec1 = osm.l2_spec(base)
+    go0, go1 = GridOperator(at(0.0)), GridOperator(spec1)
+    igo = osm.OneStepGridOperator(go0, go1, time_dependent=lambda t: dict(f=(1.0 + 40.0 * t) * f, g=np.cos(30.0 * t) * g))
+    method = EXPLICIT[mname]()
+    n = base.num_dofs
+    time, dt = 0.25, 0.05
+    igo.preStep(method, time, dt)
+    xs = [mt_vector(n, seed=11 + i) - 0.5 for i in range(method.s())]
+    for r in range(1, method.s() + 1):
+        got = igo.explicit_stage(r, xs[:r], np.zeros(n))
+        want = explicit_stage(base, spec1, method, r, time, dt, xs[:r], spec0_at=at)
+        frozen = explicit_stage(at(time), spec1, method, r, time, dt, xs[:r])
+        assert rel_err(got, want) < 1e-10, r
+        if r > 1 and any(method.d(i) != 0.0 and abs(method.b(r, i)) > 1e-6 for i in range(r)):
+            assert rel_err(frozen, want) > 1e-3, r   # the test does distinguish the two
+
+
+def test_explicit_then_implicit_method_keeps_the_dt_assembling_mode(cuda_lib):
+    """An explicit method used once must not leave DoNotAssembleDT behind for a later implicit method (the reference fixes
+    `implicit` per grid-operator type, onestep.hh:74-75; here one handle may see both)."""
+    spec0 = CASES["dg_fast_scalar"]()
+    igo, orc, _keep = _pair(spec0)
+    n = spec0.num_dofs
+    xs = [mt_vector(n, seed=3), mt_vector(n, seed=4)]
+    igo.preStep(osm.HeunParameter(), 0.0, 0.05)
+    igo.explicit_stage(1, xs[:1], np.zeros(n))
+    method = osm.Alexander2Parameter()
+    igo.preStep(method, 0.0, 0.05)
+    orc.preStep(method, 0.0, 0.05)
+    igo.preStage(1, xs[:1])
+    orc.preStage(1, xs[:1])
+    x = mt_vector(n, seed=5)
+    assert rel_err(igo.residual(x, np.zeros(n)), orc.residual(x)) < TOL
+
+
 def test_explicit_rk4_keeps_the_stationary_solution(cuda_lib):
     """The heat problem of testinstationaryfastdgassembler.cc stepped explicitly (RK4, dt well inside the diffusive
     stability limit of the 8x8 k=1 DG grid): 20 steps from the interpolated stationary solution stay within the
