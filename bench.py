@@ -157,11 +157,16 @@ def other_configs(torch, dev, peak):
              "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                           "algorithmic_bytes_per_launch": alg_bytes}, "note": note}
         if flops is not None:
-            tf = flops / (ms * 1e-3) / 1e12
-            r["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                                  "frac": tf / FP64_PEAK_TFLOPS, "flops_per_launch": flops,
-                                  "note": "canonical sum-factorised count of SURVEY.md 8d (357 flop/DOF at k=4), "
-                                          "peak = measured DFMA rate (profiles/r01_fp64_peak.txt)"}
+            # the fp64 pipe issues one instruction (DFMA, DADD or DMUL alike) per slot: the fraction of the pipe's issue
+            # slots the kernel fills is (fp64 instructions executed) x 2 / time against the DFMA peak in flop/s
+            tf = flops["slots"] * 2.0 / (ms * 1e-3) / 1e12
+            r["roofline_fp64"] = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s (DFMA-equivalent)",
+                                  "frac": tf / FP64_PEAK_TFLOPS, "fp64_instructions_per_launch": flops["slots"],
+                                  "note": flops["note"] + "; peak = measured DFMA rate (profiles/r01_fp64_peak.txt)",
+                                  "canonical_tflops": flops["canonical"] / (ms * 1e-3) / 1e12,
+                                  "canonical_note": "SURVEY.md 8d count for a sum-factorised quadrature kernel (357 flop/DOF "
+                                                    "at k=4); the Kronecker form executes about a third of it, so this "
+                                                    "rate is NOT a pipe utilisation"}
         return r
 
     out = {}
@@ -215,12 +220,15 @@ def other_configs(torch, dev, peak):
     n = spec.num_dofs
     x, r = rand(n, 2), torch.zeros(n, dtype=torch.float64, device=dev)
     c3 = {"dofs": n, "cells": list(cells)}
+    # dg_kron_3d_kernel<4>: 1661 fp64 instructions per thread (1306 DFMA + 84 DADD + 271 DMUL, cuobjdump -sass), five
+    # threads per 125-DOF cell -> 66.4 fp64 instructions per DOF
+    k4 = {"slots": 1661.0 * 5.0 * nc, "canonical": 357.0 * n,
+          "note": "1661 fp64 instructions per thread x 5 threads per cell (SASS count), 66.4 per DOF"}
     ms = _time_events(torch, lambda: go.residual(x, r), 20)
     c3["residual"] = rec(ms, 32.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(),
-                         "r += R(x) = J x + cached R(0): 32 B/DOF + kappa; compute-bound config", flops=357.0 * n)
+                         "r += R(x) = J x + cached R(0): 32 B/DOF + kappa; compute-bound config", flops=k4)
     ms = _time_events(torch, lambda: go.apply(x, r), 20)
-    c3["jacobian_apply"] = rec(ms, 16.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(), "y = J x: 16 B/DOF + kappa",
-                               flops=357.0 * n)
+    c3["jacobian_apply"] = rec(ms, 16.0 * n + 8.0 * nc, n, "DOF/s", go.last_kernel(), "y = J x: 16 B/DOF + kappa", flops=k4)
     out["cfg3_dg_k4_3d_64"] = c3
     del go, x, r
     torch.cuda.empty_cache()
