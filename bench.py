@@ -206,6 +206,24 @@ def other_configs(torch, dev, peak):
         torch.cuda.empty_cache()
         return res
 
+    # cfg2 with convection and reaction (second variant): b = (1, 0.5, 0.25), c = 1, same kernel family
+    cells = (128, 128, 128)
+    nc = 128 ** 3
+    kappa = 10.0 ** (2.0 * rand(nc, 42) - 1.0)
+    bvec = torch.tensor([1.0, 0.5, 0.25], dtype=torch.float64, device=dev).repeat(nc, 1).contiguous()
+    spec = abi.ProblemSpec(cells, space=abi.SPACE_QKDG, degree=2, alpha=ALPHA, a_mode=abi.A_SCALAR, A=kappa, b=bvec,
+                           c=torch.ones(nc, dtype=torch.float64, device=dev))
+    go = GridOperator(spec)
+    go.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = spec.num_dofs
+    x, r = rand(n, 2), torch.zeros(n, dtype=torch.float64, device=dev)
+    ms = _time_events(torch, lambda: go.apply(x, r), 100, warm=10)
+    out["cfg2_dg_k2_3d_128_convection"] = {
+        "dofs": n, "cells": list(cells),
+        "jacobian_apply": rec(ms, 16.0 * n + 40.0 * nc, n, "DOF/s", go.last_kernel(),
+                              "y = J x with b = (1, 0.5, 0.25), c = 1: 16 B/DOF + kappa, b (3), c per cell")}
+    del go, x, r, bvec
+    torch.cuda.empty_cache()
     out["cfg1_q1_2d_256"] = fem((256, 256), 1, 200)
     out["cfg1_q1_2d_256"]["note"] = ("0.5 MB working set: L2-resident and launch-latency bound by construction "
                                      "(the reference's own CPU-runnable case)")

@@ -45,6 +45,7 @@ struct Kron1D {
   // t_i += E0[i]*(a u'(0)) + E1[i]*(a u'(1)) + m0[i]*FL + mk[i]*FR + q0[i]*GL + q1[i]*GR   (k = 2)
   double E0[MAX_N1], E1[MAX_N1], m0[MAX_N1], mk[MAX_N1], q0[MAX_N1], q1[MAX_N1];
   double MinvK[MAX_N1 * MAX_N1];  // Minv * stiffness
+  double Dn[MAX_N1 * MAX_N1];     // nodal derivative matrix: Dn[i][j] = p_j'(i / k)
 };
 
 struct Error : std::runtime_error {
@@ -144,7 +145,7 @@ struct Operator;  // operator.cu
 // dg_generic.cu: reference-order gather kernels, any supported (dim,k), any coefficient mode
 void launch_dg_generic(const DevParams& P, const double* x, double* y, bool residual, bool overwrite,
                        int* errflag, cudaStream_t s);
-// dg_fast.cu: Kronecker-factorised kernel (k = 2, dim = 3, diagonal A, b = 0)
+// dg_fast.cu: Kronecker-factorised kernel (k = 2, dim = 3, diagonal A, cell-wise constant b and c)
 bool dg_fast_supported(const DevParams& P);
 struct FastPlan;
 FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K);
@@ -154,7 +155,7 @@ void dg_fast_plan_destroy(FastPlan*);
 // [ztile_lo, ztile_hi): optional window of tile layers along z (PART_ALL only), used to pipeline
 // host transfers with the computation
 int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0,
-                   bool overwrite, int part, cudaStream_t s, int ztile_lo = 0, int ztile_hi = 1 << 30);
+                   bool overwrite, int part, cudaStream_t s, int* errflag, int ztile_lo = 0, int ztile_hi = 1 << 30);
 int dg_fast_ztiles(const DevParams& P);
 void dg_fast_ztile_layers(const DevParams& P, int lo, int hi, int* z0, int* z1);
 
@@ -167,10 +168,11 @@ void dg_kron_plan_destroy(KronPlan*);
 int launch_dg_kron(KronPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
                    cudaStream_t s);
 
-// dg_small.cu: Kronecker-factorised kernel for small cells (dim = 2 with k = 1, 2; dim = 3 with k = 1), thread per cell
+// dg_small.cu: Kronecker-factorised kernel for small cells (dim = 2 with k = 1, 2; dim = 3 with k = 1), thread per cell;
+// cell-wise constant diagonal A, b and c
 bool dg_small_supported(const DevParams& P);
 int launch_dg_small(const DevParams& P, const Kron1D& K, const double* x, double* y, const double* r0, bool overwrite,
-                    cudaStream_t s);
+                    cudaStream_t s, int* errflag = nullptr);
 
 // dg_blockjac.cu: exact matrix-free block-Jacobi preconditioner z = D^-1 r (fast diagonalisation of the Kronecker-sum blocks)
 struct BlockJacPlan;
@@ -196,6 +198,10 @@ void p2p_connect(P2PHalo*, const DevParams& P, int dir, int side, const pdb200_i
 void p2p_destroy(P2PHalo*);
 int p2p_push(P2PHalo*, const DevParams& P, const double* x, cudaStream_t s);       // returns launches
 int p2p_wait_unpack(P2PHalo*, const DevParams& P, double* x, cudaStream_t s);
+// both spaces: owner -> ghost copy (QkDG: push + wait_unpack; conforming Qk: lattice planes, direction by direction)
+int p2p_exchange(P2PHalo*, const DevParams& P, double* x, cudaStream_t s);
+int p2p_zero_ghosts(P2PHalo*, const DevParams& P, double* x, cudaStream_t s);  // x := 0 on everything not owned
+bool p2p_is_qk(const P2PHalo*);
 void p2p_check(P2PHalo*);  // throws if a spin-wait timed out
 cudaStream_t p2p_stream(P2PHalo*);
 cudaEvent_t p2p_event(P2PHalo*, int i);

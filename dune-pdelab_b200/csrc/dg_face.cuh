@@ -13,8 +13,17 @@ template <int K>
 struct SmallConst {
   static constexpr int N1 = K + 1;
   double MinvK[N1 * N1], M[N1 * N1], m0[N1], mk[N1], q0[N1], q1[N1], d0[N1], d1[N1];
-  double ih2[3];
+  double Dn[N1 * N1];  // nodal derivative matrix Dn[i][j] = p_j'(i / k): u'(x_i) = sum_j Dn_ij u_j (convection)
+  double ih2[3], ih[3];
   double alpha_pen, theta, vol;
+};
+
+// Convection with a cell-wise constant velocity along one direction (convectiondiffusiondg.hh:178-187, 426-448, 797-822,
+// 860): cb = b_d / h_d of the cell (volume term, integrated by parts: cb [u'(x_i) + (M^-1 e_0)_i u(0) - (M^-1 e_k)_i u(1)]),
+// cu?s / cu?o = beta / h_d on the own / the neighbour's trace at the lower (L) and upper (R) face, whichever is upwind;
+// beta comes from the velocity of the larger-index cell.  All zero without a velocity field.
+struct Conv1 {
+  double cb = 0.0, cuLs = 0.0, cuLo = 0.0, cuRs = 0.0, cuRo = 0.0;
 };
 
 template <int DIM, int K>
@@ -45,20 +54,54 @@ __device__ __forceinline__ double s_load_adiag(const DevParams& P, long long cel
 template <int K>
 __device__ __forceinline__ bool direction_coefs(const DevParams& P, const SmallConst<K>& C, long long cell, const int (&g)[3],
                                                 int d, const long long (&stride)[3], double& A0, double (&cs)[2],
-                                                double (&co)[2], double (&cg)[2], bool (&onb)[2]) {
+                                                double (&co)[2], double (&cg)[2], bool (&onb)[2], Conv1* V = nullptr,
+                                                int* errflag = nullptr) {
   bool constrained = false;
   onb[0] = g[d] == 0;
   onb[1] = g[d] == P.N[d] - 1;
   const double a = s_load_adiag(P, cell, d);
+  const bool conv = V != nullptr && P.b != nullptr;
+  const double bself = conv ? __ldg(P.b + cell * P.dim + d) : 0.0;
+  if (conv) V->cb = bself * C.ih[d];
 #pragma unroll
   for (int side = 0; side < 2; side++) {
     int kind = onb[side] ? 1 : 0;
+    bool outflow = false;
     if (onb[side]) {
       if (P.side_kind[d][side] == PDB200_SIDE_PROCESSOR) {
         kind = 2;
         constrained = true;
       } else if (P.bctype) {
-        kind = P.bctype[bface_index(P, g, d, side)] == PDB200_BC_DIRICHLET ? 1 : 2;
+        const int bt = P.bctype[bface_index(P, g, d, side)];
+        kind = bt == PDB200_BC_DIRICHLET ? 1 : 2;
+        outflow = bt == PDB200_BC_OUTFLOW;
+      }
+    }
+    if (conv) {
+      // lower face: this cell is the inside (larger-index) cell, n = -e_d; upper interior face: the neighbour is, its
+      // outer normal is -e_d and ITS velocity counts (:426-438); boundary faces: own velocity, n = +-e_d (:797)
+      double beta, cself = 0.0, cother = 0.0;
+      bool self;
+      if (side == 0) {
+        beta = -bself;
+        self = beta >= 0.0;
+      } else {
+        beta = kind == 0 ? __ldg(P.b + (cell + stride[d]) * P.dim + d) : bself;
+        self = kind == 0 ? !(-beta >= 0.0) : beta >= 0.0;
+      }
+      if (outflow) {
+        if (beta < -1e-30 && errflag) *errflag = 1;  // "Outflow boundary condition on inflow!" :802-806
+        cself = beta * C.ih[d];
+      } else if (kind != 2) {
+        if (self) cself = beta * C.ih[d];
+        else if (kind == 0) cother = beta * C.ih[d];
+      }
+      if (side == 0) {
+        V->cuLs = cself;
+        V->cuLo = cother;
+      } else {
+        V->cuRs = cself;
+        V->cuRo = cother;
       }
     }
     const long long other = onb[side] ? cell : cell + (side ? stride[d] : -stride[d]);
@@ -84,7 +127,7 @@ __device__ __forceinline__ bool direction_coefs(const DevParams& P, const SmallC
 template <int K>
 __device__ __forceinline__ void own_matrix(const SmallConst<K>& C, double A0, double csL, double cgL, double csR,
                                            double cgR, double (&T)[(K + 1) * (K + 1)], double (&eL)[K + 1],
-                                           double (&eR)[K + 1]) {
+                                           double (&eR)[K + 1], const Conv1& V = Conv1()) {
   constexpr int N1 = K + 1;
   const double ctL = -C.theta * csL, ctR = C.theta * csR;
 #pragma unroll
@@ -95,8 +138,9 @@ __device__ __forceinline__ void own_matrix(const SmallConst<K>& C, double A0, do
 #pragma unroll
     for (int j = 0; j < N1; j++) {
       double v = fma(A0, C.MinvK[i * N1 + j], fma(m0c, C.d0[j], mkc * C.d1[j]));
-      if (j == 0) v += eL[i];
-      if (j == K) v += eR[i];
+      v = fma(V.cb, C.Dn[i * N1 + j], v);                       // convection, volume part: cb u'(x_i)
+      if (j == 0) v += fma(C.m0[i], V.cuLs + V.cb, eL[i]);      // own trace at the lower face
+      if (j == K) v += fma(C.mk[i], V.cuRs - V.cb, eR[i]);      // own trace at the upper face
       T[i * N1 + j] = v;
     }
   }
@@ -116,8 +160,12 @@ inline void fill_small_const(SmallConst<K>& C, const DevParams& P, const Kron1D&
     C.q1[i] = K1.q1[i];
     C.d0[i] = K1.d0[i];
     C.d1[i] = K1.d1[i];
+    for (int j = 0; j < N1; j++) C.Dn[i * N1 + j] = K1.Dn[i * MAX_N1 + j];
   }
-  for (int d = 0; d < 3; d++) C.ih2[d] = d < P.dim ? 1.0 / (P.h[d] * P.h[d]) : 0.0;
+  for (int d = 0; d < 3; d++) {
+    C.ih2[d] = d < P.dim ? 1.0 / (P.h[d] * P.h[d]) : 0.0;
+    C.ih[d] = d < P.dim ? 1.0 / P.h[d] : 0.0;
+  }
   C.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
   C.theta = P.theta;
   C.vol = P.vol;
@@ -156,17 +204,17 @@ template <int DIM, int K, int AXIS, bool FIRST>
 __device__ __forceinline__ void small_sweep(const SmallConst<K>& C, const double (&o)[SL<DIM, K>::N],
                                             const double (&l)[SL<DIM, K>::N], const double (&r)[SL<DIM, K>::N], double A0,
                                             double csL, double coL, double cgL, double csR, double coR, double cgR,
-                                            double creact, double (&t)[SL<DIM, K>::N]) {
+                                            double creact, double (&t)[SL<DIM, K>::N], const Conv1& V = Conv1()) {
   constexpr int N1 = K + 1, N = SL<DIM, K>::N;
   constexpr int S = AXIS == 0 ? 1 : (AXIS == 1 ? N1 : N1 * N1);
   double T[N1 * N1], eL[N1], eR[N1], PL1[N1], PL2[N1], PR1[N1], PR2[N1];
-  own_matrix<K>(C, A0, csL, cgL, csR, cgR, T, eL, eR);
+  own_matrix<K>(C, A0, csL, cgL, csR, cgR, T, eL, eR, V);
 #pragma unroll
   for (int i = 0; i < N1; i++) {
     PL1[i] = C.m0[i] * coL;
-    PL2[i] = -eL[i];
+    PL2[i] = fma(C.m0[i], V.cuLo, -eL[i]);  // the neighbour's trace: jump terms and, if it is upwind, the convective flux
     PR1[i] = -C.mk[i] * coR;
-    PR2[i] = -eR[i];
+    PR2[i] = fma(C.mk[i], V.cuRo, -eR[i]);
   }
 #pragma unroll
   for (int hi = 0; hi < N / (S * N1); hi++)

@@ -1,6 +1,6 @@
 // dg_fast.cu — bandwidth-oriented jacobian_apply for the headline configuration:
-//   QkDG k = 2, dim = 3, cell-wise constant DIAGONAL diffusion tensor, b = 0, optional c,
-//   SIPG/NIPG/IIPG with or without harmonic weights, Dirichlet / Neumann / None boundary faces.
+//   QkDG k = 2, dim = 3, cell-wise constant DIAGONAL diffusion tensor, optional cell-wise constant velocity b and
+//   reaction c, SIPG/NIPG/IIPG with or without harmonic weights, Dirichlet / Neumann / Outflow / None boundary faces.
 //
 // What it computes is exactly GridOperator::jacobian_apply for ConvectionDiffusionDG
 // (gridoperator/gridoperator.hh:192-197 -> localoperator/convectiondiffusiondg.hh:106-188,
@@ -10,20 +10,34 @@
 //     y_e = |K| (M (x) M (x) M) [ sum_d (1/h_d) M^-1 L_d(z_{e-d}, z_e, z_{e+d}) + c_e z_e ]
 // with M the exact 1-D mass matrix and L_d the 1-D SIPG operator along direction d (volume
 // stiffness + both face terms, coefficients from A_dd of the cell and its two d-neighbours).
+// With a cell-wise constant velocity the convective terms are 1-D operators as well (HAS_B variants): the volume term
+// -u b.grad psi (:178-187) becomes (b_d / h_d) [ u'(x_i) + (M^-1 e_0)_i u(0) - (M^-1 e_k)_i u(1) ] along direction d
+// (integration by parts; u' is a polynomial of the space), and the upwind flux (:426-448) a selection between the two
+// traces at either face, with the velocity of the larger-index cell.
 // Derivation and the numpy statement of the same formula: DESIGN.md §5, tests/kron_reference.py.
 // Results agree with the quadrature form to rounding (tests: <= 1e-12 relative to the oracle).
 //
 // Mapping to the machine (B200, sm_100a):
 //   * CTA = 8x4x4 cells, one thread per cell (128 threads, 3 CTAs/SM).
-//   * The cell tile plus its face halo (320 cells * 216 B = 69 KB) is brought into shared memory
-//     by 5 TMA tensor copies (cp.async.bulk.tensor.4d) completing on one mbarrier; out-of-domain
-//     cells are zero-filled by the TMA unit.  The global tensor is viewed as
-//     [54 doubles = 2 cells][Nx/2][Ny][Nz] so that all strides are multiples of 16 B.
+//   * The cell tile plus its x/y halo (12 x 6 x 4 cells) is brought into shared memory by ONE TMA tensor copy
+//     (cp.async.bulk.tensor.4d; out-of-domain cells are zero-filled by the TMA unit; the global tensor is viewed as
+//     [54 doubles = 2 cells][Nx/2][Ny][Nz] so that all strides are multiples of 16 B), the two z-halo layers by
+//     eight 1-D bulk copies (cp.async.bulk, one x-row of 8 cells each), all completing on one mbarrier.
+//   * Shared memory is the busiest unit of this kernel (189 LDS.64 + 27 STS.64 per cell against 1083 fp64
+//     instructions: the 128 B/clk crossbar and the fp64 pipe are equally loaded), so every access is laid out
+//     bank-conflict free: a half-warp holds the rows cy and cy + 2 of one z-layer; rows of the main region are
+//     12 cells = 648 words apart (two rows = 16 banks), and the z-halo rows and the output rows — moved by 1-D bulk
+//     copies, which only need 16-byte alignment — put the rows cy >= 2 another 64 B (16 banks) further on.
+//     (The first version used five TMA boxes and one dense output box: 31 % of its shared-memory wavefronts were
+//     conflict replays — profiles/r01_v5_dg_fast_ncu_full_summary.json.)
 //   * A thread keeps its 27 DOFs and 27 accumulators in registers; neighbour traces and normal
-//     derivatives are read from the shared tile (lane mapping chosen so that the 216-B cell
-//     stride is bank-conflict free).
-//   * The result tile is staged in shared memory and written with ONE TMA tensor store, so global
-//     traffic is fully coalesced: 8 B/DOF read (+ halo re-reads served by L2) + 8 B/DOF written.
+//     derivatives are read from the shared tile.
+//   * A warp is one z-layer of the tile.  The z-sweep runs FIRST; after ONE block-wide barrier behind it a warp
+//     only ever touches its own layer, so each warp stages its 4 result rows in its own (dead) layer and sends
+//     them off with 4 bulk row stores (or reduce-adds) as soon as IT is done — no barrier, staging pass or store
+//     loop of the whole block at the end (27 % of the warp samples in the first layout,
+//     profiles/r02_v6_dg_fast_ncu_full_summary.json).  Global traffic is fully coalesced: 8 B/DOF read (+ halo
+//     re-reads served by L2) + 8 B/DOF written.
 
 #include <cuda.h>
 
@@ -40,23 +54,31 @@ namespace {
 constexpr int TX = 8, TY = 4, TZ = 4;
 constexpr int NLOC = 27;
 constexpr int ROWX = TX + 4;                      // cells per x-row in smem: x0-2 .. x0+TX+1
-constexpr int R0 = 0;                             // x-rows   [TZ][TY][ROWX] cells
-constexpr int R1 = R0 + TZ * TY * ROWX * NLOC;    // y-halo lower  [TZ][TX]
-constexpr int R2 = R1 + TZ * TX * NLOC;           // y-halo upper
-constexpr int R3 = R2 + TZ * TX * NLOC;           // z-halo lower  [TY][TX]
-constexpr int R4 = R3 + TY * TX * NLOC;           // z-halo upper
-constexpr int SMEM_DOUBLES = R4 + TY * TX * NLOC;
-constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;      // 69,120 B
-constexpr int R0TILE = TX * TY * TZ * NLOC;       // R(0) tile behind the output stage (residual form)
-static_assert((R0TILE * 8) % 128 == 0 && 2 * R0TILE <= SMEM_DOUBLES, "R(0) tile must fit behind the stage");
-static_assert((R1 * 8) % 128 == 0 && (R2 * 8) % 128 == 0 && (R3 * 8) % 128 == 0 && (R4 * 8) % 128 == 0,
-              "TMA destinations must be 128-byte aligned");
+constexpr int ROWY = TY + 2;                      // rows per z-layer: y0-1 .. y0+TY
+constexpr int XROW = TX * NLOC;                   // doubles of one x-row of the tile (8 cells)
+constexpr int BANKSHIFT = 8;                      // 8 doubles = 64 B = 16 banks
+constexpr int R0 = 0;                             // rows region [TZ][ROWY][ROWX] cells (one TMA box)
+constexpr int ROWS_BYTES = TZ * ROWY * ROWX * NLOC * 8;
+constexpr int ZHALF = 2 * XROW + BANKSHIFT;       // z-halo: rows {0,1} | 64 B | rows {2,3}
+constexpr int ZSIZE = 2 * ZHALF;                  // (the second pad keeps the next region 16-byte aligned and apart)
+constexpr int R3 = R0 + TZ * ROWY * ROWX * NLOC;  // z-halo lower
+constexpr int R4 = R3 + ZSIZE;                    // z-halo upper
+constexpr int SMEM_DOUBLES = R4 + ZSIZE;
+constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;      // 76,288 B: three CTAs per SM
+constexpr int LAYER = ROWY * ROWX * NLOC;         // doubles of one z-layer of the rows region
+// output stage of warp cz: the first ZSIZE doubles of its own layer (rows laid out like a z-halo layer), and behind
+// it the rows of R(0) in the residual form
+static_assert(2 * ZSIZE <= LAYER, "stage and R(0) rows must fit into one layer");
+static_assert((R3 * 8) % 16 == 0 && (R4 * 8) % 16 == 0 && (XROW * 8) % 16 == 0 && (LAYER * 8) % 16 == 0 && (ZSIZE * 8) % 16 == 0,
+              "bulk copies need 16-byte alignment");
+__host__ __device__ constexpr int zhalo_row(int cy) { return (cy >> 1) * ZHALF + (cy & 1) * XROW; }
 
 struct FastConst {
   // see Kron1D; all six vectors are pre-multiplied by |K| / 30^3 so that the three mass sweeps can
   // use the integer matrix 30 M = [[4,2,-1],[2,16,2],[-1,2,4]] of the quadratic Lagrange basis
   double E0[3], E1[3], m0[3], mk[3], q0[3], q1[3];
   double ih2[3];     // 1/h_d^2
+  double ih[3];      // 1/h_d
   double alpha_pen;  // alpha * k (k + dim - 1)
   double theta, scale;  // scale = |K| / 27000
 };
@@ -72,6 +94,7 @@ struct TileFrame {
   int org[3];  // cell coordinate of tile (0,0,0)
   int lim[3];  // exclusive upper bound of the tiled cell range
   double* out; // the output vector (ghost rows are written with plain stores)
+  int* err;    // device error flag: "Outflow boundary condition on inflow" (convectiondiffusiondg.hh:802-806)
   int pf;      // L2 prefetch distance in tiles of the launch's linear block order (0 = off)
   int accumulate;    // y += J x (TMA reduce-add store) instead of y = J x
   const double* r0;  // residual form: R(0) is added to the staged tile before it leaves
@@ -100,6 +123,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint64_t* bar) {
   asm volatile(
@@ -108,24 +132,26 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 // warms L2 with the core box of a tile that a later CTA will load (no shared-memory destination)
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
                "r"(c2), "r"(c3)
                : "memory");
 }
-// y += tile: the L2 performs the read-modify-write (every element is touched once per launch, so
-// the result does not depend on the order in which the tiles arrive)
-__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
-                                                  int c3) {
-  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+// (accumulate forms: the bulk reduce-add lets the L2 perform the read-modify-write; every element is touched once per
+// launch, so the result does not depend on the order in which the rows arrive)
+// 1-D bulk copies (16-byte aligned, size a multiple of 16): one x-row of cells
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+               "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait() {
@@ -188,11 +214,19 @@ __device__ __forceinline__ double penalty_coef(double cs, double co, double ih2,
 //   t_i += P1_i u'_s(0) + P2_i u'_s(1) + P3_i u'_l(1) + P4_i u'_r(0) + P5_i [u]_L + P6_i [u]_R
 // The own values are re-read from shared memory in every sweep instead of being kept in 54
 // registers: the kernel is fp64-issue bound, not LDS bound, and the registers buy occupancy.
-template <int S, bool FIRST, bool HAS_C, bool WEIGHTS_ON>
+// convection along one direction (HAS_B): cb = b_d / h_d of the cell; cuLs / cuLo = (beta_L / h_d) on the own /
+// the neighbour's trace at the lower face, whichever is upwind (convectiondiffusiondg.hh:426-448; boundary faces
+// :797-822, 860), cuRs / cuRo the same at the upper face
+struct Conv1D {
+  double cb, cuLs, cuLo, cuRs, cuRo;
+};
+
+template <int S, bool FIRST, bool HAS_C, bool WEIGHTS_ON, bool HAS_B>
 __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)[NLOC], const double* __restrict__ nl,
                                       const double* __restrict__ nr, const FastConst& F, double creact, double A0,
-                                      double ih2, double csL, double coL, double csR, double coR) {
+                                      double ih2, double csL, double coL, double csR, double coR, const Conv1D& V) {
   double P1[3], P2[3], P3[3], P4[3], P5[3], P6[3];
+  double P5o[3], P6o[3];  // HAS_B: the jumps split into their two traces (the upwind flux weights them differently)
   const double ctL = -F.theta * csL, ctR = F.theta * csR;
   const double cgL = penalty_coef<WEIGHTS_ON>(csL, coL, ih2, F.alpha_pen);
   const double cgR = penalty_coef<WEIGHTS_ON>(csR, coR, ih2, F.alpha_pen);
@@ -204,6 +238,17 @@ __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)
     P4[i] = -F.mk[i] * coR;
     P5[i] = fma(F.m0[i], cgL, F.q0[i] * ctL);
     P6[i] = fma(F.mk[i], cgR, F.q1[i] * ctR);
+    if (HAS_B) {
+      P5o[i] = fma(F.m0[i], V.cuLo, -P5[i]);          // on the left neighbour's trace l2
+      P6o[i] = fma(F.mk[i], V.cuRo, -P6[i]);          // on the right neighbour's trace r0
+      P5[i] = fma(F.m0[i], V.cuLs + V.cb, P5[i]);     // on the own trace o0 (upwind flux + boundary part of the volume term)
+      P6[i] = fma(F.mk[i], V.cuRs - V.cb, P6[i]);     // on the own trace o2
+    }
+  }
+  const double sb = HAS_B ? V.cb * F.scale : 0.0;     // b_d / h_d u'(x_i): u'(0) = dls, u'(1/2) = o2 - o0, u'(1) = drs
+  if (HAS_B) {
+    P1[0] += sb;
+    P2[2] += sb;
   }
   constexpr int SA = S == 1 ? 3 : 1;  // strides of the two tangential node indices
   constexpr int SB = S == 9 ? 3 : 9;
@@ -232,8 +277,16 @@ __device__ __forceinline__ void sweep(const double* __restrict__ no, double (&t)
         acc = fma(P2[i], drs, acc);
         acc = fma(P3[i], dlo, acc);
         acc = fma(P4[i], dro, acc);
-        acc = fma(P5[i], jl, acc);
-        acc = fma(P6[i], jr, acc);
+        if (HAS_B) {
+          acc = fma(P5[i], o0, acc);
+          acc = fma(P5o[i], l2, acc);
+          acc = fma(P6[i], o2, acc);
+          acc = fma(P6o[i], r0, acc);
+          if (i == 1) acc = fma(sb, o2 - o0, acc);
+        } else {
+          acc = fma(P5[i], jl, acc);
+          acc = fma(P6[i], jr, acc);
+        }
         t[base + i * S] = acc;
       }
     }
@@ -259,38 +312,62 @@ __device__ __forceinline__ void mass_sweep(double (&t)[NLOC]) {
     }
 }
 
-template <int AMODE, bool HAS_C, bool WEIGHTS_ON>
+template <int AMODE, bool HAS_C, bool WEIGHTS_ON, bool HAS_B>
 __global__ void __launch_bounds__(TX* TY* TZ, 3)
-    dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_yh,
-                         const __grid_constant__ CUtensorMap tm_zh, const __grid_constant__ CUtensorMap tm_out,
-                         const __grid_constant__ CUtensorMap tm_pf, const __grid_constant__ CUtensorMap tm_r0,
-                         const DevParams P, const FastConst F, const TileFrame TF) {
+    dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_pf,
+                         const double* __restrict__ xin, const DevParams P, const FastConst F, const TileFrame TF) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t wbar[TZ];  // residual form: the R(0) rows of every warp arrive on its own barrier
   const int tid = threadIdx.x;
   const int x0 = (blockIdx.x + TF.off[0]) * TX, y0 = TF.org[1] + (blockIdx.y + TF.off[1]) * TY,
             z0 = TF.org[2] + (blockIdx.z + TF.off[2]) * TZ;
 
   if (tid == 0) {
     mbar_init(&bar, 1);
+    if (TF.r0)
+      for (int w = 0; w < TZ; w++) mbar_init(&wbar[w], 1);
     fence_mbar_init();
   }
   __syncthreads();
+  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
+  const int ncx = min(TX, Nx - x0);                   // cells of an x-row inside the vector (even: Nx is even)
+  const int nrow = min(TY, Ny - y0);                  // rows of the tile inside the vector
+  const bool zlo_in = z0 - 1 >= 0, zup_in = z0 + TZ < Nz;
   if (tid == 0) {
-    mbar_expect_tx(&bar, SMEM_BYTES);
-    tma_load_4d(tile + R0, &tm_rows, 0, x0 / 2 - 1, y0, z0, &bar);
-    tma_load_4d(tile + R1, &tm_yh, 0, x0 / 2, y0 - 1, z0, &bar);
-    tma_load_4d(tile + R2, &tm_yh, 0, x0 / 2, y0 + TY, z0, &bar);
-    tma_load_4d(tile + R3, &tm_zh, 0, x0 / 2, y0, z0 - 1, &bar);
-    tma_load_4d(tile + R4, &tm_zh, 0, x0 / 2, y0, z0 + TZ, &bar);
-    if (TF.pf) {  // the tile TF.pf places further on in launch order: every input byte is prefetched once
-      unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
-      const unsigned px = lin % gridDim.x;
-      lin /= gridDim.x;
-      const unsigned py = lin % gridDim.y, pz = lin / gridDim.y;
-      if (pz < gridDim.z)
-        tma_prefetch_4d(&tm_pf, 0, (px + TF.off[0]) * (TX / 2), TF.org[1] + (py + TF.off[1]) * TY,
-                        TF.org[2] + (pz + TF.off[2]) * TZ);
+    const uint32_t rowbytes = (uint32_t)ncx * NLOC * 8;
+    mbar_expect_tx(&bar, ROWS_BYTES + ((zlo_in ? nrow : 0) + (zup_in ? nrow : 0)) * rowbytes);
+    tma_load_4d(tile + R0, &tm_rows, 0, x0 / 2 - 1, y0 - 1, z0, &bar);
+    // z-halo layers: one bulk copy per x-row; a layer outside the vector is zeroed by the threads that read it
+    for (int r = 0; r < nrow; r++) {
+      if (zlo_in)
+        bulk_load(tile + R3 + zhalo_row(r), xin + (((long long)(z0 - 1) * Ny + y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
+      if (zup_in)
+        bulk_load(tile + R4 + zhalo_row(r), xin + (((long long)(z0 + TZ) * Ny + y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
+    }
+  }
+  if (TF.pf && tid < ROWY * (TZ + 2) + 1) {
+    // L2 prefetch for the tile TF.pf places further on in launch order: thread 0 the core box of the vector (every
+    // input byte is prefetched once), threads 1.. one x-row each of the coefficient box that tile's cells will load
+    unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
+    const unsigned px = lin % gridDim.x;
+    lin /= gridDim.x;
+    const unsigned py = lin % gridDim.y, pz = lin / gridDim.y;
+    if (pz < gridDim.z) {
+      const int qx = (px + TF.off[0]) * TX, qy = TF.org[1] + (py + TF.off[1]) * TY, qz = TF.org[2] + (pz + TF.off[2]) * TZ;
+      if (tid == 0) {
+        tma_prefetch_4d(&tm_pf, 0, qx / 2, qy, qz);
+      } else if (AMODE != PDB200_A_IDENTITY) {
+        const int r = tid - 1, ky = qy - 1 + r % ROWY, kz = qz - 1 + r / ROWY;
+        if (ky >= 0 && ky < Ny && kz >= 0 && kz < Nz && qx < Nx) {
+          const long long c0 = (long long)max(qx - 1, 0) + (long long)Nx * (ky + (long long)Ny * kz);
+          const int per = AMODE == PDB200_A_SCALAR ? 1 : (AMODE == PDB200_A_DIAGONAL ? 3 : 9);
+          const double* a = P.A + c0 * per;
+          prefetch_l2(a);                                   // 10 cells: at most two (scalar) .. six 128-byte lines
+          for (int o = 16; o < 10 * per; o += 16) prefetch_l2(a + o);
+          prefetch_l2(a + 10 * per - 1);
+        }
+      }
     }
   }
 
@@ -301,7 +378,6 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
   const int cz = tid >> 5;
   const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
-  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
   const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
 
   // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
@@ -310,6 +386,8 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   double A0[3], csL[3], coL[3], csR[3], coR[3];
   double creact = 0.0;
   bool constrained = false;
+  double bs[3] = {0.0, 0.0, 0.0}, bo[3] = {0.0, 0.0, 0.0};  // HAS_B: own velocity and b_d of the upper d-neighbour
+  int kinds = 0;                                             // HAS_B: face kinds, 2 bits each, face 2 d + side
   if (active) {
     const int cell = gx + Nx * (gy + Ny * gz);
     const int stride[3] = {1, Nx, Nx * Ny};
@@ -326,6 +404,13 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
       }
     }
     if (HAS_C) creact = __ldg(P.c + cell) * F.scale;
+    if (HAS_B) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        bs[d] = __ldg(P.b + (long long)cell * 3 + d);
+        bo[d] = onb[d][1] ? bs[d] : __ldg(P.b + (long long)(cell + stride[d]) * 3 + d);
+      }
+    }
     const bool any_b = onb[0][0] | onb[0][1] | onb[1][0] | onb[1][1] | onb[2][0] | onb[2][1];
     if (any_b) {  // rare: cells on the box surface
       // boundary-face numbers of pdelab_b200.h: tangential coordinates lexicographic, lower direction fastest
@@ -339,33 +424,86 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
               kind[d][side] = 2;
               constrained = true;
             } else if (P.bctype) {
-              kind[d][side] = P.bctype[P.bf_off[d][side] + bf[d]] == PDB200_BC_DIRICHLET ? 1 : 2;
+              const int bt = P.bctype[P.bf_off[d][side] + bf[d]];
+              kind[d][side] = bt == PDB200_BC_DIRICHLET ? 1 : (HAS_B && bt == PDB200_BC_OUTFLOW ? 3 : 2);
             }
           }
+    }
+    if (HAS_B) {
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int side = 0; side < 2; side++) kinds |= kind[d][side] << (2 * (2 * d + side));
     }
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       A0[d] = a[d] * F.ih2[d];
-      face_coef<WEIGHTS_ON>(kind[d][0], a[d], ao[d][0], F.ih2[d], csL[d], coL[d]);
-      face_coef<WEIGHTS_ON>(kind[d][1], a[d], ao[d][1], F.ih2[d], csR[d], coR[d]);
+      face_coef<WEIGHTS_ON>(kind[d][0] == 3 ? 2 : kind[d][0], a[d], ao[d][0], F.ih2[d], csL[d], coL[d]);
+      face_coef<WEIGHTS_ON>(kind[d][1] == 3 ? 2 : kind[d][1], a[d], ao[d][1], F.ih2[d], csR[d], coR[d]);
     }
   }
 
   // ---- shared-memory addresses of the cell and its six face neighbours -------------------------
-  const int so = R0 + ((cz * TY + cy) * ROWX + cx + 2) * NLOC;
+  const int so = R0 + ((cz * ROWY + cy + 1) * ROWX + cx + 2) * NLOC;
   const int xl = so - NLOC, xr = so + NLOC;
-  const int yl = cy > 0 ? so - ROWX * NLOC : R1 + (cz * TX + cx) * NLOC;
-  const int yr = cy < TY - 1 ? so + ROWX * NLOC : R2 + (cz * TX + cx) * NLOC;
-  const int zl = cz > 0 ? so - TY * ROWX * NLOC : R3 + (cy * TX + cx) * NLOC;
-  const int zr = cz < TZ - 1 ? so + TY * ROWX * NLOC : R4 + (cy * TX + cx) * NLOC;
+  const int yl = so - ROWX * NLOC, yr = so + ROWX * NLOC;
+  const int zl = cz > 0 ? so - ROWY * ROWX * NLOC : R3 + zhalo_row(cy) + cx * NLOC;
+  const int zr = cz < TZ - 1 ? so + ROWY * ROWX * NLOC : R4 + zhalo_row(cy) + cx * NLOC;
+  // a z-halo layer outside the vector: every thread zeroes the slot only it reads (the TMA box does this by itself)
+  if (active && ((cz == 0 && !zlo_in) || (cz == TZ - 1 && !zup_in))) {
+    double* __restrict__ slot = tile + (cz == 0 && !zlo_in ? zl : zr);
+#pragma unroll
+    for (int i = 0; i < NLOC; i++) slot[i] = 0.0;
+  }
 
   mbar_wait(&bar, 0);
 
   double t[NLOC];
+  // convection coefficients of direction d from the velocities and the face kinds
+  auto conv = [&](int d) {
+    Conv1D V = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (HAS_B) {
+      const double ih = F.ih[d];
+      V.cb = bs[d] * ih;
+      const int kL = (kinds >> (4 * d)) & 3, kR = (kinds >> (4 * d + 2)) & 3;
+      // lower face: this cell is the larger-index (inside) cell, n = -e_d, beta = -b_d (:426-438)
+      const double betaL = -bs[d];
+      const bool selfL = betaL >= 0.0;
+      V.cuLs = (kL == 3 || (kL != 2 && selfL)) ? betaL * ih : 0.0;
+      V.cuLo = (kL == 0 && !selfL) ? betaL * ih : 0.0;
+      // upper face: interior -> the neighbour is the inside cell, its normal is -e_d and its velocity counts
+      const double betaR = bo[d];
+      const bool selfR = kR == 0 ? !(-betaR >= 0.0) : betaR >= 0.0;
+      V.cuRs = (kR == 3 || (kR != 2 && selfR)) ? betaR * ih : 0.0;
+      V.cuRo = (kR == 0 && !selfR) ? betaR * ih : 0.0;
+      if ((kL == 3 && betaL < -1e-30) || (kR == 3 && betaR < -1e-30)) *TF.err = 1;  // :802-806
+    }
+    return V;
+  };
+  // the z-sweep first: it is the only one that reads other warps' layers
+  if (active)
+    sweep<9, true, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], F.ih2[2], csL[2], coL[2], csR[2],
+                                             coR[2], conv(2));
+  __syncthreads();  // from here on a warp reads and writes its own layer only
   if (active) {
-    sweep<1, true, HAS_C, WEIGHTS_ON>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], F.ih2[0], csL[0], coL[0], csR[0], coR[0]);
-    sweep<3, false, HAS_C, WEIGHTS_ON>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], F.ih2[1], csL[1], coL[1], csR[1], coR[1]);
-    sweep<9, false, HAS_C, WEIGHTS_ON>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], F.ih2[2], csL[2], coL[2], csR[2], coR[2]);
+    sweep<1, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], F.ih2[0], csL[0], coL[0], csR[0],
+                                              coR[0], conv(0));
+    sweep<3, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], F.ih2[1], csL[1], coL[1], csR[1],
+                                              coR[1], conv(1));
+  }
+  __syncwarp();  // every lane is done reading the layer: it becomes the warp's output stage
+  double* const stage = tile + R0 + cz * LAYER;
+  const uint32_t rowbytes = (uint32_t)ncx * NLOC * 8;
+  const bool rowlane = lane < TY && y0 + lane < Ny && gz < Nz;  // lane r sends row r of the layer, if inside the vector
+  if (TF.r0 && lane == 0) {
+    // residual form R(x) = J x + R(0) (the operator is affine): the rows of the cached R(0) travel into the layer
+    // behind the stage while the mass sweeps run; they are added to y by reduce-adds, no thread touches them
+    const int nr = gz < Nz ? nrow : 0;
+    mbar_expect_tx(&wbar[cz], nr * rowbytes);
+    for (int r = 0; r < nr; r++)
+      bulk_load(stage + ZSIZE + zhalo_row(r), TF.r0 + (((long long)gz * Ny + y0 + r) * Nx + x0) * NLOC, rowbytes, &wbar[cz]);
+  }
+  if (active) {
     mass_sweep<1>(t);
     mass_sweep<3>(t);
     mass_sweep<9>(t);
@@ -374,18 +512,11 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
       for (int i = 0; i < NLOC; i++) t[i] = 0.0;
     }
   }
-  __syncthreads();  // every thread is done reading the input tile: reuse R0 as the output stage
-  if (TF.r0 && tid == 0) {
-    // residual form R(x) = J x + R(0) (the operator is affine): fetch the tile of the cached R(0)
-    // behind the staging area; it is added to y by a second TMA reduce, no thread touches it
-    mbar_expect_tx(&bar, TX * TY * TZ * NLOC * 8);
-    tma_load_4d(tile + R0TILE, &tm_r0, 0, x0 / 2, y0, z0, &bar);
-  }
-  {  // the TMA store writes the whole box (clipped to the vector): cells of the box outside the
+  {  // the row stores write the whole box (clipped to the vector): cells of the box outside the
      // tiled range are ghost rows, which are zero
-    const int dst = ((cz * TY + cy) * TX + cx) * NLOC;
+    double* __restrict__ dst = stage + zhalo_row(cy) + cx * NLOC;
 #pragma unroll
-    for (int i = 0; i < NLOC; i++) tile[dst + i] = active ? t[i] : 0.0;
+    for (int i = 0; i < NLOC; i++) dst[i] = active ? t[i] : 0.0;
     if (TF.accumulate && active && constrained) {  // constrained rows are SET to zero, not incremented
       double* __restrict__ row = TF.out + (long long)(gx + Nx * (gy + Ny * gz)) * NLOC;
 #pragma unroll
@@ -393,15 +524,16 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     }
   }
   fence_proxy_async();
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  if (rowlane) {
+    double* dst = TF.out + (((long long)gz * Ny + y0 + lane) * Nx + x0) * NLOC;
     if (TF.accumulate)
-      tma_reduce_add_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
+      bulk_reduce_add(dst, stage + zhalo_row(lane), rowbytes);
     else
-      tma_store_4d(&tm_out, tile, 0, x0 / 2, y0, z0);
-    if (TF.r0) {  // residual form: y += R(0) tile, which has been travelling since the input tile died
-      mbar_wait(&bar, 1);
-      tma_reduce_add_4d(&tm_out, tile + R0TILE, 0, x0 / 2, y0, z0);
+      bulk_store(dst, stage + zhalo_row(lane), rowbytes);
+    if (TF.r0) {
+      mbar_wait(&wbar[cz], 0);
+      bulk_reduce_add(dst, stage + ZSIZE + zhalo_row(lane), rowbytes);
     }
   }
 
@@ -423,7 +555,7 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
         for (int i = tid; i < nx; i += TX * TY * TZ) row[i] = 0.0;
       }
   }
-  if (tid == 0) tma_store_commit_and_wait();
+  if (rowlane) tma_store_commit_and_wait();
 }
 
 // y += t (+ r0): accumulate semantics of the reference engines; r0 = R(0) turns J x into the residual
@@ -448,7 +580,7 @@ struct FastPlan {
   EncodeFn encode = nullptr;
   struct Maps {
     const void* ptr = nullptr;
-    CUtensorMap rows, yh, zh, core;
+    CUtensorMap rows, core;  // rows: the input box of a tile; core: its cells without halo (L2 prefetch)
   };
   std::vector<Maps> cache;  // tensor maps embed the global address: keep the most recent few
   double* scratch = nullptr;
@@ -456,7 +588,8 @@ struct FastPlan {
 };
 
 bool dg_fast_supported(const DevParams& P) {
-  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && P.k == 2 && P.m >= 3 && kron_coefficients(P) &&
+  // a cell-wise constant velocity is a Kronecker term too (HAS_B variants)
+  return P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.dim == 3 && P.k == 2 && P.m >= 3 && P.pw == 0 && P.a_mode != PDB200_A_FULL &&
          P.N[0] % 2 == 0;
 }
 
@@ -472,6 +605,7 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
     F.q0[i] = K.q0[i] * F.scale;
     F.q1[i] = K.q1[i] * F.scale;
     F.ih2[i] = 1.0 / (P.h[i] * P.h[i]);
+    F.ih[i] = 1.0 / P.h[i];
   }
   F.alpha_pen = P.alpha * P.k * (P.k + P.dim - 1);
   F.theta = P.theta;
@@ -480,8 +614,10 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   PDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled is not available in this driver");
   plan->encode = (EncodeFn)fn;
-#define PDB_SET_SMEM(AM, HC, WO)                                                                          \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define PDB_SET_SMEM(AM, HC, WO)                                                                                 \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                SMEM_BYTES));                                                                     \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                 SMEM_BYTES));
 #define PDB_SET_SMEM4(AM) PDB_SET_SMEM(AM, false, false) PDB_SET_SMEM(AM, false, true) PDB_SET_SMEM(AM, true, false) PDB_SET_SMEM(AM, true, true)
   PDB_SET_SMEM4(PDB200_A_IDENTITY) PDB_SET_SMEM4(PDB200_A_SCALAR) PDB_SET_SMEM4(PDB200_A_DIAGONAL)
@@ -514,9 +650,7 @@ static FastPlan::Maps& get_maps(FastPlan* plan, const void* ptr, const DevParams
   if (plan->cache.size() >= 16) plan->cache.erase(plan->cache.begin());
   FastPlan::Maps m;
   m.ptr = ptr;
-  encode_map(plan, &m.rows, ptr, P, ROWX / 2, TY, TZ);
-  encode_map(plan, &m.yh, ptr, P, TX / 2, 1, TZ);
-  encode_map(plan, &m.zh, ptr, P, TX / 2, TY, 1);
+  encode_map(plan, &m.rows, ptr, P, ROWX / 2, ROWY, TZ);
   encode_map(plan, &m.core, ptr, P, TX / 2, TY, TZ);
   plan->cache.push_back(m);
   return plan->cache.back();
@@ -569,17 +703,17 @@ void dg_fast_ztile_layers(const DevParams& P, int lo, int hi, int* z0, int* z1) 
 }
 
 int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
-                   int part, cudaStream_t s, int ztile_lo, int ztile_hi) {
+                   int part, cudaStream_t s, int* errflag, int ztile_lo, int ztile_hi) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
   if (part != PDB200_PART_ALL && !overwrite) throw Error("partial application needs the overwrite form");
   double* out = y;  // accumulate semantics (y += J z [+ R(0)]) through the TMA reduce-add store
   const FastPlan::Maps mx = get_maps(plan, x, P);
-  const FastPlan::Maps my = get_maps(plan, out, P);
-  const FastPlan::Maps mr = r0 ? get_maps(plan, r0, P) : my;
+  if ((uintptr_t)out % 16 != 0 || (r0 && (uintptr_t)r0 % 16 != 0)) throw Error("fast DG kernel: vectors must be 16-byte aligned");
   TileFrame TF;
   int nt[3];
   tile_frame(P, TF, nt);
   TF.out = out;
+  TF.err = errflag;
   TF.accumulate = overwrite ? 0 : 1;
   TF.r0 = r0;
   {
@@ -615,8 +749,11 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
     }
   }
   int launches = 0;
-#define PDB_LAUNCH(AM, HC, WO) \
-  dg_fast_q2_3d_kernel<AM, HC, WO><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.yh, mx.zh, my.core, mx.core, mr.core, P, plan->F, TF)
+#define PDB_LAUNCH(AM, HC, WO)                                                                                            \
+  do {                                                                                                                     \
+    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
+    else dg_fast_q2_3d_kernel<AM, HC, WO, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
+  } while (0)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \
     if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \

@@ -4,7 +4,8 @@
 // and dim = 3 with k = 1 (n = 8).
 //
 // Same operator identity as dg_fast.cu / dg_kron.cu, valid for cell-wise constant
-// DIAGONAL diffusion tensors and b = 0:
+// DIAGONAL diffusion tensors and cell-wise constant velocities (the convective terms fold into T, PL2 and PR2:
+// dg_face.cuh Conv1); without convection:
 //     y_e = |K| (M (x) ... (x) M) [ sum_d M^-1 L_d(z_{e-d}, z_e, z_{e+d}) / h_d^2 + c_e z_e ]
 // i.e. exactly GridOperator::jacobian_apply for ConvectionDiffusionDG
 // (localoperator/convectiondiffusiondg.hh:106-188, 271-471, 684-879); per line of n1 = k+1 nodes
@@ -29,7 +30,7 @@ using namespace dgface;
 template <int DIM, int K>
 __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const SmallConst<K> C, const double* __restrict__ z,
                                                        double* __restrict__ y, const double* __restrict__ r0,
-                                                       int accumulate) {
+                                                       int accumulate, int* __restrict__ errflag) {
   constexpr int N = SL<DIM, K>::N;
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= P.ncells) return;
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const 
   for (int d = 0; d < DIM; d++) {
     double A0, cs[2], co[2], cg[2];
     bool onb[2];
-    constrained |= direction_coefs<K>(P, C, cell, g, d, stride, A0, cs, co, cg, onb);
+    Conv1 V;
+    constrained |= direction_coefs<K>(P, C, cell, g, d, stride, A0, cs, co, cg, onb, &V, errflag);
     double nb[2][N];
 #pragma unroll
     for (int side = 0; side < 2; side++) {
@@ -60,11 +62,11 @@ __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const 
       }
     }
     if (d == 0)
-      small_sweep<DIM, K, 0, true>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], creact, t);
+      small_sweep<DIM, K, 0, true>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], creact, t, V);
     else if (d == 1)
-      small_sweep<DIM, K, 1, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t);
+      small_sweep<DIM, K, 1, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t, V);
     else
-      small_sweep<DIM, K, 2, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t);
+      small_sweep<DIM, K, 2, false>(C, o, nb[0], nb[1], A0, cs[0], co[0], cg[0], cs[1], co[1], cg[1], 0.0, t, V);
   }
   small_mass<DIM, K, 0>(C, C.vol, t);
   small_mass<DIM, K, 1>(C, 1.0, t);
@@ -90,27 +92,28 @@ __global__ void __launch_bounds__(128) dg_small_kernel(const DevParams P, const 
 
 template <int DIM, int K>
 void launch_variant(const DevParams& P, const Kron1D& K1, const double* z, double* y, const double* r0, bool overwrite,
-                    cudaStream_t s) {
+                    cudaStream_t s, int* errflag) {
   SmallConst<K> C;
   fill_small_const<K>(C, P, K1);
   const unsigned blocks = (unsigned)((P.ncells + 127) / 128);
-  dg_small_kernel<DIM, K><<<blocks, 128, 0, s>>>(P, C, z, y, r0, overwrite ? 0 : 1);
+  dg_small_kernel<DIM, K><<<blocks, 128, 0, s>>>(P, C, z, y, r0, overwrite ? 0 : 1, errflag);
   PDB_CUDA(cudaGetLastError());
 }
 
 }  // namespace
 
 bool dg_small_supported(const DevParams& P) {
-  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && kron_coefficients(P) && P.m >= P.k + 1)) return false;
+  // cell-wise constant diagonal A; a cell-wise constant velocity is a Kronecker term too
+  if (!(P.dg && P.basis == PDB200_BASIS_LAGRANGE && P.pw == 0 && P.a_mode != PDB200_A_FULL && P.m >= P.k + 1)) return false;
   return (P.dim == 2 && (P.k == 1 || P.k == 2)) || (P.dim == 3 && P.k == 1);
 }
 
 int launch_dg_small(const DevParams& P, const Kron1D& K1, const double* z, double* y, const double* r0, bool overwrite,
-                    cudaStream_t s) {
+                    cudaStream_t s, int* errflag) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
-  if (P.dim == 2 && P.k == 1) launch_variant<2, 1>(P, K1, z, y, r0, overwrite, s);
-  else if (P.dim == 2 && P.k == 2) launch_variant<2, 2>(P, K1, z, y, r0, overwrite, s);
-  else if (P.dim == 3 && P.k == 1) launch_variant<3, 1>(P, K1, z, y, r0, overwrite, s);
+  if (P.dim == 2 && P.k == 1) launch_variant<2, 1>(P, K1, z, y, r0, overwrite, s, errflag);
+  else if (P.dim == 2 && P.k == 2) launch_variant<2, 2>(P, K1, z, y, r0, overwrite, s, errflag);
+  else if (P.dim == 3 && P.k == 1) launch_variant<3, 1>(P, K1, z, y, r0, overwrite, s, errflag);
   else throw Error("dg_small: unsupported (dim, degree)");
   return 1;
 }

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "host_tables.h"
 
 namespace pdb {
 namespace {
@@ -75,15 +76,23 @@ struct MailboxHeader {
   unsigned long long ready[6];      // [my side] epoch of the data the neighbour across that side has delivered
   unsigned long long ack[6];        // [my side] last epoch the neighbour across that side has consumed
   unsigned long long buf_off[6];    // byte offset of the receive buffer of each side
-  unsigned long long layer_doubles[6];
+  unsigned long long layer_doubles[6];  // doubles received across each side
+  unsigned long long send_doubles[6];   // conforming Qk: doubles sent across each side (k vs k+1 planes)
   unsigned long long magic;
 };
 constexpr unsigned long long MAILBOX_MAGIC = 0x70646232303068ull;  // "pdb200h"
 constexpr int P2P_BLOCKS = 64;  // CTAs per side
 constexpr unsigned long long SPIN_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
 
+// conforming Qk: a slab of lattice planes lo_d .. lo_d + n_d - 1 over the full tangential extent of the local box
+struct QkBox {
+  int lo[3], n[3];
+  long long count;
+};
+
 struct SideDesc {
   int active, dir, layer_src, layer_dst;
+  QkBox qsend, qrecv;              // conforming Qk: the planes sent across this side / received from it
   long long total;                 // doubles in the layer
   long long chunk, stride;         // contiguous run and its repeat stride, in doubles (see copy_layer)
   double* peer_buf;                // receive buffer in the NEIGHBOUR's mailbox for its side (dir, 1-side)
@@ -208,9 +217,96 @@ __global__ void p2p_unpack_kernel(const DevParams P, const SideTable T, double* 
   }
 }
 
+// ---- conforming Qk on the same mailboxes ---------------------------------------------------------------------
+// Every lattice point has ONE owner: the interface plane between two ranks' owned cells belongs to the lower rank
+// (the rule of gridfunctionspace/genericdatahandle.hh:894-947 on a Cartesian partition).  Across its upper side a
+// rank sends the k+1 lattice planes of its last owned cell layer and receives the k planes beyond the interface,
+// across its lower side it sends k planes and receives k+1.  The planes are scattered over the sub-entity groups of
+// the container; the container index of a lattice point is closed-form arithmetic (qk_lattice_index), so pack and
+// unpack need no index arrays.  Directions are exchanged one after the other over the full tangential extent: edge
+// and corner neighbours are reached in two / three hops, without messages of their own.
+__device__ __forceinline__ long long qk_box_index(const QkLayout& L, const QkBox& B, long long i) {
+  int l[3] = {0, 0, 0};
+  for (int d = 0; d < L.dim; d++) {
+    l[d] = B.lo[d] + (int)(i % B.n[d]);
+    i /= B.n[d];
+  }
+  return qk_lattice_index(L, l);
+}
+
+// grid = (blocks per side, 2): the two sides of direction `dir`
+__global__ void qk_push_kernel(const QkLayout L, const SideTable T, int dir, const double* __restrict__ x,
+                               unsigned long long epoch, unsigned int* counters) {
+  const int sidx = 2 * dir + blockIdx.y;
+  const SideDesc& S = T.s[sidx];
+  if (!S.active) return;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.qsend.count; i += step)
+    S.peer_buf[i] = x[qk_box_index(L, S.qsend, i)];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&counters[sidx], 1u);
+    if (done == gridDim.x - 1) {
+      counters[sidx] = 0;
+      __threadfence_system();
+      st_release_sys(S.peer_ready, epoch);
+    }
+  }
+}
+
+__global__ void qk_unpack_kernel(const QkLayout L, const SideTable T, int dir, double* __restrict__ x,
+                                 unsigned long long epoch, unsigned int* counters) {
+  const int sidx = 2 * dir + blockIdx.y;
+  const SideDesc& S = T.s[sidx];
+  if (!S.active) return;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.qrecv.count; i += step)
+    x[qk_box_index(L, S.qrecv, i)] = S.my_buf[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&counters[6 + sidx], 1u);
+    if (done == gridDim.x - 1) {
+      counters[6 + sidx] = 0;
+      st_release_sys(S.peer_ack, epoch);
+    }
+  }
+}
+
+// one warp waits for the two sides of a direction (see p2p_wait_kernel)
+__global__ void qk_wait_kernel(const SideTable T, int dir, int which, unsigned long long want, int* err) {
+  const int s = 2 * dir + threadIdx.x;
+  if (threadIdx.x < 2 && T.s[s].active) {
+    const unsigned long long* flag = which ? T.s[s].my_ready : T.s[s].my_ack;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < want) {
+      if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+}
+
+// x := 0 on the lattice points this rank does not own (the slabs below / above the owned range of every direction)
+struct QkBoxes6 {
+  QkBox b[6];
+};
+__global__ void qk_zero_boxes_kernel(const QkLayout L, const QkBoxes6 B, double* __restrict__ x) {
+  const QkBox& box = B.b[blockIdx.y];
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < box.count; i += step)
+    x[qk_box_index(L, box, i)] = 0.0;
+}
+
 }  // namespace
 
 struct P2PHalo {
+  bool qk = false;                   // conforming Qk: lattice-plane exchange, direction by direction
+  QkLayout L;
+  QkBoxes6 nonowned;                 // conforming Qk: the lattice points of the local box this rank does not own
   unsigned char* mailbox = nullptr;  // device memory of this rank (cudaMalloc, IPC-exported)
   size_t mailbox_bytes = 0;
   MailboxHeader header;              // host copy
@@ -225,18 +321,46 @@ struct P2PHalo {
   bool vec2 = true;  // every chunk is an even number of doubles: 16-byte accesses
 };
 
+// lattice slab of direction d, planes a..b, full extent elsewhere
+static QkBox qk_slab(const DevParams& P, int d, int a, int b) {
+  QkBox B;
+  B.count = 1;
+  for (int e = 0; e < 3; e++) {
+    B.lo[e] = 0;
+    B.n[e] = e < P.dim ? P.k * P.N[e] + 1 : 1;
+    if (e == d) {
+      B.lo[e] = a;
+      B.n[e] = std::max(0, b - a + 1);
+    }
+    B.count *= B.n[e];
+  }
+  return B;
+}
+
 P2PHalo* p2p_create(const DevParams& P, pdb200_ipc_handle* mine) {
-  if (!P.dg) throw Error("p2p halo exchange is implemented for QkDG spaces");
   static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(pdb200_ipc_handle), "handle size");
   P2PHalo* H = new P2PHalo;
   std::memset(&H->header, 0, sizeof(H->header));
   std::memset(&H->table, 0, sizeof(H->table));
+  std::memset(&H->nonowned, 0, sizeof(H->nonowned));
+  H->qk = !P.dg;
+  if (H->qk) H->L = make_qk_layout(P);
   size_t off = (sizeof(MailboxHeader) + 255) / 256 * 256;
   for (int d = 0; d < P.dim; d++)
     for (int s = 0; s < 2; s++) {
       if (P.side_kind[d][s] != PDB200_SIDE_PROCESSOR) continue;
       if (P.N[d] < 3) throw Error("halo exchange needs at least 3 cell layers in the exchange direction");
-      const unsigned long long n = (unsigned long long)(P.ncells / P.N[d]) * P.n;
+      unsigned long long n = (unsigned long long)(P.ncells / P.N[d]) * P.n;
+      if (H->qk) {
+        const int k = P.k, nd = P.N[d];
+        SideDesc& S = H->table.s[2 * d + s];
+        // upper side: I own the interface plane; lower side: the neighbour does
+        S.qsend = s ? qk_slab(P, d, k * (nd - 2), k * (nd - 1)) : qk_slab(P, d, k + 1, 2 * k);
+        S.qrecv = s ? qk_slab(P, d, k * (nd - 1) + 1, k * nd) : qk_slab(P, d, 0, k);
+        H->nonowned.b[2 * d + s] = S.qrecv;   // exactly the planes received are the ones not owned
+        n = (unsigned long long)S.qrecv.count;
+        H->header.send_doubles[2 * d + s] = (unsigned long long)S.qsend.count;
+      }
       H->header.buf_off[2 * d + s] = off;
       H->header.layer_doubles[2 * d + s] = n;
       off += (n * sizeof(double) + 255) / 256 * 256;
@@ -274,7 +398,8 @@ void p2p_connect(P2PHalo* H, const DevParams& P, int dir, int side, const pdb200
   MailboxHeader ph;
   PDB_CUDA(cudaMemcpy(&ph, base, sizeof(ph), cudaMemcpyDeviceToHost));
   if (ph.magic != MAILBOX_MAGIC) throw Error("p2p_connect: the peer handle is not a pdelab_b200 mailbox");
-  if (ph.layer_doubles[sp] != H->header.layer_doubles[s])
+  if (H->qk ? (ph.layer_doubles[sp] != H->header.send_doubles[s] || ph.send_doubles[sp] != H->header.layer_doubles[s])
+            : ph.layer_doubles[sp] != H->header.layer_doubles[s])
     throw Error("p2p_connect: the neighbour's layer size differs (inconsistent partition)");
   unsigned char* pb = (unsigned char*)base;
   SideDesc& S = H->table.s[s];
@@ -317,7 +442,43 @@ static void p2p_require_connected(P2PHalo* H, const DevParams& P) {
   if (H->nactive != need) throw Error("p2p halo: not every processor side is connected");
 }
 
+// owner -> ghost copy of a conforming Qk vector: per direction wait(ack), push, wait(ready), unpack
+static int qk_exchange(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
+  p2p_require_connected(H, P);
+  if (H->nactive == 0) return 0;
+  H->epoch++;
+  int launches = 0;
+  for (int d = 0; d < P.dim; d++) {
+    if (!H->table.s[2 * d].active && !H->table.s[2 * d + 1].active) continue;
+    qk_wait_kernel<<<1, 32, 0, s>>>(H->table, d, 0, H->epoch - 1, H->err);
+    qk_push_kernel<<<dim3(P2P_BLOCKS, 2), 256, 0, s>>>(H->L, H->table, d, x, H->epoch, H->counters);
+    qk_wait_kernel<<<1, 32, 0, s>>>(H->table, d, 1, H->epoch, H->err);
+    qk_unpack_kernel<<<dim3(P2P_BLOCKS, 2), 256, 0, s>>>(H->L, H->table, d, x, H->epoch, H->counters);
+    launches += 4;
+  }
+  PDB_CUDA(cudaGetLastError());
+  return launches;
+}
+
+// owner -> ghost copy of x across all connected sides (QkDG: two kernels; conforming Qk: direction by direction)
+int p2p_exchange(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
+  if (H->qk) return qk_exchange(H, P, x, s);
+  return p2p_push(H, P, x, s) + p2p_wait_unpack(H, P, x, s);
+}
+
+// x := 0 on everything this rank does not own: the ghost cell layers (QkDG) / the lattice planes it receives (Qk)
+int p2p_zero_ghosts(P2PHalo* H, const DevParams& P, double* x, cudaStream_t s) {
+  if (!H->qk) return launch_halo_zero(P, x, s);
+  if (H->nactive == 0) return 0;
+  qk_zero_boxes_kernel<<<dim3(P2P_BLOCKS, 6), 256, 0, s>>>(H->L, H->nonowned, x);
+  PDB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+bool p2p_is_qk(const P2PHalo* H) { return H->qk; }
+
 int p2p_push(P2PHalo* H, const DevParams& P, const double* x, cudaStream_t s) {
+  if (H->qk) throw Error("p2p_push: conforming spaces exchange direction by direction (p2p_exchange)");
   p2p_require_connected(H, P);
   if (H->nactive == 0) return 0;
   H->epoch++;

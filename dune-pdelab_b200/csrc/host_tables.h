@@ -220,6 +220,7 @@ inline void host_fill_tables(DevParams& P, Kron1D& K, std::vector<double>& xq, s
     }
     K.d0[i] = (double)d0[i];
     K.d1[i] = (double)d1[i];
+    for (int j = 0; j < n1; j++) K.Dn[i * MAX_N1 + j] = (double)host_lagrange_dp_ld(k, j, (long double)i / k);
     K.E0[i] = (double)E0;  // valid for k = 2 (u' linear): K o = e0 u'(0) + e1 u'(1)
     K.E1[i] = (double)E1;
     K.m0[i] = (double)Mi[i][0];

@@ -126,8 +126,8 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
   const bool use_small = !use_fast && !use_kron && dg_small_supported(P) && op->kernel_choice != PDB200_KERNEL_GENERIC;
   if (op->kernel_choice == PDB200_KERNEL_FAST && !use_fast && !use_kron && !use_small)
     throw Error("PDB200_KERNEL_FAST requested but the configuration has no fast kernel "
-                "(needs QkDG with diagonal A and b=0: dim=3 with k in {2,3,4} and even cells[0], dim=3 with k=1, "
-                "or dim=2 with k in {1,2})");
+                "(needs QkDG with cell-wise constant diagonal A: dim=3 with k=2 and even cells[0] (b allowed), or with "
+                "b=0: dim=3 with k in {1,3,4}, dim=2 with k in {1,2})");
   if (use_fast || use_kron || use_small) {
     const double* r0 = nullptr;
     if (residual) {
@@ -139,14 +139,14 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
     }
     if (use_fast) {
       if (!op->fast) op->fast = dg_fast_plan_create(P, op->K);
-      op->launches += launch_dg_fast(op->fast, P, x, y, r0, overwrite, part, op->stream);
+      op->launches += launch_dg_fast(op->fast, P, x, y, r0, overwrite, part, op->stream, op->errflag);
       op->last_kernel = residual ? "dg_fast_q2_3d+r0" : "dg_fast_q2_3d";
     } else if (use_kron) {
       if (!op->kron) op->kron = dg_kron_plan_create(P, op->K);
       op->launches += launch_dg_kron(op->kron, P, x, y, r0, overwrite, op->stream);
       op->last_kernel = residual ? "dg_kron_3d+r0" : "dg_kron_3d";
     } else {
-      op->launches += launch_dg_small(P, op->K, x, y, r0, overwrite, op->stream);
+      op->launches += launch_dg_small(P, op->K, x, y, r0, overwrite, op->stream, op->errflag);
       op->last_kernel = residual ? "dg_small+r0" : "dg_small";
     }
   } else {
@@ -159,6 +159,13 @@ void run_vector_device(pdb200_operator* op, const double* x, double* y, Mode mod
 
 // y = J x on the overlapping partition: exchange of x's ghost layers hidden behind the interior tiles
 void apply_p2p_device(pdb200_operator* h, double* x, double* y) {
+  if (p2p_is_qk(h->p2p)) {
+    // conforming Qk: the lattice planes travel direction by direction (corners in two / three hops), then every rank
+    // evaluates complete rows for the closure of its owned cells; no tile split to hide the exchange behind
+    h->launches += p2p_exchange(h->p2p, h->P, x, h->stream);
+    run_vector_device(h, x, y, Mode::OnTheFly);
+    return;
+  }
   cudaStream_t side = p2p_stream(h->p2p);
   PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 0), h->stream));  // x is ready
   PDB_CUDA(cudaStreamWaitEvent(side, p2p_event(h->p2p, 0), 0));
@@ -211,7 +218,7 @@ bool run_onthefly_host_pipelined(pdb200_operator* op, const double* x, double* y
   }
   for (int c = 0; c < nwin; c++) {
     PDB_CUDA(cudaStreamWaitEvent(op->stream, ev_in[std::min(c + 1, nwin - 1)], 0));  // needs one layer of the next window
-    op->launches += launch_dg_fast(op->fast, P, op->dx, op->dy, nullptr, true, PDB200_PART_ALL, op->stream, tlo[c], thi[c]);
+    op->launches += launch_dg_fast(op->fast, P, op->dx, op->dy, nullptr, true, PDB200_PART_ALL, op->stream, op->errflag, tlo[c], thi[c]);
     PDB_CUDA(cudaEventRecord(ev_out[c], op->stream));
     PDB_CUDA(cudaStreamWaitEvent(op->d2h_stream, ev_out[c], 0));
     PDB_CUDA(cudaMemcpyAsync(y + zin0[c] * layer, op->dy + zin0[c] * layer, (zin1[c] - zin0[c]) * layer * sizeof(double),
@@ -706,33 +713,34 @@ void solve_device(pdb200_operator* h, int solver, int precond, const double* val
     // every inner product is the disjoint dot product without a mask; the global sums go through the peer mailboxes.
     if (!h->p2p || !h->comm)
       throw Error("pdb200_solve_ovlp: call pdb200_halo_p2p_create / _connect and pdb200_comm_create / _connect first");
-    if (!P.dg) throw Error("pdb200_solve_ovlp: implemented for QkDG spaces (face-neighbour ghost layers)");
+    // Conforming Qk: "ghost" = every lattice point the rank does not own (the planes it receives, including the
+    // interface plane towards a lower neighbour); the rows of owned points are complete because the ghost cell layer
+    // supplies all adjacent cells and the boundary of the extended box is constrained.
     if (!values) {
       ops.apply = [h](const double* in, double* out) {
         apply_p2p_device(h, const_cast<double*>(in), out);
-        h->launches += launch_halo_zero(h->P, out, h->stream);
-        h->launches += launch_halo_zero(h->P, const_cast<double*>(in), h->stream);
+        h->launches += p2p_zero_ghosts(h->p2p, h->P, out, h->stream);
+        h->launches += p2p_zero_ghosts(h->p2p, h->P, const_cast<double*>(in), h->stream);
       };
     } else {
       auto mv = ops.apply;
       ops.apply = [h, mv](const double* in, double* out) {
-        h->launches += p2p_push(h->p2p, h->P, in, h->stream);
-        h->launches += p2p_wait_unpack(h->p2p, h->P, const_cast<double*>(in), h->stream);
+        h->launches += p2p_exchange(h->p2p, h->P, const_cast<double*>(in), h->stream);
         mv(in, out);
-        h->launches += launch_halo_zero(h->P, out, h->stream);
-        h->launches += launch_halo_zero(h->P, const_cast<double*>(in), h->stream);
+        h->launches += p2p_zero_ghosts(h->p2p, h->P, out, h->stream);
+        h->launches += p2p_zero_ghosts(h->p2p, h->P, const_cast<double*>(in), h->stream);
       };
     }
     ops.allreduce = [h](double* P1, double* P2) {
       comm_allreduce_partials(h->comm, P1, P2, krylov_partial_count(), h->stream);
     };
-    h->launches += launch_halo_zero(P, r, h->stream);
+    h->launches += p2p_zero_ghosts(h->p2p, P, r, h->stream);
+    if (ops.dinv && !P.dg) h->launches += p2p_zero_ghosts(h->p2p, P, const_cast<double*>(ops.dinv), h->stream);
   }
   h->launches += krylov_solve(h->krylov, solver, P.ndofs, ops, z, r, reduction, maxiter, h->stream, res);
   if (ovlp) {
     // hand back a consistent solution (the reference's vectors are consistent on the whole overlap)
-    h->launches += p2p_push(h->p2p, h->P, z, h->stream);
-    h->launches += p2p_wait_unpack(h->p2p, h->P, z, h->stream);
+    h->launches += p2p_exchange(h->p2p, h->P, z, h->stream);
     PDB_CUDA(cudaStreamSynchronize(h->stream));
     p2p_check(h->p2p);
     comm_check(h->comm);
@@ -953,8 +961,7 @@ int pdb200_halo_exchange_p2p(pdb200_handle h, double* x) {
   ensure_device(h);
   if (!h->p2p) throw Error("call pdb200_halo_p2p_create / _connect first");
   if (!is_device_pointer(x)) throw Error("halo_exchange_p2p expects a device pointer");
-  h->launches += p2p_push(h->p2p, h->P, x, h->stream);
-  h->launches += p2p_wait_unpack(h->p2p, h->P, x, h->stream);
+  h->launches += p2p_exchange(h->p2p, h->P, x, h->stream);
   PDB_CATCH
 }
 int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y) {

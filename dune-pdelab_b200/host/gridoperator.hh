@@ -38,6 +38,7 @@
 #include <memory>
 #include <string>
 #include <type_traits>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pdelab_b200.h"
@@ -582,18 +583,23 @@ namespace detail {
 template <int dim>
 struct Sampled {
   int a_mode = PDB200_A_IDENTITY;
+  int pointwise = 0;  // PDB200_POINTWISE_* bits: which of A, b, c, bctype are in the point-wise layout
   std::vector<double> A, b, c, f, g, j, o;
   std::vector<std::int8_t> bctype;
   bool has_b = false, has_c = false, has_f = false, has_g = false, has_j = false, has_o = false;
 };
 
+// The call-backs are sampled exactly where the reference evaluates them (include/pdelab_b200.h, layout (2)): A, b and
+// c at every volume quadrature point (convectiondiffusiondg.hh:143-146,178,181; convectiondiffusionfem.hh:97-100,
+// 127-129), A and b at the quadrature points of every face in the local coordinates of the cell (:370-371,426,755,
+// 797), the QkDG boundary type per face quadrature point (:763).  A field that turns out constant on every cell
+// (every boundary face) is handed over in the cell-wise layout — the same numbers, and the Kronecker kernels apply.
+// A is only sampled per point when permeabilityIsConstantPerCell() is false, like the reference (:127,143).
 template <class GV, class Param>
-Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree, int intorderadd) {
+Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree, int intorderadd, bool dg) {
   constexpr int dim = GV::dimension;
   Sampled<dim> S;
-  if (!param.permeabilityIsConstantPerCell())
-    throw Exception("pdelab_b200: permeabilityIsConstantPerCell() must be true (A is sampled at the cell centre, "
-                    "convectiondiffusiondg.hh:127-131)");
+  const bool a_per_cell = param.permeabilityIsConstantPerCell();
   const int m = (2 * degree + intorderadd) / 2 + 1;  // convectiondiffusiondg.hh:139
   std::vector<double> xq(m), wq(m);
   check(pdb200_gauss_legendre(m, xq.data(), wq.data()), "pdb200_gauss_legendre");
@@ -601,64 +607,114 @@ Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree,
   int nq = 1, nfq = 1;
   for (int d = 0; d < dim; d++) nq *= m;
   for (int d = 1; d < dim; d++) nfq *= m;
-  S.A.resize(ncells * dim * dim);
-  S.b.resize(ncells * dim);
-  S.c.resize(ncells);
+  const int NP = nq + 2 * dim * nfq;
+  // local coordinates of the NP sample points of a cell
+  std::vector<FieldVector<double, dim>> xp(NP);
+  for (int q = 0; q < nq; q++) {
+    int r = q;
+    for (int d = 0; d < dim; d++) {
+      xp[q][d] = xq[r % m];
+      r /= m;
+    }
+  }
+  for (int dir = 0; dir < dim; dir++)
+    for (int side = 0; side < 2; side++)
+      for (int q = 0; q < nfq; q++) {
+        auto& x = xp[nq + (2 * dir + side) * nfq + q];
+        int r = q;
+        for (int d = 0; d < dim; d++) {
+          if (d == dir) {
+            x[d] = side;
+          } else {
+            x[d] = xq[r % m];
+            r /= m;
+          }
+        }
+      }
+  const int na = a_per_cell ? 1 : NP;
+  std::vector<double> Afull((std::size_t)ncells * na * dim * dim), bfull((std::size_t)ncells * NP * dim),
+      cfull((std::size_t)ncells * nq);
   S.f.resize(ncells * nq);
-  bool diag = true, scalar = true, ident = true;
+  bool diag = true, scalar = true, ident = true, a_const = true, b_const = true, c_const = true;
   const FieldVector<double, dim> centre(0.5);
   for (long long e = 0; e < ncells; e++) {
     const auto cell = gv.cell(e);
-    const auto A = param.A(cell, centre);
-    for (int i = 0; i < dim; i++)
-      for (int j = 0; j < dim; j++) {
-        S.A[(e * dim + i) * dim + j] = A[i][j];
-        if (i != j && A[i][j] != 0.0) diag = false;
-        if (i == j && A[i][i] != A[0][0]) scalar = false;
-        if (i == j && A[i][i] != 1.0) ident = false;
-      }
-    const auto b = param.b(cell, centre);
-    for (int i = 0; i < dim; i++) {
-      S.b[e * dim + i] = b[i];
-      S.has_b |= b[i] != 0.0;
+    for (int pt = 0; pt < na; pt++) {
+      const auto A = a_per_cell ? param.A(cell, centre) : param.A(cell, xp[pt]);
+      double* out = &Afull[((std::size_t)e * na + pt) * dim * dim];
+      for (int i = 0; i < dim; i++)
+        for (int j = 0; j < dim; j++) {
+          out[i * dim + j] = A[i][j];
+          if (i != j && A[i][j] != 0.0) diag = false;
+          if (i == j && A[i][i] != A[0][0]) scalar = false;
+          if (i == j && A[i][i] != 1.0) ident = false;
+          if (pt > 0 && out[i * dim + j] != Afull[(std::size_t)e * na * dim * dim + i * dim + j]) a_const = false;
+        }
     }
-    S.c[e] = param.c(cell, centre);
-    S.has_c |= S.c[e] != 0.0;
-    for (int q = 0; q < nq; q++) {
-      FieldVector<double, dim> x;
-      int r = q;
-      for (int d = 0; d < dim; d++) {
-        x[d] = xq[r % m];
-        r /= m;
+    for (int pt = 0; pt < NP; pt++) {
+      const auto b = param.b(cell, xp[pt]);
+      for (int i = 0; i < dim; i++) {
+        bfull[((std::size_t)e * NP + pt) * dim + i] = b[i];
+        S.has_b |= b[i] != 0.0;
+        if (b[i] != bfull[(std::size_t)e * NP * dim + i]) b_const = false;
       }
-      const double f = param.f(cell, x);
+    }
+    for (int q = 0; q < nq; q++) {
+      const double c = param.c(cell, xp[q]);
+      cfull[(std::size_t)e * nq + q] = c;
+      S.has_c |= c != 0.0;
+      if (c != cfull[(std::size_t)e * nq]) c_const = false;
+      const double f = param.f(cell, xp[q]);
       S.f[e * nq + q] = f;
       S.has_f |= f != 0.0;
     }
   }
   // compress A to the cheapest layout that represents it exactly (selects the Kronecker kernel)
-  if (diag) {
-    std::vector<double> a;
-    if (ident) {
+  const bool a_pw = !a_per_cell && !a_const;
+  const int nae = a_pw ? NP : 1;  // entries per cell that are kept
+  {
+    const std::size_t ne = (std::size_t)ncells * nae;
+    auto src = [&](std::size_t k) { return &Afull[(a_pw ? k : k * na) * dim * dim]; };  // cell-wise: the first sample
+    if (diag && ident) {
       S.a_mode = PDB200_A_IDENTITY;
-    } else if (scalar) {
+    } else if (diag && scalar) {
       S.a_mode = PDB200_A_SCALAR;
-      a.resize(ncells);
-      for (long long e = 0; e < ncells; e++) a[e] = S.A[e * dim * dim];
-    } else {
+      S.A.resize(ne);
+      for (std::size_t k = 0; k < ne; k++) S.A[k] = src(k)[0];
+    } else if (diag) {
       S.a_mode = PDB200_A_DIAGONAL;
-      a.resize(ncells * dim);
-      for (long long e = 0; e < ncells; e++)
-        for (int i = 0; i < dim; i++) a[e * dim + i] = S.A[(e * dim + i) * dim + i];
+      S.A.resize(ne * dim);
+      for (std::size_t k = 0; k < ne; k++)
+        for (int i = 0; i < dim; i++) S.A[k * dim + i] = src(k)[i * dim + i];
+    } else {
+      S.a_mode = PDB200_A_FULL;
+      S.A.resize(ne * dim * dim);
+      for (std::size_t k = 0; k < ne; k++)
+        for (int i = 0; i < dim * dim; i++) S.A[k * dim * dim + i] = src(k)[i];
     }
-    S.A.swap(a);
+    if (a_pw && S.a_mode != PDB200_A_IDENTITY) S.pointwise |= PDB200_POINTWISE_A;
+  }
+  if (b_const) {
+    S.b.resize((std::size_t)ncells * dim);
+    for (long long e = 0; e < ncells; e++)
+      for (int i = 0; i < dim; i++) S.b[e * dim + i] = bfull[(std::size_t)e * NP * dim + i];
   } else {
-    S.a_mode = PDB200_A_FULL;
+    S.b.swap(bfull);
+    S.pointwise |= PDB200_POINTWISE_B;
+  }
+  if (c_const) {
+    S.c.resize(ncells);
+    for (long long e = 0; e < ncells; e++) S.c[e] = cfull[(std::size_t)e * nq];
+  } else {
+    S.c.swap(cfull);
+    S.pointwise |= PDB200_POINTWISE_C;
   }
   // boundary faces in the numbering of pdelab_b200.h
   long long nbf = 0;
   for (int d = 0; d < dim; d++) nbf += 2 * (ncells / gv.grid().cells()[d]);
   S.bctype.resize(nbf);
+  std::vector<std::int8_t> bcq(dg ? nbf * nfq : 0);  // QkDG: the type at every face quadrature point (:763)
+  bool bc_const = true;
   S.g.assign(nbf * nfq, 0.0);
   S.j.assign(nbf * nfq, 0.0);
   S.o.assign(nbf * nfq, 0.0);
@@ -669,14 +725,22 @@ Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree,
       const long long nt = ncells / gv.grid().cells()[d];
       for (long long t = 0; t < nt; t++, bf++) {
         const auto is = gv.boundaryFace(d, side, t);
-        const auto bc = param.bctype(is, fcentre);
-        S.bctype[bf] = (std::int8_t)bc;
+        // ConvectionDiffusionFEM and the conforming constraints: the type at the face centre
+        // (convectiondiffusionfem.hh:226-229, constraints/conforming.hh:63-70)
+        S.bctype[bf] = (std::int8_t)param.bctype(is, fcentre);
         for (int q = 0; q < nfq; q++) {
           FieldVector<double, dim - 1> xf;
           int r = q;
           for (int i = 0; i < dim - 1; i++) {
             xf[i] = xq[r % m];
             r /= m;
+          }
+          auto bc = param.bctype(is, fcentre);
+          if (dg) {
+            bc = param.bctype(is, xf);
+            bcq[bf * nfq + q] = (std::int8_t)bc;
+            if (q == 0) S.bctype[bf] = (std::int8_t)bc;  // the cell-wise layout, used if the type is constant on every face
+            if (bcq[bf * nfq + q] != bcq[bf * nfq]) bc_const = false;
           }
           const auto xin = is.geometryInInside().global(xf);
           if (bc == ConvectionDiffusionBoundaryConditions::Dirichlet) {
@@ -692,6 +756,10 @@ Sampled<GV::dimension> sample_parameters(const GV& gv, Param& param, int degree,
         }
       }
     }
+  if (dg && !bc_const) {
+    S.bctype.swap(bcq);
+    S.pointwise |= PDB200_POINTWISE_BCTYPE;
+  }
   return S;
 }
 
@@ -751,17 +819,33 @@ class GridOperator {
     void setWeight(double w) {
       if (w != 1.0) throw Exception("pdelab_b200: engine weights other than 1 are not supported");
     }
+    // default/localassembler.hh:259-283: whether this operator's engines run the pre- / post-processing steps of a
+    // joint assembly (set by setupGridOperators).  The flags are kept for interface parity: the device path of a joint
+    // assembly is the fused stage operator of OneStepGridOperator, which applies the constraints once, at the end.
+    bool doPreProcessing() const { return pre_; }
+    void preProcessing(bool v) { pre_ = v; }
+    bool doPostProcessing() const { return post_; }
+    void postProcessing(bool v) { post_ = v; }
+    bool pre_ = true, post_ = true;
+  };
+  // global assembler facade (gridoperator/default/assembler.hh:35-83): what callers reach through go.assembler()
+  struct Assembler {
+    const GFSU* gfsu;
+    const GFSV* gfsv;
+    const GFSU& trialGridFunctionSpace() const { return *gfsu; }
+    const GFSV& testGridFunctionSpace() const { return *gfsv; }
   };
 
   // gridoperator.hh:76-82
   GridOperator(const GFSU& gfsu, const CU& cu, const GFSV& gfsv, const CV& cv, LOP& lop, const MB& mb = MB())
-      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&cu), cv_(&cv), la_{&lop, &cu, &cv} {
+      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&cu), cv_(&cv), la_{&lop, &cu, &cv}, as_{&gfsu, &gfsv} {
     la_.go = this;
     init();
   }
   // gridoperator.hh:85-89 (empty constraints)
   GridOperator(const GFSU& gfsu, const GFSV& gfsv, LOP& lop, const MB& mb = MB())
-      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&empty_cu_), cv_(&empty_cv_), la_{&lop, &empty_cu_, &empty_cv_} {
+      : gfsu_(gfsu), gfsv_(gfsv), lop_(lop), mb_(mb), cu_(&empty_cu_), cv_(&empty_cv_), la_{&lop, &empty_cu_, &empty_cv_},
+        as_{&gfsu, &gfsv} {
     la_.go = this;
     init();
   }
@@ -776,7 +860,20 @@ class GridOperator {
   typename GFSU::SizeType globalSizeU() const { return num_dofs(); }  // gridoperator.hh:104-107
   typename GFSV::SizeType globalSizeV() const { return num_dofs(); }
   LocalAssembler& localAssembler() const { return la_; }
+  Assembler& assembler() { return as_; }  // gridoperator.hh:115-117
+  const Assembler& assembler() const { return as_; }
   const MB& matrixBackend() const { return mb_; }
+  // gridoperator.hh:122-151: operators of a joint assembly — the first one pre-processes, the last one post-processes
+  template <class GridOperatorTuple>
+  static void setupGridOperators(GridOperatorTuple tuple) {
+    constexpr std::size_t size = std::tuple_size<GridOperatorTuple>::value;
+    std::size_t index = 0;
+    std::apply(
+        [&](auto&... go) {
+          ((go.localAssembler().preProcessing(index == 0), go.localAssembler().postProcessing(index == size - 1), ++index), ...);
+        },
+        tuple);
+  }
   pdb200_handle handle() const { return h_; }  // for stream control / device-pointer calls
 
   // re-sample the parameter call-backs (the reference re-evaluates them on every assembly)
@@ -795,8 +892,9 @@ class GridOperator {
     if (!time_dependent_ || (time_set_ && t == time_)) return;
     time_ = t;
     time_set_ = true;
-    auto S = detail::sample_parameters(gfsu_.gridView(), lop_.parameters(), FEM::degree, lop_.intorderadd);
-    const bool same_layout = S.a_mode == S_.a_mode && S.has_b == S_.has_b && S.has_c == S_.has_c && S.has_f == S_.has_f &&
+    auto S = detail::sample_parameters(gfsu_.gridView(), lop_.parameters(), FEM::degree, lop_.intorderadd,
+                                       FEM::space == PDB200_SPACE_QKDG);
+    const bool same_layout = S.a_mode == S_.a_mode && S.pointwise == S_.pointwise && S.has_b == S_.has_b && S.has_c == S_.has_c && S.has_f == S_.has_f &&
                              S.has_g == S_.has_g && S.has_j == S_.has_j && S.has_o == S_.has_o && S.bctype == S_.bctype;
     if (!same_layout) {  // a field switched on or off, or the boundary types moved: new operator (new constraint set)
       update();
@@ -909,7 +1007,7 @@ class GridOperator {
   void init() {
     static_assert(std::is_same<GFSU, GFSV>::value, "Galerkin: trial and test space coincide on this path");
     const auto& gv = gfsu_.gridView();
-    S_ = detail::sample_parameters(gv, lop_.parameters(), FEM::degree, lop_.intorderadd);
+    S_ = detail::sample_parameters(gv, lop_.parameters(), FEM::degree, lop_.intorderadd, FEM::space == PDB200_SPACE_QKDG);
     auto& S = S_;
     pdb200_problem& p = p_;
     p = pdb200_problem{};
@@ -930,6 +1028,7 @@ class GridOperator {
     p.dg_alpha = lop_.alpha;
     p.intorderadd = lop_.intorderadd;
     p.a_mode = S.a_mode;
+    p.pointwise = S.pointwise;
     p.A = S.A.empty() ? nullptr : S.A.data();
     p.b = S.has_b ? S.b.data() : nullptr;
     p.c = S.has_c ? S.c.data() : nullptr;
@@ -952,6 +1051,7 @@ class GridOperator {
   const CU* cu_;
   const CV* cv_;
   mutable LocalAssembler la_;
+  Assembler as_;
   detail::Sampled<dim> S_;  // sampled call-backs (kept alive: p_ points into them)
   pdb200_problem p_{};
   pdb200_handle h_ = nullptr;

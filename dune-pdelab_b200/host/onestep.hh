@@ -201,6 +201,7 @@ class OneStepGridOperator {
 
   // onestep.hh:66-76
   OneStepGridOperator(GO0& go0, GO1& go1) : go0_(go0), go1_(go1), la_{this} {
+    GO0::setupGridOperators(std::tie(go0_, go1_));  // onestep.hh:73: go0 pre-processes, go1 post-processes
     create();
     if (!implicit) dt_mode_ = PDB200_ONESTEP_DO_NOT_ASSEMBLE_DT;
   }

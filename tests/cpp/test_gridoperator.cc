@@ -83,6 +83,48 @@ class LayeredProblem : public PoissonProblem<GridView, RangeType> {
   }
 };
 
+// spatially varying fields: a rotating velocity, a reaction term that varies inside the cells, a diffusion tensor that
+// is NOT constant per cell and a boundary type that changes inside boundary faces — every call-back must be sampled
+// where the reference evaluates it (convectiondiffusiondg.hh:143-146,178,181,367-382,426,752-763)
+template <typename GridView, typename RangeType>
+class RotatingProblem : public PoissonProblem<GridView, RangeType> {
+ public:
+  using Traits = PDELab::ConvectionDiffusionParameterTraits<GridView, RangeType>;
+  static constexpr bool permeabilityIsConstantPerCell() { return false; }
+  template <typename Element, typename Coord>
+  typename Traits::PermTensorType A(const Element& e, const Coord& x) const {
+    auto g = e.geometry().global(x);
+    typename Traits::PermTensorType K(0.0);
+    for (int i = 0; i < Traits::dimDomain; i++) K[i][i] = (1.0 + 0.5 * std::sin(3.0 * g[0] + 2.0 * g[1])) * (1 + 0.3 * i);
+    return K;
+  }
+  template <typename Element, typename Coord>
+  typename Traits::RangeType b(const Element& e, const Coord& x) const {
+    auto g = e.geometry().global(x);
+    typename Traits::RangeType v(0.0);
+    v[0] = -(g[1] - 0.5);
+    v[1] = g[0] - 0.5;
+    return v;
+  }
+  template <typename Element, typename Coord>
+  RangeType c(const Element& e, const Coord& x) const {
+    auto g = e.geometry().global(x);
+    return 1.0 + g[0] * g[1];
+  }
+  template <typename Intersection, typename Coord>
+  auto bctype(const Intersection& is, const Coord& x) const {
+    auto g = is.geometry().global(x);
+    double s = 0;
+    for (std::size_t i = 0; i < g.size(); i++) s += (7.0 - 2.0 * i) * g[i];
+    return std::sin(s) > 0.2 ? PDELab::ConvectionDiffusionBoundaryConditions::Dirichlet
+                             : PDELab::ConvectionDiffusionBoundaryConditions::Neumann;
+  }
+  template <typename Intersection, typename Coord>
+  RangeType j(const Intersection& is, const Coord& x) const {
+    return 0.25 + is.geometry().global(x)[0];
+  }
+};
+
 template <class V>
 double rel_err(const V& a, const std::vector<double>& b) {
   double e = 0, n = 0;
@@ -196,6 +238,59 @@ void dg_case(int ncells, double alpha, double tol, const char* name, bool check_
   using V = typename GridOperator::Domain;
   const std::size_t N = gridFunctionSpace.size();
   EXPECT(gridOperator.globalSizeU() == N, name << ": globalSizeU == gfs.size() == " << N);
+  EXPECT(&gridOperator.assembler().trialGridFunctionSpace() == &gridFunctionSpace &&
+             gridOperator.localAssembler().doPreProcessing() && gridOperator.localAssembler().doPostProcessing(),
+         name << ": assembler() and the pre-/post-processing flags (gridoperator.hh:115-151)");
+  if (std::is_same<Problem, RotatingProblem<GridView, RangeType>>::value) {
+    // the sampled arrays hold the call-backs' values at the reference's evaluation points (layout (2) of pdelab_b200.h)
+    const pdb200_problem& P = gridOperator.problem();
+    const int all = PDB200_POINTWISE_A | PDB200_POINTWISE_B | PDB200_POINTWISE_C | PDB200_POINTWISE_BCTYPE;
+    EXPECT(P.pointwise == all && P.a_mode == PDB200_A_DIAGONAL, name << ": A, b, c, bctype handed over per quadrature point");
+    const int m = degree + 1;
+    std::vector<double> xq(m), wq(m);
+    pdb200_gauss_legendre(m, xq.data(), wq.data());
+    int nq = 1, nfq = 1;
+    for (int d = 0; d < dim; d++) nq *= m;
+    for (int d = 1; d < dim; d++) nfq *= m;
+    const int NP = nq + 2 * dim * nfq;
+    const double h = 1.0 / ncells;
+    double worst = 0;
+    for (long long e = 0; e < gridView.size(0); e++) {
+      int c[3] = {0, 0, 0};
+      long long r = e;
+      for (int d = 0; d < dim; d++) {
+        c[d] = (int)(r % ncells);
+        r /= ncells;
+      }
+      for (int pt = 0; pt < NP; pt++) {
+        double X[3] = {0, 0, 0};
+        if (pt < nq) {
+          int q = pt;
+          for (int d = 0; d < dim; d++) {
+            X[d] = (c[d] + xq[q % m]) * h;
+            q /= m;
+          }
+        } else {
+          const int f = (pt - nq) / nfq, dir = f / 2, side = f % 2;
+          int q = (pt - nq) % nfq;
+          for (int d = 0; d < dim; d++) {
+            if (d == dir) {
+              X[d] = (c[d] + side) * h;
+            } else {
+              X[d] = (c[d] + xq[q % m]) * h;
+              q /= m;
+            }
+          }
+        }
+        worst = std::max(worst, std::abs(P.b[(e * NP + pt) * dim + 0] + (X[1] - 0.5)));
+        worst = std::max(worst, std::abs(P.b[(e * NP + pt) * dim + 1] - (X[0] - 0.5)));
+        for (int i = 0; i < dim; i++)
+          worst = std::max(worst, std::abs(P.A[(e * NP + pt) * dim + i] - (1.0 + 0.5 * std::sin(3.0 * X[0] + 2.0 * X[1])) * (1 + 0.3 * i)));
+        if (pt < nq) worst = std::max(worst, std::abs(P.c[e * nq + pt] - (1.0 + X[0] * X[1])));
+      }
+    }
+    EXPECT(worst < 1e-14, name << ": sampled A, b, c equal the call-backs at the quadrature points (max deviation " << worst << ")");
+  }
 
   // --- oracle parity of residual / jacobian_apply / jacobian on random data ---------------------
   std::mt19937_64 rng;  // default seed 5489, test/test-blocked-istl-ordering.cc:45-48
@@ -677,6 +772,8 @@ int main() {
     dg_case<2, 2, LayeredProblem>(6, 3.0, 0, "DG k=2 2D 6^2 layered diagonal A + c", false);
     dg_case<3, 2, LayeredProblem>(4, 3.0, 0, "DG k=2 3D 4^3 layered diagonal A + c (Kronecker kernel)", false);
     dg_case<3, 2, PoissonProblem>(8, 3.0, 1e-6, "DG k=2 3D 8^3 Poisson (Kronecker kernel)", true);
+    dg_case<2, 2, RotatingProblem>(5, 3.0, 0, "DG k=2 2D 5^2 rotating b(x), c(x), A(x), bctype per face point", false);
+    dg_case<3, 1, RotatingProblem>(3, 3.0, 0, "DG k=1 3D 3^3 rotating b(x), c(x), A(x), bctype per face point", false);
     fem_case<2, 2>(32, 1e-7, "Q2 2D 32^2 (testmatrixfree)");
     fem_case<2, 1>(16, 1e-4, "Q1 2D 16^2");
     fem_case<3, 2>(4, 1e-5, "Q2 3D 4^3");

@@ -218,3 +218,77 @@ def test_small_cell_kernel_matches_oracle(cuda_lib, case):
     r = go.residual(z, y0.copy())
     assert go.last_kernel() == "dg_small+r0"
     assert rel_err(r, orc.residual(z, y0.copy())) < TOL
+
+
+# ---- convection in the Kronecker kernel (cell-wise constant velocity): volume term -u b.grad psi and the upwind face
+# flux with the velocity of the larger-index cell (convectiondiffusiondg.hh:178-187, 426-448, 797-822, 860) ----------
+FAST_B_CASES = [
+    dict(cells=(8, 4, 4), a="scalar", with_b=True), dict(cells=(16, 8, 8), a="diagonal", with_b=True, with_c=True),
+    dict(cells=(6, 5, 3), a="scalar", with_b=True, extent=(1.0, 0.7, 1.3)),
+    dict(cells=(10, 9, 7), a="diagonal", with_b=True, with_c=True, bc="mixed"),
+    dict(cells=(12, 4, 5), a="scalar", with_b=True, method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF, alpha=1.0),
+    dict(cells=(2, 1, 1), a="identity", with_b=True),
+]
+
+
+@pytest.mark.parametrize("case", FAST_B_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_fast_kernel_with_convection_matches_oracle(cuda_lib, case):
+    spec = dg_problem(degree=2, kernel=abi.KERNEL_FAST, with_f=True, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    want = orc.jacobian_apply(z)
+    y = go.apply(z, np.full(spec.num_dofs, np.nan))
+    assert go.last_kernel() == "dg_fast_q2_3d"
+    assert rel_err(y, want) < TOL
+    y0 = mt_vector(spec.num_dofs, seed=7)
+    assert rel_err(go.jacobian_apply(z, y0.copy()), want + y0) < TOL
+    assert rel_err(go.residual(z, y0.copy()), orc.residual(z, y0.copy())) < TOL       # J z + cached R(0)
+    assert go.last_kernel() == "dg_fast_q2_3d+r0"
+
+
+def _outflow_problem(cells, b, kernel):
+    """constant velocity b > 0: inflow faces (lower sides) Dirichlet, outflow faces (upper sides) Outflow"""
+    spec = dg_problem(cells, degree=2, a="scalar", with_c=True, with_f=True, kernel=kernel)
+    nc = spec.ncells
+    bct = np.full(spec.num_boundary_faces, abi.BC_DIRICHLET, dtype=np.int8)
+    for d in range(3):
+        o = spec.boundary_face_offset(d, 1)
+        bct[o:o + nc // cells[d]] = abi.BC_OUTFLOW
+    rng = np.random.default_rng(3)
+    return spec.replace(b=np.tile(np.asarray(b, dtype=float), (nc, 1)), bctype=bct,
+                        g=rng.standard_normal((spec.num_boundary_faces, spec.nfq)),
+                        o=rng.standard_normal((spec.num_boundary_faces, spec.nfq)))
+
+
+def test_fast_kernel_outflow_faces_and_the_inflow_exception(cuda_lib):
+    from pdelab_b200.capi import PDELabError
+    spec = _outflow_problem((8, 6, 4), (1.0, 0.5, 0.25), abi.KERNEL_FAST)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    assert rel_err(go.apply(z, np.zeros_like(z)), orc.jacobian_apply(z)) < TOL
+    assert go.last_kernel() == "dg_fast_q2_3d"
+    assert rel_err(go.residual(z, np.zeros_like(z)), orc.residual(z)) < TOL
+    # the same faces with the velocity reversed: "Outflow boundary condition on inflow!" (:802-806)
+    bad = _outflow_problem((8, 6, 4), (-1.0, 0.5, 0.25), abi.KERNEL_FAST)
+    with pytest.raises(PDELabError, match="Outflow boundary condition on inflow"):
+        _ops(bad)[0].apply(z, np.zeros_like(z))
+
+
+SMALL_B_CASES = [
+    dict(cells=(9, 7), degree=1, a="scalar", with_b=True), dict(cells=(6, 5), degree=2, a="diagonal", with_b=True, with_c=True),
+    dict(cells=(8, 6), degree=2, a="scalar", with_b=True, bc="mixed"),
+    dict(cells=(5, 4, 3), degree=1, a="diagonal", with_b=True, with_c=True, extent=(1.0, 0.7, 1.3)),
+    dict(cells=(7, 5), degree=1, a="identity", with_b=True, method=abi.DG_NIPG, weights=abi.DG_WEIGHTS_OFF),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_B_CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()))
+def test_small_kernel_with_convection_matches_oracle(cuda_lib, case):
+    spec = dg_problem(kernel=abi.KERNEL_FAST, with_f=True, **case)
+    go, orc = _ops(spec)
+    z = mt_vector(spec.num_dofs)
+    y0 = mt_vector(spec.num_dofs, seed=7)
+    assert rel_err(go.apply(z, np.full(spec.num_dofs, np.nan)), orc.jacobian_apply(z)) < TOL
+    assert go.last_kernel() == "dg_small"
+    assert rel_err(go.jacobian_apply(z, y0.copy()), orc.jacobian_apply(z, y0.copy())) < TOL
+    assert rel_err(go.residual(z, y0.copy()), orc.residual(z, y0.copy())) < TOL

@@ -137,6 +137,23 @@ def test_cfg2_dg_k2_128_jacobian_apply_equals_the_oracle(cuda_lib):
     assert _rel_np(y.cpu().numpy(), want) < 1e-12
 
 
+def test_cfg2_with_convection_and_reaction_equals_the_oracle(cuda_lib):
+    """SURVEY 8d's second cfg2 variant: constant b = (1, 0.5, 0.25), c = 1 — through the Kronecker kernel at 128^3."""
+    from oracle import Oracle
+    spec = _dg_spec((128, 128, 128), 2, abi.KERNEL_AUTO)
+    nc = spec.ncells
+    b = torch.tensor([1.0, 0.5, 0.25], dtype=torch.float64, device="cuda").repeat(nc, 1).contiguous()
+    c = torch.ones(nc, dtype=torch.float64, device="cuda")
+    spec = spec.replace(b=b, c=c)
+    go = GridOperator(spec)
+    z = _rand(spec.num_dofs, 2)
+    y = torch.empty_like(z)
+    go.apply(z, y)
+    assert go.last_kernel() == "dg_fast_q2_3d"
+    want = Oracle(_np_spec(spec)).jacobian_apply(z.cpu().numpy(), threads=_threads())
+    assert _rel_np(y.cpu().numpy(), want) < 1e-12
+
+
 def test_cfg3_dg_k4_64_residual_equals_the_oracle(cuda_lib):
     """configs[2]: DG k=4 on 64^3 cells, r += R(x) with a source term."""
     from oracle import Oracle

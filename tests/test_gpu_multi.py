@@ -420,3 +420,148 @@ def test_overlapping_solver_matches_global_problem(cuda_lib, world, cells, solve
         ref_it = rit if rit is not None else ref_it
     assert len(its) == 1, its
     assert abs(its.pop() - ref_it) <= max(2, ref_it // 10), (res[0][2], ref_it)
+
+
+# ---- conforming Qk on the peer-to-peer mailboxes (csrc/halo.cu: lattice planes, direction by direction) and in the
+# overlapping Krylov solvers (owner mask = the planes a rank receives) -------------------------------------------
+
+def _qk_p2p_worker(rank, world, port, cells, degree, solve, out):
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [os.path.join(here, "..", "oracle"), here, os.path.join(here, "..", "dune-pdelab_b200", "python")]
+        import torch.distributed as dist
+        from oracle import Oracle
+        from pdelab_b200.capi import GridOperator
+        from pdelab_b200.partition import OverlappingPartition, OverlappingSolverBackend, P2PHaloExchanger, QkHaloExchanger
+        from problems import kappa_field, mt_vector
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        part = OverlappingPartition.strong(cells, world, rank)
+        ncg = int(np.prod(cells))
+        kg = kappa_field(ncg)
+        gspec = abi.ProblemSpec(cells, space=abi.SPACE_QK, degree=degree, a_mode=abi.A_SCALAR, A=kg)
+        gidx = part.local_cell_grid().reshape(-1)
+        spec = abi.ProblemSpec(part.local_cells, space=abi.SPACE_QK, degree=degree, lower=part.local_lower,
+                               upper=part.local_upper, a_mode=abi.A_SCALAR, A=kg[gidx], side_kind=part.side_kind, device=dev)
+        go = GridOperator(spec)
+        # index bookkeeping only (owner mask, local -> global numbering); no communication through this object
+        book = QkHaloExchanger(go, part, degree, torch.device("cuda", dev), dist=dist)
+        own, gp = book.owned_point_mask(), book.global_point_index(cells)
+        if solve is None:
+            halo = P2PHaloExchanger(go, part, dist)
+            zg = mt_vector(gspec.num_dofs)
+            want = Oracle(gspec).jacobian_apply(zg)
+            z = np.full(own.size, 1e300)                 # everything not owned is poisoned
+            z[own] = zg[gp[own]]
+            zd = torch.from_numpy(z).cuda()
+            errs, consistent = [], True
+            for it in range(3):                          # several epochs: flags / acks keep working
+                zd.copy_(torch.from_numpy(z))
+                yd = torch.full_like(zd, float("nan"))
+                if it == 1:
+                    halo.exchange(zd)                    # the plain exchange entry point ...
+                    go.apply(zd, yd)
+                else:
+                    halo.apply(zd, yd)                   # ... and y = J x with the exchange in front
+                go.synchronize()
+                consistent &= bool(np.array_equal(zd.cpu().numpy(), zg[gp]))
+                y = yd.cpu().numpy()
+                errs.append(float(np.abs(y[own] - want[gp[own]]).max() / np.abs(want).max()))
+            out.put((rank, max(errs), consistent, go.last_kernel(), int(own.sum()), None, None))
+        else:
+            solver, precond, assembled = solve
+            ls = OverlappingSolverBackend(go, part, dist, solver=solver, precond=precond, maxiter=3000)
+            bg = mt_vector(gspec.num_dofs, seed=3)
+            gg = GridOperator(gspec.replace(device=dev))
+            gcon = gg.constrained_dofs().astype(np.int64)
+            bg[gcon] = 0.0                               # Dirichlet rows: zero defect (the update stays zero there)
+            b = np.full(own.size, 1e300)                 # rows that are not owned are ignored
+            b[own] = bg[gp[own]]
+            bd = torch.from_numpy(b).cuda()
+            zd = torch.zeros_like(bd)
+            if assembled:
+                rowptr, colidx = go.fill_pattern()
+                values = torch.zeros(colidx.size, dtype=torch.float64, device="cuda")
+                go.jacobian(torch.zeros_like(bd), values, fresh=True)
+                res = ls.apply(values, zd, bd, 1e-9)
+            else:
+                res = ls.apply(zd, bd, 1e-9)
+            go.synchronize()
+            z = zd.cpu().numpy()
+            parts = [None] * world
+            dist.all_gather_object(parts, (gp[own], z[own]))
+            zg = np.zeros(gspec.num_dofs)
+            for gi, zi in parts:
+                zg[gi] = zi
+            jz = Oracle(gspec).jacobian_apply(zg)
+            free = np.ones(zg.size, dtype=bool)
+            free[gcon] = False
+            err = float(np.linalg.norm((jz - bg)[free]) / np.linalg.norm(bg[free]))
+            consistent = bool(np.array_equal(z, zg[gp]))   # consistent on the whole extended box on return
+            ref_it = None
+            if rank == 0:
+                zz = torch.zeros(gspec.num_dofs, dtype=torch.float64, device="cuda")
+                bb = torch.from_numpy(bg.copy()).cuda()
+                vals = None
+                if assembled:
+                    rp, ci = gg.fill_pattern()
+                    vals = torch.zeros(ci.size, dtype=torch.float64, device="cuda")
+                    gg.jacobian(torch.zeros_like(bb), vals, fresh=True)
+                ref_it = gg.solve(zz, bb, 1e-9, solver=solver, precond=precond, values=vals, maxiter=3000)["iterations"]
+            out.put((rank, err, consistent, go.last_kernel(), int(own.sum()), res, ref_it))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        import traceback
+        out.put((rank, 1.0, False, "", 0, traceback.format_exc(), None))
+
+
+def _run_qk_p2p(world, cells, degree, solve):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_qk_p2p_worker, args=(r, world, port, cells, degree, solve, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert not isinstance(r[5], str), r[5]
+    assert sum(r[4] for r in res) == int(np.prod([degree * c + 1 for c in cells]))   # every point has one owner
+    return res
+
+
+@pytest.mark.parametrize("world,cells,degree", [(2, (8, 6, 10), 2), (4, (6, 10, 8), 1), (4, (6, 9, 8), 2), (2, (9, 12), 2),
+                                                (4, (10, 12), 1)])
+def test_qk_p2p_mailbox_exchange_and_apply_match_global_oracle(cuda_lib, world, cells, degree):
+    for rank, err, consistent, kern, _, _, _ in _run_qk_p2p(world, cells, degree, None):
+        assert consistent, rank          # after the exchange the extended box equals the global vector bit for bit
+        assert err < 1e-12, (rank, err)  # owned rows equal the undivided oracle
+        assert kern == "fem_kron"
+
+
+@pytest.mark.parametrize("world,cells,degree,solver,precond,assembled", [
+    (2, (8, 6, 10), 2, abi.SOLVER_CG, abi.PRECOND_JACOBI, False),
+    (4, (6, 10, 8), 1, abi.SOLVER_BICGSTAB, abi.PRECOND_NONE, False),
+    (4, (6, 8, 8), 2, abi.SOLVER_CG, abi.PRECOND_NONE, False),
+    (2, (6, 4, 8), 2, abi.SOLVER_BICGSTAB, abi.PRECOND_JACOBI, True),
+    (2, (12, 10), 1, abi.SOLVER_CG, abi.PRECOND_JACOBI, True),
+])
+def test_qk_overlapping_solver_matches_global_problem(cuda_lib, world, cells, degree, solver, precond, assembled):
+    """ISTLBackend_OVLP-style solve of a conforming Qk problem on 2 and 4 ranks (ovlpistlsolverbackend.hh:40-134 works
+    for any GFS): the gathered solution solves the undivided problem on the unconstrained rows, it is consistent on the
+    overlap on return, all ranks agree on the iteration count and it is the single-domain solver's."""
+    res = _run_qk_p2p(world, cells, degree, (solver, precond, assembled))
+    its, ref_it = set(), None
+    for rank, err, consistent, kern, _, r, rit in res:
+        assert r["converged"] == 1, (rank, r)
+        assert err < 1e-7, (rank, err)
+        assert consistent, rank
+        its.add(r["iterations"])
+        ref_it = rit if rit is not None else ref_it
+    assert len(its) == 1, its
+    assert abs(its.pop() - ref_it) <= max(2, ref_it // 10), (res[0][5], ref_it)
