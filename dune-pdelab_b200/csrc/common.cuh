@@ -206,6 +206,32 @@ void p2p_check(P2PHalo*);  // throws if a spin-wait timed out
 cudaStream_t p2p_stream(P2PHalo*);
 cudaEvent_t p2p_event(P2PHalo*, int i);
 
+// One-launch step of the overlapping partition (dg_fast.cu runs it, halo.cu owns the mailboxes): the table lives in
+// device memory; side index = 2 * dir + side.  Flags and epochs are the ones of p2p_push / p2p_wait_unpack, so fused
+// and unfused steps can alternate on the same mailboxes.
+struct FusedSide {
+  int active;
+  long long total2, chunk2, stride2, src_off2;  // the layer sent across this side, in 16-byte elements (see copy_layer)
+  double2* peer_buf;                            // receive buffer in the neighbour's mailbox
+  unsigned long long *peer_ready, *peer_ack;
+  const double* my_buf;                         // my receive buffer for this side: the neighbour's boundary layer
+  unsigned long long *my_ready, *my_ack;
+};
+struct FusedTable {
+  FusedSide s[6];
+  unsigned int* counters;  // [12]: push blocks done per side, tiles that have consumed a side's buffer
+  int* err;                // spin-wait time-out flag (p2p_check)
+};
+// device table once every processor side is connected and every layer moves in 16-byte elements, else nullptr
+const FusedTable* p2p_fused_table(P2PHalo*, const DevParams& P);
+unsigned long long p2p_next_epoch(P2PHalo*);
+// dg_fast.cu: y = J x with the ghost exchange inside the launch (push blocks, interior tiles, then the tiles that
+// read a neighbour's layer straight from the mailbox); x's ghost layers are neither read nor written
+bool dg_fast_fused_supported(const DevParams& P);
+int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, double* y, const FusedTable* table,
+                         const FusedTable& table_host, unsigned long long epoch, cudaStream_t s, int* errflag);
+const FusedTable& p2p_fused_table_host(P2PHalo*);
+
 // halo.cu: all-ranks reduction of inner-product partials over peer-mapped mailboxes (overlapping solvers)
 struct PeerComm;
 PeerComm* comm_create(int rank, int size, pdb200_ipc_handle* mine);

@@ -32,11 +32,13 @@
 //     conflict replays — profiles/r01_v5_dg_fast_ncu_full_summary.json.)
 //   * A thread keeps its 27 DOFs and 27 accumulators in registers; neighbour traces and normal
 //     derivatives are read from the shared tile.
-//   * A warp is one z-layer of the tile.  The z-sweep runs FIRST; after ONE block-wide barrier behind it a warp
-//     only ever touches its own layer, so each warp stages its 4 result rows in its own (dead) layer and sends
-//     them off with 4 bulk row stores (or reduce-adds) as soon as IT is done — no barrier, staging pass or store
-//     loop of the whole block at the end (27 % of the warp samples in the first layout,
-//     profiles/r02_v6_dg_fast_ncu_full_summary.json).  Global traffic is fully coalesced: 8 B/DOF read (+ halo
+//   * A warp is one z-layer of the tile.  The z-sweep runs FIRST; behind it a warp only ever touches its own
+//     layer, so each warp stages its 4 result rows in its own (dead) layer and sends them off with 4 bulk row
+//     stores (or reduce-adds) as soon as IT is done — no barrier, staging pass or store loop of the whole block at
+//     the end (27 % of the warp samples in the first layout, profiles/r02_v6_dg_fast_ncu_full_summary.json).  The
+//     one dependency between warps — a layer may be overwritten once the warps above and below have read it — is
+//     a split barrier: mbarrier arrive behind the z-sweep, wait behind the x/y sweeps (a bar.sync at the arrive
+//     point held 5 % of the warp samples, profiles/r02_v7_dg_fast_ncu_full_summary.json).  Global traffic is fully coalesced: 8 B/DOF read (+ halo
 //     re-reads served by L2) + 8 B/DOF written.
 
 #include <cuda.h>
@@ -98,6 +100,16 @@ struct TileFrame {
   int pf;      // L2 prefetch distance in tiles of the launch's linear block order (0 = off)
   int accumulate;    // y += J x (TMA reduce-add store) instead of y = J x
   const double* r0;  // residual form: R(0) is added to the staged tile before it leaves
+  // ---- one-launch step of the overlapping partition (fz != nullptr): 1-D grid =
+  //      [push blocks][interior tiles][slabs of tiles that read a neighbour's layer from the mailbox]
+  const FusedTable* fz;
+  unsigned long long epoch;
+  int npush, push_blocks;  // push blocks in front of the tiles, blocks per side
+  int push_side[6];        // push block b works for side push_side[b / push_blocks]
+  int nboxes;              // tile boxes in launch order: box 0 = interior
+  int box_start[8];        // first linear tile number of every box (box_start[nboxes] = number of tiles)
+  int box[7][6];           // {offset[3], extent[3]} in tiles
+  int side_tiles[6];       // tiles that read the receive buffer of a side (the last one sends the ack)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +121,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -159,6 +174,85 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long f_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void f_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long f_globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= want; a neighbour that never shows up ends in the error flag (p2p_check), not in a hung GPU
+__device__ __forceinline__ void f_spin(const unsigned long long* flag, unsigned long long want, int* err) {
+  if (f_ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = f_globaltimer_ns();
+  while (f_ld_acquire_sys(flag) < want) {
+    if (f_globaltimer_ns() - t0 > 10ull * 1000 * 1000 * 1000) {
+      atomicExch(err, 1);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+// linear tile number of the fused launch -> tile coordinates; false behind the last tile
+__device__ __forceinline__ bool fused_tile(const TileFrame& TF, int t, int& bx, int& by, int& bz) {
+  if (t >= TF.box_start[TF.nboxes]) return false;
+  int b = 0;
+  while (t >= TF.box_start[b + 1]) b++;
+  t -= TF.box_start[b];
+  const int ex = TF.box[b][3], ey = TF.box[b][4];
+  bx = TF.box[b][0] + t % ex;
+  t /= ex;
+  by = TF.box[b][1] + t % ey;
+  bz = TF.box[b][2] + t / ey;
+  return true;
+}
+
+// A push block of the fused launch: the owned boundary layer of x goes straight into the neighbour's receive buffer
+// (remote 16-byte stores over NVLink), the last block of a side publishes ready = epoch.  Same protocol as
+// p2p_push_kernel (halo.cu), which replaces the CopyDataHandle communication of boilerplate/pdelab.hh:872-880.
+__device__ __forceinline__ void fused_push(const TileFrame& TF, const double* __restrict__ xin, int b) {
+  const int side = TF.push_side[b / TF.push_blocks], blk = b % TF.push_blocks;
+  const FusedSide& S = TF.fz->s[side];
+  if (threadIdx.x == 0) f_spin(S.my_ack, TF.epoch - 1, TF.fz->err);  // the neighbour has consumed the previous layer
+  __syncthreads();
+  const double2* __restrict__ src = (const double2*)xin;
+  double2* __restrict__ dst = S.peer_buf;
+  const long long total = S.total2, chunk = S.chunk2, stride = S.stride2, off = S.src_off2;
+  const long long step = (long long)TF.push_blocks * blockDim.x;
+  long long i = (long long)blk * blockDim.x + threadIdx.x;
+  for (; i + 3 * step < total; i += 4 * step) {  // four independent loads in flight per thread
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long j = i + u * step, c = j / chunk;
+      v[u] = src[off + c * stride + (j - c * chunk)];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) dst[i + u * step] = v[u];
+  }
+  for (; i < total; i += step) {
+    const long long c = i / chunk;
+    dst[i] = src[off + c * stride + (i - c * chunk)];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&TF.fz->counters[side], 1u);
+    if (done == (unsigned)TF.push_blocks - 1) {
+      TF.fz->counters[side] = 0;
+      __threadfence_system();
+      f_st_release_sys(S.peer_ready, TF.epoch);
+    }
+  }
+}
+
 // cell indices fit 32 bits on one GPU (512^3 = 2^27 cells); only the byte offset is 64-bit
 template <int AMODE>
 __device__ __forceinline__ double load_adiag(const DevParams& P, int cell, int d) {
@@ -173,16 +267,14 @@ __device__ __forceinline__ double load_adiag(const DevParams& P, int cell, int d
 // following convectiondiffusiondg.hh:326-346 (interior) and :717-734 (Dirichlet boundary).
 // kind: 0 interior, 1 Dirichlet boundary, 2 no u-dependent term (None/Neumann/Outflow with b=0,
 // processor boundary).
-// 1/x for positive normal x: MUFU.RCP64H seed (>= 20 bits) + two Newton steps with a quadratic
-// correction in the first (error 2^-20 -> 2^-60 -> rounding).  Branch-free on purpose: the IEEE
-// division's slow-path call serialises the six face set-ups.
+// 1/x for positive normal x: MUFU.RCP64H seed (>= 20 bits) + one Newton step with a quadratic
+// correction (error 2^-20 -> 2^-60, i.e. below the rounding of the products it enters).  Branch-free on
+// purpose: the IEEE division's slow-path call serialises the six face set-ups.
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, fma(e, e, e), y);  // y (1 + e + e^2): cubic convergence
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);  // y (1 + e + e^2): cubic convergence
 }
 
 // Branch-free (selects only) so that the six reciprocal chains of a cell interleave.  The penalty
@@ -318,43 +410,98 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
                          const double* __restrict__ xin, const DevParams P, const FastConst F, const TileFrame TF) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t zbar;      // "every warp is done with the z-sweep" (arrive early, wait late)
   __shared__ __align__(8) uint64_t wbar[TZ];  // residual form: the R(0) rows of every warp arrive on its own barrier
   const int tid = threadIdx.x;
-  const int x0 = (blockIdx.x + TF.off[0]) * TX, y0 = TF.org[1] + (blockIdx.y + TF.off[1]) * TY,
-            z0 = TF.org[2] + (blockIdx.z + TF.off[2]) * TZ;
+  int bx = blockIdx.x + TF.off[0], by = blockIdx.y + TF.off[1], bz = blockIdx.z + TF.off[2];
+  if (TF.fz) {  // one-launch step of the overlapping partition: push blocks, then the tiles in list order
+    if ((int)blockIdx.x < TF.npush) {
+      fused_push(TF, xin, blockIdx.x);
+      return;
+    }
+    fused_tile(TF, blockIdx.x - TF.npush, bx, by, bz);
+  }
+  const int x0 = bx * TX, y0 = TF.org[1] + by * TY, z0 = TF.org[2] + bz * TZ;
+  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
+  // fused step: halo rows / layers of this tile that are a neighbour's boundary layer (read from the mailbox)
+  const bool py0 = TF.fz && y0 == 1 && P.side_kind[1][0] == PDB200_SIDE_PROCESSOR;
+  const bool py1 = TF.fz && y0 + TY == Ny - 1 && P.side_kind[1][1] == PDB200_SIDE_PROCESSOR;
+  const bool pz0 = TF.fz && z0 == 1 && P.side_kind[2][0] == PDB200_SIDE_PROCESSOR;
+  const bool pz1 = TF.fz && z0 + TZ == Nz - 1 && P.side_kind[2][1] == PDB200_SIDE_PROCESSOR;
+
+  // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
+  // stride maps the 16 lanes of a 64-bit shared access onto 16 distinct bank pairs
+  const int lane = tid & 31;
+  const int cx = lane & 7;
+  const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
+  const int cz = tid >> 5;
+  const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
+  const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
+
+  // ---- the diffusion coefficients of the cell and its six face neighbours: the loads are the first thing the
+  // kernel issues, so that their L2 / HBM round trips run under the barrier set-up and the TMA requests -----------
+  const int cell = gx + Nx * (gy + Ny * gz);
+  const bool onb[3][2] = {{gx == 0, gx == Nx - 1}, {gy == 0, gy == Ny - 1}, {gz == 0, gz == Nz - 1}};
+  double a[3] = {1.0, 1.0, 1.0}, ao[3][2] = {{1.0, 1.0}, {1.0, 1.0}, {1.0, 1.0}};
+  if (active) {
+    const int stride[3] = {1, Nx, Nx * Ny};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      a[d] = load_adiag<AMODE>(P, cell, d);
+#pragma unroll
+      for (int side = 0; side < 2; side++)
+        ao[d][side] = load_adiag<AMODE>(P, onb[d][side] ? cell : cell + (side ? stride[d] : -stride[d]), d);
+    }
+  }
 
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&zbar, TZ);
     if (TF.r0)
       for (int w = 0; w < TZ; w++) mbar_init(&wbar[w], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
   const int ncx = min(TX, Nx - x0);                   // cells of an x-row inside the vector (even: Nx is even)
   const int nrow = min(TY, Ny - y0);                  // rows of the tile inside the vector
   const bool zlo_in = z0 - 1 >= 0, zup_in = z0 + TZ < Nz;
   if (tid == 0) {
     const uint32_t rowbytes = (uint32_t)ncx * NLOC * 8;
+    if (py0 | py1 | pz0 | pz1) {  // the neighbours' layers must have arrived (their push blocks run first)
+      if (py0) f_spin(TF.fz->s[2].my_ready, TF.epoch, TF.fz->err);
+      if (py1) f_spin(TF.fz->s[3].my_ready, TF.epoch, TF.fz->err);
+      if (pz0) f_spin(TF.fz->s[4].my_ready, TF.epoch, TF.fz->err);
+      if (pz1) f_spin(TF.fz->s[5].my_ready, TF.epoch, TF.fz->err);
+      asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what remote stores wrote
+    }
     mbar_expect_tx(&bar, ROWS_BYTES + ((zlo_in ? nrow : 0) + (zup_in ? nrow : 0)) * rowbytes);
     tma_load_4d(tile + R0, &tm_rows, 0, x0 / 2 - 1, y0 - 1, z0, &bar);
-    // z-halo layers: one bulk copy per x-row; a layer outside the vector is zeroed by the threads that read it
+    // z-halo layers: one bulk copy per x-row; a layer outside the vector is zeroed by the threads that read it.  In
+    // the fused step a ghost layer is read from the receive buffer ([Ny][Nx] cells) instead of from x.
+    const double* zlo_src = pz0 ? TF.fz->s[4].my_buf : xin + (long long)(z0 - 1) * Ny * Nx * NLOC;
+    const double* zup_src = pz1 ? TF.fz->s[5].my_buf : xin + (long long)(z0 + TZ) * Ny * Nx * NLOC;
     for (int r = 0; r < nrow; r++) {
-      if (zlo_in)
-        bulk_load(tile + R3 + zhalo_row(r), xin + (((long long)(z0 - 1) * Ny + y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
-      if (zup_in)
-        bulk_load(tile + R4 + zhalo_row(r), xin + (((long long)(z0 + TZ) * Ny + y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
+      if (zlo_in) bulk_load(tile + R3 + zhalo_row(r), zlo_src + ((long long)(y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
+      if (zup_in) bulk_load(tile + R4 + zhalo_row(r), zup_src + ((long long)(y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
     }
   }
   if (TF.pf && tid < ROWY * (TZ + 2) + 1) {
     // L2 prefetch for the tile TF.pf places further on in launch order: thread 0 the core box of the vector (every
     // input byte is prefetched once), threads 1.. one x-row each of the coefficient box that tile's cells will load
-    unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
-    const unsigned px = lin % gridDim.x;
-    lin /= gridDim.x;
-    const unsigned py = lin % gridDim.y, pz = lin / gridDim.y;
-    if (pz < gridDim.z) {
-      const int qx = (px + TF.off[0]) * TX, qy = TF.org[1] + (py + TF.off[1]) * TY, qz = TF.org[2] + (pz + TF.off[2]) * TZ;
+    int pbx, pby, pbz;
+    bool pvalid;
+    if (TF.fz) {
+      pvalid = fused_tile(TF, (int)blockIdx.x - TF.npush + TF.pf, pbx, pby, pbz);
+    } else {
+      unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
+      pbx = lin % gridDim.x + TF.off[0];
+      lin /= gridDim.x;
+      pby = lin % gridDim.y + TF.off[1];
+      pbz = lin / gridDim.y + TF.off[2];
+      pvalid = lin / gridDim.y < gridDim.z;
+    }
+    if (pvalid) {
+      const int qx = pbx * TX, qy = TF.org[1] + pby * TY, qz = TF.org[2] + pbz * TZ;
       if (tid == 0) {
         tma_prefetch_4d(&tm_pf, 0, qx / 2, qy, qz);
       } else if (AMODE != PDB200_A_IDENTITY) {
@@ -371,38 +518,20 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     }
   }
 
-  // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
-  // stride maps the 16 lanes of a 64-bit shared access onto 16 distinct bank pairs
-  const int lane = tid & 31;
-  const int cx = lane & 7;
-  const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
-  const int cz = tid >> 5;
-  const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
-  const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
-
-  // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
-  // before the first use so that the L2 round trips overlap instead of adding up; everything up
-  // to the reciprocals is branch-free so that the six face set-ups interleave. -------------------
+  // ---- per-cell coefficients (overlaps the TMA latency); everything up to the reciprocals is branch-free so
+  // that the six face set-ups interleave. -------------------------------------------------------------------
   double A0[3], csL[3], coL[3], csR[3], coR[3];
   double creact = 0.0;
   bool constrained = false;
   double bs[3] = {0.0, 0.0, 0.0}, bo[3] = {0.0, 0.0, 0.0};  // HAS_B: own velocity and b_d of the upper d-neighbour
   int kinds = 0;                                             // HAS_B: face kinds, 2 bits each, face 2 d + side
   if (active) {
-    const int cell = gx + Nx * (gy + Ny * gz);
     const int stride[3] = {1, Nx, Nx * Ny};
-    const bool onb[3][2] = {{gx == 0, gx == Nx - 1}, {gy == 0, gy == Ny - 1}, {gz == 0, gz == Nz - 1}};
-    double a[3], ao[3][2];
     int kind[3][2];
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      a[d] = load_adiag<AMODE>(P, cell, d);
+    for (int d = 0; d < 3; d++)
 #pragma unroll
-      for (int side = 0; side < 2; side++) {
-        kind[d][side] = onb[d][side] ? 1 : 0;
-        ao[d][side] = load_adiag<AMODE>(P, onb[d][side] ? cell : cell + (side ? stride[d] : -stride[d]), d);
-      }
-    }
+      for (int side = 0; side < 2; side++) kind[d][side] = onb[d][side] ? 1 : 0;
     if (HAS_C) creact = __ldg(P.c + cell) * F.scale;
     if (HAS_B) {
 #pragma unroll
@@ -457,6 +586,22 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   }
 
   mbar_wait(&bar, 0);
+  if (py0 | py1) {
+    // fused step: the y-halo row of this warp's layer is a neighbour's boundary layer — the TMA box brought x's
+    // (stale) ghost row; the warp overwrites the eight cells its y-sweep reads from the receive buffer
+    // ([Nz][Nx] cells).  L1 may hold the previous epoch's lines: ld.global.cg.
+    if (gz < Nz) {
+      const int n2 = ncx * NLOC / 2;
+#pragma unroll 1
+      for (int sd = 0; sd < 2; sd++) {
+        if (!(sd ? py1 : py0)) continue;
+        const double2* __restrict__ src = (const double2*)(TF.fz->s[2 + sd].my_buf + ((long long)gz * Nx + x0) * NLOC);
+        double2* __restrict__ dst = (double2*)(tile + R0 + ((cz * ROWY + (sd ? ROWY - 1 : 0)) * ROWX + 2) * NLOC);
+        for (int i = lane; i < n2; i += 32) dst[i] = __ldcg(src + i);
+      }
+    }
+    __syncwarp();
+  }
 
   double t[NLOC];
   // convection coefficients of direction d from the velocities and the face kinds
@@ -484,12 +629,31 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   if (active)
     sweep<9, true, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], F.ih2[2], csL[2], coL[2], csR[2],
                                              coR[2], conv(2));
-  __syncthreads();  // from here on a warp reads and writes its own layer only
+  // from here on a warp reads and writes its own layer only; the layer may be WRITTEN (R(0) rows, output stage) once
+  // the warps above and below are done with their z-sweeps: every warp arrives here and waits behind its x/y sweeps
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&zbar);
   if (active) {
     sweep<1, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], F.ih2[0], csL[0], coL[0], csR[0],
                                               coR[0], conv(0));
     sweep<3, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], F.ih2[1], csL[1], coL[1], csR[1],
                                               coR[1], conv(1));
+  }
+  mbar_wait(&zbar, 0);
+  if ((py0 | py1 | pz0 | pz1) && tid == 0) {
+    // every warp has its halo data in shared memory: this tile is done with the receive buffers; the last tile of a
+    // side hands the buffer back to the neighbour (ack = epoch)
+    __threadfence();
+#pragma unroll 1
+    for (int sd = 2; sd < 6; sd++) {
+      if (!(sd == 2 ? py0 : (sd == 3 ? py1 : (sd == 4 ? pz0 : pz1)))) continue;
+      const unsigned int done = atomicAdd(&TF.fz->counters[6 + sd], 1u);
+      if (done == (unsigned)TF.side_tiles[sd] - 1) {
+        TF.fz->counters[6 + sd] = 0;
+        __threadfence();
+        f_st_release_sys(TF.fz->s[sd].peer_ack, TF.epoch);
+      }
+    }
   }
   __syncwarp();  // every lane is done reading the layer: it becomes the warp's output stage
   double* const stage = tile + R0 + cz * LAYER;
@@ -661,6 +825,7 @@ static FastPlan::Maps& get_maps(FastPlan* plan, const void* ptr, const DevParams
 // exchange is in flight.  Returns the interior tile box [lo, hi) per direction.
 static void tile_frame(const DevParams& P, TileFrame& F, int nt[3]) {
   const int T[3] = {TX, TY, TZ};
+  F = TileFrame{};  // fz = nullptr: not a fused launch
   for (int d = 0; d < 3; d++) {
     const bool glo = d > 0 && P.side_kind[d][0] == PDB200_SIDE_PROCESSOR;
     const bool ghi = d > 0 && P.side_kind[d][1] == PDB200_SIDE_PROCESSOR;
@@ -774,6 +939,102 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
 #undef PDB_LAUNCH
   PDB_CUDA(cudaGetLastError());
   return launches;
+}
+
+// The fused step needs every ghost layer exactly one cell outside a tile (never inside a tile box): the owned extent of
+// a split direction is a multiple of the tile extent; x is never split.
+bool dg_fast_fused_supported(const DevParams& P) {
+  if (!dg_fast_supported(P)) return false;
+  if (P.side_kind[0][0] == PDB200_SIDE_PROCESSOR || P.side_kind[0][1] == PDB200_SIDE_PROCESSOR) return false;
+  const int T[3] = {TX, TY, TZ};
+  bool any = false;
+  for (int d = 1; d < 3; d++) {
+    const bool lo = P.side_kind[d][0] == PDB200_SIDE_PROCESSOR, hi = P.side_kind[d][1] == PDB200_SIDE_PROCESSOR;
+    any |= lo | hi;
+    if (hi && (P.N[d] - 1 - (lo ? 1 : 0)) % T[d] != 0) return false;
+    if ((lo || hi) && P.N[d] - (lo ? 1 : 0) - (hi ? 1 : 0) < T[d]) return false;
+  }
+  return any;
+}
+
+int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, double* y, const FusedTable* table,
+                         const FusedTable& th, unsigned long long epoch, cudaStream_t s, int* errflag) {
+  if (!dg_fast_fused_supported(P)) throw Error("fused overlapping step: unsupported partition");
+  const FastPlan::Maps mx = get_maps(plan, x, P);
+  if ((uintptr_t)y % 16 != 0) throw Error("fast DG kernel: vectors must be 16-byte aligned");
+  TileFrame TF;
+  int nt[3];
+  tile_frame(P, TF, nt);
+  TF.out = y;
+  TF.err = errflag;
+  TF.accumulate = 0;
+  TF.r0 = nullptr;
+  {
+    const char* e = getenv("PDB200_FAST_PREFETCH");
+    TF.pf = e ? atoi(e) : 444;
+  }
+  TF.fz = table;
+  TF.epoch = epoch;
+  {
+    const char* e = getenv("PDB200_PUSH_BLOCKS");
+    TF.push_blocks = e ? std::max(1, atoi(e)) : 32;
+  }
+  int nside = 0;
+  for (int i = 0; i < 6; i++)
+    if (th.s[i].active) TF.push_side[nside++] = i;
+  TF.npush = nside * TF.push_blocks;
+  int lo[3], hi[3];
+  interior_tile_box(P, TF, nt, lo, hi);
+  TF.nboxes = 0;
+  int count = 0;
+  auto add = [&](int ox, int oy, int oz, int ex, int ey, int ez) {
+    if (TF.nboxes > 0 && (ex <= 0 || ey <= 0 || ez <= 0)) return;  // box 0 (interior) always exists, possibly empty
+    const int b[6] = {ox, oy, oz, std::max(ex, 0), std::max(ey, 0), std::max(ez, 0)};
+    for (int i = 0; i < 6; i++) TF.box[TF.nboxes][i] = b[i];
+    TF.box_start[TF.nboxes] = count;
+    count += b[3] * b[4] * b[5];
+    TF.nboxes++;
+  };
+  add(lo[0], lo[1], lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+  if (TF.box[0][3] * TF.box[0][4] * TF.box[0][5] == 0) {  // degenerate: no interior, the whole box is boundary
+    for (int d = 0; d < 3; d++) lo[d] = hi[d] = 0;
+    lo[2] = hi[2] = nt[2];
+    TF.box[0][3] = TF.box[0][4] = TF.box[0][5] = 1;  // extents must not be zero for the decode; count stays 0
+    add(0, 0, 0, nt[0], nt[1], nt[2]);
+  } else {
+    add(0, 0, 0, nt[0], nt[1], lo[2]);
+    add(0, 0, hi[2], nt[0], nt[1], nt[2] - hi[2]);
+    add(0, 0, lo[2], nt[0], lo[1], hi[2] - lo[2]);
+    add(0, hi[1], lo[2], nt[0], nt[1] - hi[1], hi[2] - lo[2]);
+  }
+  TF.box_start[TF.nboxes] = count;
+  if (count != nt[0] * nt[1] * nt[2]) throw Error("fused overlapping step: tile list does not cover the box");
+  // tiles reading the receive buffer of a side: the first / last tile layer of that direction
+  for (int i = 0; i < 6; i++) TF.side_tiles[i] = 0;
+  for (int d = 1; d < 3; d++)
+    for (int sd = 0; sd < 2; sd++)
+      if (P.side_kind[d][sd] == PDB200_SIDE_PROCESSOR) TF.side_tiles[2 * d + sd] = nt[0] * nt[d == 1 ? 2 : 1];
+  const unsigned grid = (unsigned)(TF.npush + count);
+#define PDB_LAUNCH(AM, HC, WO)                                                                                            \
+  do {                                                                                                                     \
+    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
+    else dg_fast_q2_3d_kernel<AM, HC, WO, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
+  } while (0)
+#define PDB_LAUNCH_A(AM)                                \
+  do {                                                  \
+    if (P.c && P.weights_on) PDB_LAUNCH(AM, true, true);        \
+    else if (P.c) PDB_LAUNCH(AM, true, false);          \
+    else if (P.weights_on) PDB_LAUNCH(AM, false, true); \
+    else PDB_LAUNCH(AM, false, false);                  \
+  } while (0)
+  const int am = P.a_mode == PDB200_A_IDENTITY || P.a_mode == PDB200_A_SCALAR ? P.a_mode : PDB200_A_DIAGONAL;
+  if (am == PDB200_A_IDENTITY) PDB_LAUNCH_A(PDB200_A_IDENTITY);
+  else if (am == PDB200_A_SCALAR) PDB_LAUNCH_A(PDB200_A_SCALAR);
+  else PDB_LAUNCH_A(PDB200_A_DIAGONAL);
+#undef PDB_LAUNCH_A
+#undef PDB_LAUNCH
+  PDB_CUDA(cudaGetLastError());
+  return 1;
 }
 
 }  // namespace pdb

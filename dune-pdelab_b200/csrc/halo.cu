@@ -319,6 +319,9 @@ struct P2PHalo {
   cudaEvent_t ev[2] = {};
   int nactive = 0;
   bool vec2 = true;  // every chunk is an even number of doubles: 16-byte accesses
+  FusedTable fused_host;             // the one-launch step of dg_fast.cu (QkDG)
+  FusedTable* fused_dev = nullptr;
+  bool fused_built = false;
 };
 
 // lattice slab of direction d, planes a..b, full extent elsewhere
@@ -429,6 +432,7 @@ void p2p_destroy(P2PHalo* H) {
   if (H->mailbox) cudaFree(H->mailbox);
   if (H->counters) cudaFree(H->counters);
   if (H->err) cudaFree(H->err);
+  if (H->fused_dev) cudaFree(H->fused_dev);
   if (H->stream) cudaStreamDestroy(H->stream);
   for (auto& e : H->ev)
     if (e) cudaEventDestroy(e);
@@ -510,6 +514,38 @@ void p2p_check(P2PHalo* H) {
     throw Error("p2p halo exchange timed out waiting for a neighbour");
   }
 }
+
+const FusedTable* p2p_fused_table(P2PHalo* H, const DevParams& P) {
+  if (H->qk || !H->vec2 || H->nactive == 0) return nullptr;
+  if (!H->fused_built) {
+    p2p_require_connected(H, P);
+    std::memset(&H->fused_host, 0, sizeof(FusedTable));
+    for (int i = 0; i < 6; i++) {
+      const SideDesc& S = H->table.s[i];
+      FusedSide& F = H->fused_host.s[i];
+      F.active = S.active;
+      if (!S.active) continue;
+      F.total2 = S.total / 2;
+      F.chunk2 = S.chunk / 2;
+      F.stride2 = S.stride / 2;
+      F.src_off2 = (long long)S.layer_src * (S.chunk / 2);
+      F.peer_buf = (double2*)S.peer_buf;
+      F.peer_ready = S.peer_ready;
+      F.peer_ack = S.peer_ack;
+      F.my_buf = S.my_buf;
+      F.my_ready = S.my_ready;
+      F.my_ack = S.my_ack;
+    }
+    H->fused_host.counters = H->counters;
+    H->fused_host.err = H->err;
+    PDB_CUDA(cudaMalloc(&H->fused_dev, sizeof(FusedTable)));
+    PDB_CUDA(cudaMemcpy(H->fused_dev, &H->fused_host, sizeof(FusedTable), cudaMemcpyHostToDevice));
+    H->fused_built = true;
+  }
+  return H->fused_dev;
+}
+const FusedTable& p2p_fused_table_host(P2PHalo* H) { return H->fused_host; }
+unsigned long long p2p_next_epoch(P2PHalo* H) { return ++H->epoch; }
 
 cudaStream_t p2p_stream(P2PHalo* H) { return H->stream; }
 cudaEvent_t p2p_event(P2PHalo* H, int i) { return H->ev[i]; }

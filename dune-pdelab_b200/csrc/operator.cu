@@ -166,6 +166,26 @@ void apply_p2p_device(pdb200_operator* h, double* x, double* y) {
     run_vector_device(h, x, y, Mode::OnTheFly);
     return;
   }
+  {
+    // QkDG k = 2 in 3-D with tile-aligned owned extents: ONE launch per step — push blocks, interior tiles, then the
+    // tiles next to a processor side, which read the neighbour's layer straight from the mailbox (no unpack pass, no
+    // side stream, no event fork / join).  PDB200_P2P_FUSED=0 keeps the multi-launch schedule below.
+    static const bool fused_on = [] {
+      const char* e = getenv("PDB200_P2P_FUSED");
+      return !(e && e[0] == '0');
+    }();
+    const DevParams& P = h->P;
+    if (fused_on && P.dg && h->kernel_choice != PDB200_KERNEL_GENERIC && dg_fast_fused_supported(P)) {
+      const FusedTable* table = p2p_fused_table(h->p2p, P);
+      if (table) {
+        if (!h->fast) h->fast = dg_fast_plan_create(P, h->K);
+        h->launches += launch_dg_fast_fused(h->fast, P, x, y, table, p2p_fused_table_host(h->p2p), p2p_next_epoch(h->p2p),
+                                            h->stream, h->errflag);
+        h->last_kernel = "dg_fast_q2_3d+halo";
+        return;
+      }
+    }
+  }
   cudaStream_t side = p2p_stream(h->p2p);
   PDB_CUDA(cudaEventRecord(p2p_event(h->p2p, 0), h->stream));  // x is ready
   PDB_CUDA(cudaStreamWaitEvent(side, p2p_event(h->p2p, 0), 0));

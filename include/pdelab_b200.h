@@ -372,9 +372,13 @@ int pdb200_halo_p2p_connect(pdb200_handle h, int dir, int side, const pdb200_ipc
 /* owner -> ghost copy of the DEVICE vector x across all connected sides (two kernels: push into
  * the neighbours' mailboxes, wait + unpack); asynchronous on the handle's stream */
 int pdb200_halo_exchange_p2p(pdb200_handle h, double* x);
-/* y = J x on the overlapping partition with the exchange hidden behind the interior tiles:
- * side stream: push, wait + unpack, BOUNDARY;  main stream: INTERIOR, (join).
- * x's ghost layers are updated as a side effect.  Device pointers only. */
+/* y = J x on the overlapping partition with the exchange hidden behind the interior tiles.
+ * QkDG k = 2 in 3-D whose owned extents in the split directions are multiples of the 8x4x4 tile: ONE launch —
+ * push blocks (remote stores into the neighbours' mailboxes), interior tiles, then the tiles next to a processor
+ * side, which wait for the neighbour's layer and read it straight from the mailbox; x's ghost layers are neither
+ * read nor written.  Otherwise: side stream: push, wait + unpack, BOUNDARY;  main stream: INTERIOR, (join), and
+ * x's ghost layers are updated as a side effect.  Callers must not rely on x's ghost layers afterwards (use
+ * pdb200_halo_exchange_p2p for a consistent vector).  Device pointers only. */
 int pdb200_onthefly_apply_p2p(pdb200_handle h, double* x, double* y);
 
 /* ---- overlapping solvers on several GPUs --------------------------------------------------------------------
