@@ -32,13 +32,13 @@
 //     conflict replays — profiles/r01_v5_dg_fast_ncu_full_summary.json.)
 //   * A thread keeps its 27 DOFs and 27 accumulators in registers; neighbour traces and normal
 //     derivatives are read from the shared tile.
-//   * A warp is one z-layer of the tile.  The z-sweep runs FIRST; behind it a warp only ever touches its own
-//     layer, so each warp stages its 4 result rows in its own (dead) layer and sends them off with 4 bulk row
-//     stores (or reduce-adds) as soon as IT is done — no barrier, staging pass or store loop of the whole block at
-//     the end (27 % of the warp samples in the first layout, profiles/r02_v6_dg_fast_ncu_full_summary.json).  The
-//     one dependency between warps — a layer may be overwritten once the warps above and below have read it — is
-//     a split barrier: mbarrier arrive behind the z-sweep, wait behind the x/y sweeps (a bar.sync at the arrive
-//     point held 5 % of the warp samples, profiles/r02_v7_dg_fast_ncu_full_summary.json).  Global traffic is fully coalesced: 8 B/DOF read (+ halo
+//   * A warp is one z-layer of the tile.  The z-sweep runs FIRST; after ONE block-wide barrier behind it a warp
+//     only ever touches its own layer, so each warp stages its 4 result rows in its own (dead) layer and sends
+//     them off with 4 bulk row stores (or reduce-adds) as soon as IT is done — no barrier, staging pass or store
+//     loop of the whole block at the end (27 % of the warp samples in the first layout,
+//     profiles/r02_v6_dg_fast_ncu_full_summary.json).  (Tried on top, A/B on one box against this version: the
+//     barrier split into an mbarrier arrive behind the z-sweep and a wait behind the x/y sweeps, and the coefficient
+//     loads issued before the barrier set-up — 1-2 % slower, not kept.)  Global traffic is fully coalesced: 8 B/DOF read (+ halo
 //     re-reads served by L2) + 8 B/DOF written.
 
 #include <cuda.h>
@@ -106,9 +106,12 @@ struct TileFrame {
   unsigned long long epoch;
   int npush, push_blocks;  // push blocks in front of the tiles, blocks per side
   int push_side[6];        // push block b works for side push_side[b / push_blocks]
-  int nboxes;              // tile boxes in launch order: box 0 = interior
+  int tail_start, tail_z;  // the upper part of the interior box runs LAST (box nboxes - 1; same x/y extents as box 0)
+  int nboxes;              // tile boxes in launch order: box 0 = lower part of the interior
   int box_start[8];        // first linear tile number of every box (box_start[nboxes] = number of tiles)
   int box[7][6];           // {offset[3], extent[3]} in tiles
+  unsigned div_m[7][2];    // division by extent[0] and extent[1] as multiply-high + shifts (fast_div)
+  unsigned char div_s[7][2][2];
   int side_tiles[6];       // tiles that read the receive buffer of a side (the last one sends the ack)
 };
 
@@ -121,9 +124,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -200,24 +200,30 @@ __device__ __forceinline__ void f_spin(const unsigned long long* flag, unsigned 
   }
 }
 
+// n / d for any 32-bit n by multiply-high and two shifts (Granlund & Montgomery): every CTA decodes its tile number,
+// and two hardware-emulated divisions cost ~50 issue slots per warp — 3 % of this kernel
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned s1, unsigned s2) {
+  const unsigned t = __umulhi(m, n);
+  return (t + ((n - t) >> s1)) >> s2;
+}
 // linear tile number of the fused launch -> tile coordinates; false behind the last tile
 __device__ __forceinline__ bool fused_tile(const TileFrame& TF, int t, int& bx, int& by, int& bz) {
   if (t >= TF.box_start[TF.nboxes]) return false;
   int b = 0;
   while (t >= TF.box_start[b + 1]) b++;
-  t -= TF.box_start[b];
-  const int ex = TF.box[b][3], ey = TF.box[b][4];
-  bx = TF.box[b][0] + t % ex;
-  t /= ex;
-  by = TF.box[b][1] + t % ey;
-  bz = TF.box[b][2] + t / ey;
+  const unsigned u = (unsigned)(t - TF.box_start[b]);
+  const unsigned q = fast_div(u, TF.div_m[b][0], TF.div_s[b][0][0], TF.div_s[b][0][1]);  // u / ex
+  const unsigned r = fast_div(q, TF.div_m[b][1], TF.div_s[b][1][0], TF.div_s[b][1][1]);  // q / ey
+  bx = TF.box[b][0] + (int)(u - q * (unsigned)TF.box[b][3]);
+  by = TF.box[b][1] + (int)(q - r * (unsigned)TF.box[b][4]);
+  bz = TF.box[b][2] + (int)r;
   return true;
 }
 
 // A push block of the fused launch: the owned boundary layer of x goes straight into the neighbour's receive buffer
 // (remote 16-byte stores over NVLink), the last block of a side publishes ready = epoch.  Same protocol as
 // p2p_push_kernel (halo.cu), which replaces the CopyDataHandle communication of boilerplate/pdelab.hh:872-880.
-__device__ __forceinline__ void fused_push(const TileFrame& TF, const double* __restrict__ xin, int b) {
+__device__ __noinline__ void fused_push(const TileFrame& TF, const double* __restrict__ xin, int b) {
   const int side = TF.push_side[b / TF.push_blocks], blk = b % TF.push_blocks;
   const FusedSide& S = TF.fz->s[side];
   if (threadIdx.x == 0) f_spin(S.my_ack, TF.epoch - 1, TF.fz->err);  // the neighbour has consumed the previous layer
@@ -227,15 +233,15 @@ __device__ __forceinline__ void fused_push(const TileFrame& TF, const double* __
   const long long total = S.total2, chunk = S.chunk2, stride = S.stride2, off = S.src_off2;
   const long long step = (long long)TF.push_blocks * blockDim.x;
   long long i = (long long)blk * blockDim.x + threadIdx.x;
-  for (; i + 3 * step < total; i += 4 * step) {  // four independent loads in flight per thread
-    double2 v[4];
+  for (; i + 7 * step < total; i += 8 * step) {  // eight independent loads in flight per thread
+    double2 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 8; u++) {
       const long long j = i + u * step, c = j / chunk;
       v[u] = src[off + c * stride + (j - c * chunk)];
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) dst[i + u * step] = v[u];
+    for (int u = 0; u < 8; u++) dst[i + u * step] = v[u];
   }
   for (; i < total; i += step) {
     const long long c = i / chunk;
@@ -249,6 +255,45 @@ __device__ __forceinline__ void fused_push(const TileFrame& TF, const double* __
       TF.fz->counters[side] = 0;
       __threadfence_system();
       f_st_release_sys(S.peer_ready, TF.epoch);
+    }
+  }
+}
+
+// The three places where a tile next to a processor side differs from any other tile; kept out of line so that the
+// code of all other tiles stays what it is without the fused step.  pmask: bit (sd - 2) set = the tile reads the
+// receive buffer of side sd (2, 3: lower / upper y; 4, 5: lower / upper z).
+__device__ __noinline__ void fused_wait_sides(const TileFrame& TF, int pmask) {
+#pragma unroll 1
+  for (int sd = 2; sd < 6; sd++)
+    if (pmask >> (sd - 2) & 1) f_spin(TF.fz->s[sd].my_ready, TF.epoch, TF.fz->err);
+  asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies that follow read what remote stores wrote
+}
+// the y-halo row of a warp's layer is a neighbour's boundary layer: the TMA box brought x's (stale) ghost row; the warp
+// overwrites the eight cells its y-sweep reads from the receive buffer ([Nz][Nx] cells).  L1 may hold the previous
+// epoch's lines: ld.global.cg.
+__device__ __noinline__ void fused_patch_y(const TileFrame& TF, double* tile, int pmask, int gz, int Nx, int x0, int ncx,
+                                           int cz, int lane) {
+  const int n2 = ncx * NLOC / 2;
+#pragma unroll 1
+  for (int sd = 0; sd < 2; sd++) {
+    if (!(pmask >> sd & 1)) continue;
+    const double2* __restrict__ src = (const double2*)(TF.fz->s[2 + sd].my_buf + ((long long)gz * Nx + x0) * NLOC);
+    double2* __restrict__ dst = (double2*)(tile + R0 + ((cz * ROWY + (sd ? ROWY - 1 : 0)) * ROWX + 2) * NLOC);
+    for (int i = lane; i < n2; i += 32) dst[i] = __ldcg(src + i);
+  }
+}
+// every warp has its halo data in shared memory: this tile is done with the receive buffers; the last tile of a side
+// hands the buffer back to the neighbour (ack = epoch)
+__device__ __noinline__ void fused_ack(const TileFrame& TF, int pmask) {
+  __threadfence();
+#pragma unroll 1
+  for (int sd = 2; sd < 6; sd++) {
+    if (!(pmask >> (sd - 2) & 1)) continue;
+    const unsigned int done = atomicAdd(&TF.fz->counters[6 + sd], 1u);
+    if (done == (unsigned)TF.side_tiles[sd] - 1) {
+      TF.fz->counters[6 + sd] = 0;
+      __threadfence();
+      f_st_release_sys(TF.fz->s[sd].peer_ack, TF.epoch);
     }
   }
 }
@@ -404,82 +449,39 @@ __device__ __forceinline__ void mass_sweep(double (&t)[NLOC]) {
     }
 }
 
-template <int AMODE, bool HAS_C, bool WEIGHTS_ON, bool HAS_B>
-__global__ void __launch_bounds__(TX* TY* TZ, 3)
-    dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_pf,
-                         const double* __restrict__ xin, const DevParams P, const FastConst F, const TileFrame TF) {
+// One tile of 8 x 4 x 4 cells.  LIST: the tile comes from the tile list of the one-launch overlapping step (1-D grid),
+// BND: it is next to a processor side and reads the neighbour's boundary layer from the mailbox — bits of pmask: lower y,
+// upper y, lower z, upper z.  The code of every other tile is the same with and without the fused step.
+template <int AMODE, bool HAS_C, bool WEIGHTS_ON, bool HAS_B, bool LIST, bool BND>
+__device__ __forceinline__ void tile_body(const CUtensorMap& tm_rows, const CUtensorMap& tm_pf, const double* __restrict__ xin,
+                                          const DevParams& P, const FastConst& F, const TileFrame& TF, const int bx,
+                                          const int by, const int bz, const int pmask) {
   extern __shared__ __align__(128) double tile[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(8) uint64_t zbar;      // "every warp is done with the z-sweep" (arrive early, wait late)
   __shared__ __align__(8) uint64_t wbar[TZ];  // residual form: the R(0) rows of every warp arrive on its own barrier
   const int tid = threadIdx.x;
-  int bx = blockIdx.x + TF.off[0], by = blockIdx.y + TF.off[1], bz = blockIdx.z + TF.off[2];
-  if (TF.fz) {  // one-launch step of the overlapping partition: push blocks, then the tiles in list order
-    if ((int)blockIdx.x < TF.npush) {
-      fused_push(TF, xin, blockIdx.x);
-      return;
-    }
-    fused_tile(TF, blockIdx.x - TF.npush, bx, by, bz);
-  }
   const int x0 = bx * TX, y0 = TF.org[1] + by * TY, z0 = TF.org[2] + bz * TZ;
-  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
-  // fused step: halo rows / layers of this tile that are a neighbour's boundary layer (read from the mailbox)
-  const bool py0 = TF.fz && y0 == 1 && P.side_kind[1][0] == PDB200_SIDE_PROCESSOR;
-  const bool py1 = TF.fz && y0 + TY == Ny - 1 && P.side_kind[1][1] == PDB200_SIDE_PROCESSOR;
-  const bool pz0 = TF.fz && z0 == 1 && P.side_kind[2][0] == PDB200_SIDE_PROCESSOR;
-  const bool pz1 = TF.fz && z0 + TZ == Nz - 1 && P.side_kind[2][1] == PDB200_SIDE_PROCESSOR;
-
-  // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
-  // stride maps the 16 lanes of a 64-bit shared access onto 16 distinct bank pairs
-  const int lane = tid & 31;
-  const int cx = lane & 7;
-  const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
-  const int cz = tid >> 5;
-  const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
-  const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
-
-  // ---- the diffusion coefficients of the cell and its six face neighbours: the loads are the first thing the
-  // kernel issues, so that their L2 / HBM round trips run under the barrier set-up and the TMA requests -----------
-  const int cell = gx + Nx * (gy + Ny * gz);
-  const bool onb[3][2] = {{gx == 0, gx == Nx - 1}, {gy == 0, gy == Ny - 1}, {gz == 0, gz == Nz - 1}};
-  double a[3] = {1.0, 1.0, 1.0}, ao[3][2] = {{1.0, 1.0}, {1.0, 1.0}, {1.0, 1.0}};
-  if (active) {
-    const int stride[3] = {1, Nx, Nx * Ny};
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      a[d] = load_adiag<AMODE>(P, cell, d);
-#pragma unroll
-      for (int side = 0; side < 2; side++)
-        ao[d][side] = load_adiag<AMODE>(P, onb[d][side] ? cell : cell + (side ? stride[d] : -stride[d]), d);
-    }
-  }
 
   if (tid == 0) {
     mbar_init(&bar, 1);
-    mbar_init(&zbar, TZ);
     if (TF.r0)
       for (int w = 0; w < TZ; w++) mbar_init(&wbar[w], 1);
     fence_mbar_init();
   }
   __syncthreads();
+  const int Nx = P.N[0], Ny = P.N[1], Nz = P.N[2];
   const int ncx = min(TX, Nx - x0);                   // cells of an x-row inside the vector (even: Nx is even)
   const int nrow = min(TY, Ny - y0);                  // rows of the tile inside the vector
   const bool zlo_in = z0 - 1 >= 0, zup_in = z0 + TZ < Nz;
   if (tid == 0) {
     const uint32_t rowbytes = (uint32_t)ncx * NLOC * 8;
-    if (py0 | py1 | pz0 | pz1) {  // the neighbours' layers must have arrived (their push blocks run first)
-      if (py0) f_spin(TF.fz->s[2].my_ready, TF.epoch, TF.fz->err);
-      if (py1) f_spin(TF.fz->s[3].my_ready, TF.epoch, TF.fz->err);
-      if (pz0) f_spin(TF.fz->s[4].my_ready, TF.epoch, TF.fz->err);
-      if (pz1) f_spin(TF.fz->s[5].my_ready, TF.epoch, TF.fz->err);
-      asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what remote stores wrote
-    }
     mbar_expect_tx(&bar, ROWS_BYTES + ((zlo_in ? nrow : 0) + (zup_in ? nrow : 0)) * rowbytes);
     tma_load_4d(tile + R0, &tm_rows, 0, x0 / 2 - 1, y0 - 1, z0, &bar);
-    // z-halo layers: one bulk copy per x-row; a layer outside the vector is zeroed by the threads that read it.  In
-    // the fused step a ghost layer is read from the receive buffer ([Ny][Nx] cells) instead of from x.
-    const double* zlo_src = pz0 ? TF.fz->s[4].my_buf : xin + (long long)(z0 - 1) * Ny * Nx * NLOC;
-    const double* zup_src = pz1 ? TF.fz->s[5].my_buf : xin + (long long)(z0 + TZ) * Ny * Nx * NLOC;
+    if (BND) fused_wait_sides(TF, pmask);  // the neighbours' layers must have arrived (their push blocks run first)
+    // z-halo layers: one bulk copy per x-row; a layer outside the vector is zeroed by the threads that read it.  Next
+    // to a processor side the layer is read from the receive buffer ([Ny][Nx] cells) instead of from x's ghost layer.
+    const double* zlo_src = BND && (pmask & 4) ? TF.fz->s[4].my_buf : xin + (long long)(z0 - 1) * Ny * Nx * NLOC;
+    const double* zup_src = BND && (pmask & 8) ? TF.fz->s[5].my_buf : xin + (long long)(z0 + TZ) * Ny * Nx * NLOC;
     for (int r = 0; r < nrow; r++) {
       if (zlo_in) bulk_load(tile + R3 + zhalo_row(r), zlo_src + ((long long)(y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
       if (zup_in) bulk_load(tile + R4 + zhalo_row(r), zup_src + ((long long)(y0 + r) * Nx + x0) * NLOC, rowbytes, &bar);
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     // input byte is prefetched once), threads 1.. one x-row each of the coefficient box that tile's cells will load
     int pbx, pby, pbz;
     bool pvalid;
-    if (TF.fz) {
+    if (LIST) {
       pvalid = fused_tile(TF, (int)blockIdx.x - TF.npush + TF.pf, pbx, pby, pbz);
     } else {
       unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + TF.pf;
@@ -518,20 +520,38 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
     }
   }
 
-  // ---- per-cell coefficients (overlaps the TMA latency); everything up to the reciprocals is branch-free so
-  // that the six face set-ups interleave. -------------------------------------------------------------------
+  // lane -> cell: half-warps cover rows {0,2} / {1,3} of a z-layer so that the 54-word cell
+  // stride maps the 16 lanes of a 64-bit shared access onto 16 distinct bank pairs
+  const int lane = tid & 31;
+  const int cx = lane & 7;
+  const int cy = ((lane >> 3) & 1) * 2 + (lane >> 4);
+  const int cz = tid >> 5;
+  const int gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
+  const bool active = gx < Nx && gy < TF.lim[1] && gz < TF.lim[2];
+
+  // ---- per-cell coefficients (overlaps the TMA latency).  All coefficient loads are issued
+  // before the first use so that the L2 round trips overlap instead of adding up; everything up
+  // to the reciprocals is branch-free so that the six face set-ups interleave. -------------------
   double A0[3], csL[3], coL[3], csR[3], coR[3];
   double creact = 0.0;
   bool constrained = false;
   double bs[3] = {0.0, 0.0, 0.0}, bo[3] = {0.0, 0.0, 0.0};  // HAS_B: own velocity and b_d of the upper d-neighbour
   int kinds = 0;                                             // HAS_B: face kinds, 2 bits each, face 2 d + side
   if (active) {
+    const int cell = gx + Nx * (gy + Ny * gz);
     const int stride[3] = {1, Nx, Nx * Ny};
+    const bool onb[3][2] = {{gx == 0, gx == Nx - 1}, {gy == 0, gy == Ny - 1}, {gz == 0, gz == Nz - 1}};
+    double a[3], ao[3][2];
     int kind[3][2];
 #pragma unroll
-    for (int d = 0; d < 3; d++)
+    for (int d = 0; d < 3; d++) {
+      a[d] = load_adiag<AMODE>(P, cell, d);
 #pragma unroll
-      for (int side = 0; side < 2; side++) kind[d][side] = onb[d][side] ? 1 : 0;
+      for (int side = 0; side < 2; side++) {
+        kind[d][side] = onb[d][side] ? 1 : 0;
+        ao[d][side] = load_adiag<AMODE>(P, onb[d][side] ? cell : cell + (side ? stride[d] : -stride[d]), d);
+      }
+    }
     if (HAS_C) creact = __ldg(P.c + cell) * F.scale;
     if (HAS_B) {
 #pragma unroll
@@ -586,20 +606,8 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   }
 
   mbar_wait(&bar, 0);
-  if (py0 | py1) {
-    // fused step: the y-halo row of this warp's layer is a neighbour's boundary layer — the TMA box brought x's
-    // (stale) ghost row; the warp overwrites the eight cells its y-sweep reads from the receive buffer
-    // ([Nz][Nx] cells).  L1 may hold the previous epoch's lines: ld.global.cg.
-    if (gz < Nz) {
-      const int n2 = ncx * NLOC / 2;
-#pragma unroll 1
-      for (int sd = 0; sd < 2; sd++) {
-        if (!(sd ? py1 : py0)) continue;
-        const double2* __restrict__ src = (const double2*)(TF.fz->s[2 + sd].my_buf + ((long long)gz * Nx + x0) * NLOC);
-        double2* __restrict__ dst = (double2*)(tile + R0 + ((cz * ROWY + (sd ? ROWY - 1 : 0)) * ROWX + 2) * NLOC);
-        for (int i = lane; i < n2; i += 32) dst[i] = __ldcg(src + i);
-      }
-    }
+  if (BND && (pmask & 3)) {  // the y-halo row of this warp's layer comes from the receive buffer (read by its y-sweep only)
+    if (gz < Nz) fused_patch_y(TF, tile, pmask, gz, Nx, x0, ncx, cz, lane);
     __syncwarp();
   }
 
@@ -629,31 +637,13 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   if (active)
     sweep<9, true, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + zl, tile + zr, F, creact, A0[2], F.ih2[2], csL[2], coL[2], csR[2],
                                              coR[2], conv(2));
-  // from here on a warp reads and writes its own layer only; the layer may be WRITTEN (R(0) rows, output stage) once
-  // the warps above and below are done with their z-sweeps: every warp arrives here and waits behind its x/y sweeps
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&zbar);
+  __syncthreads();  // from here on a warp reads and writes its own layer only
+  if (BND && tid == 0) fused_ack(TF, pmask);  // all halo data is in shared memory or consumed: the receive buffers are free
   if (active) {
     sweep<1, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + xl, tile + xr, F, creact, A0[0], F.ih2[0], csL[0], coL[0], csR[0],
                                               coR[0], conv(0));
     sweep<3, false, HAS_C, WEIGHTS_ON, HAS_B>(tile + so, t, tile + yl, tile + yr, F, creact, A0[1], F.ih2[1], csL[1], coL[1], csR[1],
                                               coR[1], conv(1));
-  }
-  mbar_wait(&zbar, 0);
-  if ((py0 | py1 | pz0 | pz1) && tid == 0) {
-    // every warp has its halo data in shared memory: this tile is done with the receive buffers; the last tile of a
-    // side hands the buffer back to the neighbour (ack = epoch)
-    __threadfence();
-#pragma unroll 1
-    for (int sd = 2; sd < 6; sd++) {
-      if (!(sd == 2 ? py0 : (sd == 3 ? py1 : (sd == 4 ? pz0 : pz1)))) continue;
-      const unsigned int done = atomicAdd(&TF.fz->counters[6 + sd], 1u);
-      if (done == (unsigned)TF.side_tiles[sd] - 1) {
-        TF.fz->counters[6 + sd] = 0;
-        __threadfence();
-        f_st_release_sys(TF.fz->s[sd].peer_ack, TF.epoch);
-      }
-    }
   }
   __syncwarp();  // every lane is done reading the layer: it becomes the warp's output stage
   double* const stage = tile + R0 + cz * LAYER;
@@ -705,21 +695,67 @@ __global__ void __launch_bounds__(TX* TY* TZ, 3)
   // constrain_residual); only tiles at the ends of the tiled range take this path ----------------
   const bool gzl = TF.org[2] && z0 == TF.org[2], gzu = TF.lim[2] < Nz && z0 + TZ >= TF.lim[2];
   const bool gyl = TF.org[1] && y0 == TF.org[1], gyu = TF.lim[1] < Ny && y0 + TY >= TF.lim[1];
-  if (gzl | gzu | gyl | gyu) {
+  bool zissued = false;
+  if ((gzl | gzu | gyl | gyu) && cz == 0) {
+    // warp 0 zeroes one x-row in the (dead) lower z-halo region and sends it to every ghost row next to the tile as a
+    // bulk store.  (A loop of plain stores over these rows cost 5-6 % of the whole launch on a 128 x 130 x 130 box.)
+    double* __restrict__ zsrc = tile + R3;
+    for (int i = lane; i < XROW; i += 32) zsrc[i] = 0.0;
+    fence_proxy_async();
+    __syncwarp();
     const int ya = gyl ? 0 : y0, yb = gyu ? Ny : min(y0 + TY, TF.lim[1]);
     const int za = gzl ? 0 : z0, zb = gzu ? Nz : min(z0 + TZ, TF.lim[2]);
-    const int nx = (min(x0 + TX, Nx) - x0) * NLOC;
-    double* __restrict__ yout = TF.out;
-    for (int zz = za; zz < zb; zz++)
-      for (int yy = ya; yy < yb; yy++) {
-        const bool ghost = (TF.org[1] && yy == 0) || (TF.lim[1] < Ny && yy == Ny - 1) || (TF.org[2] && zz == 0) ||
-                           (TF.lim[2] < Nz && zz == Nz - 1);
-        if (!ghost) continue;
-        double* row = yout + (((long long)zz * Ny + yy) * Nx + x0) * NLOC;
-        for (int i = tid; i < nx; i += TX * TY * TZ) row[i] = 0.0;
-      }
+    const int ny = yb - ya, cnt = ny * (zb - za);
+    for (int i = lane; i < cnt; i += 32) {
+      const int zz = za + i / ny, yy = ya + i % ny;
+      const bool ghost = (TF.org[1] && yy == 0) || (TF.lim[1] < Ny && yy == Ny - 1) || (TF.org[2] && zz == 0) ||
+                         (TF.lim[2] < Nz && zz == Nz - 1);
+      if (!ghost) continue;
+      bulk_store(TF.out + (((long long)zz * Ny + yy) * Nx + x0) * NLOC, zsrc, rowbytes);
+      zissued = true;
+    }
   }
-  if (rowlane) tma_store_commit_and_wait();
+  if (rowlane || zissued) tma_store_commit_and_wait();
+}
+
+template <int AMODE, bool HAS_C, bool WEIGHTS_ON, bool HAS_B, bool FUSED>
+__global__ void __launch_bounds__(TX* TY* TZ, 3)
+    dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_pf,
+                         const double* __restrict__ xin, const __grid_constant__ DevParams P,
+                         const __grid_constant__ FastConst F, const __grid_constant__ TileFrame TF) {
+  if (FUSED) {  // one-launch step of the overlapping partition: 1-D grid = push blocks, then the tiles in list order
+    if ((int)blockIdx.x < TF.npush) {
+      fused_push(TF, xin, blockIdx.x);
+      return;
+    }
+    const unsigned t = blockIdx.x - TF.npush;
+    const bool head = t < (unsigned)TF.box_start[1], tail = t >= (unsigned)TF.tail_start;
+    if (head | tail) {
+      // an interior tile: the lower part of the interior box runs first, the upper part last (the tiles next to a
+      // processor side sit in between: late enough for the neighbours' layers to have arrived, and not in the tail of
+      // the launch).  Decoded from scalars of the constant bank only, so that the tile coordinates stay in uniform
+      // registers like blockIdx of the 3-D launch: the tile body runs at the 168-register cap, and per-thread
+      // coordinates cost it 9 % (A/B on one box).
+      const unsigned u = head ? t : t - (unsigned)TF.tail_start;
+      const unsigned q = fast_div(u, TF.div_m[0][0], TF.div_s[0][0][0], TF.div_s[0][0][1]);
+      const unsigned r = fast_div(q, TF.div_m[0][1], TF.div_s[0][1][0], TF.div_s[0][1][1]);
+      tile_body<AMODE, HAS_C, WEIGHTS_ON, HAS_B, true, false>(tm_rows, tm_pf, xin, P, F, TF, TF.box[0][0] + (int)(u - q * (unsigned)TF.box[0][3]),
+                                                              TF.box[0][1] + (int)(q - r * (unsigned)TF.box[0][4]),
+                                                              (head ? TF.box[0][2] : TF.tail_z) + (int)r, 0);
+    } else {  // a tile next to a processor side
+      int bx, by, bz;
+      fused_tile(TF, (int)t, bx, by, bz);
+      const int y0 = TF.org[1] + by * TY, z0 = TF.org[2] + bz * TZ;
+      const int pmask = (y0 == 1 && P.side_kind[1][0] == PDB200_SIDE_PROCESSOR ? 1 : 0) |
+                        (y0 + TY == P.N[1] - 1 && P.side_kind[1][1] == PDB200_SIDE_PROCESSOR ? 2 : 0) |
+                        (z0 == 1 && P.side_kind[2][0] == PDB200_SIDE_PROCESSOR ? 4 : 0) |
+                        (z0 + TZ == P.N[2] - 1 && P.side_kind[2][1] == PDB200_SIDE_PROCESSOR ? 8 : 0);
+      tile_body<AMODE, HAS_C, WEIGHTS_ON, HAS_B, true, true>(tm_rows, tm_pf, xin, P, F, TF, bx, by, bz, pmask);
+    }
+  } else {
+    tile_body<AMODE, HAS_C, WEIGHTS_ON, HAS_B, false, false>(tm_rows, tm_pf, xin, P, F, TF, blockIdx.x + TF.off[0],
+                                                             blockIdx.y + TF.off[1], blockIdx.z + TF.off[2], 0);
+  }
 }
 
 // y += t (+ r0): accumulate semantics of the reference engines; r0 = R(0) turns J x into the residual
@@ -779,9 +815,13 @@ FastPlan* dg_fast_plan_create(const DevParams& P, const Kron1D& K) {
   if (!fn || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled is not available in this driver");
   plan->encode = (EncodeFn)fn;
 #define PDB_SET_SMEM(AM, HC, WO)                                                                                 \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 SMEM_BYTES));                                                                     \
-  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                SMEM_BYTES));                                                                     \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                SMEM_BYTES));                                                                     \
+  PDB_CUDA(cudaFuncSetAttribute(dg_fast_q2_3d_kernel<AM, HC, WO, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                 SMEM_BYTES));
 #define PDB_SET_SMEM4(AM) PDB_SET_SMEM(AM, false, false) PDB_SET_SMEM(AM, false, true) PDB_SET_SMEM(AM, true, false) PDB_SET_SMEM(AM, true, true)
   PDB_SET_SMEM4(PDB200_A_IDENTITY) PDB_SET_SMEM4(PDB200_A_SCALAR) PDB_SET_SMEM4(PDB200_A_DIAGONAL)
@@ -867,6 +907,9 @@ void dg_fast_ztile_layers(const DevParams& P, int lo, int hi, int* z0, int* z1) 
   *z1 = hi >= nt[2] ? P.N[2] : std::min(TF.org[2] + hi * TZ, P.N[2]);  // the last one the upper ghost layer
 }
 
+int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, double* y, const FusedTable* table,
+                         const FusedTable& th, unsigned long long epoch, cudaStream_t s, int* errflag);
+
 int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* y, const double* r0, bool overwrite,
                    int part, cudaStream_t s, int* errflag, int ztile_lo, int ztile_hi) {
   if (r0 && overwrite) throw Error("the residual form accumulates (r += J x + R(0))");
@@ -884,9 +927,12 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
   {
     static const int pf_env = [] {
       const char* e = getenv("PDB200_FAST_PREFETCH");
-      return e ? atoi(e) : 444;  // three tiles per SM ahead: measured 1-2 % (profiles/r01_prefetch_sweep.txt)
+      // L2 prefetch distance in tiles.  It bought 1-2 % with the first shared-memory layout (444 = three tiles per SM
+      // ahead, profiles/r01_prefetch_sweep.txt) and costs ~1 % with the present one (A/B on one box, round 2): off.
+      return e ? atoi(e) : 0;
     }();
     TF.pf = pf_env;
+
   }
   // boxes of tiles to launch: {offset, extent}
   int boxes[7][6], nboxes = 0;
@@ -896,6 +942,14 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
     for (int i = 0; i < 6; i++) boxes[nboxes][i] = b[i];
     nboxes++;
   };
+  {
+    // tuning aid: the tile-list (1-D grid) variant of the kernel on a box without processor sides
+    static const bool linear = [] { const char* e = getenv("PDB200_FAST_LINEAR"); return e && e[0] == '1'; }();
+    if (linear && part == PDB200_PART_ALL && overwrite && !r0 && ztile_lo <= 0 && ztile_hi >= nt[2]) {
+      static const FusedTable none{};
+      return launch_dg_fast_fused(plan, P, x, y, nullptr, none, 0, s, errflag);
+    }
+  }
   if (part == PDB200_PART_ALL) {
     const int zlo = std::max(0, ztile_lo), zhi = std::min(nt[2], ztile_hi);  // optional window of tile layers
     add(0, 0, zlo, nt[0], nt[1], zhi - zlo);
@@ -916,8 +970,8 @@ int launch_dg_fast(FastPlan* plan, const DevParams& P, const double* x, double* 
   int launches = 0;
 #define PDB_LAUNCH(AM, HC, WO)                                                                                            \
   do {                                                                                                                     \
-    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
-    else dg_fast_q2_3d_kernel<AM, HC, WO, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
+    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
+    else dg_fast_q2_3d_kernel<AM, HC, WO, false, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
   } while (0)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \
@@ -959,7 +1013,7 @@ bool dg_fast_fused_supported(const DevParams& P) {
 
 int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, double* y, const FusedTable* table,
                          const FusedTable& th, unsigned long long epoch, cudaStream_t s, int* errflag) {
-  if (!dg_fast_fused_supported(P)) throw Error("fused overlapping step: unsupported partition");
+  if (table && !dg_fast_fused_supported(P)) throw Error("fused overlapping step: unsupported partition");
   const FastPlan::Maps mx = get_maps(plan, x, P);
   if ((uintptr_t)y % 16 != 0) throw Error("fast DG kernel: vectors must be 16-byte aligned");
   TileFrame TF;
@@ -971,7 +1025,7 @@ int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, do
   TF.r0 = nullptr;
   {
     const char* e = getenv("PDB200_FAST_PREFETCH");
-    TF.pf = e ? atoi(e) : 444;
+    TF.pf = e ? atoi(e) : 0;
   }
   TF.fz = table;
   TF.epoch = epoch;
@@ -995,19 +1049,34 @@ int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, do
     count += b[3] * b[4] * b[5];
     TF.nboxes++;
   };
-  add(lo[0], lo[1], lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
-  if (TF.box[0][3] * TF.box[0][4] * TF.box[0][5] == 0) {  // degenerate: no interior, the whole box is boundary
-    for (int d = 0; d < 3; d++) lo[d] = hi[d] = 0;
-    lo[2] = hi[2] = nt[2];
+  // the interior box is cut along z: the lower part runs first, the upper part last
+  const bool has_interior = hi[0] > lo[0] && hi[1] > lo[1] && hi[2] > lo[2];
+  const int zcut = has_interior ? lo[2] + (hi[2] - lo[2] + 1) / 2 : lo[2];
+  add(lo[0], lo[1], lo[2], hi[0] - lo[0], hi[1] - lo[1], zcut - lo[2]);
+  if (!has_interior) {  // degenerate: the whole box is boundary
     TF.box[0][3] = TF.box[0][4] = TF.box[0][5] = 1;  // extents must not be zero for the decode; count stays 0
     add(0, 0, 0, nt[0], nt[1], nt[2]);
+    TF.tail_start = count;
+    TF.tail_z = 0;
   } else {
     add(0, 0, 0, nt[0], nt[1], lo[2]);
     add(0, 0, hi[2], nt[0], nt[1], nt[2] - hi[2]);
     add(0, 0, lo[2], nt[0], lo[1], hi[2] - lo[2]);
     add(0, hi[1], lo[2], nt[0], nt[1] - hi[1], hi[2] - lo[2]);
+    TF.tail_start = count;
+    TF.tail_z = zcut;
+    add(lo[0], lo[1], zcut, hi[0] - lo[0], hi[1] - lo[1], hi[2] - zcut);  // (may be empty)
   }
   TF.box_start[TF.nboxes] = count;
+  for (int b = 0; b < TF.nboxes; b++)
+    for (int i = 0; i < 2; i++) {
+      const unsigned d = (unsigned)std::max(1, TF.box[b][3 + i]);
+      unsigned l = 0;
+      while ((1ull << l) < d) l++;
+      TF.div_m[b][i] = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+      TF.div_s[b][i][0] = (unsigned char)std::min(l, 1u);
+      TF.div_s[b][i][1] = (unsigned char)(l > 0 ? l - 1 : 0);
+    }
   if (count != nt[0] * nt[1] * nt[2]) throw Error("fused overlapping step: tile list does not cover the box");
   // tiles reading the receive buffer of a side: the first / last tile layer of that direction
   for (int i = 0; i < 6; i++) TF.side_tiles[i] = 0;
@@ -1017,8 +1086,8 @@ int launch_dg_fast_fused(FastPlan* plan, const DevParams& P, const double* x, do
   const unsigned grid = (unsigned)(TF.npush + count);
 #define PDB_LAUNCH(AM, HC, WO)                                                                                            \
   do {                                                                                                                     \
-    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
-    else dg_fast_q2_3d_kernel<AM, HC, WO, false><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
+    if (P.b) dg_fast_q2_3d_kernel<AM, HC, WO, true, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF); \
+    else dg_fast_q2_3d_kernel<AM, HC, WO, false, true><<<grid, TX * TY * TZ, SMEM_BYTES, s>>>(mx.rows, mx.core, x, P, plan->F, TF);  \
   } while (0)
 #define PDB_LAUNCH_A(AM)                                \
   do {                                                  \

@@ -67,11 +67,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PDB200_LIB", LIB_PATH)  # tuning aid: A/B of two builds on the same box (tools/)
+    if not os.path.exists(path):
         raise PDELabError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(pdelab_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.pdb200_last_error.restype = C.c_char_p
     lib.pdb200_last_kernel.restype = C.c_char_p
     lib.pdb200_last_kernel.argtypes = [C.c_void_p]

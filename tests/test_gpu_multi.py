@@ -220,7 +220,7 @@ def test_256_cubed_over_four_ranks_matches_the_undivided_oracle(cuda_lib, tmp_pa
     for rank, err, kern, nown, tb in res:
         assert tb is None, tb
         assert err < 1e-12, (rank, err)
-        assert kern == "dg_fast_q2_3d"
+        assert kern == "dg_fast_q2_3d+halo"    # the one-launch step: 128 owned layers are tile-aligned
         owned += nown
     assert owned == ncg          # every cell has exactly one owner
 

@@ -29,12 +29,11 @@ def run(cells, side_kind, reps=200):
     print(json.dumps({"cells": cells, "side_kind": side_kind, "ms": round(ms, 4), "kernel": go.last_kernel()}), flush=True)
 
 D = [[0, 0], [0, 0], [0, 0]]
-run((128, 128, 128), D)
-run((128, 128, 129), D)
-run((128, 128, 129), [[0, 0], [0, 0], [0, 1]])
-run((128, 128, 129), [[0, 0], [0, 0], [1, 0]])
-run((128, 128, 130), [[0, 0], [0, 0], [1, 1]])
-run((128, 128, 132), D)
-run((128, 130, 130), [[0, 0], [1, 1], [1, 1]])
-run((128, 129, 130), [[0, 0], [0, 1], [1, 1]])
-run((128, 128, 128), D)
+CASES = [((128, 128, 128), D), ((128, 128, 129), D), ((128, 128, 129), [[0, 0], [0, 0], [0, 1]]),
+         ((128, 128, 129), [[0, 0], [0, 0], [1, 0]]), ((128, 128, 130), [[0, 0], [0, 0], [1, 1]]), ((128, 128, 132), D),
+         ((128, 130, 130), [[0, 0], [1, 1], [1, 1]]), ((128, 129, 130), [[0, 0], [0, 1], [1, 1]]), ((128, 128, 128), D),
+         ((128, 130, 130), D), ((128, 130, 128), [[0, 0], [1, 1], [0, 0]]), ((128, 132, 128), D), ((128, 128, 132), D)]
+# the kernel runs into sw_power_cap after ~0.1 s: compare cases from a cold start, one case per process
+# (python tools/bench_box.py 2; sleep 5; python tools/bench_box.py 0; ...)
+for i in ([int(a) for a in sys.argv[1:]] or range(len(CASES))):
+    run(*CASES[i])
