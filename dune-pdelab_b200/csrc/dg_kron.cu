@@ -41,11 +41,18 @@ template <int K>
 struct KronCfg;
 template <>
 struct KronCfg<4> {
+  // 24 cells = 4 warps of 6 cells, 105 KB of shared memory: TWO CTAs per SM, so that one CTA's tile load / result
+  // store runs under the other's sweeps (the 4 x 4 x 3 tile of round 1 filled the SM with ONE CTA of 152 KB: a third of
+  // the tile time was load and store latency with nothing to overlap it)
+#ifdef PDB200_KRON4_BIG_TILE
   static constexpr int TX = 4, TY = 4, TZ = 3;  // 48 cells = 8 warps of 6 cells
+#else
+  static constexpr int TX = 4, TY = 2, TZ = 3;
+#endif
 };
 template <>
 struct KronCfg<3> {
-  static constexpr int TX = 8, TY = 4, TZ = 2;  // 64 cells = 8 warps of 8 cells
+  static constexpr int TX = 8, TY = 2, TZ = 2;  // 32 cells = 4 warps of 8 cells, 73 KB: three CTAs per SM
 };
 
 template <int K>

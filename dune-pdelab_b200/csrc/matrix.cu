@@ -795,6 +795,168 @@ __global__ void __launch_bounds__(256) qk_mv_interior_short_kernel(const DevPara
   }
 }
 
+// Long rows (45 / 75 / 125 entries: the face, edge and vertex groups of Q2 in 3-D, 95 % of the non-zeros): the values of
+// 32 consecutive rows of the line are ONE contiguous piece of the array, so a stage of the ring is ONE bulk copy
+// (cp.async.bulk -> mbarrier) issued by one thread; three stages are in flight per CTA while the previous ones are
+// consumed, which is what the single-buffered version above lacks (it waits for its chunk behind a barrier:
+// long-scoreboard bound at 27 % of the HBM peak, profiles/r01_spmv_staged_ncu_summary.json; the warp-per-row kernel
+// gathers x with 32 sectors per load instead).  Consumers: thread = (row of the chunk, eighth of the slots), all its
+// <= 16 x loads in flight at once; shared reads are conflict-free (odd row stride), for a fixed slot the 32 lanes read
+// 32 consecutive x, the eight partial sums of a row meet in shared memory.  Bulk copies need 16-byte aligned sources and row starts are odd as often as even
+// (all row lengths are odd): the copy starts one entry early where needed and the consumers skip it.
+constexpr int MVP_ROWS = 32, MVP_PARTS = 8, MVP_STAGES = 3, MVP_THREADS = MVP_ROWS * MVP_PARTS;
+__device__ __forceinline__ uint32_t mv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int DIM, int K, int L>
+__global__ void __launch_bounds__(MVP_THREADS) qk_mv_interior_pipe_kernel(const DevParams P, const QkDecode D, int g,
+                                                                          const QkLut* __restrict__ lut_g,
+                                                                          const u64* __restrict__ rowptr, u64 nnz_total,
+                                                                          const double* __restrict__ values,
+                                                                          const double* __restrict__ x, double* __restrict__ y) {
+  extern __shared__ __align__(16) double vs[];  // [STAGES][ROWS * L + 2]
+  __shared__ uint32_t col0s[128];
+  __shared__ double part_sum[2][MVP_THREADS];
+  __shared__ __align__(8) uint64_t full[MVP_STAGES];
+  const int s = D.sbits[g];
+  const bool vt[3] = {!(s & 1), !((s >> 1) & 1), !((s >> 2) & 1)};
+  const int N0 = P.N[0];
+  const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
+  const int a1 = (int)blockIdx.x + (vt[1] ? 1 : 0), a2 = DIM == 3 ? (int)blockIdx.y + (vt[2] ? 1 : 0) : 0;
+  const int lo0 = vt[0] ? 1 : 0, hi0 = N0 - 1;
+  int shape = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) shape |= (vt[d] ? 1 : 0) << d;
+  if ((int)threadIdx.x < L) {
+    const int off = lut_g->slot2off[shape][threadIdx.x];
+    const int o[3] = {off & 7, (off >> 3) & 7, off >> 6};
+    int e[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) e[d] = o[d] - (vt[d] ? K : 1);
+    long long c;
+    if (K == 1) {
+      c = (lo0 + e[0]) + (long long)(N0 + 1) * ((a1 + e[1]) + (long long)(P.N[1] + 1) * (DIM == 3 ? a2 + e[2] : 0));
+    } else {
+      int par = 0, sh[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const int q = ((s >> d) & 1) + e[d];
+        const int pb = q & 1;
+        par |= pb << d;
+        sh[d] = (q - pb) / 2;
+      }
+      const int g2 = D.group_of_s[par];
+      c = (long long)D.start[g2] + (lo0 + sh[0]) +
+          (long long)D.sz0[g2] * ((a1 + sh[1]) + (long long)D.sz1[g2] * (DIM == 3 ? a2 + sh[2] : 0));
+    }
+    col0s[threadIdx.x] = (uint32_t)c;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MVP_STAGES; i++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mv_smem_u32(&full[i])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const u64 row0 = (u64)D.start[g] + (u64)lo0 + (u64)sz0 * ((u64)a1 + (u64)sz1 * (u64)a2);
+  const u64 base = rowptr[row0];
+  const int nrows = hi0 - lo0 + 1;
+  // the line is cut into gridDim.z pieces of whole chunks
+  const int chunks_all = (nrows + MVP_ROWS - 1) / MVP_ROWS, per = (chunks_all + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int ch0 = (int)blockIdx.z * per, ch1 = min(chunks_all, ch0 + per);
+  const int stage_doubles = MVP_ROWS * L + 2;
+  // chunk ch: entries [c0, c0 + nr * L) of the array; the copy covers [c0 - par, ...) rounded up to 16 bytes.  A chunk
+  // that a bulk copy cannot move (the rounded-up window would end behind the array, or the array is not 16-byte
+  // aligned) is loaded by the threads themselves; every thread evaluates the same predicate.
+  const bool unaligned = ((uintptr_t)values & 15) != 0;
+  auto window = [&](int ch, u64& a, u64& len) {
+    const int r0 = ch * MVP_ROWS, nr = min(MVP_ROWS, nrows - r0);
+    const u64 c0 = base + (u64)r0 * L;
+    a = c0 & ~(u64)1;
+    len = (((c0 - a) + (u64)nr * L) + 1) & ~(u64)1;
+    return !(unaligned || a + len > nnz_total);
+  };
+  auto issue = [&](int ch) {  // thread 0 only
+    u64 a, len;
+    if (!window(ch, a, len)) return;
+    const uint32_t bytes = (uint32_t)(len * 8);
+    const int st = (ch - ch0) % MVP_STAGES;
+    const uint32_t bar = mv_smem_u32(&full[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     mv_smem_u32(vs + (size_t)st * stage_doubles)),
+                 "l"(values + a), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (threadIdx.x == 0)
+    for (int ch = ch0; ch < min(ch1, ch0 + MVP_STAGES); ch++) issue(ch);
+  const int rl = threadIdx.x % MVP_ROWS, part = threadIdx.x / MVP_ROWS;
+  constexpr int NJ = (L + MVP_PARTS - 1) / MVP_PARTS;
+  uint32_t cr[NJ];  // the columns of this thread's slots (slot = part + 8 j) relative to the row
+#pragma unroll
+  for (int j = 0; j < NJ; j++) cr[j] = col0s[min(part + j * MVP_PARTS, L - 1)];
+  unsigned phase = 0;  // bit st: parity of the next completion of full[st]
+  for (int ch = ch0; ch < ch1; ch++) {
+    const int it = ch - ch0, st = it % MVP_STAGES;
+    const int r0 = ch * MVP_ROWS, nr = min(MVP_ROWS, nrows - r0);
+    const u64 c0 = base + (u64)r0 * L;
+    const int par = (int)(c0 & 1);
+    double* __restrict__ stage = vs + (size_t)st * stage_doubles;
+    // the x values first: all loads of the thread in flight before anything waits (the "+d" list below keeps the
+    // compiler from sinking them between the multiply-adds)
+    double xv[NJ], vv[NJ];
+    {
+      const double* __restrict__ xr = x + (r0 + min(rl, nr - 1));
+#pragma unroll
+      for (int j = 0; j < NJ; j++) xv[j] = __ldg(xr + cr[j]);
+    }
+    u64 wa, wl;
+    if (!window(ch, wa, wl)) {
+      for (int i = threadIdx.x; i < nr * L; i += MVP_THREADS) stage[par + i] = values[c0 + i];
+      __syncthreads();
+    } else {
+      const uint32_t bar = mv_smem_u32(&full[st]), parity = (phase >> st) & 1u;
+      phase ^= 1u << st;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "MVWAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra MVDONE;\n\t"
+          "bra MVWAIT;\n\t"
+          "MVDONE:\n\t"
+          "}" ::"r"(bar),
+          "r"(parity)
+          : "memory");
+    }
+    {
+      const double* __restrict__ v = stage + par + min(rl, nr - 1) * L;
+#pragma unroll
+      for (int j = 0; j < NJ; j++) vv[j] = v[min(part + j * MVP_PARTS, L - 1)];
+    }
+    if constexpr (NJ == 16)
+      asm volatile("" : "+d"(xv[0]), "+d"(xv[1]), "+d"(xv[2]), "+d"(xv[3]), "+d"(xv[4]), "+d"(xv[5]), "+d"(xv[6]), "+d"(xv[7]),
+                        "+d"(xv[8]), "+d"(xv[9]), "+d"(xv[10]), "+d"(xv[11]), "+d"(xv[12]), "+d"(xv[13]), "+d"(xv[14]), "+d"(xv[15]));
+    else if constexpr (NJ == 10)
+      asm volatile("" : "+d"(xv[0]), "+d"(xv[1]), "+d"(xv[2]), "+d"(xv[3]), "+d"(xv[4]), "+d"(xv[5]), "+d"(xv[6]), "+d"(xv[7]),
+                        "+d"(xv[8]), "+d"(xv[9]));
+    else
+      asm volatile("" : "+d"(xv[0]), "+d"(xv[1]), "+d"(xv[2]), "+d"(xv[3]), "+d"(xv[4]), "+d"(xv[5]));
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j += 2) {
+      if (part + j * MVP_PARTS < L) acc0 = fma(vv[j], xv[j], acc0);
+      if (j + 1 < NJ && part + (j + 1) * MVP_PARTS < L) acc1 = fma(vv[j + 1], xv[j + 1], acc1);
+    }
+    part_sum[it & 1][threadIdx.x] = acc0 + acc1;
+    __syncthreads();  // the stage is consumed, the partial sums are there (and those of chunk ch - 1 have been read)
+    if (threadIdx.x == 0 && ch + MVP_STAGES < ch1) issue(ch + MVP_STAGES);
+    if (part == 0 && rl < nr) {
+      double a = part_sum[it & 1][rl];
+#pragma unroll
+      for (int q = 1; q < MVP_PARTS; q++) a += part_sum[it & 1][q * MVP_ROWS + rl];
+      y[row0 + r0 + rl] = a;
+    }
+  }
+}
+
 __global__ void set_flags_kernel(unsigned char* __restrict__ flags, const uint64_t* __restrict__ idx, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[idx[i]] = 1;
@@ -1344,6 +1506,7 @@ static int launch_qk_mv_interior(MatrixPlan* p, const double* values, const doub
     if (n1 <= 0 || n2 <= 0 || nrow0 <= 0) continue;
     // long lines (2-D grids) are cut along x so that the launch fills the machine
     const long long lines = (long long)n1 * n2;
+    static const bool mv_pipe = [] { const char* e = getenv("PDB200_MV_PIPE"); return !(e && e[0] == '0'); }();
     if (L <= 32) {
       const size_t smem = (size_t)256 * L * sizeof(double);
       if (smem > 48 * 1024)
@@ -1352,6 +1515,19 @@ static int launch_qk_mv_interior(MatrixPlan* p, const double* values, const doub
       const int chunks = (nrow0 + 255) / 256;
       const int nz = (int)std::max<long long>(1, std::min<long long>(chunks, (148 * 8 + lines - 1) / lines));
       qk_mv_interior_short_kernel<DIM, K, 1><<<dim3(n1, n2, nz), 256, smem, s>>>(P, D, g, L, p->lut, p->rowptr, values, x, y);
+    } else if (mv_pipe && DIM == 3 && K == 2 && (L == 45 || L == 75 || L == 125)) {  // ring of bulk copies
+      const size_t smem = (size_t)MVP_STAGES * (MVP_ROWS * L + 2) * sizeof(double);
+      const int chunks = (nrow0 + MVP_ROWS - 1) / MVP_ROWS;
+      const int nz = (int)std::max<long long>(1, std::min<long long>(chunks, (148 * 8 + lines - 1) / lines));
+#define PDB_MV_PIPE(LL)                                                                                                      \
+  do {                                                                                                                       \
+    PDB_CUDA(cudaFuncSetAttribute(qk_mv_interior_pipe_kernel<3, 2, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    qk_mv_interior_pipe_kernel<3, 2, LL><<<dim3(n1, n2, nz), MVP_THREADS, smem, s>>>(P, D, g, p->lut, p->rowptr, p->nnz, values, x, y); \
+  } while (0)
+      if (L == 45) PDB_MV_PIPE(45);
+      else if (L == 75) PDB_MV_PIPE(75);
+      else PDB_MV_PIPE(125);
+#undef PDB_MV_PIPE
     } else if (L > 64) {  // 75 / 125 entries: the chunk would cap the occupancy; one warp per row instead
       qk_mv_interior_kernel<DIM, K><<<dim3(n1, n2), 256, 0, s>>>(P, D, g, L, p->lut, p->rowptr, values, x, y);
     } else {
