@@ -718,8 +718,11 @@ __device__ __forceinline__ void tile_body(const CUtensorMap& tm_rows, const CUte
   if (rowlane || zissued) tma_store_commit_and_wait();
 }
 
+#ifndef PDB200_FAST_MINB
+#define PDB200_FAST_MINB 3  // tuning aid (tools/build_variant.sh): resident CTAs per SM the register cap is set for
+#endif
 template <int AMODE, bool HAS_C, bool WEIGHTS_ON, bool HAS_B, bool FUSED>
-__global__ void __launch_bounds__(TX* TY* TZ, 3)
+__global__ void __launch_bounds__(TX* TY* TZ, PDB200_FAST_MINB)
     dg_fast_q2_3d_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_pf,
                          const double* __restrict__ xin, const __grid_constant__ DevParams P,
                          const __grid_constant__ FastConst F, const __grid_constant__ TileFrame TF) {
