@@ -605,6 +605,140 @@ __global__ void __launch_bounds__(256, 4) qk_interior_kernel(const DevParams P, 
   }
 }
 
+// ---- values of the interior rows, several x-lines per CTA --------------------------------------------
+// The decode of a thread's slot (which cells couple the row's and the column's lattice point, and with which local
+// indices) is the same for every line of an entity group, and with one line per CTA it dominated short lines: two
+// dependent table look-ups and the coefficient rows cost about as long as writing the line.  Here a CTA decodes once
+// and walks QKV_LINES consecutive lines; the coefficient rows of the next line arrive by cp.async while the current
+// one is written.  Along a line a thread takes CONSECUTIVE rows, so the coefficient of the upper x-cell of one row is
+// the lower x-cell's of the next: per entry at most four shared-memory loads (one per (y, z) candidate pair) instead
+// of eight, with the addresses held in four running pointers.  Sum order = ascending cell index, as in
+// qk_interior_kernel and the reference's scatter (assemblerutilities.hh:449-460).
+constexpr int QKV_LINES = 8;
+
+__device__ __forceinline__ void qk_cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int DIM, int K, bool VT0>
+__global__ void __launch_bounds__(256, 4)
+    qk_interior_values_kernel(const DevParams P, const QkDecode D, int g, int L, int n1, const QkLut* __restrict__ lut_g,
+                              const double* __restrict__ tab_g, const u64* __restrict__ rowptr, double* __restrict__ values,
+                              int fresh) {
+  constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  extern __shared__ double kap[];  // [2 buffers][rows (j2 * 2 + j1)][KS] coefficients of the candidate cells of a line
+  const int s = D.sbits[g];
+  const bool vt[3] = {VT0, !((s >> 1) & 1), !((s >> 2) & 1)};  // vertex-type direction: two candidate cells
+  const int N0 = P.N[0], KS = qk_kap_stride(N0);
+  const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
+  const int sh1 = vt[1] ? 1 : 0, sh2 = DIM == 3 && vt[2] ? 1 : 0;
+  const int a2 = DIM == 3 ? (int)blockIdx.y + sh2 : 0, cb2 = DIM == 3 ? (int)blockIdx.y : 0;
+  const int l0 = (int)blockIdx.x * QKV_LINES, l1 = min(n1, l0 + QKV_LINES);  // lines of this CTA: a1 = l + sh1
+  const int lo0 = VT0 ? 1 : 0, hi0 = N0 - 1;
+  const int R = (int)blockDim.x / L;  // row chunks of a line worked on side by side
+  const int rsub = (int)threadIdx.x / L, slot = (int)threadIdx.x - rsub * L;
+  const bool active = rsub < R;
+  int shape = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) shape |= (vt[d] ? 1 : 0) << d;
+  const int off = active ? lut_g->slot2off[shape][slot] : 0;
+  const int o[3] = {off & 7, (off >> 3) & 7, off >> 6};
+  int e[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < DIM; d++) e[d] = o[d] - (vt[d] ? K : 1);
+  // per direction: candidate cell (0: lower / only, 1: upper), local row index, local column index
+  int nd[3] = {1, 1, 1}, dl[3][2] = {}, li[3][2] = {}, lj[3][2] = {};
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    int n = 0;
+    if (vt[d]) {
+      if (e[d] <= 0) { dl[d][n] = 0; li[d][n] = K; lj[d][n] = e[d] + K; n++; }
+      if (e[d] >= 0) { dl[d][n] = 1; li[d][n] = 0; lj[d][n] = e[d]; n++; }
+    } else {
+      dl[d][n] = 0; li[d][n] = 1; lj[d][n] = e[d] + 1; n++;
+    }
+    nd[d] = n;
+  }
+  // per (y, z) candidate pair m = c1 + 2 c2: coefficient row and the table entries of the lower / upper (or only) x-cell
+  double cL[4], cU[4];
+  int ro[4];
+  bool any[4];
+#pragma unroll
+  for (int c2 = 0; c2 < 2; c2++)
+#pragma unroll
+    for (int c1 = 0; c1 < 2; c1++) {
+      const int m = c1 + 2 * c2;
+      const bool on = active && c1 < nd[1] && c2 < nd[2];
+      const int i12 = N1 * (li[1][c1] + N1 * (DIM == 3 ? li[2][c2] : 0));
+      const int j12 = N1 * (lj[1][c1] + N1 * (DIM == 3 ? lj[2][c2] : 0));
+      cL[m] = cU[m] = 0.0;
+#pragma unroll
+      for (int c0 = 0; c0 < 2; c0++)
+        if (on && c0 < nd[0]) {
+          const double tv = tab_g[(li[0][c0] + i12) * N + lj[0][c0] + j12];
+          if (VT0 && dl[0][c0] == 0) cL[m] = tv; else cU[m] = tv;
+        }
+      ro[m] = on ? (dl[2][c2] * 2 + dl[1][c1]) * KS : 0;
+      any[m] = __any_sync(0xffffffffu, on);
+    }
+  const int cn1 = vt[1] ? 2 : 1, cn2 = DIM == 3 ? (vt[2] ? 2 : 1) : 1;
+  const int BS = ((cn2 - 1) * 2 + cn1) * KS;  // doubles per buffer: rows (j2 * 2 + j1)
+  const bool ident = P.a_mode == PDB200_A_IDENTITY;
+  if (ident)
+    for (int i = threadIdx.x; i < 2 * BS; i += blockDim.x) kap[i] = 1.0;
+  auto stage = [&](int l, int buf) {  // coefficient rows of line l -> buffer buf
+    if (ident) return;
+    double* kb = kap + buf * BS;
+    for (int i = threadIdx.x; i < cn2 * cn1 * N0; i += blockDim.x) {
+      const int x = i % N0, j1 = (i / N0) % cn1, j2 = i / (N0 * cn1);
+      qk_cp_async8(kb + (j2 * 2 + j1) * KS + x, P.A + cell_index(P.N, x, l + j1, cb2 + j2));
+    }
+  };
+  auto line_base = [&](int l) { return rowptr[D.start[g] + (u64)lo0 + (u64)sz0 * ((u64)(l + sh1) + (u64)sz1 * (u64)a2)]; };
+  const int nrows = hi0 - lo0 + 1, chunk = (nrows + R - 1) / R;
+  const int a_beg = lo0 + rsub * chunk, a_end = min(hi0 + 1, a_beg + chunk);
+  stage(l0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  u64 base = line_base(l0);
+  for (int l = l0; l < l1; l++) {
+    const int buf = (l - l0) & 1;
+    u64 next_base = 0;
+    if (l + 1 < l1) {
+      stage(l + 1, buf ^ 1);
+      next_base = line_base(l + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the rows of the next line has arrived
+    __syncthreads();
+    if (active && a_beg < a_end) {
+      const double* kb = kap + buf * BS + a_beg;
+      const double* kp0 = kb + ro[0];
+      const double* kp1 = kb + ro[1];
+      const double* kp2 = kb + ro[2];
+      const double* kp3 = kb + ro[3];
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      if (VT0) {
+        if (any[0]) p0 = kp0[-1];
+        if (any[1]) p1 = kp1[-1];
+        if (any[2]) p2 = kp2[-1];
+        if (any[3]) p3 = kp3[-1];
+      }
+      double* dst = values + base + (size_t)(a_beg - lo0) * L + slot;
+#pragma unroll 4
+      for (int a0 = a_beg; a0 < a_end; a0++, dst += L) {
+        double v = 0.0;
+        if (any[0]) { const double u = *kp0++; if (VT0) v = fma(cL[0], p0, v); v = fma(cU[0], u, v); p0 = u; }
+        if (any[1]) { const double u = *kp1++; if (VT0) v = fma(cL[1], p1, v); v = fma(cU[1], u, v); p1 = u; }
+        if (any[2]) { const double u = *kp2++; if (VT0) v = fma(cL[2], p2, v); v = fma(cU[2], u, v); p2 = u; }
+        if (any[3]) { const double u = *kp3++; if (VT0) v = fma(cL[3], p3, v); v = fma(cU[3], u, v); p3 = u; }
+        *dst = fresh ? v : *dst + v;
+      }
+    }
+    __syncthreads();  // the buffer is restaged two lines on
+    base = next_base;
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(QK_THREADS)
     qk_mv_kernel(const QkDecode D, const QkLut* __restrict__ lut_g, const u64* __restrict__ rowptr, u64 nrows,
@@ -1479,12 +1613,30 @@ static int launch_qk_interior(MatrixPlan* p, double* values, IDX* colidx, bool f
     const int nrow0 = vt[0] ? P.N[0] - 1 : P.N[0];
     if (n1 <= 0 || n2 <= 0 || nrow0 <= 0) continue;
     const int threads = 256;
-    const size_t smem = VALUES ? (size_t)4 * qk_kap_stride(P.N[0]) * sizeof(double) : 0;
-    if (smem > 48 * 1024)
-      PDB_CUDA(cudaFuncSetAttribute(qk_interior_kernel<DIM, K, IDX, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    qk_interior_kernel<DIM, K, IDX, VALUES><<<dim3(n1, n2), threads, smem, s>>>(P, D, g, L, p->lut, p->tables, p->rowptr,
-                                                                               values, colidx, fresh ? 1 : 0);
+    const size_t smem2 = (size_t)2 * ((DIM == 3 && vt[2] ? 2 : 0) + (vt[1] ? 2 : 1)) * qk_kap_stride(P.N[0]) * sizeof(double);
+    if (VALUES && smem2 <= 160 * 1024) {
+      const dim3 grid((n1 + QKV_LINES - 1) / QKV_LINES, n2);
+      if (vt[0]) {
+        if (smem2 > 48 * 1024)
+          PDB_CUDA(cudaFuncSetAttribute(qk_interior_values_kernel<DIM, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        qk_interior_values_kernel<DIM, K, true><<<grid, threads, smem2, s>>>(P, D, g, L, n1, p->lut, p->tables, p->rowptr, values,
+                                                                           fresh ? 1 : 0);
+      } else {
+        if (smem2 > 48 * 1024)
+          PDB_CUDA(cudaFuncSetAttribute(qk_interior_values_kernel<DIM, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        qk_interior_values_kernel<DIM, K, false><<<grid, threads, smem2, s>>>(P, D, g, L, n1, p->lut, p->tables, p->rowptr, values,
+                                                                            fresh ? 1 : 0);
+      }
+    } else if (VALUES) {  // lines too long for two coefficient buffers: one line per CTA
+      const size_t smem = (size_t)4 * qk_kap_stride(P.N[0]) * sizeof(double);
+      if (smem > 48 * 1024)
+        PDB_CUDA(cudaFuncSetAttribute(qk_interior_kernel<DIM, K, IDX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      qk_interior_kernel<DIM, K, IDX, true><<<dim3(n1, n2), threads, smem, s>>>(P, D, g, L, p->lut, p->tables, p->rowptr, values,
+                                                                              colidx, fresh ? 1 : 0);
+    } else {
+      qk_interior_kernel<DIM, K, IDX, false><<<dim3(n1, n2), threads, 0, s>>>(P, D, g, L, p->lut, p->tables, p->rowptr, values,
+                                                                             colidx, 0);
+    }
     PDB_CUDA(cudaGetLastError());
     launches++;
   }
