@@ -450,15 +450,6 @@ __global__ void __launch_bounds__(KronDims<K>::THREADS, 1)
   }
 }
 
-__global__ void kron_axpy_kernel(double* __restrict__ y, const double* __restrict__ t, const double* __restrict__ r0,
-                                 long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  if (r0)
-    for (; i < n; i += stride) y[i] += t[i] + r0[i];
-  else
-    for (; i < n; i += stride) y[i] += t[i];
-}
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -362,7 +362,7 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
   res->conv_rate = 0.0;
   double def0 = 0.0, def = 0.0;
   double it = 0.0, it_done = 0.0;
-  double *PA, *PB, *PC, *PD, *PE;
+  double *PA, *PB, *PC, *PD;
   // global sums of the overlapping scalar product: every producer of block partials is followed by the reduction
   auto AR = [&](double* P1, double* P2) {
     if (ops.allreduce) {
@@ -373,7 +373,7 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
   if (solver == PDB200_SOLVER_BICGSTAB) {
     const bool gp = (bool)ops.prec;  // general preconditioner: y = W p / y = W r by separate launches
     ensure(w, n, dinv || gp ? 6 : 5);
-    PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB, PE = PD + NB;
+    PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB;
     double *r = w->vec[0], *rt = w->vec[1], *p = w->vec[2], *v = w->vec[3], *t = w->vec[4];
     double* y = dinv || gp ? w->vec[5] : nullptr;
     // r = b - A x  (BiCGSTABSolver::apply: op.applyscaleadd(-1, x, r))
@@ -417,8 +417,7 @@ int krylov_solve(KrylovWork* w, int solver, long long n, const KrylovOps& ops, d
   } else if (solver == PDB200_SOLVER_CG) {
     const bool gp = (bool)ops.prec;
     ensure(w, n, dinv || gp ? 4 : 3);
-    PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB, PE = PD + NB;
-    (void)PE;
+    PA = w->partials, PB = PA + NB, PC = PB + NB, PD = PC + NB;
     double *r = w->vec[0], *p = w->vec[1], *q = w->vec[2];
     double* z = dinv || gp ? w->vec[3] : nullptr;
     ops.apply(x, r);
