@@ -27,6 +27,7 @@
 // rounding); QkDG blocks are integrated with the reference's quadrature loops.
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -622,7 +623,7 @@ __device__ __forceinline__ void qk_cp_async8(double* dst, const double* src) {
 
 template <int DIM, int K, bool VT0>
 __global__ void __launch_bounds__(256, 4)
-    qk_interior_values_kernel(const DevParams P, const QkDecode D, int g, int L, int n1, const QkLut* __restrict__ lut_g,
+    qk_interior_values_kernel(const DevParams P, const QkDecode D, int g, int L, int n1, int lpb, const QkLut* __restrict__ lut_g,
                               const double* __restrict__ tab_g, const u64* __restrict__ rowptr, double* __restrict__ values,
                               int fresh) {
   constexpr int N1 = K + 1, N = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(256, 4)
   const int sz0 = (int)D.sz0[g], sz1 = (int)D.sz1[g];
   const int sh1 = vt[1] ? 1 : 0, sh2 = DIM == 3 && vt[2] ? 1 : 0;
   const int a2 = DIM == 3 ? (int)blockIdx.y + sh2 : 0, cb2 = DIM == 3 ? (int)blockIdx.y : 0;
-  const int l0 = (int)blockIdx.x * QKV_LINES, l1 = min(n1, l0 + QKV_LINES);  // lines of this CTA: a1 = l + sh1
+  const int l0 = (int)blockIdx.x * lpb, l1 = min(n1, l0 + lpb);  // lines of this CTA: a1 = l + sh1
   const int lo0 = VT0 ? 1 : 0, hi0 = N0 - 1;
   const int R = (int)blockDim.x / L;  // row chunks of a line worked on side by side
   const int rsub = (int)threadIdx.x / L, slot = (int)threadIdx.x - rsub * L;
@@ -1615,16 +1616,19 @@ static int launch_qk_interior(MatrixPlan* p, double* values, IDX* colidx, bool f
     const int threads = 256;
     const size_t smem2 = (size_t)2 * ((DIM == 3 && vt[2] ? 2 : 0) + (vt[1] ? 2 : 1)) * qk_kap_stride(P.N[0]) * sizeof(double);
     if (VALUES && smem2 <= 160 * 1024) {
-      const dim3 grid((n1 + QKV_LINES - 1) / QKV_LINES, n2);
+      // lines per CTA: 8 on a full machine, fewer on small grids so that every SM still gets a few CTAs
+      int lpb = (int)std::max<long long>(1, std::min<long long>(QKV_LINES, (long long)n1 * n2 / (4 * 148)));
+      if (const char* e = getenv("PDB200_QKV_LINES")) lpb = std::max(1, atoi(e));  // tests: the multi-line walk on small grids
+      const dim3 grid((n1 + lpb - 1) / lpb, n2);
       if (vt[0]) {
         if (smem2 > 48 * 1024)
           PDB_CUDA(cudaFuncSetAttribute(qk_interior_values_kernel<DIM, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        qk_interior_values_kernel<DIM, K, true><<<grid, threads, smem2, s>>>(P, D, g, L, n1, p->lut, p->tables, p->rowptr, values,
+        qk_interior_values_kernel<DIM, K, true><<<grid, threads, smem2, s>>>(P, D, g, L, n1, lpb, p->lut, p->tables, p->rowptr, values,
                                                                            fresh ? 1 : 0);
       } else {
         if (smem2 > 48 * 1024)
           PDB_CUDA(cudaFuncSetAttribute(qk_interior_values_kernel<DIM, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        qk_interior_values_kernel<DIM, K, false><<<grid, threads, smem2, s>>>(P, D, g, L, n1, p->lut, p->tables, p->rowptr, values,
+        qk_interior_values_kernel<DIM, K, false><<<grid, threads, smem2, s>>>(P, D, g, L, n1, lpb, p->lut, p->tables, p->rowptr, values,
                                                                             fresh ? 1 : 0);
       }
     } else if (VALUES) {  // lines too long for two coefficient buffers: one line per CTA

@@ -66,6 +66,18 @@ def test_fem_pattern_and_jacobian_match_oracle(cuda_lib, case):
     _check(fem_problem(**case))
 
 
+@pytest.mark.parametrize("lines", [2, 3, 8])
+@pytest.mark.parametrize("case", [dict(cells=(9, 7, 6), degree=2, a="scalar"), dict(cells=(6, 11, 5), degree=1, a="scalar"),
+                                  dict(cells=(12, 19), degree=2, a="scalar"), dict(cells=(5, 9, 4), degree=2, a="identity")],
+                         ids=_id)
+def test_multi_line_values_kernel_on_small_grids(cuda_lib, case, lines, monkeypatch):
+    """The interior values kernel walks several x-lines per CTA on big grids only (one line per CTA below ~600 lines);
+    PDB200_QKV_LINES forces the walk - line counts that are no multiple of it, the double-buffered coefficient rows and
+    the accumulate form - on grids the oracle assembles in full."""
+    monkeypatch.setenv("PDB200_QKV_LINES", str(lines))
+    _check(fem_problem(**case))
+
+
 @pytest.mark.parametrize("case", DG_CASES, ids=_id)
 def test_dg_pattern_and_jacobian_match_oracle(cuda_lib, case):
     spec = dg_problem(**case)
