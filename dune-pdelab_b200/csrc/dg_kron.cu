@@ -44,10 +44,16 @@ struct KronCfg<4> {
   // 24 cells = 4 warps of 6 cells, 105 KB of shared memory: TWO CTAs per SM, so that one CTA's tile load / result
   // store runs under the other's sweeps (the 4 x 4 x 3 tile of round 1 filled the SM with ONE CTA of 152 KB: a third of
   // the tile time was load and store latency with nothing to overlap it)
-#ifdef PDB200_KRON4_BIG_TILE
+  // A warp (6 cells x 5 planes) is ONE x-row of the tile: six cells stored 125 doubles apart put the 15 + 14 lanes of
+  // the two half-warps on distinct bank pairs in the x- and y-sweeps (tools/smem_bank_sim.py: 0 % replays instead of
+  // 33 % with the 4 x 2 x 3 tile, whose warps straddle two rows; the z-sweep and the y-plane transposes stay at 50 %).
+  // Same 24 cells, 88 cells of shared memory and two CTAs per SM as 4 x 2 x 3.
+#if defined(PDB200_KRON4_BIG_TILE)
   static constexpr int TX = 4, TY = 4, TZ = 3;  // 48 cells = 8 warps of 6 cells
-#else
+#elif defined(PDB200_KRON4_TILE_423)
   static constexpr int TX = 4, TY = 2, TZ = 3;
+#else
+  static constexpr int TX = 6, TY = 2, TZ = 2;
 #endif
 };
 template <>

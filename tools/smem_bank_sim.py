@@ -11,7 +11,8 @@ import itertools
 
 K = 4
 N1, NPL, NLOC = K + 1, (K + 1) ** 2, (K + 1) ** 3
-TX, TY, TZ = 4, 2, 3
+import sys
+TX, TY, TZ = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (4, 2, 3)  # tile of KronCfg<4>
 ROWX, CPW = TX + 4, 32 // N1
 CELLS = TX * TY * TZ
 WARPS = CELLS // CPW
