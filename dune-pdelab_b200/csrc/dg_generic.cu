@@ -103,7 +103,7 @@ template <int DIM, int K, bool RESIDUAL>
 __global__ void __launch_bounds__(128) dg_generic_kernel(const DevParams P, const double* __restrict__ x,
                                                          double* __restrict__ y, int overwrite,
                                                          int* __restrict__ errflag) {
-  constexpr int N1 = K + 1, N = Loc<DIM, K>::N;
+  constexpr int N = Loc<DIM, K>::N;
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= P.ncells) return;
   int c[3];
